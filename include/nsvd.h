@@ -1,0 +1,167 @@
+/*
+ * nsvd.h — C-ABI of the B200-native NestedLoRA training-step library (libnsvd.so).
+ *
+ * The reference (jongharyu/neural-svd) is pure Python/PyTorch and has NO FFI; the drop-in
+ * boundary is its Python API (methods/nestedlora.py:254-267 `NestedLoRA.compute_loss_operator`,
+ * :365-378 `NestedLoRAForCDK.compute_loss`).  This header is the C-ABI a maintainer would bind
+ * underneath that API (ctypes stub shown in INTEGRATION.md): plain pointers and sizes, no torch
+ * types.  Every entry point names the reference code it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *  - everything is fp32, row-major, contiguous; tensors are owned by the caller (PyTorch's
+ *    caching allocator in the shipped host code); the library never allocates device memory:
+ *    scratch is passed in (`nsvd_*_bytes` tell how much);
+ *  - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued on it, nothing
+ *    synchronises the host;
+ *  - return value: 0 on success, otherwise a `cudaError_t` value or NSVD_E_* below;
+ *    `nsvd_last_error()` returns a static message for the calling thread;
+ *  - there is no CPU fallback: without an sm_100 device every compute call fails.
+ */
+#ifndef NSVD_H_
+#define NSVD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSVD_ABI_VERSION 1
+
+enum {
+  NSVD_E_BADARG = 10001,   /* shape / enum / alignment violation */
+  NSVD_E_NODEVICE = 10002, /* no sm_100 device */
+  NSVD_E_WORKSPACE = 10003 /* workspace too small */
+};
+
+/* potentials: examples/operator/pde/schrodinger/potentials.py:5-8 and :24-27 */
+enum { NSVD_POT_HYDROGEN = 0, NSVD_POT_HARMONIC = 1 };
+
+/* arithmetic engines for the dense contractions.
+ *   FP32_SIMT   : CUDA-core fp32 FMA. Reference-grade accuracy; validation and tiny batches.
+ *   BF16X3_TC   : tcgen05 tensor cores, every fp32 operand split into bf16 hi+lo and the
+ *                 product formed as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM
+ *                 (~2^-16 relative operand error, measured 1e-5 on loss/grad: DESIGN.md §4). */
+enum { NSVD_ENGINE_FP32_SIMT = 0, NSVD_ENGINE_BF16X3_TC = 1 };
+
+/* One problem instance = what the reference spreads over get_problem (pde/problems.py:23-130),
+ * get_wavefunctions (pde/__init__.py:19-55) and the Gaussian sampler (pde/main_pde.py:89-100). */
+typedef struct nsvd_problem {
+  int32_t n_points;        /* B: collocation points held by this rank                          */
+  int32_t n_copies;        /* L: number of eigenfunctions = parallel MLP copies (mlp.py:167)    */
+  int32_t n_fourier;       /* M_ff: Fourier mapping size; layer-0 fan-in is 2*M_ff (utils.py:102)*/
+  int32_t hidden;          /* hidden width of the 3 hidden layers; must be 128                  */
+  int32_t potential;       /* NSVD_POT_*                                                        */
+  int32_t has_exp_mask;    /* ExponentialMask present (pde/boundary.py:39-53)                   */
+  float pot_coef;          /* charge Z (hydrogen) or k (harmonic)                               */
+  float scale_kinetic;     /* kappa, problems.py:28 (1.0 for single-particle problems)          */
+  float op_scale;          /* OperatorWrapper.scale  (examples/__init__.py:2-9)                 */
+  float op_shift;          /* OperatorWrapper.shift                                             */
+  float sampling_sigma;    /* sigma of the Gaussian importance density (main_pde.py:94-100)     */
+  float hard_mul_const;    /* WaveFunctions.hard_mul_const (pde/__init__.py:9-16)               */
+} nsvd_problem_t;
+
+/* Parameters in the reference's own layout (ParallelMLP, mlp.py:181-199):
+ *   Bff (2, M_ff); W[0] (L,128,2*M_ff); W[1],W[2] (L,128,128); W[3] (L,1,128);
+ *   b[0..2] (L,128,1); b[3] (L,1,1); mask_scales (L) or NULL.                                 */
+typedef struct nsvd_params {
+  const float* Bff;
+  const float* W[4];
+  const float* b[4];
+  const float* mask_scales;
+} nsvd_params_t;
+
+typedef struct nsvd_grads {
+  float* dW[4];
+  float* db[4];
+  float* dmask_scales; /* may be NULL when has_exp_mask == 0 */
+} nsvd_grads_t;
+
+int nsvd_abi_version(void);
+const char* nsvd_last_error(void);
+/* 0 when device `dev` is an sm_100 part this library can run on. */
+int nsvd_device_ok(int dev);
+
+/* Scratch sizes for nsvd_fwd_streams / nsvd_mlp_bwd.  `saved_bytes`: value-stream activations
+ * kept from forward to backward (whole batch).  `work_bytes`: micro-batch scratch, reusable. */
+int nsvd_scratch_bytes(const nsvd_problem_t* pb, int engine, size_t* saved_bytes, size_t* work_bytes);
+
+/* K1  fwd_streams.  Replaces, in one pass and in forward mode (no autograd double backward):
+ *   GaussianFourierFeatureTransform.forward  examples/utils.py:126-143
+ *   ParallelMLP.forward                      examples/models/mlp.py:204-221
+ *   WaveFunctions.forward / ExponentialMask  pde/__init__.py:15-16, pde/boundary.py:46-53
+ *   VectorizedLaplacian (exact, importance)  pde/diff_ops.py:9-23,54-93
+ *   NegativeHamiltonian.__call__             pde/schrodinger/__init__.py:16-22
+ *   OperatorWrapper.__call__                 examples/__init__.py:7-9
+ * in : x (B,2);  out: F (B,L), TF (B,L); `saved` is filled for nsvd_mlp_bwd.                    */
+int nsvd_fwd_streams(const nsvd_problem_t* pb, const nsvd_params_t* pr, int engine, const float* x,
+                     float* F, float* TF, void* saved, size_t saved_bytes, void* work,
+                     size_t work_bytes, void* stream);
+
+/* K2  gram_reduce.  Replaces compute_lambda / compute_loss_metric / the operator term
+ * (methods/nestedlora.py:10-11,57-64,92) up to normalisation: writes the UN-normalised sums
+ *   terms = [ F1^T F1 (L*L) | F2^T F2 (L*L) | sum_b sum_l v_l F_bl TF_bl (1) ]
+ * where F1 = rows [0,b1), F2 = rows [b1,B).  This is the buffer that is all-reduced across
+ * ranks.  `partials` must hold nsvd_gram_partials_bytes(B, L) bytes.  Deterministic.           */
+size_t nsvd_gram_partials_bytes(int32_t n_points, int32_t n_copies);
+int nsvd_gram_reduce(const float* F, const float* TF, const float* vector_mask, int32_t n_points,
+                     int32_t n_copies, int32_t b1, float* terms, void* partials, void* stream);
+
+/* Full cross Grams for evaluation (methods/spectrum.py:74-75): cov += w^2 F^T F, quad += w^2 F^T TF
+ * with optional per-row weight `roww` (sqrt_ws, may be NULL).  Accumulates into cov, quad (L*L). */
+int nsvd_cross_gram(const float* F, const float* TF, const float* roww, int32_t n_points,
+                    int32_t n_copies, float* cov, float* quad, void* partials, void* stream);
+
+/* Loss value from (all-reduced) terms: NestedLoRALossFunctionEVD.forward, nestedlora.py:70-94.
+ * Bg, B1g, B2g are the GLOBAL row counts.  Writes loss[0] and coef (2*L*L):
+ *   coef[0:L*L]   = (2/B1g) * M * Lambda2   (applied to rows of F1)
+ *   coef[L*L:]    = (2/B2g) * M * Lambda1   (applied to rows of F2)                             */
+int nsvd_loss_finalize(const float* terms, const float* matrix_mask, int32_t n_copies, int64_t Bg,
+                       int64_t B1g, int64_t B2g, float* loss, float* coef, void* stream);
+
+/* K3  loss_dF.  The reference's hand-written backward (nestedlora.py:98-111), summed over the
+ * views f, f1, f2:  dF = gscale * ( -(4/Bg) v (.) TF + F_half . coef_half ).
+ * TF == NULL drops the operator term, coef == NULL drops the metric term (used by the
+ * stand-alone NestedLoRALossFunctionEVD, whose f, f1, f2 need not alias).                      */
+int nsvd_loss_dF(const float* F, const float* TF, const float* vector_mask, const float* coef,
+                 const float* grad_scale /*device scalar or NULL (=1)*/, int32_t n_points,
+                 int32_t n_copies, int32_t b1, int64_t Bg, float* dF, void* stream);
+
+/* K4  mlp_bwd.  Replaces the autograd backward through the central model evaluation
+ * (value stream only).  Gradients are WRITTEN (not accumulated) into `gr`.   */
+int nsvd_mlp_bwd(const nsvd_problem_t* pb, const nsvd_params_t* pr, int engine, const float* x,
+                 const float* dF, const void* saved, size_t saved_bytes, nsvd_grads_t* gr,
+                 void* work, size_t work_bytes, void* stream);
+
+/* K5/K6  CDK loss (methods/nestedlora.py:270-332).  f, g: (B, L) WITHOUT the constant column;
+ * vector_mask (Lp), matrix_mask (Lp,Lp) with Lp = L + first_const.
+ *   fwd: terms = [Fp^T Fp | Gp^T Gp | sum v f g] un-normalised (all-reducible), then
+ *   nsvd_cdk_finalize -> losses[3] = {loss, loss_operator, loss_metric}, coef (2*Lp*Lp);
+ *   bwd: grad_f, grad_g (B, L).  rs_joint (B) = diag(Fp Gp^T) is produced by fwd when non-NULL;
+ *   nsvd_cdk_offdiag writes off_diagonal(Fp Gp^T) (B*B-B) on request (methods/utils.py:16-22). */
+size_t nsvd_cdk_work_bytes(int32_t n_rows, int32_t n_feat, int32_t first_const);
+int nsvd_cdk_fwd(const float* f, const float* g, const float* vector_mask, int32_t n_rows,
+                 int32_t n_feat, int32_t first_const, float* terms, float* rs_joint, void* work,
+                 size_t work_bytes, void* stream);
+int nsvd_cdk_finalize(const float* terms, const float* matrix_mask, int32_t Lp, int64_t Bg,
+                      float* losses, float* coef, void* stream);
+int nsvd_cdk_bwd(const float* f, const float* g, const float* vector_mask, const float* coef,
+                 const float* grad_scale, int32_t n_rows, int32_t n_feat, int32_t first_const,
+                 int64_t Bg, float* grad_f, float* grad_g, void* stream);
+int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_feat,
+                     int32_t first_const, float* rs_indep, void* stream);
+
+/* Self-test hooks for the tcgen05 building block (tests/test_gpu_tc_gemm.py):
+ *   D (M,N) fp32 = A . B^T with bf16x3 splitting; A (M,K), B (N,K) fp32 when *_kmajor = 1,
+ *   A (K,M) / B (K,N) when 0 (MN-major operands, as the weight-gradient GEMMs use them).       */
+int nsvd_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K,
+                          int32_t a_kmajor, int32_t b_kmajor, void* work, size_t work_bytes,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSVD_H_ */

@@ -1,0 +1,15 @@
+"""neural_svd_b200 — B200-native (sm_100a) NestedLoRA training step, drop-in for the hot path of
+jongharyu/neural-svd (methods/nestedlora.py on the operators of examples/operator + the CDK loss).
+
+Public names mirror the reference's; see DESIGN.md and INTEGRATION.md.
+"""
+from .models import (ExponentialMask, GaussianFourierFeatureTransform, ParallelMLP, WaveFunctions,
+                     get_mlp_eigfuncs, get_wavefunctions)
+from .nestedlora import (NestedLoRA, NestedLoRAForCDK, NestedLoRALossFunctionEVD, NestedLoRALossFunctionForCDK,
+                         get_joint_nesting_masks, get_sequential_nesting_masks)
+from .operators import (GaussianImportance, NegativeHamiltonian, OperatorWrapper, get_problem,
+                        harmonic_oscillator_potential, hydrogen_potential, make_gaussian_sampler)
+from .fused import compute_loss_operator, get_engine, set_engine
+from .dist import PointParallel, shard_points
+
+__all__ = [n for n in dir() if not n.startswith("_")]

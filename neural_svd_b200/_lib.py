@@ -1,0 +1,93 @@
+"""ctypes binding of libnsvd.so — the thin host layer above the C-ABI (include/nsvd.h).
+
+There is deliberately no fallback: if the library cannot be loaded, or a call fails, a
+RuntimeError is raised.  Only pointers, sizes and the CUDA stream handle cross this boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+from . import build as _build
+
+c_f32p = C.POINTER(C.c_float)
+
+
+class Problem(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("n_copies", C.c_int32), ("n_fourier", C.c_int32),
+                ("hidden", C.c_int32), ("potential", C.c_int32), ("has_exp_mask", C.c_int32),
+                ("pot_coef", C.c_float), ("scale_kinetic", C.c_float), ("op_scale", C.c_float),
+                ("op_shift", C.c_float), ("sampling_sigma", C.c_float), ("hard_mul_const", C.c_float)]
+
+
+class Params(C.Structure):
+    _fields_ = [("Bff", C.c_void_p), ("W", C.c_void_p * 4), ("b", C.c_void_p * 4),
+                ("mask_scales", C.c_void_p)]
+
+
+class Grads(C.Structure):
+    _fields_ = [("dW", C.c_void_p * 4), ("db", C.c_void_p * 4), ("dmask_scales", C.c_void_p)]
+
+
+POT_HYDROGEN, POT_HARMONIC = 0, 1
+ENGINE_FP32_SIMT, ENGINE_BF16X3_TC = 0, 1
+ENGINES = {"fp32": ENGINE_FP32_SIMT, "fp32_simt": ENGINE_FP32_SIMT, "bf16x3": ENGINE_BF16X3_TC,
+           "tc": ENGINE_BF16X3_TC}
+
+_vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+_PB, _PR, _GR = C.POINTER(Problem), C.POINTER(Params), C.POINTER(Grads)
+
+# name -> (restype, argtypes); every symbol declared in include/nsvd.h
+SIGNATURES = {
+    "nsvd_abi_version": (C.c_int, []),
+    "nsvd_last_error": (C.c_char_p, []),
+    "nsvd_device_ok": (C.c_int, [C.c_int]),
+    "nsvd_scratch_bytes": (C.c_int, [_PB, C.c_int, C.POINTER(_sz), C.POINTER(_sz)]),
+    "nsvd_fwd_streams": (C.c_int, [_PB, _PR, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "nsvd_gram_partials_bytes": (_sz, [_i32, _i32]),
+    "nsvd_gram_reduce": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "nsvd_cross_gram": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "nsvd_loss_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "nsvd_loss_dF": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp]),
+    "nsvd_mlp_bwd": (C.c_int, [_PB, _PR, C.c_int, _vp, _vp, _vp, _sz, _GR, _vp, _sz, _vp]),
+    "nsvd_cdk_work_bytes": (_sz, [_i32, _i32, _i32]),
+    "nsvd_cdk_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "nsvd_cdk_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "nsvd_cdk_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp]),
+    "nsvd_cdk_offdiag": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "nsvd_tc_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the tree is newer than the .so).  Raises if impossible."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            path = _build.build()
+            lib = C.CDLL(path)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)        # AttributeError if a declared symbol is missing
+                fn.restype, fn.argtypes = res, args
+            if lib.nsvd_abi_version() != 1:
+                raise RuntimeError("libnsvd.so ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().nsvd_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

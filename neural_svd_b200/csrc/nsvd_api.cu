@@ -1,0 +1,173 @@
+// nsvd_api.cu — extern "C" entry points of libnsvd.so (see include/nsvd.h).
+#include <stdarg.h>
+#include <string.h>
+#include "nsvd_simt.cuh"
+
+namespace nsvd {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static int check_problem(const nsvd_problem_t* pb) {
+  NSVD_CHECK_ARG(pb != nullptr, "problem is NULL");
+  NSVD_CHECK_ARG(pb->n_points >= 2, "n_points must be >= 2 (got %d)", pb->n_points);
+  NSVD_CHECK_ARG(pb->n_copies >= 1 && pb->n_copies <= 64, "n_copies must be in [1,64] (got %d)", pb->n_copies);
+  NSVD_CHECK_ARG(pb->hidden == kHidden, "hidden must be %d (got %d)", kHidden, pb->hidden);
+  NSVD_CHECK_ARG(pb->n_fourier >= 8 && pb->n_fourier % 8 == 0, "n_fourier must be a positive multiple of 8 (got %d)", pb->n_fourier);
+  NSVD_CHECK_ARG(pb->potential == NSVD_POT_HYDROGEN || pb->potential == NSVD_POT_HARMONIC, "unknown potential %d", pb->potential);
+  NSVD_CHECK_ARG(pb->sampling_sigma > 0.f, "sampling_sigma must be > 0");
+  return 0;
+}
+static int check_params(const nsvd_problem_t* pb, const nsvd_params_t* pr) {
+  NSVD_CHECK_ARG(pr != nullptr && pr->Bff != nullptr, "params / Bff is NULL");
+  for (int i = 0; i < 4; ++i) NSVD_CHECK_ARG(pr->W[i] && pr->b[i], "W[%d] or b[%d] is NULL", i, i);
+  NSVD_CHECK_ARG(!pb->has_exp_mask || pr->mask_scales, "has_exp_mask set but mask_scales is NULL");
+  return 0;
+}
+}  // namespace nsvd
+
+using namespace nsvd;
+
+extern "C" {
+
+int nsvd_abi_version(void) { return NSVD_ABI_VERSION; }
+const char* nsvd_last_error(void) { return g_err; }
+
+int nsvd_device_ok(int dev) {
+  cudaDeviceProp p;
+  cudaError_t e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties(%d): %s", dev, cudaGetErrorString(e));
+    return NSVD_E_NODEVICE;
+  }
+  if (p.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, p.major, p.minor);
+    return NSVD_E_NODEVICE;
+  }
+  return 0;
+}
+
+int nsvd_scratch_bytes(const nsvd_problem_t* pb, int engine, size_t* saved_bytes, size_t* work_bytes) {
+  int rc = check_problem(pb);
+  if (rc) return rc;
+  NSVD_CHECK_ARG(saved_bytes && work_bytes, "output pointers are NULL");
+  if (engine == NSVD_ENGINE_FP32_SIMT) simt_scratch_bytes(*pb, saved_bytes, work_bytes);
+  else if (engine == NSVD_ENGINE_BF16X3_TC) tc_scratch_bytes(*pb, saved_bytes, work_bytes);
+  else NSVD_CHECK_ARG(false, "unknown engine %d", engine);
+  return 0;
+}
+
+int nsvd_fwd_streams(const nsvd_problem_t* pb, const nsvd_params_t* pr, int engine, const float* x,
+                     float* F, float* TF, void* saved, size_t saved_bytes, void* work,
+                     size_t work_bytes, void* stream) {
+  int rc = check_problem(pb);
+  if (rc) return rc;
+  if ((rc = check_params(pb, pr))) return rc;
+  NSVD_CHECK_ARG(x && F && TF && saved && work, "NULL buffer");
+  size_t ns, nw;
+  if ((rc = nsvd_scratch_bytes(pb, engine, &ns, &nw))) return rc;
+  if (saved_bytes < ns || work_bytes < nw) {
+    set_error("scratch too small: saved %zu < %zu or work %zu < %zu", saved_bytes, ns, work_bytes, nw);
+    return NSVD_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == NSVD_ENGINE_FP32_SIMT) return simt_forward(*pb, *pr, x, F, TF, saved, work, st);
+  return tc_forward(*pb, *pr, x, F, TF, saved, work, work_bytes, st);
+}
+
+int nsvd_mlp_bwd(const nsvd_problem_t* pb, const nsvd_params_t* pr, int engine, const float* x,
+                 const float* dF, const void* saved, size_t saved_bytes, nsvd_grads_t* gr, void* work,
+                 size_t work_bytes, void* stream) {
+  int rc = check_problem(pb);
+  if (rc) return rc;
+  if ((rc = check_params(pb, pr))) return rc;
+  NSVD_CHECK_ARG(x && dF && saved && work && gr, "NULL buffer");
+  for (int i = 0; i < 4; ++i) NSVD_CHECK_ARG(gr->dW[i] && gr->db[i], "dW[%d] or db[%d] is NULL", i, i);
+  size_t ns, nw;
+  if ((rc = nsvd_scratch_bytes(pb, engine, &ns, &nw))) return rc;
+  if (saved_bytes < ns || work_bytes < nw) {
+    set_error("scratch too small: saved %zu < %zu or work %zu < %zu", saved_bytes, ns, work_bytes, nw);
+    return NSVD_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == NSVD_ENGINE_FP32_SIMT) return simt_backward(*pb, *pr, x, dF, saved, *gr, work, st);
+  return tc_backward(*pb, *pr, x, dF, saved, *gr, work, work_bytes, st);
+}
+
+size_t nsvd_gram_partials_bytes(int32_t n_points, int32_t n_copies) {
+  return gram_partials_bytes(n_points, n_copies);
+}
+
+int nsvd_gram_reduce(const float* F, const float* TF, const float* vector_mask, int32_t n_points,
+                     int32_t n_copies, int32_t b1, float* terms, void* partials, void* stream) {
+  NSVD_CHECK_ARG(F && TF && vector_mask && terms && partials, "NULL buffer");
+  NSVD_CHECK_ARG(n_points >= 1 && n_copies >= 1 && n_copies <= 64, "bad shape B=%d L=%d", n_points, n_copies);
+  NSVD_CHECK_ARG(b1 >= 0 && b1 <= n_points, "b1=%d out of range", b1);
+  return gram_reduce(F, TF, vector_mask, n_points, n_copies, b1, terms, partials, (cudaStream_t)stream);
+}
+
+int nsvd_cross_gram(const float* F, const float* TF, const float* roww, int32_t n_points,
+                    int32_t n_copies, float* cov, float* quad, void* partials, void* stream) {
+  NSVD_CHECK_ARG(F && TF && cov && quad && partials, "NULL buffer");
+  NSVD_CHECK_ARG(n_points >= 1 && n_copies >= 1 && n_copies <= 64, "bad shape B=%d L=%d", n_points, n_copies);
+  return cross_gram(F, TF, roww, n_points, n_copies, cov, quad, partials, (cudaStream_t)stream);
+}
+
+int nsvd_loss_finalize(const float* terms, const float* matrix_mask, int32_t n_copies, int64_t Bg,
+                       int64_t B1g, int64_t B2g, float* loss, float* coef, void* stream) {
+  NSVD_CHECK_ARG(terms && matrix_mask && loss && coef, "NULL buffer");
+  NSVD_CHECK_ARG(Bg > 0 && B1g > 0 && B2g > 0 && B1g + B2g == Bg, "bad counts B=%ld B1=%ld B2=%ld", (long)Bg, (long)B1g, (long)B2g);
+  return loss_finalize(terms, matrix_mask, n_copies, Bg, B1g, B2g, loss, coef, (cudaStream_t)stream);
+}
+
+int nsvd_loss_dF(const float* F, const float* TF, const float* vector_mask, const float* coef,
+                 const float* grad_scale, int32_t n_points, int32_t n_copies, int32_t b1, int64_t Bg,
+                 float* dF, void* stream) {
+  NSVD_CHECK_ARG(F && vector_mask && dF && (TF || coef), "NULL buffer");
+  NSVD_CHECK_ARG(b1 >= 0 && b1 <= n_points && Bg > 0, "bad b1/Bg");
+  NSVD_CHECK_ARG(n_copies >= 1 && n_copies <= 64, "n_copies %d out of [1,64]", n_copies);
+  return loss_dF(F, TF, vector_mask, coef, grad_scale, n_points, n_copies, b1, Bg, dF, (cudaStream_t)stream);
+}
+
+size_t nsvd_cdk_work_bytes(int32_t n_rows, int32_t n_feat, int32_t first_const) {
+  return cdk_work_bytes(n_rows, n_feat, first_const);
+}
+int nsvd_cdk_fwd(const float* f, const float* g, const float* vector_mask, int32_t n_rows, int32_t n_feat,
+                 int32_t first_const, float* terms, float* rs_joint, void* work, size_t work_bytes,
+                 void* stream) {
+  NSVD_CHECK_ARG(f && g && vector_mask && terms && work, "NULL buffer");
+  NSVD_CHECK_ARG(n_rows >= 1 && n_feat >= 1 && (first_const == 0 || first_const == 1), "bad shape");
+  if (work_bytes < cdk_work_bytes(n_rows, n_feat, first_const)) {
+    set_error("cdk work too small");
+    return NSVD_E_WORKSPACE;
+  }
+  return cdk_fwd(f, g, vector_mask, n_rows, n_feat, first_const, terms, rs_joint, work, (cudaStream_t)stream);
+}
+int nsvd_cdk_finalize(const float* terms, const float* matrix_mask, int32_t Lp, int64_t Bg, float* losses,
+                      float* coef, void* stream) {
+  NSVD_CHECK_ARG(terms && matrix_mask && losses && coef && Lp >= 1 && Bg >= 1, "bad args");
+  return cdk_finalize(terms, matrix_mask, Lp, Bg, losses, coef, (cudaStream_t)stream);
+}
+int nsvd_cdk_bwd(const float* f, const float* g, const float* vector_mask, const float* coef,
+                 const float* grad_scale, int32_t n_rows, int32_t n_feat, int32_t first_const, int64_t Bg,
+                 float* grad_f, float* grad_g, void* stream) {
+  NSVD_CHECK_ARG(f && g && vector_mask && coef && grad_f && grad_g, "NULL buffer");
+  return cdk_bwd(f, g, vector_mask, coef, grad_scale, n_rows, n_feat, first_const, Bg, grad_f, grad_g,
+                 (cudaStream_t)stream);
+}
+int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_feat, int32_t first_const,
+                     float* rs_indep, void* stream) {
+  NSVD_CHECK_ARG(f && g && rs_indep && n_rows >= 2, "bad args");
+  return cdk_offdiag(f, g, n_rows, n_feat, first_const, rs_indep, (cudaStream_t)stream);
+}
+
+int nsvd_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K,
+                          int32_t a_kmajor, int32_t b_kmajor, void* work, size_t work_bytes, void* stream) {
+  NSVD_CHECK_ARG(A && B && D && work, "NULL buffer");
+  return tc_gemm_selftest(A, B, D, M, N, K, a_kmajor, b_kmajor, work, work_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,817 @@
+// nsvd_simt.cu — fp32 CUDA-core engine of the NestedLoRA step + the engine-independent
+// HBM-bound kernels (K2 gram_reduce, K3 loss_dF, CDK element-wise pieces).
+//
+// The fp32 engine is the validation-grade path (reference-level accuracy, used for tiny batches
+// and to cross-check the tcgen05 engine on the device).  It follows the forward-mode restatement
+// of SURVEY.md §8(a); reference file:line citations are in include/nsvd.h next to each entry.
+#include "nsvd_common.cuh"
+#include "nsvd_simt.cuh"
+
+namespace nsvd {
+
+// ------------------------------------------------------------------------------------------
+// generic strided batched SGEMM:  C[b](m,n) (+)= sum_k A[b](m,k) * B[b](k,n)
+// ------------------------------------------------------------------------------------------
+template <int BM, int BN, int BK>
+__global__ void __launch_bounds__(256) sgemm_strided_kernel(SGemm g) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int bz = blockIdx.z;
+  const float* __restrict__ A = g.A + (long)bz * g.a_bs;
+  const float* __restrict__ B = g.B + (long)bz * g.b_bs;
+  float* __restrict__ C = g.C + (long)bz * g.c_bs;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
+  float acc[4][4] = {};
+  const bool a_kc = (g.a_cs == 1), b_kc = (g.b_rs == 1);
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < (BM * BK) / 256; ++i) {
+      int e = tid + i * 256;
+      int m = a_kc ? e / BK : e % BM;
+      int k = a_kc ? e % BK : e / BM;
+      float v = 0.f;
+      if (m0 + m < g.M && k0 + k < g.K) v = A[(long)(m0 + m) * g.a_rs + (long)(k0 + k) * g.a_cs];
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < (BN * BK) / 256; ++i) {
+      int e = tid + i * 256;
+      int n = b_kc ? e / BK : e % BN;
+      int k = b_kc ? e % BK : e / BN;
+      float v = 0.f;
+      if (n0 + n < g.N && k0 + k < g.K) v = B[(long)(k0 + k) * g.b_rs + (long)(n0 + n) * g.b_cs];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][tm + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tn + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + tm + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tn + j;
+      if (n >= g.N) continue;
+      long idx = (long)m * g.c_rs + n;
+      float v = g.alpha * acc[i][j];
+      C[idx] = g.accumulate ? C[idx] + v : v;
+    }
+  }
+}
+
+int sgemm_strided(const SGemm& g, int batch, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
+  dim3 grid(cdiv(g.N, 64), cdiv(g.M, 64), batch);
+  sgemm_strided_kernel<64, 64, 16><<<grid, 256, 0, st>>>(g);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// column sums of a batched row-major matrix: out[b][n] (+)= sum_m X[b][m][n]   (deterministic)
+__global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M, int N,
+                              long x_bs, int accumulate) {
+  // block = 32 columns x 8 row-lanes
+  __shared__ float sm[8][33];
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const float* Xb = X + (long)b * x_bs;
+  float s = 0.f;
+  if (n < N)
+    for (int m = threadIdx.y; m < M; m += 8) s += Xb[(long)m * N + n];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    float* o = out + (long)b * N + n;
+    *o = accumulate ? *o + t : t;
+  }
+}
+
+int colsum(const float* X, float* out, int M, int N, int batch, long x_bs, int accumulate,
+           cudaStream_t st) {
+  dim3 grid(cdiv(N, 32), batch);
+  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(X, out, M, N, x_bs, accumulate);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fourier features, all four streams (examples/utils.py:126-143 + derivatives)
+//   phis[s][p][k], k in [0,2M): [sin | cos] blocks
+// ------------------------------------------------------------------------------------------
+__global__ void features_f32_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
+                                    float* __restrict__ phis, float* __restrict__ phi_saved, int P,
+                                    int M) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)P * M) return;
+  int p = (int)(i / M), j = (int)(i % M);
+  float b0 = Bff[j], b1 = Bff[M + j];
+  float ph = fmaf(x[2 * p + 1], b1, x[2 * p] * b0);
+  float s, c;
+  sincosf(ph, &s, &c);
+  const long K0 = 2L * M, SP = (long)P * K0;
+  float* o = phis + (long)p * K0;
+  float nb2 = -(b0 * b0 + b1 * b1);
+  o[j] = s;
+  o[M + j] = c;
+  o[SP + j] = c * b0;
+  o[SP + M + j] = -s * b0;
+  o[2 * SP + j] = c * b1;
+  o[2 * SP + M + j] = -s * b1;
+  o[3 * SP + j] = nb2 * s;
+  o[3 * SP + M + j] = nb2 * c;
+  if (phi_saved) {
+    phi_saved[(long)p * K0 + j] = s;
+    phi_saved[(long)p * K0 + M + j] = c;
+  }
+}
+
+// softplus on the 4-stream pre-activations Z[l][s][p][h] (in place) ; saves the value stream.
+__global__ void softplus_streams_kernel(float* __restrict__ Z, const float* __restrict__ bias,
+                                        float* __restrict__ a_saved, int L, int P, long Btot,
+                                        long p_off) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n = (long)L * P * kHidden;
+  if (i >= n) return;
+  int h = (int)(i % kHidden);
+  int p = (int)((i / kHidden) % P);
+  int l = (int)(i / ((long)kHidden * P));
+  long SP = (long)P * kHidden;
+  float* z = Z + (long)l * 4 * SP + (long)p * kHidden + h;
+  float z0 = z[0] + bias[l * kHidden + h];
+  float z1 = z[SP], z2 = z[2 * SP], z3 = z[3 * SP];
+  float a, sg;
+  softplus_sig(z0, a, sg);
+  z[0] = a;
+  z[SP] = sg * z1;
+  z[2 * SP] = sg * z2;
+  z[3 * SP] = sg * z3 + sg * (1.f - sg) * (z1 * z1 + z2 * z2);
+  a_saved[((long)l * Btot + p_off + p) * kHidden + h] = a;
+}
+
+// last layer (128 -> 1) on 4 streams + operator epilogue.  One warp per (point, copy).
+__global__ void head_operator_kernel(const float* __restrict__ A2, const float* __restrict__ W3,
+                                     const float* __restrict__ b3, const float* __restrict__ x,
+                                     const float* __restrict__ mscales, nsvd_problem_t pb,
+                                     float* __restrict__ F, float* __restrict__ TF,
+                                     float* __restrict__ U0, int P, long p_off) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int L = pb.n_copies;
+  if (w >= P * L) return;
+  int p = w / L, l = w % L;
+  long SP = (long)P * kHidden;
+  const float* a = A2 + (long)l * 4 * SP + (long)p * kHidden;
+  float u[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int h = lane + 32 * q;
+    float wv = W3[l * kHidden + h];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) u[s] = fmaf(a[s * SP + h], wv, u[s]);
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) u[s] = warp_sum(u[s]);
+  if (lane == 0) {
+    u[0] += b3[l];
+    long pg = p_off + p;
+    PointGeom g = point_geom(x[2 * pg], x[2 * pg + 1], pb);
+    float f, tf;
+    operator_epilogue(g, pb, pb.has_exp_mask != 0, pb.has_exp_mask ? mscales[l] : 1.f, u[0], u[1],
+                      u[2], u[3], f, tf);
+    F[pg * L + l] = f;
+    TF[pg * L + l] = tf;
+    U0[pg * L + l] = u[0];
+  }
+}
+
+// backward of the head: du = dF * c * m * rho ; dZ2 = du W3 (.) sigma(a2) ; T3 = du * a2 (for dW3)
+__global__ void head_bwd_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
+                                const float* __restrict__ a2, const float* __restrict__ W3,
+                                const float* __restrict__ x, const float* __restrict__ mscales,
+                                nsvd_problem_t pb, float* __restrict__ dZ2, float* __restrict__ T3,
+                                float* __restrict__ du_out, float* __restrict__ ds_out, int P,
+                                long Btot, long p_off) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int L = pb.n_copies;
+  if (w >= P * L) return;
+  int p = w / L, l = w % L;
+  long pg = p_off + p;
+  PointGeom g = point_geom(x[2 * pg], x[2 * pg + 1], pb);
+  float m = 1.f, sc = 1.f;
+  if (pb.has_exp_mask) {
+    sc = mscales[l];
+    m = expf(-g.r / sc);
+  }
+  float cm = pb.hard_mul_const * m * g.rho;
+  float df = dF[pg * L + l];
+  float du = df * cm;
+  if (lane == 0) {
+    du_out[(long)p * L + l] = du;
+    ds_out[(long)p * L + l] = pb.has_exp_mask ? du * U0[pg * L + l] * g.r / (sc * sc) : 0.f;
+  }
+  const float* a = a2 + ((long)l * Btot + pg) * kHidden;
+  long o = ((long)l * P + p) * kHidden;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int h = lane + 32 * q;
+    float av = a[h];
+    dZ2[o + h] = du * W3[l * kHidden + h] * sig_from_softplus(av);
+    T3[o + h] = du * av;
+  }
+}
+
+// dZ = dA (.) sigma(a)   with a from the saved value stream (layout [L][Btot][H])
+__global__ void dact_kernel(float* __restrict__ dA, const float* __restrict__ a_saved, int L, int P,
+                            long Btot, long p_off) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n = (long)L * P * kHidden;
+  if (i >= n) return;
+  int h = (int)(i % kHidden);
+  int p = (int)((i / kHidden) % P);
+  int l = (int)(i / ((long)kHidden * P));
+  float a = a_saved[((long)l * Btot + p_off + p) * kHidden + h];
+  dA[i] *= sig_from_softplus(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 engine: forward and backward drivers
+// ------------------------------------------------------------------------------------------
+static const int kSimtMicroBatch = 2048;
+
+void simt_scratch_bytes(const nsvd_problem_t& pb, size_t* saved, size_t* work) {
+  long B = pb.n_points, L = pb.n_copies, K0 = 2L * pb.n_fourier;
+  long P = B < kSimtMicroBatch ? B : kSimtMicroBatch;
+  *saved = sizeof(float) * (size_t)(B * K0 + 3 * L * B * kHidden + B * L) + 256;
+  size_t fwd = (size_t)(4 * P * K0 + 2 * 4 * L * P * kHidden);
+  size_t bwd = (size_t)(3 * L * P * kHidden + 2 * P * L);
+  *work = sizeof(float) * (fwd > bwd ? fwd : bwd) + 256;
+}
+
+struct SimtSaved {
+  float *phi, *a[3], *u0;
+};
+static SimtSaved carve_saved(const nsvd_problem_t& pb, void* saved) {
+  long B = pb.n_points, L = pb.n_copies, K0 = 2L * pb.n_fourier;
+  SimtSaved s;
+  float* p = (float*)saved;
+  s.phi = p;
+  p += B * K0;
+  for (int i = 0; i < 3; ++i) {
+    s.a[i] = p;
+    p += L * B * kHidden;
+  }
+  s.u0 = p;
+  return s;
+}
+
+int simt_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x, float* F,
+                 float* TF, void* saved, void* work, cudaStream_t st) {
+  const long B = pb.n_points, L = pb.n_copies, M = pb.n_fourier, K0 = 2 * M;
+  SimtSaved sv = carve_saved(pb, saved);
+  for (long p0 = 0; p0 < B; p0 += kSimtMicroBatch) {
+    int P = (int)((B - p0) < kSimtMicroBatch ? (B - p0) : kSimtMicroBatch);
+    float* phis = (float*)work;
+    float* bufA = phis + 4L * P * K0;
+    float* bufB = bufA + 4L * L * P * kHidden;
+    long n = (long)P * M;
+    features_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(x + 2 * p0, pr.Bff, phis, sv.phi + p0 * K0, P,
+                                                      (int)M);
+    NSVD_LAUNCH_CHECK();
+    // layer 0: Z[l] (4P x H) = phis (4P x K0) . W0[l]^T
+    SGemm g{};
+    g.A = phis; g.a_rs = K0; g.a_cs = 1; g.a_bs = 0;
+    g.B = pr.W[0]; g.b_rs = 1; g.b_cs = K0; g.b_bs = (long)kHidden * K0;
+    g.C = bufA; g.c_rs = kHidden; g.c_bs = 4L * P * kHidden;
+    g.M = 4 * P; g.N = kHidden; g.K = (int)K0; g.alpha = 1.f; g.accumulate = 0;
+    int rc = sgemm_strided(g, (int)L, st);
+    if (rc) return rc;
+    long ne = L * P * kHidden;
+    softplus_streams_kernel<<<cdiv(ne, 256), 256, 0, st>>>(bufA, pr.b[0], sv.a[0], (int)L, P, B, p0);
+    NSVD_LAUNCH_CHECK();
+    float* cur = bufA;
+    float* nxt = bufB;
+    for (int i = 1; i <= 2; ++i) {
+      SGemm h{};
+      h.A = cur; h.a_rs = kHidden; h.a_cs = 1; h.a_bs = 4L * P * kHidden;
+      h.B = pr.W[i]; h.b_rs = 1; h.b_cs = kHidden; h.b_bs = (long)kHidden * kHidden;
+      h.C = nxt; h.c_rs = kHidden; h.c_bs = 4L * P * kHidden;
+      h.M = 4 * P; h.N = kHidden; h.K = kHidden; h.alpha = 1.f; h.accumulate = 0;
+      rc = sgemm_strided(h, (int)L, st);
+      if (rc) return rc;
+      softplus_streams_kernel<<<cdiv(ne, 256), 256, 0, st>>>(nxt, pr.b[i], sv.a[i], (int)L, P, B, p0);
+      NSVD_LAUNCH_CHECK();
+      float* t = cur; cur = nxt; nxt = t;
+    }
+    long nw = (long)P * L;
+    head_operator_kernel<<<cdiv(nw * 32, 256), 256, 0, st>>>(cur, pr.W[3], pr.b[3], x, pr.mask_scales,
+                                                             pb, F, TF, sv.u0, P, p0);
+    NSVD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int simt_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x, const float* dF,
+                  const void* saved, nsvd_grads_t& gr, void* work, cudaStream_t st) {
+  const long B = pb.n_points, L = pb.n_copies, M = pb.n_fourier, K0 = 2 * M;
+  SimtSaved sv = carve_saved(pb, const_cast<void*>(saved));
+  for (long p0 = 0; p0 < B; p0 += kSimtMicroBatch) {
+    int P = (int)((B - p0) < kSimtMicroBatch ? (B - p0) : kSimtMicroBatch);
+    int acc = p0 > 0;
+    float* dZ = (float*)work;
+    float* dN = dZ + L * P * kHidden;
+    float* T3 = dN + L * P * kHidden;
+    float* du = T3 + L * P * kHidden;
+    float* ds = du + (long)P * L;
+    long nw = (long)P * L;
+    head_bwd_kernel<<<cdiv(nw * 32, 256), 256, 0, st>>>(dF, sv.u0, sv.a[2], pr.W[3], x,
+                                                        pr.mask_scales, pb, dZ, T3, du, ds, P, B, p0);
+    NSVD_LAUNCH_CHECK();
+    int rc;
+    // dW3[l][h] = sum_p T3[l][p][h];  db3[l] = sum_p du[p][l];  dscales[l] = sum_p ds[p][l]
+    if ((rc = colsum(T3, gr.dW[3], P, kHidden, (int)L, (long)P * kHidden, acc, st))) return rc;
+    if ((rc = colsum(du, gr.db[3], P, (int)L, 1, 0, acc, st))) return rc;
+    if (pb.has_exp_mask && gr.dmask_scales)
+      if ((rc = colsum(ds, gr.dmask_scales, P, (int)L, 1, 0, acc, st))) return rc;
+    for (int i = 2; i >= 1; --i) {
+      // dW_i[l] (H x H) (+)= dZ[l]^T (H x P) . a_{i-1}[l] (P x H)
+      SGemm w{};
+      w.A = dZ; w.a_rs = 1; w.a_cs = kHidden; w.a_bs = (long)P * kHidden;
+      w.B = sv.a[i - 1] + p0 * kHidden; w.b_rs = kHidden; w.b_cs = 1; w.b_bs = B * kHidden;
+      w.C = gr.dW[i]; w.c_rs = kHidden; w.c_bs = (long)kHidden * kHidden;
+      w.M = kHidden; w.N = kHidden; w.K = P; w.alpha = 1.f; w.accumulate = acc;
+      if ((rc = sgemm_strided(w, (int)L, st))) return rc;
+      if ((rc = colsum(dZ, gr.db[i], P, kHidden, (int)L, (long)P * kHidden, acc, st))) return rc;
+      // dA[l] (P x H) = dZ[l] (P x H) . W_i[l] (H x H)
+      SGemm d{};
+      d.A = dZ; d.a_rs = kHidden; d.a_cs = 1; d.a_bs = (long)P * kHidden;
+      d.B = pr.W[i]; d.b_rs = kHidden; d.b_cs = 1; d.b_bs = (long)kHidden * kHidden;
+      d.C = dN; d.c_rs = kHidden; d.c_bs = (long)P * kHidden;
+      d.M = P; d.N = kHidden; d.K = kHidden; d.alpha = 1.f; d.accumulate = 0;
+      if ((rc = sgemm_strided(d, (int)L, st))) return rc;
+      long ne = L * P * kHidden;
+      dact_kernel<<<cdiv(ne, 256), 256, 0, st>>>(dN, sv.a[i - 1], (int)L, P, B, p0);
+      NSVD_LAUNCH_CHECK();
+      float* t = dZ; dZ = dN; dN = t;
+    }
+    // dW0[l] (H x K0) (+)= dZ0[l]^T (H x P) . Phi (P x K0)
+    SGemm w{};
+    w.A = dZ; w.a_rs = 1; w.a_cs = kHidden; w.a_bs = (long)P * kHidden;
+    w.B = sv.phi + p0 * K0; w.b_rs = K0; w.b_cs = 1; w.b_bs = 0;
+    w.C = gr.dW[0]; w.c_rs = K0; w.c_bs = (long)kHidden * K0;
+    w.M = kHidden; w.N = (int)K0; w.K = P; w.alpha = 1.f; w.accumulate = acc;
+    if ((rc = sgemm_strided(w, (int)L, st))) return rc;
+    if ((rc = colsum(dZ, gr.db[0], P, kHidden, (int)L, (long)P * kHidden, acc, st))) return rc;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 gram_reduce  (HBM-bound): two-stage deterministic reduction.
+//   stage 1: each block owns a contiguous row range inside ONE half and accumulates the LxL
+//            Gram of F (and optionally the cross Gram F^T TF) in registers: thread (i,j) holds a
+//            TI x TJ sub-block; rows are staged through shared memory with float4 loads.
+//   stage 2: one block per output element group sums the per-block partials in fixed order.
+// ------------------------------------------------------------------------------------------
+constexpr int kGramRows = 64;  // rows staged per iteration
+
+template <int LT>  // LT = L rounded up to a multiple of 16 (16, 32, 48, 64) ; threads = 256
+__global__ void __launch_bounds__(256)
+gram_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
+                   const float* __restrict__ vmask, const float* __restrict__ roww, int L,
+                   long row_begin, long row_end, int rows_per_block, int cross,
+                   float* __restrict__ partials, int partial_stride, int block_off) {
+  // thread tile: (LT/16) x (LT/16) outputs; 16x16 threads
+  constexpr int T = LT / 16;
+  __shared__ float sF[kGramRows][LT + 1];
+  __shared__ float sT[kGramRows][LT + 1];
+  __shared__ float sred[8];
+  const int tid = threadIdx.x, ti = tid / 16, tj = tid % 16;
+  long r0 = row_begin + (long)blockIdx.x * rows_per_block;
+  long r1 = r0 + rows_per_block < row_end ? r0 + rows_per_block : row_end;
+  float acc[T][T] = {};
+  float accx[T][T] = {};
+  float ops = 0.f;
+  for (long rb = r0; rb < r1; rb += kGramRows) {
+    int nr = (int)((r1 - rb) < kGramRows ? (r1 - rb) : kGramRows);
+    for (int e = tid; e < kGramRows * LT; e += 256) {
+      int rr = e / LT, c = e % LT;
+      float f = 0.f, t = 0.f;
+      if (rr < nr && c < L) {
+        long idx = (rb + rr) * L + c;
+        float w = roww ? roww[rb + rr] : 1.f;
+        f = F[idx] * w;
+        t = TF[idx] * w;
+        if (!cross) ops += vmask[c] * f * t;
+      }
+      sF[rr][c] = f;
+      sT[rr][c] = t;
+    }
+    __syncthreads();
+    for (int rr = 0; rr < nr; ++rr) {
+      float a[T], b[T], bx[T];
+#pragma unroll
+      for (int i = 0; i < T; ++i) a[i] = sF[rr][ti * T + i];
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
+        b[j] = sF[rr][tj * T + j];
+        bx[j] = sT[rr][tj * T + j];
+      }
+#pragma unroll
+      for (int i = 0; i < T; ++i)
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+          acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          if (cross) accx[i][j] = fmaf(a[i], bx[j], accx[i][j]);
+        }
+    }
+    __syncthreads();
+  }
+  float* out = partials + (long)(block_off + blockIdx.x) * partial_stride;
+#pragma unroll
+  for (int i = 0; i < T; ++i)
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+      int gi = ti * T + i, gj = tj * T + j;
+      if (gi < L && gj < L) {
+        out[gi * L + gj] = acc[i][j];
+        if (cross) out[L * L + gi * L + gj] = accx[i][j];
+      }
+    }
+  if (!cross) {
+    ops = warp_sum(ops);
+    if ((tid & 31) == 0) sred[tid >> 5] = ops;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += sred[i];
+      out[L * L] = t;
+    }
+  }
+}
+
+// stage 2: out[e] (+)= sum over blocks [b0, b1) of partials[b][src_off + e]
+__global__ void gram_stage2_kernel(const float* __restrict__ partials, int partial_stride, int b0,
+                                   int b1, int src_off, int n, float* __restrict__ out,
+                                   int accumulate) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float s = 0.f;
+  for (int b = b0; b < b1; ++b) s += partials[(long)b * partial_stride + src_off + e];
+  out[e] = accumulate ? out[e] + s : s;
+}
+
+static int gram_blocks_for(long rows) {
+  // aim for >= 2 waves of 148 SMs x 2 CTAs when there is enough work; >= 256 rows per block
+  long nb = (rows + 255) / 256;
+  if (nb > 592) nb = 592;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+size_t gram_partials_bytes(int B, int L) {
+  long half = (B + 1) / 2;
+  int nb = 2 * gram_blocks_for(half) + 2;
+  return sizeof(float) * (size_t)nb * (size_t)(2 * L * L + 1) + 256;
+}
+
+template <int LT>
+static int gram_launch(const float* F, const float* TF, const float* vmask, const float* roww, int L,
+                       long rb, long re, int cross, float* partials, int stride, int block_off,
+                       int* nblocks, cudaStream_t st) {
+  long rows = re - rb;
+  if (rows <= 0) {
+    *nblocks = 0;
+    return 0;
+  }
+  int nb = gram_blocks_for(rows);
+  int rpb = (int)((rows + nb - 1) / nb);
+  nb = (int)((rows + rpb - 1) / rpb);
+  gram_stage1_kernel<LT><<<nb, 256, 0, st>>>(F, TF, vmask, roww, L, rb, re, rpb, cross, partials,
+                                             stride, block_off);
+  NSVD_LAUNCH_CHECK();
+  *nblocks = nb;
+  return 0;
+}
+
+static int gram_dispatch(const float* F, const float* TF, const float* vmask, const float* roww, int L,
+                         long rb, long re, int cross, float* partials, int stride, int block_off,
+                         int* nblocks, cudaStream_t st) {
+  if (L <= 16) return gram_launch<16>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
+  if (L <= 32) return gram_launch<32>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
+  if (L <= 48) return gram_launch<48>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
+  if (L <= 64) return gram_launch<64>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
+  set_error("gram_reduce: n_copies %d > 64 is handled by the CDK path", L);
+  return NSVD_E_BADARG;
+}
+
+int gram_reduce(const float* F, const float* TF, const float* vmask, int B, int L, int b1,
+                float* terms, void* partials_v, cudaStream_t st) {
+  float* partials = (float*)partials_v;
+  int stride = 2 * L * L + 1, n1 = 0, n2 = 0, rc;
+  if ((rc = gram_dispatch(F, TF, vmask, nullptr, L, 0, b1, 0, partials, stride, 0, &n1, st))) return rc;
+  if ((rc = gram_dispatch(F, TF, vmask, nullptr, L, b1, B, 0, partials, stride, n1, &n2, st))) return rc;
+  int LL = L * L;
+  gram_stage2_kernel<<<cdiv(LL, 128), 128, 0, st>>>(partials, stride, 0, n1, 0, LL, terms, 0);
+  NSVD_LAUNCH_CHECK();
+  gram_stage2_kernel<<<cdiv(LL, 128), 128, 0, st>>>(partials, stride, n1, n1 + n2, 0, LL, terms + LL, 0);
+  NSVD_LAUNCH_CHECK();
+  gram_stage2_kernel<<<1, 32, 0, st>>>(partials, stride, 0, n1 + n2, LL, 1, terms + 2 * LL, 0);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+int cross_gram(const float* F, const float* TF, const float* roww, int B, int L, float* cov,
+               float* quad, void* partials_v, cudaStream_t st) {
+  float* partials = (float*)partials_v;
+  int stride = 2 * L * L + 1, n1 = 0, rc;
+  if ((rc = gram_dispatch(F, TF, nullptr, roww, L, 0, B, 1, partials, stride, 0, &n1, st))) return rc;
+  int LL = L * L;
+  gram_stage2_kernel<<<cdiv(LL, 128), 128, 0, st>>>(partials, stride, 0, n1, 0, LL, cov, 1);
+  NSVD_LAUNCH_CHECK();
+  gram_stage2_kernel<<<cdiv(LL, 128), 128, 0, st>>>(partials, stride, 0, n1, LL, LL, quad, 1);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// loss + backward coefficient matrices from the (all-reduced) terms.  One block.
+__global__ void loss_finalize_kernel(const float* __restrict__ terms, const float* __restrict__ Mm,
+                                     int L, double Bg, double B1g, double B2g,
+                                     float* __restrict__ loss, float* __restrict__ coef) {
+  __shared__ double sred[32];
+  int LL = L * L;
+  double s = 0.0;
+  for (int e = threadIdx.x; e < LL; e += blockDim.x) {
+    double lam1 = (double)terms[e] / B1g, lam2 = (double)terms[LL + e] / B2g;
+    double m = Mm[e];
+    s += m * lam1 * lam2;
+    coef[e] = (float)(2.0 / B1g * m * lam2);
+    coef[LL + e] = (float)(2.0 / B2g * m * lam1);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sred[i];
+    loss[0] = (float)(-2.0 * (double)terms[2 * LL] / Bg + t);
+  }
+}
+
+int loss_finalize(const float* terms, const float* Mm, int L, long Bg, long B1g, long B2g,
+                  float* loss, float* coef, cudaStream_t st) {
+  loss_finalize_kernel<<<1, 256, 0, st>>>(terms, Mm, L, (double)Bg, (double)B1g, (double)B2g, loss, coef);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// K3 loss_dF: dF[b][m] = gs * ( -(4/Bg) v_m TF[b][m] + sum_l F[b][l] coef_half[l][m] )
+template <int LT>
+__global__ void __launch_bounds__(256)
+loss_dF_kernel(const float* __restrict__ F, const float* __restrict__ TF,
+               const float* __restrict__ vmask, const float* __restrict__ coef,
+               const float* __restrict__ gscale, int B, int L, int b1, float c4, float* __restrict__ dF) {
+  extern __shared__ float sm[];
+  float* sC = sm;                 // [2][L][LT]
+  float* sV = sm + 2 * L * LT;    // [LT]
+  for (int e = threadIdx.x; e < 2 * L * LT; e += blockDim.x) {
+    int h = e / (L * LT), r = (e / LT) % L, c = e % LT;
+    sC[e] = (coef && c < L) ? coef[h * L * L + r * L + c] : 0.f;
+  }
+  for (int e = threadIdx.x; e < LT; e += blockDim.x) sV[e] = e < L ? vmask[e] : 0.f;
+  __syncthreads();
+  const float gs = gscale ? gscale[0] : 1.f;
+  // each thread produces 4 consecutive outputs of one row
+  constexpr int Q = LT / 4;
+  long total = (long)B * Q;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long b = i / Q;
+    int m0 = (int)(i % Q) * 4;
+    if (m0 >= L) continue;
+    const float* frow = F + b * L;
+    const float* C = sC + (b < b1 ? 0 : L * LT);
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    for (int l = 0; l < L; ++l) {
+      float fv = __ldg(frow + l);
+      const float* cr = C + l * LT + m0;
+      o0 = fmaf(fv, cr[0], o0);
+      o1 = fmaf(fv, cr[1], o1);
+      o2 = fmaf(fv, cr[2], o2);
+      o3 = fmaf(fv, cr[3], o3);
+    }
+    float o[4] = {o0, o1, o2, o3};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int m = m0 + q;
+      if (m < L) dF[b * L + m] = gs * (o[q] - (TF ? c4 * sV[m] * TF[b * L + m] : 0.f));
+    }
+  }
+}
+
+int loss_dF(const float* F, const float* TF, const float* vmask, const float* coef,
+            const float* gscale, int B, int L, int b1, long Bg, float* dF, cudaStream_t st) {
+  float c4 = (float)(4.0 / (double)Bg);
+  int LT = L <= 16 ? 16 : (L <= 32 ? 32 : (L <= 48 ? 48 : 64));
+  if (L > 64) {
+    set_error("loss_dF: n_copies %d > 64", L);
+    return NSVD_E_BADARG;
+  }
+  size_t smem = sizeof(float) * (2 * L * LT + LT);
+  long total = (long)B * (LT / 4);
+  int nb = cdiv(total, 256);
+  if (nb > 148 * 8) nb = 148 * 8;
+  if (nb < 1) nb = 1;
+#define NSVD_DF(LTV)                                                                               \
+  loss_dF_kernel<LTV><<<nb, 256, smem, st>>>(F, TF, vmask, coef, gscale, B, L, b1, c4, dF)
+  if (LT == 16) NSVD_DF(16);
+  else if (LT == 32) NSVD_DF(32);
+  else if (LT == 48) NSVD_DF(48);
+  else NSVD_DF(64);
+#undef NSVD_DF
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// CDK (methods/nestedlora.py:270-332), v1 on the fp32 building blocks
+// ------------------------------------------------------------------------------------------
+// pad a leading constant-1 column: out (B, Lp) from in (B, L)
+__global__ void cdk_pad_kernel(const float* __restrict__ in, float* __restrict__ out, long B, int L,
+                               int first_const) {
+  int Lp = L + first_const;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Lp) return;
+  long b = i / Lp;
+  int c = (int)(i % Lp);
+  out[i] = (first_const && c == 0) ? 1.f : in[b * L + c - first_const];
+}
+
+// per-row  sum_l v_l f g  and diag(Fp Gp^T); one warp per row; rowsum partials reduced by colsum
+__global__ void cdk_rowdots_kernel(const float* __restrict__ fp, const float* __restrict__ gp,
+                                   const float* __restrict__ v, long B, int Lp,
+                                   float* __restrict__ opdot, float* __restrict__ rs_joint) {
+  long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= B) return;
+  float a = 0.f, d = 0.f;
+  for (int c = lane; c < Lp; c += 32) {
+    float p = fp[w * Lp + c] * gp[w * Lp + c];
+    d += p;
+    a = fmaf(v[c], p, a);
+  }
+  a = warp_sum(a);
+  d = warp_sum(d);
+  if (lane == 0) {
+    opdot[w] = a;
+    if (rs_joint) rs_joint[w] = d;
+  }
+}
+
+size_t cdk_work_bytes(int B, int L, int fc) {
+  long Lp = L + fc;
+  return sizeof(float) * (size_t)(2L * B * Lp + B + 64) + 256;
+}
+
+int cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int fc, float* terms,
+            float* rs_joint, void* work, cudaStream_t st) {
+  int Lp = L + fc;
+  float* fp = (float*)work;
+  float* gp = fp + (long)B * Lp;
+  float* opdot = gp + (long)B * Lp;
+  long n = (long)B * Lp;
+  cdk_pad_kernel<<<cdiv(n, 256), 256, 0, st>>>(f, fp, B, L, fc);
+  NSVD_LAUNCH_CHECK();
+  cdk_pad_kernel<<<cdiv(n, 256), 256, 0, st>>>(g, gp, B, L, fc);
+  NSVD_LAUNCH_CHECK();
+  int rc;
+  for (int which = 0; which < 2; ++which) {
+    const float* X = which ? gp : fp;
+    SGemm w{};
+    w.A = X; w.a_rs = 1; w.a_cs = Lp; w.a_bs = 0;
+    w.B = X; w.b_rs = Lp; w.b_cs = 1; w.b_bs = 0;
+    w.C = terms + (long)which * Lp * Lp; w.c_rs = Lp; w.c_bs = 0;
+    w.M = Lp; w.N = Lp; w.K = B; w.alpha = 1.f; w.accumulate = 0;
+    if ((rc = sgemm_strided(w, 1, st))) return rc;
+  }
+  cdk_rowdots_kernel<<<cdiv((long)B * 32, 256), 256, 0, st>>>(fp, gp, v, B, Lp, opdot, rs_joint);
+  NSVD_LAUNCH_CHECK();
+  return colsum(opdot, terms + 2L * Lp * Lp, B, 1, 1, 0, 0, st);
+}
+
+__global__ void cdk_finalize_kernel(const float* __restrict__ terms, const float* __restrict__ Mm,
+                                    int Lp, double Bg, float* __restrict__ losses,
+                                    float* __restrict__ coef) {
+  __shared__ double sred[32];
+  int LL = Lp * Lp;
+  double s = 0.0;
+  for (int e = threadIdx.x; e < LL; e += blockDim.x) {
+    double lf = (double)terms[e] / Bg, lg = (double)terms[LL + e] / Bg;
+    double m = Mm[e];
+    s += m * lf * lg;
+    coef[e] = (float)(2.0 / Bg * m * lg);        // multiplies rows of Fp
+    coef[LL + e] = (float)(2.0 / Bg * m * lf);   // multiplies rows of Gp
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sred[i];
+    double lop = -2.0 * (double)terms[2 * LL] / Bg;
+    losses[0] = (float)(lop + t);
+    losses[1] = (float)lop;
+    losses[2] = (float)t;
+  }
+}
+
+int cdk_finalize(const float* terms, const float* Mm, int Lp, long Bg, float* losses, float* coef,
+                 cudaStream_t st) {
+  cdk_finalize_kernel<<<1, 1024, 0, st>>>(terms, Mm, Lp, (double)Bg, losses, coef);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// grad_f[b][c] = gs * ( -(2/Bg) v_{c+fc} g[b][c] + sum_i Fp[b][i] coefF[i][c+fc] ),  same for g.
+// Written as a batched SGEMM over the un-padded inputs + a rank-1 term for the constant column.
+__global__ void cdk_bwd_epilogue_kernel(float* __restrict__ grad, const float* __restrict__ other,
+                                        const float* __restrict__ v, const float* __restrict__ coef,
+                                        const float* __restrict__ gscale, long B, int L, int fc,
+                                        float c2) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L) return;
+  int c = (int)(i % L);
+  int Lp = L + fc;
+  float gs = gscale ? gscale[0] : 1.f;
+  float acc = grad[i];
+  if (fc) acc += coef[c + fc];  // row 0 of coef (constant-1 input column)
+  grad[i] = gs * (acc - c2 * v[c + fc] * other[i]);
+  (void)Lp;
+}
+
+int cdk_bwd(const float* f, const float* g, const float* v, const float* coef, const float* gscale,
+            int B, int L, int fc, long Bg, float* grad_f, float* grad_g, cudaStream_t st) {
+  int Lp = L + fc, rc;
+  float c2 = (float)(2.0 / (double)Bg);
+  for (int which = 0; which < 2; ++which) {
+    const float* X = which ? g : f;
+    const float* O = which ? f : g;
+    float* G = which ? grad_g : grad_f;
+    const float* C = coef + (long)which * Lp * Lp;
+    // G (B x L) = X (B x L) . C[fc:, fc:] (L x L)
+    SGemm d{};
+    d.A = X; d.a_rs = L; d.a_cs = 1; d.a_bs = 0;
+    d.B = C + (long)fc * Lp + fc; d.b_rs = Lp; d.b_cs = 1; d.b_bs = 0;
+    d.C = G; d.c_rs = L; d.c_bs = 0;
+    d.M = B; d.N = L; d.K = L; d.alpha = 1.f; d.accumulate = 0;
+    if ((rc = sgemm_strided(d, 1, st))) return rc;
+    long n = (long)B * L;
+    cdk_bwd_epilogue_kernel<<<cdiv(n, 256), 256, 0, st>>>(G, O, v, C, gscale, B, L, fc, c2);
+    NSVD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// off_diagonal(Fp Gp^T): out[i*(B-1) + (j - (j>i))] = fc + f_i . g_j, i != j   (methods/utils.py:16-22)
+__global__ void cdk_offdiag_kernel(const float* __restrict__ f, const float* __restrict__ g, int B,
+                                   int L, int fc, float* __restrict__ out) {
+  __shared__ float sf[32][33], sg[32][33];
+  int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  int tx = threadIdx.x, ty = threadIdx.y;
+  float acc = fc ? 1.f : 0.f;
+  for (int k0 = 0; k0 < L; k0 += 32) {
+    sf[ty][tx] = (i0 + ty < B && k0 + tx < L) ? f[(long)(i0 + ty) * L + k0 + tx] : 0.f;
+    sg[ty][tx] = (j0 + ty < B && k0 + tx < L) ? g[(long)(j0 + ty) * L + k0 + tx] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc = fmaf(sf[ty][k], sg[tx][k], acc);
+    __syncthreads();
+  }
+  int i = i0 + ty, j = j0 + tx;
+  if (i < B && j < B && i != j) out[(long)i * (B - 1) + (j - (j > i ? 1 : 0))] = acc;
+}
+
+int cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* out, cudaStream_t st) {
+  dim3 grid(cdiv(B, 32), cdiv(B, 32));
+  cdk_offdiag_kernel<<<grid, dim3(32, 32), 0, st>>>(f, g, B, L, fc, out);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace nsvd

@@ -1,0 +1,264 @@
+"""Fused NestedLoRA step: the autograd boundary above the C-ABI kernels.
+
+Replaces, for one call of `NestedLoRA.compute_loss_operator` + `loss.backward()`
+(methods/nestedlora.py:254-267, examples/operator/__init__.py:62-68):
+    K1 nsvd_fwd_streams  ->  K2 nsvd_gram_reduce  -> [all-reduce #1] -> nsvd_loss_finalize
+    K3 nsvd_loss_dF      ->  K4 nsvd_mlp_bwd      -> [all-reduce #2]
+PyTorch is used for device memory, the stream and torch.distributed only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .operators import describe_importance, describe_operator
+
+_ENGINE = os.environ.get("NSVD_ENGINE", "bf16x3")
+
+
+def set_engine(name: str):
+    """'bf16x3' (tcgen05 tensor cores, default) or 'fp32' (CUDA-core validation engine)."""
+    global _ENGINE
+    if name not in _lib.ENGINES:
+        raise ValueError(f"unknown engine {name!r}; choose from {sorted(_lib.ENGINES)}")
+    _ENGINE = name
+
+
+def get_engine() -> str:
+    return _ENGINE
+
+
+def _require_cuda(dev: torch.device):
+    if dev.type != "cuda":
+        raise RuntimeError("neural_svd_b200 has no CPU path: parameters and inputs must live on a CUDA (sm_100) device")
+
+
+# ------------------------------------------------------------------------------------------
+# model / problem description (duck-typed: the reference's own modules are accepted)
+# ------------------------------------------------------------------------------------------
+def describe_model(model):
+    """Pull the parameter tensors out of WaveFunctions(ParallelMLP(GaussianFourierFeatureTransform))."""
+    m = getattr(model, "model", model)          # NestedLoRA(...) -> .model
+    base = getattr(m, "base", None)
+    if base is None or not hasattr(base, "ws") or not hasattr(base, "bs"):
+        raise NotImplementedError("fused path needs WaveFunctions(base=ParallelMLP(...)) (--parallel 1)")
+    fm = getattr(base, "feature_map", None)
+    if fm is None or not hasattr(fm, "_B") or getattr(fm, "append_raw", False) or getattr(fm, "deterministic", False):
+        raise NotImplementedError("fused path needs the Gaussian Fourier feature map without raw append")
+    if getattr(base, "weight_normalization", False) or not getattr(base, "bias", True):
+        raise NotImplementedError("weight_normalization / bias=False are not supported")
+    ws, bs = list(base.ws), list(base.bs)
+    if len(ws) != 4 or len(bs) != 4:
+        raise NotImplementedError("fused path is built for 3 hidden layers (mlp_hidden_dims='128,128,128')")
+    Bff = fm._B
+    if Bff.shape[0] != 2:
+        raise NotImplementedError("fused path is built for ndim=2, n_particles=1")
+    L, H, K0 = ws[0].shape
+    Mff = Bff.shape[1]
+    ok = (H == 128 and K0 == 2 * Mff and tuple(ws[1].shape) == (L, 128, 128) and tuple(ws[2].shape) == (L, 128, 128)
+          and tuple(ws[3].shape) == (L, 1, 128) and all(tuple(b.shape) == (L, 128, 1) for b in bs[:3])
+          and tuple(bs[3].shape) == (L, 1, 1))
+    if not ok:
+        raise NotImplementedError("unexpected ParallelMLP parameter shapes for the fused path")
+    mask = getattr(m, "boundary_mask", None)
+    scales = getattr(mask, "scales", None)
+    if scales is None:
+        try:
+            unit = mask is None or float(mask(None)) == 1.0
+        except Exception:
+            unit = False
+        if not unit:
+            raise NotImplementedError("only ExponentialMask or no boundary mask")
+    elif getattr(mask, "boundary_mask", None) is not None:
+        inner = mask.boundary_mask
+        try:
+            unit = float(inner(None)) == 1.0
+        except Exception:
+            unit = False
+        if not unit:
+            raise NotImplementedError("ExponentialMask over a Dirichlet box mask is out of scope")
+    params = [Bff] + ws + bs + ([scales] if scales is not None else [])
+    for p in params:
+        if p.dtype != torch.float32:
+            raise NotImplementedError("fused path is fp32 (reference default, --use_amp off)")
+        if not p.is_contiguous():
+            raise RuntimeError("parameters must be contiguous")
+    return dict(Bff=Bff, ws=ws, bs=bs, scales=scales, L=L, Mff=Mff,
+                hard_mul_const=float(getattr(m, "hard_mul_const", 1.0)))
+
+
+def _problem(md, od, sigma, B) -> _lib.Problem:
+    return _lib.Problem(n_points=B, n_copies=md["L"], n_fourier=md["Mff"], hidden=128,
+                        potential=od["potential"], has_exp_mask=int(md["scales"] is not None),
+                        pot_coef=od["pot_coef"], scale_kinetic=od["scale_kinetic"], op_scale=od["op_scale"],
+                        op_shift=od["op_shift"], sampling_sigma=sigma, hard_mul_const=md["hard_mul_const"])
+
+
+def _params_struct(md) -> _lib.Params:
+    pr = _lib.Params()
+    pr.Bff = md["Bff"].data_ptr()
+    for i in range(4):
+        pr.W[i] = md["ws"][i].data_ptr()
+        pr.b[i] = md["bs"][i].data_ptr()
+    pr.mask_scales = md["scales"].data_ptr() if md["scales"] is not None else None
+    return pr
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class _Scratch:
+    """Per-owner cache of the kernel scratch buffers (allocated by PyTorch's caching allocator)."""
+
+    def __init__(self):
+        self.key = None
+        self.saved = self.work = self.partials = None
+        self.version = 0
+
+    def ensure(self, lib, pb: _lib.Problem, engine: int, dev):
+        key = (pb.n_points, pb.n_copies, pb.n_fourier, engine, str(dev))
+        if key != self.key:
+            ns, nw = C.c_size_t(), C.c_size_t()
+            _lib.check(lib.nsvd_scratch_bytes(C.byref(pb), engine, C.byref(ns), C.byref(nw)), "nsvd_scratch_bytes")
+            self.saved = torch.empty(ns.value, dtype=torch.uint8, device=dev)
+            self.work = torch.empty(nw.value, dtype=torch.uint8, device=dev)
+            npart = lib.nsvd_gram_partials_bytes(pb.n_points, pb.n_copies)
+            self.partials = torch.empty(npart, dtype=torch.uint8, device=dev)
+            self.key = key
+        return self
+
+
+def _scratch_of(owner) -> _Scratch:
+    sc = owner.__dict__.get("_nsvd_scratch")
+    if sc is None:
+        sc = _Scratch()
+        owner.__dict__["_nsvd_scratch"] = sc
+    return sc
+
+
+def _prep_x(x, dev):
+    if x.dim() == 3:
+        x = x.reshape(x.shape[0], -1)
+    if x.dim() != 2 or x.shape[1] != 2:
+        raise NotImplementedError(f"fused path expects x of shape (B, 2); got {tuple(x.shape)}")
+    return x.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def _forward_kernels(lib, owner, md, od, sigma, x, engine):
+    dev = md["Bff"].device
+    _require_cuda(dev)
+    x = _prep_x(x, dev)
+    B, L = x.shape[0], md["L"]
+    pb = _problem(md, od, sigma, B)
+    sc = _scratch_of(owner).ensure(lib, pb, engine, dev)
+    sc.version += 1
+    F = torch.empty((B, L), dtype=torch.float32, device=dev)
+    TF = torch.empty((B, L), dtype=torch.float32, device=dev)
+    pr = _params_struct(md)
+    _lib.check(lib.nsvd_fwd_streams(C.byref(pb), C.byref(pr), engine, _lib.ptr(x), _lib.ptr(F), _lib.ptr(TF),
+                                    _lib.ptr(sc.saved), sc.saved.numel(), _lib.ptr(sc.work), sc.work.numel(),
+                                    _stream(dev)), "nsvd_fwd_streams")
+    return x, pb, pr, sc, F, TF
+
+
+def apply_operator(model, operator, x, importance):
+    """`operator(model, x, importance) -> (Tf, f)` on the fused forward kernel (no autograd graph)."""
+    lib = _lib.load()
+    md, od = describe_model(model), describe_operator(operator)
+    sigma = describe_importance(importance)
+    with torch.no_grad():
+        _, _, _, _, F, TF = _forward_kernels(lib, getattr(model, "model", model), md, od, sigma, x,
+                                             _lib.ENGINES[_ENGINE])
+    return TF, F
+
+
+def model_values(model, x):
+    """hard_mul_const * base(x) * mask(x), shape (B, L) (WaveFunctions.forward, pde/__init__.py:15-16)."""
+    lib = _lib.load()
+    md = describe_model(model)
+    od = dict(potential=_lib.POT_HARMONIC, pot_coef=0.0, scale_kinetic=1.0, op_scale=1.0, op_shift=0.0)
+    # sigma = 1e3 keeps sqrt(w) above the 1e-5 clamp for |x| < 3.8e3, so rho == 1 and F == c * m * u.
+    with torch.no_grad():
+        _, _, _, _, F, _ = _forward_kernels(lib, getattr(model, "model", model), md, od, 1.0e3, x,
+                                            _lib.ENGINES[_ENGINE])
+    return F
+
+
+# ------------------------------------------------------------------------------------------
+# the fused training step
+# ------------------------------------------------------------------------------------------
+class _FusedOperatorStep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, method, operator, importance, x, dp, *params):
+        lib = _lib.load()
+        md, od = describe_model(method), describe_operator(operator)
+        sigma = describe_importance(importance)
+        engine = _lib.ENGINES[_ENGINE]
+        x, pb, pr, sc, F, TF = _forward_kernels(lib, method, md, od, sigma, x, engine)
+        dev = F.device
+        B, L = F.shape
+        b1 = (B + 1) // 2                                     # torch.chunk(f, 2), nestedlora.py:263
+        v = method.vector_mask.to(device=dev, dtype=torch.float32).contiguous()
+        Mm = method.matrix_mask.to(device=dev, dtype=torch.float32).contiguous()
+        terms = torch.empty(2 * L * L + 1, dtype=torch.float32, device=dev)
+        _lib.check(lib.nsvd_gram_reduce(_lib.ptr(F), _lib.ptr(TF), _lib.ptr(v), B, L, b1, _lib.ptr(terms),
+                                        _lib.ptr(sc.partials), _stream(dev)), "nsvd_gram_reduce")
+        Bg, B1g, B2g = B, b1, B - b1
+        if dp is not None:
+            Bg, B1g, B2g = dp.allreduce_terms(terms, B, b1)   # all-reduce #1
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        coef = torch.empty(2 * L * L, dtype=torch.float32, device=dev)
+        _lib.check(lib.nsvd_loss_finalize(_lib.ptr(terms), _lib.ptr(Mm), L, Bg, B1g, B2g, _lib.ptr(loss),
+                                          _lib.ptr(coef), _stream(dev)), "nsvd_loss_finalize")
+        ctx.state = dict(md=md, pb=pb, sc=sc, version=sc.version, x=x, F=F, TF=TF, v=v, coef=coef, b1=b1,
+                         Bg=Bg, engine=engine, dp=dp, nparams=len(params))
+        ctx.mark_non_differentiable(F, TF)
+        return loss, F, TF
+
+    @staticmethod
+    def backward(ctx, gloss, gF, gTF):
+        lib = _lib.load()
+        s = ctx.state
+        md, pb, sc = s["md"], s["pb"], s["sc"]
+        if sc.version != s["version"]:
+            raise RuntimeError("the scratch buffers of this NestedLoRA object were overwritten by a later forward "
+                               "call before backward ran; call backward() before the next compute_loss_operator()")
+        F, TF = s["F"], s["TF"]
+        dev = F.device
+        B, L = F.shape
+        gl = gloss.to(device=dev, dtype=torch.float32).contiguous()
+        dF = torch.empty_like(F)
+        _lib.check(lib.nsvd_loss_dF(_lib.ptr(F), _lib.ptr(TF), _lib.ptr(s["v"]), _lib.ptr(s["coef"]), _lib.ptr(gl),
+                                    B, L, s["b1"], s["Bg"], _lib.ptr(dF), _stream(dev)), "nsvd_loss_dF")
+        tensors = md["ws"] + md["bs"] + ([md["scales"]] if md["scales"] is not None else [])
+        sizes = [t.numel() for t in tensors]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        views = [v.view(t.shape) for v, t in zip(flat.split(sizes), tensors)]
+        gr = _lib.Grads()
+        for i in range(4):
+            gr.dW[i] = views[i].data_ptr()
+            gr.db[i] = views[4 + i].data_ptr()
+        gr.dmask_scales = views[8].data_ptr() if md["scales"] is not None else None
+        pr = _params_struct(md)
+        _lib.check(lib.nsvd_mlp_bwd(C.byref(pb), C.byref(pr), s["engine"], _lib.ptr(s["x"]), _lib.ptr(dF),
+                                    _lib.ptr(sc.saved), sc.saved.numel(), C.byref(gr), _lib.ptr(sc.work),
+                                    sc.work.numel(), _stream(dev)), "nsvd_mlp_bwd")
+        if s["dp"] is not None:
+            s["dp"].allreduce_grads(flat)                      # all-reduce #2
+        # params were passed as (Bff, ws0..3, bs0..3[, scales]); Bff gets no gradient (utils.py:116-118)
+        return (None, None, None, None, None, None) + tuple(views)
+
+
+def compute_loss_operator(method, operator, x, importance, dp=None):
+    """Fused equivalent of NestedLoRA.compute_loss_operator (nestedlora.py:254-267)."""
+    md = describe_model(method)
+    if getattr(method, "sort_indices", None) is not None:
+        raise NotImplementedError("register_eigvals()/sort_indices is not supported by the fused path")
+    params = [md["Bff"]] + md["ws"] + md["bs"] + ([md["scales"]] if md["scales"] is not None else [])
+    loss, F, TF = _FusedOperatorStep.apply(method, operator, importance, x, dp, *params)
+    return loss, dict(f=F, Tf=TF, eigvals=None)

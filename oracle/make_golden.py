@@ -1,0 +1,159 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (exact Laplacian, CPU).
+
+Run in the build container only (needs /root/reference):
+    python oracle/make_golden.py [case ...]
+
+For every case the reference's own `NestedLoRA.compute_loss_operator` + `loss.backward()`
+(methods/nestedlora.py:254-267; laplacian_eps=0 -> pde/diff_ops.py:54-93) is evaluated in
+fp64 (truth) and fp32 (to record the reference's own fp32 noise).  Stored per case:
+  x, seed, config json, loss, f, Tf, and per gradient tensor: Frobenius norm, 4096 sampled
+  entries (fixed indices) or the full tensor when small, and the fp32-vs-fp64 relative error.
+Weights are NOT stored (19 MB at L=16): they are regenerated from the seed by
+`nsvd_oracle.init_params_like_reference`, whose draw order is checked here against the
+reference's constructor through the stored parameter checksums.
+"""
+from __future__ import annotations
+
+import dataclasses
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import nsvd_oracle as O          # noqa: E402
+from oracle import ref_bootstrap as RB       # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+FULL_MAX = 70000       # store a gradient tensor in full when it has at most this many entries
+NSAMP = 4096
+
+CASES = {
+    # BASELINE.json configs[0]: hydrogen, B=128, sequential, L=16
+    "hyd_b128_seq_L16": dict(cfg=O.PathConfig.hydrogen(sequential=True), B=128, seed=0),
+    # configs[1]: oscillator, B=512, joint, L=16 (learnable exp mask)
+    "osc_b512_jnt_L16": dict(cfg=O.PathConfig.oscillator(), B=512, seed=1),
+    # configs[2]: hydrogen, B=512, joint, L=16
+    "hyd_b512_jnt_L16": dict(cfg=O.PathConfig.hydrogen(), B=512, seed=2),
+    # configs[3] shape at reduced B: hydrogen, L=64, joint
+    "hyd_b256_jnt_L64": dict(cfg=O.PathConfig.hydrogen(neigs=64), B=256, seed=3),
+    # small cases with full gradients: odd batch (torch.chunk -> 49/48), joint step=2, narrow features
+    "hyd_small_odd": dict(cfg=O.PathConfig.hydrogen(neigs=4, fourier_mapping_size=64, step=2), B=97, seed=4),
+    "osc_small_seq": dict(cfg=O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64, sequential=True,
+                                                      hard_mul_const=0.5), B=64, seed=5),
+}
+
+CDK_CASES = {
+    # configs[4]: B=4096, feature dim 512, L=512 (+1 const mode), joint
+    "cdk_b4096_L512": dict(B=4096, L=512, seed=10, sequential=False, const=True),
+    "cdk_small_seq": dict(B=96, L=24, seed=11, sequential=True, const=True),
+    "cdk_small_noconst": dict(B=64, L=16, seed=12, sequential=False, const=False),
+}
+
+
+def checksum(a: np.ndarray):
+    a = a.astype(np.float64)
+    return np.array([a.sum(), (a * a).sum()])
+
+
+def run_reference(ref, cfg, seed, x32, dtype):
+    method, operator, importance, gt = RB.build_reference_problem(ref, cfg, seed, 0.0, dtype)
+    x = torch.from_numpy(x32).to(dtype)
+    loss, aux = method.compute_loss_operator(operator, x, importance=importance)
+    loss.backward()
+    grads = {n: (p.grad.detach().numpy().copy() if p.grad is not None else None)
+             for n, p in method.named_parameters()}
+    params = {n: p.detach().numpy().copy() for n, p in method.named_parameters()}
+    return dict(loss=float(loss.detach()), f=aux["f"].detach().numpy(), Tf=aux["Tf"].detach().numpy(),
+                grads=grads, params=params, gt=gt)
+
+
+def make_case(ref, name, spec):
+    cfg, B, seed = spec["cfg"], spec["B"], spec["seed"]
+    g = torch.Generator().manual_seed(1000 + seed)
+    x32 = (cfg.sampling_scale * torch.randn((B, 1, cfg.ndim), generator=g)).reshape(B, -1).numpy()
+    r64 = run_reference(ref, cfg, seed, x32, torch.float64)
+    r32 = run_reference(ref, cfg, seed, x32, torch.float32)
+    mine = O.init_params_like_reference(cfg, seed)
+    out = dict(x=x32, seed=np.int64(seed), config=json.dumps(dataclasses.asdict(cfg)),
+               loss64=np.float64(r64["loss"]), loss32=np.float64(r32["loss"]),
+               f64=r64["f"], Tf64=r64["Tf"], f32=r32["f"], Tf32=r32["Tf"],
+               gt=np.asarray(r64["gt"], np.float64))
+    rs = np.random.RandomState(seed)
+    for n in O.param_names(cfg):
+        p_ref = r32["params"][n]
+        assert np.array_equal(p_ref, mine[n]), f"init draw order mismatch for {n}"
+        out[f"pck/{n}"] = checksum(p_ref)
+        g64, g32 = r64["grads"][n], r32["grads"][n]
+        if g64 is None:
+            continue
+        nrm = np.linalg.norm(g64)
+        out[f"gnorm/{n}"] = np.float64(nrm)
+        out[f"gself/{n}"] = np.float64(np.linalg.norm(g32.astype(np.float64) - g64) / max(nrm, 1e-300))
+        if g64.size <= FULL_MAX:
+            out[f"gfull/{n}"] = g64
+        else:
+            idx = rs.choice(g64.size, NSAMP, replace=False).astype(np.int64)
+            out[f"gidx/{n}"] = idx
+            out[f"gval/{n}"] = g64.reshape(-1)[idx]
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: loss64={r64['loss']:.9g} loss32={r32['loss']:.9g} "
+          f"|f|={np.linalg.norm(r64['f']):.4g} |Tf|={np.linalg.norm(r64['Tf']):.4g}")
+
+
+def make_cdk_case(ref, name, spec):
+    B, L, seed = spec["B"], spec["L"], spec["seed"]
+    g = torch.Generator().manual_seed(seed)
+    f32 = torch.randn(B, L, generator=g)
+    g32 = torch.randn(B, L, generator=g)
+    out = dict(seed=np.int64(seed), B=np.int64(B), L=np.int64(L), sequential=np.bool_(spec["sequential"]),
+               const=np.bool_(spec["const"]))
+    res = {}
+    for tag, dt in (("64", torch.float64), ("32", torch.float32)):
+        method = ref.NestedLoRAForCDK(model=None, neigs=L, step=1, sequential=spec["sequential"],
+                                      set_first_mode_const=spec["const"])
+        method.vector_mask = method.vector_mask.to(dt)
+        method.matrix_mask = method.matrix_mask.to(dt)
+        f = f32.to(dt).clone().requires_grad_()
+        gg = g32.to(dt).clone().requires_grad_()
+        loss, lop, lmet, rsj, rsi = method.compute_loss(f, gg)
+        loss.backward()
+        res[tag] = dict(loss=float(loss.detach()), lop=float(lop.detach()), lmet=float(lmet.detach()), rsj=rsj.detach().numpy(),
+                        rsi=rsi.detach().numpy(), gf=f.grad.numpy(), gg=gg.grad.numpy())
+    r = res["64"]
+    out.update(loss64=np.float64(r["loss"]), lop64=np.float64(r["lop"]), lmet64=np.float64(r["lmet"]),
+               loss32=np.float64(res["32"]["loss"]))
+    rs = np.random.RandomState(seed)
+    if B * L <= FULL_MAX:
+        out.update(f=f32.numpy(), g=g32.numpy(), gf64=r["gf"], gg64=r["gg"], rsj64=r["rsj"], rsi64=r["rsi"])
+    else:
+        out["fck"], out["gck"] = checksum(f32.numpy()), checksum(g32.numpy())
+        idx = rs.choice(B * L, NSAMP, replace=False).astype(np.int64)
+        out.update(gidx=idx, gfval=r["gf"].reshape(-1)[idx], ggval=r["gg"].reshape(-1)[idx],
+                   gfnorm=np.float64(np.linalg.norm(r["gf"])), ggnorm=np.float64(np.linalg.norm(r["gg"])),
+                   rsj64=r["rsj"])
+        idx2 = rs.choice(r["rsi"].size, NSAMP, replace=False).astype(np.int64)
+        out.update(rsi_idx=idx2, rsi_val=r["rsi"][idx2], rsi_norm=np.float64(np.linalg.norm(r["rsi"])))
+    out["gself"] = np.float64(np.linalg.norm(res["32"]["gf"] - r["gf"]) / np.linalg.norm(r["gf"]))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name}: loss64={r['loss']:.9g} loss32={res['32']['loss']:.9g}")
+
+
+def main(argv):
+    os.makedirs(GOLD, exist_ok=True)
+    ref = RB.import_reference("/root/reference")
+    torch.set_num_threads(os.cpu_count() or 1)
+    want = set(argv) if argv else None
+    for name, spec in CASES.items():
+        if want is None or name in want:
+            make_case(ref, name, spec)
+    for name, spec in CDK_CASES.items():
+        if want is None or name in want:
+            make_cdk_case(ref, name, spec)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,166 @@
+"""Parity of the sm_100a path (through the Python API -> C-ABI) against the golden vectors of the
+UNMODIFIED reference and against the CPU oracle.  Tolerance (north star): loss and parameter
+gradients within 1e-4 relative (Frobenius, per tensor)."""
+import numpy as np
+import pytest
+import torch
+
+import neural_svd_b200 as N
+from conftest import build_problem, golden_grad_errors, load_golden, rel
+from oracle import nsvd_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+ENGINES = ["fp32", "bf16x3"]
+PDE_CASES = ["hyd_small_odd", "osc_small_seq", "hyd_b128_seq_L16", "osc_b512_jnt_L16", "hyd_b512_jnt_L16",
+             "hyd_b256_jnt_L64"]
+
+
+def _step(name, engine):
+    d, cfg = load_golden(name)
+    N.set_engine(engine)
+    method, operator, importance, _ = build_problem(cfg, int(d["seed"]), "cuda")
+    x = torch.from_numpy(d["x"]).cuda()
+    loss, aux = method.compute_loss_operator(operator, x, importance=importance)
+    loss.backward()
+    grads = {n: p.grad.detach().cpu().numpy() for n, p in method.named_parameters() if p.grad is not None}
+    return d, cfg, method, float(loss), aux, grads
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", PDE_CASES)
+def test_step_matches_reference_golden(name, engine):
+    d, cfg, method, loss, aux, grads = _step(name, engine)
+    assert abs(loss - float(d["loss64"])) <= TOL * abs(float(d["loss64"]))
+    assert rel(aux["f"].cpu().numpy(), d["f64"]) < TOL
+    assert rel(aux["Tf"].cpu().numpy(), d["Tf64"]) < TOL
+    assert aux["eigvals"] is None and aux["f"].shape == d["f64"].shape
+    names = [n for n in O.param_names(cfg) if n != "model.base.feature_map._B"]
+    assert sorted(grads) == sorted(names)                      # _B gets no gradient
+    errs = golden_grad_errors(d, names, grads)
+    assert len(errs) == len(names)
+    assert max(errs.values()) < TOL, errs
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_step_matches_oracle_on_fresh_inputs(engine):
+    # seeded inputs that are in no fixture, at a ragged size (B not a multiple of the 128-row tile)
+    cfg = O.PathConfig.oscillator(neigs=6, fourier_mapping_size=40, sequential=False, step=2)
+    N.set_engine(engine)
+    method, operator, importance, _ = build_problem(cfg, 77, "cuda")
+    g = torch.Generator().manual_seed(5)
+    x = cfg.sampling_scale * torch.randn(301, 2, generator=g)
+    # perturb biases / scales so that they are exercised (reference initialises biases to zero)
+    with torch.no_grad():
+        for i, b in enumerate(method.model.base.bs):
+            b.add_(0.1 * torch.randn(b.shape, generator=g).to(b.device))
+        method.model.boundary_mask.scales.mul_(1 + 0.2 * torch.rand(6, generator=g).to("cuda"))
+    params = {n: p.detach().cpu().numpy().astype(np.float64) for n, p in method.named_parameters()}
+    r = O.train_step(x.numpy().astype(np.float64), params, cfg)
+    loss, aux = method.compute_loss_operator(operator, x.cuda(), importance=importance)
+    loss.backward()
+    assert abs(float(loss) - r["loss"]) <= TOL * abs(r["loss"])
+    assert rel(aux["Tf"].cpu().numpy(), r["Tf"]) < TOL
+    for n, p in method.named_parameters():
+        if p.grad is not None:
+            assert rel(p.grad.cpu().numpy(), r["grads"][n]) < TOL, n
+
+
+def test_grad_output_scaling_and_accumulation():
+    d, cfg = load_golden("hyd_small_odd")
+    N.set_engine("fp32")
+    method, operator, importance, _ = build_problem(cfg, int(d["seed"]), "cuda")
+    x = torch.from_numpy(d["x"]).cuda()
+    loss, _ = method.compute_loss_operator(operator, x, importance=importance)
+    loss.backward()
+    g1 = method.model.base.ws[1].grad.clone()
+    loss, _ = method.compute_loss_operator(operator, x, importance=importance)
+    (3.0 * loss).backward()                                  # accumulates 3x on top of 1x
+    assert torch.allclose(method.model.base.ws[1].grad, 4.0 * g1, rtol=1e-5, atol=1e-7)
+
+
+def test_operator_protocol_and_model_forward():
+    d, cfg = load_golden("osc_small_seq")
+    N.set_engine("fp32")
+    method, operator, importance, _ = build_problem(cfg, int(d["seed"]), "cuda")
+    x = torch.from_numpy(d["x"]).cuda()
+    Tf, f = operator(method, x, importance=importance)       # examples/__init__.py:7-9 protocol
+    assert rel(Tf.cpu().numpy(), d["Tf64"]) < TOL and rel(f.cpu().numpy(), d["f64"]) < TOL
+    vals = method(x)                                          # NestedLoRA.forward -> WaveFunctions.forward
+    params = {n: p.detach().cpu().numpy().astype(np.float64) for n, p in method.named_parameters()}
+    u = O.forward_streams(d["x"].astype(np.float64), params, cfg)
+    r = np.sqrt((d["x"].astype(np.float64) ** 2).sum(1))[:, None]
+    want = cfg.hard_mul_const * u[0] * np.exp(-r / params["model.boundary_mask.scales"][None, :])
+    assert rel(vals.cpu().numpy(), want) < TOL
+
+
+@pytest.mark.parametrize("seq", [False, True])
+@pytest.mark.parametrize("B,L", [(97, 5), (1000, 16), (513, 33), (2048, 64)])
+def test_standalone_loss_function_matches_oracle(B, L, seq):
+    # NestedLoRALossFunctionEVD.apply(f, Tf, f1, f2, v, M): K2 + K3 on random inputs (nestedlora.py:67-111)
+    g = torch.Generator().manual_seed(B + L)
+    f = torch.randn(B, L, generator=g)
+    Tf = torch.randn(B, L, generator=g)
+    v, M = O.nesting_masks(L, seq)
+    loss_o, lam1, lam2 = O.loss_forward(f.numpy().astype(np.float64), Tf.numpy().astype(np.float64), v, M)
+    dF_o = O.loss_dF(f.numpy().astype(np.float64), Tf.numpy().astype(np.float64), v, M, lam1, lam2)
+    fc = f.cuda().requires_grad_()
+    f1, f2 = torch.chunk(fc, 2)
+    loss = N.NestedLoRALossFunctionEVD.apply(fc, Tf.cuda(), f1, f2, torch.from_numpy(v), torch.from_numpy(M))
+    loss.backward()
+    assert abs(float(loss) - loss_o) < 1e-5 * abs(loss_o)
+    assert rel(fc.grad.cpu().numpy(), dF_o) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["cdk_small_seq", "cdk_small_noconst"])
+def test_cdk_matches_reference_golden(name):
+    d, _ = load_golden(name)
+    m = N.NestedLoRAForCDK(None, int(d["L"]), step=1, sequential=bool(d["sequential"]),
+                           set_first_mode_const=bool(d["const"]))
+    f = torch.from_numpy(d["f"]).cuda().requires_grad_()
+    g = torch.from_numpy(d["g"]).cuda().requires_grad_()
+    loss, lop, lmet, rsj, rsi = m.compute_loss(f, g)
+    loss.backward()
+    assert abs(float(loss) - float(d["loss64"])) < TOL * abs(float(d["loss64"]))
+    assert abs(float(lop) - float(d["lop64"])) < TOL * abs(float(d["lop64"]))
+    assert abs(float(lmet) - float(d["lmet64"])) < TOL * abs(float(d["lmet64"]))
+    assert rel(f.grad.cpu().numpy(), d["gf64"]) < TOL and rel(g.grad.cpu().numpy(), d["gg64"]) < TOL
+    assert rel(rsj.cpu().numpy(), d["rsj64"]) < TOL and rel(rsi.cpu().numpy(), d["rsi64"]) < TOL
+    assert rsi.shape == (f.shape[0] ** 2 - f.shape[0],)
+
+
+def test_cdk_full_size_config5():
+    d, _ = load_golden("cdk_b4096_L512")
+    g = torch.Generator().manual_seed(int(d["seed"]))
+    f = torch.randn(int(d["B"]), int(d["L"]), generator=g).cuda().requires_grad_()
+    gg = torch.randn(int(d["B"]), int(d["L"]), generator=g).cuda().requires_grad_()
+    m = N.NestedLoRAForCDK(None, int(d["L"]))
+    loss, lop, lmet, rsj, rsi = m.compute_loss(f, gg)
+    loss.backward()
+    assert abs(float(loss) - float(d["loss64"])) < TOL * abs(float(d["loss64"]))
+    assert rel(f.grad.cpu().numpy().reshape(-1)[d["gidx"]], d["gfval"]) < TOL
+    assert rel(gg.grad.cpu().numpy().reshape(-1)[d["gidx"]], d["ggval"]) < TOL
+    assert rel(rsj.cpu().numpy(), d["rsj64"]) < TOL
+    assert rel(rsi.cpu().numpy()[d["rsi_idx"]], d["rsi_val"]) < TOL
+
+
+def test_large_batch_properties():
+    # BASELINE-size inputs where the oracle is too slow: size-independent properties instead.
+    # (1) permuting points inside each half leaves loss and gradients unchanged;
+    # (2) data-parallel split identity: terms of the two halves of a batch add up to the whole.
+    cfg = O.PathConfig.hydrogen()
+    N.set_engine("fp32")
+    method, operator, importance, _ = build_problem(cfg, 0, "cuda")
+    g = torch.Generator().manual_seed(9)
+    B = 4096
+    x = (cfg.sampling_scale * torch.randn(B, 2, generator=g)).cuda()
+    loss, aux = method.compute_loss_operator(operator, x, importance=importance)
+    loss.backward()
+    g0 = method.model.base.ws[0].grad.clone()
+    method.zero_grad()
+    perm = torch.cat([torch.randperm(B // 2, generator=g), B // 2 + torch.randperm(B // 2, generator=g)]).cuda()
+    loss2, aux2 = method.compute_loss_operator(operator, x[perm], importance=importance)
+    loss2.backward()
+    assert abs(float(loss) - float(loss2)) < 1e-5 * abs(float(loss))
+    assert torch.allclose(aux2["f"], aux["f"][perm], rtol=1e-5, atol=1e-6)
+    assert rel(method.model.base.ws[0].grad.cpu().numpy(), g0.cpu().numpy()) < 1e-5

@@ -1,0 +1,110 @@
+"""Host-side mirror of the reference interface: masks, parameter layout, recognition, errors (CPU)."""
+import re
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+import neural_svd_b200 as N
+from neural_svd_b200 import fused, operators
+from conftest import build_problem, load_golden, ref_args
+from oracle import nsvd_oracle as O
+
+
+@pytest.mark.parametrize("L,seq,step,const", [(16, False, 1, False), (16, True, 1, False), (7, False, 3, False),
+                                              (512, False, 1, True), (24, True, 1, True), (5, False, 2, True)])
+def test_masks_match_reference_formula(L, seq, step, const):
+    if const:
+        m = N.NestedLoRAForCDK(None, L, step=step, sequential=seq, set_first_mode_const=True)
+    else:
+        m = N.NestedLoRA(None, L, step=step, sequential=seq)
+    v, M = O.nesting_masks(L, seq, step, const)
+    assert np.array_equal(m.vector_mask.numpy(), v) and np.array_equal(m.matrix_mask.numpy(), M)
+    assert m.vector_mask.dtype == torch.float32 and m.name == "nestedlora"
+    if not seq and step == 1 and not const:      # v_i = (L-i)/L, M_ij = min(v_i, v_j)
+        assert np.allclose(v, (L - np.arange(L)) / L)
+    if seq:
+        assert np.array_equal(M, np.triu(np.ones_like(M)))
+
+
+@pytest.mark.parametrize("name", ["hyd_small_odd", "osc_small_seq", "hyd_b128_seq_L16"])
+def test_parameter_names_shapes_and_init_draws(name):
+    d, cfg = load_golden(name)
+    method, operator, importance, gt = build_problem(cfg, int(d["seed"]))
+    names = [n for n, _ in method.named_parameters()]
+    assert names == O.param_names(cfg)            # state_dict round trip with the reference
+    for n, p in method.named_parameters():
+        a = p.detach().numpy().astype(np.float64)
+        assert np.allclose([a.sum(), (a * a).sum()], d[f"pck/{n}"], rtol=1e-12, atol=1e-12), n
+    assert not dict(method.named_parameters())["model.base.feature_map._B"].requires_grad
+    assert np.allclose(gt, d["gt"][:cfg.neigs])
+
+
+def test_describe_operator_and_importance():
+    d, cfg = load_golden("osc_small_seq")
+    method, operator, importance, _ = build_problem(cfg, 0)
+    od = operators.describe_operator(operator)
+    assert od == dict(potential=1, pot_coef=1.0, scale_kinetic=1.0, op_scale=1.0, op_shift=16.0)
+    assert operators.describe_importance(importance) == 4.0
+    md = fused.describe_model(method)
+    assert md["L"] == 4 and md["Mff"] == 64 and md["scales"] is not None and md["hard_mul_const"] == 0.5
+    # the reference's importance is a closure over a MultivariateNormal (main_pde.py:94-100)
+    from torch.distributions import MultivariateNormal
+    mvn = MultivariateNormal(loc=torch.zeros(2), covariance_matrix=16.0 ** 2 * torch.eye(2))
+    closure = lambda x: mvn.log_prob(x.view(x.shape[0], -1)).exp().view(-1, 1)  # noqa: E731
+    assert operators.describe_importance(closure) == 16.0
+    x = 16 * torch.randn(8, 2)
+    assert torch.allclose(N.GaussianImportance(16.0)(x), closure(x), rtol=1e-5)
+
+
+def test_unsupported_configurations_raise():
+    with pytest.raises(NotImplementedError):
+        operators.describe_operator(N.OperatorWrapper(N.NegativeHamiltonian(lambda x: x), 1.0, 0.0))
+    with pytest.raises(NotImplementedError):
+        operators.describe_importance(None)
+    with pytest.raises(NotImplementedError):
+        operators.describe_importance(lambda x: x)
+    a = ref_args(O.PathConfig.hydrogen(neigs=2, fourier_mapping_size=8))
+    a.parallel = False
+    with pytest.raises(NotImplementedError):
+        N.get_wavefunctions(a)
+    a.parallel, a.nonlinearity = True, "relu"
+    with pytest.raises(NotImplementedError):
+        N.get_wavefunctions(a)
+    with pytest.raises(NotImplementedError):
+        N.NestedLoRA(None, 4).compute_loss_operator(None, None, evd=False)
+
+
+def test_no_cpu_fallback():
+    d, cfg = load_golden("hyd_small_odd")
+    method, operator, importance, _ = build_problem(cfg, 0)
+    x = torch.from_numpy(d["x"])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        method.compute_loss_operator(operator, x, importance=importance)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        N.NestedLoRAForCDK(None, 4).compute_loss(torch.randn(8, 4), torch.randn(8, 4))
+
+
+def test_product_never_imports_oracle():
+    import os
+    root = os.path.dirname(os.path.abspath(N.__file__))
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_shard_points_tiles_global_halves():
+    x = torch.arange(16.0).view(8, 2)
+    parts = [N.shard_points(x, r, 2) for r in range(2)]
+    first = torch.cat([p[:2] for p in parts])
+    second = torch.cat([p[2:] for p in parts])
+    assert torch.equal(first, x[:4]) and torch.equal(second, x[4:])
+
+
+def test_potentials_match_reference_formulas():
+    x = torch.tensor([[3.0, 4.0]])
+    assert torch.allclose(N.hydrogen_potential(x, charge=2.0), torch.tensor([[-0.4]]))
+    assert torch.allclose(N.harmonic_oscillator_potential(x, k=0.5), torch.tensor([[12.5]]))
