@@ -76,7 +76,7 @@ def test_grad_output_scaling_and_accumulation():
     g1 = method.model.base.ws[1].grad.clone()
     loss, _ = method.compute_loss_operator(operator, x, importance=importance)
     (3.0 * loss).backward()                                  # accumulates 3x on top of 1x
-    assert torch.allclose(method.model.base.ws[1].grad, 4.0 * g1, rtol=1e-5, atol=1e-7)
+    assert rel(method.model.base.ws[1].grad.cpu().numpy(), 4.0 * g1.cpu().numpy()) < 1e-5
 
 
 def test_operator_protocol_and_model_forward():
