@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — collocation points/sec of one NestedLoRA loss+grad step (2D hydrogen, L=16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = fused forward (K1) + Gram/loss (K2) + dF (K3) + MLP backward (K4) on P synthetic
+collocation points PER GPU (weak scaling), plus the two all-reduces when N > 1.
+  value : whole-job points/s with x already resident in HBM (CUDA events, max over ranks);
+  e2e   : same through the public API `NestedLoRA.compute_loss_operator` + backward with x in
+          pinned HOST memory (H2D inside the timed region, loss.item() D2H);
+  roofline     : the layer-0 forward GEMM (tcgen05), timed with CUDA events inside the timed steps;
+  cpu_baseline : the reference's own CPU PyTorch path (baseline/_ref, unmodified) or, if that copy
+                 is absent, the numpy oracle port, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "collocation points/sec (loss+grad step), 2D hydrogen L=16"
+UNIT = "points/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--points", type=int, default=131072, help="collocation points per GPU per step")
+    ap.add_argument("--neigs", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="bf16x3", choices=["bf16x3", "fp32"])
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons of one GPU during the timed region (NVML, 100 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "app_clocks": 0x2}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arms
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, budget_s, steps=None, warmup=1):
+    """Times the reference's CPU implementation of the step on the host cores.
+    kind 'reference' = unmodified jongharyu/neural-svd from baseline/_ref (or /root/reference),
+    script-default finite-difference Laplacian (eps=0.01, hydrogen.sh:20) AND exact mode;
+    kind 'port' = oracle/nsvd_oracle.py (numpy, forward-mode exact Laplacian)."""
+    import numpy as np
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from oracle import nsvd_oracle as O
+    from oracle import ref_bootstrap as RB
+    root = RB.find_reference()
+    out = {"cores": cores}
+    if root is not None:
+        ref = RB.import_reference(root)
+        B = 512
+        x = (cfg.sampling_scale * torch.randn((B, 1, cfg.ndim))).reshape(B, -1)
+        res = {}
+        for tag, eps in (("fd", 0.01), ("exact", 0.0)):
+            method, operator, importance, _ = RB.build_reference_problem(ref, cfg, 0, eps)
+            ts = []
+            t_all = time.perf_counter()
+            n = 0
+            while True:
+                t0 = time.perf_counter()
+                method.zero_grad()
+                loss, _ = method.compute_loss_operator(operator, x, importance=importance)
+                loss.backward()
+                float(loss)
+                dt = time.perf_counter() - t0
+                if n >= warmup:
+                    ts.append(dt)
+                n += 1
+                if steps is not None and len(ts) >= steps:
+                    break
+                if steps is None and (time.perf_counter() - t_all > budget_s / 2 and len(ts) >= 2):
+                    break
+            res[tag] = B / statistics.median(ts)
+        out.update(kind="reference", value=res["fd"], unit=UNIT, exact_value=res["exact"],
+                   sample=f"unmodified reference (torch {torch.__version__} CPU, {cores} threads), hydrogen L={cfg.neigs}, "
+                          f"B={B} points/step, loss+grad; value = finite-difference Laplacian eps=0.01 (script default), "
+                          f"exact_value = autograd exact Laplacian (the parity oracle)")
+        return out
+    B = 2048
+    params = O.init_params_like_reference(cfg, 0)
+    x = (cfg.sampling_scale * np.random.RandomState(0).randn(B, cfg.ndim)).astype(np.float32)
+    ts, t_all = [], time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        O.train_step(x, params, cfg)
+        ts.append(time.perf_counter() - t0)
+        if (steps is not None and len(ts) >= steps) or (steps is None and time.perf_counter() - t_all > budget_s and len(ts) >= 2):
+            break
+    out.update(kind="port", value=B / statistics.median(ts), unit=UNIT,
+               sample=f"numpy oracle port (fp32, forward-mode exact Laplacian, {cores} BLAS threads), hydrogen "
+                      f"L={cfg.neigs}, B={B} points/step")
+    return out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import nsvd_oracle as O
+    cfg = O.PathConfig.hydrogen(neigs=args.neigs)
+    t0 = time.perf_counter()
+    r = cpu_reference_run(cfg, budget_s=60.0, steps=max(args.steps, 2), warmup=max(args.warmup, 1))
+    v = r["value"]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"2D hydrogen, joint nesting, L={args.neigs}, CPU sample (see cpu_baseline.sample)"},
+            "cpu_baseline": r, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import neural_svd_b200 as N
+    from neural_svd_b200 import _lib
+    from conftest import build_problem
+    from oracle import nsvd_oracle as O   # PathConfig only (hyper-parameter container) + cpu_baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run for N>1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    _lib.check(lib.nsvd_device_ok(local), "nsvd_device_ok")
+    dp = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dp = N.PointParallel()
+
+    cfg = O.PathConfig.hydrogen(neigs=args.neigs)
+    N.set_engine(args.engine)
+    method, operator, importance, _ = build_problem(cfg, 0, dev)
+    method.data_parallel = dp
+    P = args.points
+    g = torch.Generator().manual_seed(100 + rank)
+    xs_host = [(cfg.sampling_scale * torch.randn((P, 1, 2), generator=g)).reshape(P, 2).pin_memory()
+               for _ in range(4)]
+    xs_dev = [x.to(dev) for x in xs_host]
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step(x):
+        method.zero_grad(set_to_none=True)
+        loss, _ = method.compute_loss_operator(operator, x, importance=importance)
+        loss.backward()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(xs_dev[i % 4])
+    barrier()
+
+    # ---- device-resident timing: K steps, L2 flushed between steps, CUDA events on the launch stream
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.nsvd_profile_enable(1)
+    _lib.profile_read(reset=True)
+    launches0 = lib.nsvd_launch_count()
+    evs = []
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(xs_dev[i % 4])
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = lib.nsvd_launch_count() - launches0
+    lib.nsvd_profile_enable(0)
+    prof = _lib.profile_read(reset=True)
+    sampler.stop_flag = True
+    sampler.join()
+    ms = [a.elapsed_time(b) for a, b in evs]
+    t_dev = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms = float(t_dev)
+    ms_per_step = total_ms / args.steps
+    value = world * P / (ms_per_step * 1e-3)
+
+    # ---- end to end: host x (pinned) -> H2D -> step -> loss.item(); wall clock, max over ranks
+    for i in range(2):
+        float(step(xs_host[i % 4]))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        float(step(xs_host[i % 4]))     # .to(device) inside compute_loss_operator; .item() reads the loss back
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * args.steps / float(t_e2e)
+
+    if rank == 0:
+        pk = peaks()
+        L, K0 = args.neigs, 2 * cfg.fourier_mapping_size
+        l0_ms, l0_n = prof["l0_fwd"]
+        flops_l0 = 2.0 * 4 * K0 * 128 * L * P * args.steps          # algorithmic, all launches of the timed region
+        roof = None
+        if l0_n:
+            ach = flops_l0 / (l0_ms * 1e-3) / 1e12
+            roof = {"kernel": "big_gemm_kernel<K-major, L0FwdEpi> (layer-0 4-stream forward GEMM, tcgen05 bf16x3)",
+                    "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                    "issued_frac": 3 * ach / pk["tf_sust"], "launches": l0_n, "avg_launch_ms": l0_ms / l0_n,
+                    "note": "achieved = ALGORITHMIC fp32-equivalent FLOPs; every MAC is issued as 3 bf16 MMAs "
+                            "(hi*hi + hi*lo + lo*hi), so tensor-pipe issue rate = issued_frac of the bf16 peak"}
+        gram_ms, gram_n = prof["gram_reduce"]
+        df_ms, df_n = prof["loss_dF"]
+        kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
+        if gram_n:
+            kernels["gram_reduce"]["achieved_GBps"] = 8.0 * P * L * args.steps / (gram_ms * 1e-3) / 1e9
+            kernels["gram_reduce"]["hbm_frac"] = kernels["gram_reduce"]["achieved_GBps"] / pk["hbm"]
+        if df_n:
+            kernels["loss_dF"]["achieved_GBps"] = 12.0 * P * L * args.steps / (df_ms * 1e-3) / 1e9
+            kernels["loss_dF"]["hbm_frac"] = kernels["loss_dF"]["achieved_GBps"] / pk["hbm"]
+        flop_pt = L * (2 * 4 * (K0 * 128 + 2 * 128 * 128 + 128) + 2 * (K0 * 128 + 4 * 128 * 128 + 2 * 128))
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16x3 (fp32 operands split hi/lo, fp32 accumulate)" if args.engine == "bf16x3" else "f32",
+                "data": "synthetic",
+                "config": {"workload": f"2D hydrogen (H=-Lap-1/r, scale 100), joint nesting, L={L}, M_ff=1024, "
+                                       f"{P} Gaussian(sigma=16) collocation points per GPU per step, exact forward-mode "
+                                       f"Laplacian, loss+grad", "points_per_gpu": P, "neigs": L,
+                           "parallelism": f"dp{world} over points", "l2": "512 MB flush write between timed steps",
+                           "engine": args.engine, "algorithmic_mflop_per_point": flop_pt / 1e6},
+                "clocks": sampler.result(), "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": P * 2 * 4 * world,
+                        "d2h_bytes_per_step": 4 * world},
+                "roofline": roof, "kernels": kernels,
+                "step_tflops_algorithmic": flop_pt * value / 1e12}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_run(cfg, args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)

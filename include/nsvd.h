@@ -81,6 +81,13 @@ typedef struct nsvd_grads {
 } nsvd_grads_t;
 
 int nsvd_abi_version(void);
+/* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
+long nsvd_launch_count(void);
+/* Optional per-kernel-class timing with CUDA events on the launch stream (bench.py roofline).
+ * classes: 0 l0_fwd GEMM, 1 hidden_fwd, 2 hidden_bwd, 3 l0_wgrad GEMM, 4 gram_reduce, 5 loss_dF,
+ *          6 prep (features / weight folding), 7 head_bwd.  read() synchronises on the events.  */
+void nsvd_profile_enable(int on);
+int nsvd_profile_read(double* ms_per_class, long* launches_per_class, int n_classes, int reset);
 const char* nsvd_last_error(void);
 /* 0 when device `dev` is an sm_100 part this library can run on. */
 int nsvd_device_ok(int dev);

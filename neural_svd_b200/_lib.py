@@ -41,6 +41,9 @@ _PB, _PR, _GR = C.POINTER(Problem), C.POINTER(Params), C.POINTER(Grads)
 SIGNATURES = {
     "nsvd_abi_version": (C.c_int, []),
     "nsvd_last_error": (C.c_char_p, []),
+    "nsvd_launch_count": (C.c_long, []),
+    "nsvd_profile_enable": (None, [C.c_int]),
+    "nsvd_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int, C.c_int]),
     "nsvd_device_ok": (C.c_int, [C.c_int]),
     "nsvd_scratch_bytes": (C.c_int, [_PB, C.c_int, C.POINTER(_sz), C.POINTER(_sz)]),
     "nsvd_fwd_streams": (C.c_int, [_PB, _PR, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
@@ -86,6 +89,18 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().nsvd_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+KERNEL_CLASSES = ["l0_fwd", "hidden_fwd", "hidden_bwd", "l0_wgrad", "gram_reduce", "loss_dF", "prep", "head_bwd"]
+
+
+def profile_read(reset=True):
+    """{class: (total_ms, launches)} of the kernels timed since nsvd_profile_enable(1)."""
+    lib = load()
+    n = len(KERNEL_CLASSES)
+    ms, cnt = (C.c_double * n)(), (C.c_long * n)()
+    check(lib.nsvd_profile_read(ms, cnt, n, int(reset)), "nsvd_profile_read")
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(KERNEL_CLASSES)}
 
 
 def ptr(t):

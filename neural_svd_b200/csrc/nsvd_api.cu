@@ -3,7 +3,24 @@
 #include <string.h>
 #include "nsvd_simt.cuh"
 
+#include <vector>
 namespace nsvd {
+long g_launches = 0;
+static bool g_prof_on = false;
+struct ProfRec { int cls; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+ProfScope::ProfScope(int cls_, cudaStream_t st_) : cls(cls_), st(st_), on(g_prof_on) {
+  if (!on) return;
+  ProfRec r;
+  r.cls = cls;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (on) cudaEventRecord(g_prof.back().b, st);
+}
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -34,6 +51,35 @@ using namespace nsvd;
 extern "C" {
 
 int nsvd_abi_version(void) { return NSVD_ABI_VERSION; }
+long nsvd_launch_count(void) { return g_launches; }
+void nsvd_profile_enable(int on) { g_prof_on = on != 0; }
+int nsvd_profile_read(double* ms_per_class, long* launches_per_class, int n_classes, int reset) {
+  for (int i = 0; i < n_classes; ++i) {
+    ms_per_class[i] = 0.0;
+    launches_per_class[i] = 0;
+  }
+  for (auto& r : g_prof) {
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) {
+      set_error("profile: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.cls < n_classes) {
+      ms_per_class[r.cls] += ms;
+      launches_per_class[r.cls] += 1;
+    }
+  }
+  if (reset) {
+    for (auto& r : g_prof) {
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+  }
+  return 0;
+}
 const char* nsvd_last_error(void) { return g_err; }
 
 int nsvd_device_ok(int dev) {
@@ -106,6 +152,7 @@ int nsvd_gram_reduce(const float* F, const float* TF, const float* vector_mask, 
   NSVD_CHECK_ARG(F && TF && vector_mask && terms && partials, "NULL buffer");
   NSVD_CHECK_ARG(n_points >= 1 && n_copies >= 1 && n_copies <= 64, "bad shape B=%d L=%d", n_points, n_copies);
   NSVD_CHECK_ARG(b1 >= 0 && b1 <= n_points, "b1=%d out of range", b1);
+  ProfScope ps(KC_GRAM, (cudaStream_t)stream);
   return gram_reduce(F, TF, vector_mask, n_points, n_copies, b1, terms, partials, (cudaStream_t)stream);
 }
 
@@ -129,6 +176,7 @@ int nsvd_loss_dF(const float* F, const float* TF, const float* vector_mask, cons
   NSVD_CHECK_ARG(F && vector_mask && dF && (TF || coef), "NULL buffer");
   NSVD_CHECK_ARG(b1 >= 0 && b1 <= n_points && Bg > 0, "bad b1/Bg");
   NSVD_CHECK_ARG(n_copies >= 1 && n_copies <= 64, "n_copies %d out of [1,64]", n_copies);
+  ProfScope ps(KC_DF, (cudaStream_t)stream);
   return loss_dF(F, TF, vector_mask, coef, grad_scale, n_points, n_copies, b1, Bg, dF, (cudaStream_t)stream);
 }
 

@@ -31,7 +31,24 @@ void set_error(const char* fmt, ...);
     }                                                                        \
   } while (0)
 
-#define NSVD_LAUNCH_CHECK() NSVD_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro: it counts launches (nsvd_launch_count)
+#define NSVD_LAUNCH_CHECK()               \
+  do {                                    \
+    ::nsvd::g_launches++;                 \
+    NSVD_CUDA(cudaGetLastError());        \
+  } while (0)
+
+extern long g_launches;
+
+// kernel classes timed by the optional profiler (nsvd_profile_*): CUDA events on the launch stream
+enum KernelClass { KC_L0_FWD = 0, KC_HID_FWD, KC_HID_BWD, KC_L0_WGRAD, KC_GRAM, KC_DF, KC_PREP, KC_HEAD_BWD, KC_COUNT };
+struct ProfScope {
+  int cls;
+  cudaStream_t st;
+  bool on;
+  ProfScope(int cls_, cudaStream_t st_);
+  ~ProfScope();
+};
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }

@@ -345,22 +345,984 @@ int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int
 }
 
 // ------------------------------------------------------------------------------------------
-// engine entry points (filled in below)
+// shared epilogue math
 // ------------------------------------------------------------------------------------------
+// softplus on the value stream and its forward-mode derivative streams
+__device__ __forceinline__ void act_streams(float z0, float z1, float z2, float z3, float& a0, float& a1,
+                                            float& a2, float& a3) {
+  float a, sg;
+  softplus_sig(z0, a, sg);
+  a0 = a;
+  a1 = sg * z1;
+  a2 = sg * z2;
+  a3 = sg * z3 + sg * (1.f - sg) * (z1 * z1 + z2 * z2);
+}
+
+// 16 fp32 values -> 16 bf16 hi + 16 bf16 lo, two 16-byte stores each (dst 32-byte aligned)
+__device__ __forceinline__ void store_split16(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tc::split_bf16x2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  uint4* ph = reinterpret_cast<uint4*>(hi);
+  uint4* pl = reinterpret_cast<uint4*>(lo);
+  ph[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  pl[0] = make_uint4(l[0], l[1], l[2], l[3]);
+  pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+// 16 consecutive values hi+lo -> fp32
+__device__ __forceinline__ void load_merge16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* v) {
+  uint4 h[2] = {reinterpret_cast<const uint4*>(hi)[0], reinterpret_cast<const uint4*>(hi)[1]};
+  uint4 l[2] = {reinterpret_cast<const uint4*>(lo)[0], reinterpret_cast<const uint4*>(lo)[1]};
+  const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(h);
+  const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(l);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float2 a = __bfloat1622float2(hh[i]), b = __bfloat1622float2(ll[i]);
+    v[2 * i] = a.x + b.x;
+    v[2 * i + 1] = a.y + b.y;
+  }
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// weight / feature preparation (SIMT, HBM-bound, tiny next to the GEMMs)
+// ------------------------------------------------------------------------------------------
+// Folded layer-0 weights: all four streams are W'_s . [sin p ; cos p]   (probe10)
+//   rows n = l*512 + (h/64)*256 + s*64 + (h%64),  K-major, hi/lo planes.
+__global__ void fold_w0_kernel(const float* __restrict__ W0, const float* __restrict__ Bff,
+                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int L, int M) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n = (long)L * kHidden * M;
+  if (i >= n) return;
+  int j = (int)(i % M);
+  int h = (int)((i / M) % kHidden);
+  int l = (int)(i / ((long)M * kHidden));
+  const long K0 = 2L * M;
+  float ws = W0[((long)l * kHidden + h) * K0 + j], wc = W0[((long)l * kHidden + h) * K0 + M + j];
+  float b0 = Bff[j], b1 = Bff[M + j], nb2 = -(b0 * b0 + b1 * b1);
+  float vs[4] = {ws, -wc * b0, -wc * b1, nb2 * ws};  // coefficient of sin p_j
+  float vc[4] = {wc, ws * b0, ws * b1, nb2 * wc};    // coefficient of cos p_j
+  long rbase = (long)l * 512 + (h / 64) * 256 + (h % 64);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    long o = (rbase + s * 64) * K0;
+    __nv_bfloat16 a, b;
+    tc::split_bf16(vs[s], a, b);
+    hi[o + j] = a;
+    lo[o + j] = b;
+    tc::split_bf16(vc[s], a, b);
+    hi[o + M + j] = a;
+    lo[o + M + j] = b;
+  }
+}
+
+// out[l][c][r] = in[l][r][c] when transpose (128x128 blocks), hi/lo planes
+__global__ void split_w_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ hi,
+                               __nv_bfloat16* __restrict__ lo, int L, int transpose) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n = (long)L * kHidden * kHidden;
+  if (i >= n) return;
+  int c = (int)(i % kHidden), r = (int)((i / kHidden) % kHidden), l = (int)(i / (kHidden * kHidden));
+  float v = transpose ? W[((long)l * kHidden + c) * kHidden + r] : W[i];
+  __nv_bfloat16 a, b;
+  tc::split_bf16(v, a, b);
+  hi[i] = a;
+  lo[i] = b;
+}
+
+// Phi = [sin(x B), cos(x B)] as bf16 hi/lo planes (B, 2M)   (examples/utils.py:139-140)
+__global__ void features_bf16_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long P,
+                                     int M) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * M) return;
+  long p = i / M;
+  int j = (int)(i % M);
+  float ph = fmaf(x[2 * p + 1], Bff[M + j], x[2 * p] * Bff[j]);
+  float s, c;
+  sincosf(ph, &s, &c);
+  long o = p * 2L * M;
+  __nv_bfloat16 a, b;
+  tc::split_bf16(s, a, b);
+  hi[o + j] = a;
+  lo[o + j] = b;
+  tc::split_bf16(c, a, b);
+  hi[o + M + j] = a;
+  lo[o + M + j] = b;
+}
+
+// ------------------------------------------------------------------------------------------
+// layer-0 forward epilogue (S1, K-major): tile = (copy l, hidden half hc, 128 points)
+//   TMEM columns [s*64 + hh]; writes the 4 activation streams as hi/lo planes for layer 1 and
+//   the value stream into the saved buffer.
+// ------------------------------------------------------------------------------------------
+struct L0FwdEpi {
+  const float* bias;            // b0 (L,128)
+  __nv_bfloat16 *str_hi, *str_lo;  // [L][4][P][128]
+  __nv_bfloat16 *sav_hi, *sav_lo;  // [L][Btot][128]
+  int P;
+  long Btot, p_off;
+  __device__ __forceinline__ void operator()(uint32_t tmem_acc, const TileCoord& c, int ewarp, int lane) const {
+    const int q = ewarp & 3, half = ewarp >> 2;
+    const int pt = c.mt * big::BM + q * 32 + lane;
+    const int l = c.b, hc = c.nt;
+    const uint32_t tl = tmem_acc + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      const int hh = half * 32 + ch * 16;
+      float z[4][16];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) tc::tmem_ld16(tl + s * 64 + hh, z[s]);
+      tc::tmem_ld_wait();
+      const int h0 = hc * 64 + hh;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float zb = z[0][i] + __ldg(bias + l * kHidden + h0 + i);
+        act_streams(zb, z[1][i], z[2][i], z[3][i], z[0][i], z[1][i], z[2][i], z[3][i]);
+      }
+      if (pt < P) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          long o = (((long)l * 4 + s) * P + pt) * kHidden + h0;
+          store_split16(z[s], str_hi + o, str_lo + o);
+        }
+        long o = ((long)l * Btot + p_off + pt) * kHidden + h0;
+        store_split16(z[0], sav_hi + o, sav_lo + o);
+      }
+    }
+  }
+};
+
+// layer-0 weight-gradient epilogue (S1, MN-major): tile = (copy l, 256 features, k-slice of points)
+//   dW0[l][j][n] += acc   (fp32 vector reductions in L2)
+struct L0WgradEpi {
+  float* dW0;
+  int K0;
+  __device__ __forceinline__ void operator()(uint32_t tmem_acc, const TileCoord& c, int ewarp, int lane) const {
+    const int q = ewarp & 3, half = ewarp >> 2;
+    const int j = q * 32 + lane;
+    float* drow = dW0 + ((long)c.b * kHidden + j) * K0;
+    const uint32_t tl = tmem_acc + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ++ch) {
+      const int col0 = half * 128 + ch * 16;
+      float v[16];
+      tc::tmem_ld16(tl + col0, v);
+      tc::tmem_ld_wait();
+      const int n0 = c.nt * big::BN + col0;
+      if (n0 + 16 <= K0) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) red_add_v4(drow + n0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else {
+        for (int i = 0; i < 16; ++i)
+          if (n0 + i < K0) atomicAdd(drow + n0 + i, v[i]);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// S2-fwd: hidden layer i (128 -> 128) on the 4 streams of one copy; tile = (l, 128 points).
+//   smem: W_i[l] hi/lo resident (64 KB) + 2 stages of one stream tile hi/lo (64 KB each).
+//   TMEM: 4 x 128 columns (one block per stream).  kLast fuses the 128->1 head, the importance /
+//   mask product rule, the potential and the operator scale/shift (F, TF).
+// ------------------------------------------------------------------------------------------
+namespace hid {
+constexpr int PLANE = 128 * 128 * 2;  // one bf16 128x128 tile = two 16 KB K-chunks
+constexpr int CHUNK = 16384;
+constexpr int STAGES = 2;
+constexpr int STAGE_BYTES = 2 * PLANE;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (4 + EPI_WARPS) * 32;
+constexpr int SMEM_FWD = 2 * PLANE + STAGES * STAGE_BYTES + 1024 + 4096;
+constexpr int SMEM_BWD = 2 * PLANE + 2 * STAGE_BYTES + 1024 + 256;
+}  // namespace hid
+
+struct HidFwdArgs {
+  int L, P, m_tiles;
+  long Btot, p_off;
+  const float* bias;                 // b_i (L,128)
+  __nv_bfloat16 *out_hi, *out_lo;    // next-layer streams [L][4][P][128] (unused when kLast)
+  __nv_bfloat16 *sav_hi, *sav_lo;    // value stream [L][Btot][128]
+  // kLast only
+  const float* W3;                   // (L,128)
+  const float* b3;                   // (L)
+  const float* x;                    // (Btot,2)
+  const float* mscales;              // (L) or null
+  float *F, *TF, *U0;                // (Btot, L)
+  nsvd_problem_t pb;
+};
+
+template <bool kLast>
+__global__ void __launch_bounds__(hid::THREADS, 1)
+hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                  const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                  const HidFwdArgs args) {
+  using namespace hid;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;                       // [hi plane | lo plane]
+  uint8_t* sA = smem + 2 * PLANE;           // stages
+  uint64_t* bars = (uint64_t*)(sA + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                    // [2]
+  uint64_t* empty = bars + 2;               // [2]
+  uint64_t* wfull = bars + 4;
+  uint64_t* wfree = bars + 5;
+  uint64_t* tfull = bars + 6;
+  uint64_t* tempty = bars + 7;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  float* ubuf = (float*)(bars + 16);        // [128][4] partial head sums (kLast)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = args.L * args.m_tiles;
+  const int tpc = (T + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * tpc;
+  const int t_end = (t_begin + tpc < T) ? t_begin + tpc : T;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAh);
+    tma_prefetch_desc(&tmAl);
+    tma_prefetch_desc(&tmWh);
+    tma_prefetch_desc(&tmWl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(wfull, 1);
+    mbar_init(wfree, 1);
+    mbar_init(tfull, 1);
+    mbar_init(tempty, EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, cur_l = -1;
+      uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int l = t / args.m_tiles, mt = t % args.m_tiles;
+        const int i = t - t_begin;
+        if (l != cur_l) {
+          if (i > 0) mbar_wait(wfree, (uint32_t)((i - 1) & 1), 10);  // MMAs of the previous tile retired
+          mbar_arrive_expect_tx(wfull, 2 * PLANE);
+          tma_load_3d(sW, &tmWh, wfull, 0, 0, l);
+          tma_load_3d(sW + CHUNK, &tmWh, wfull, 64, 0, l);
+          tma_load_3d(sW + PLANE, &tmWl, wfull, 0, 0, l);
+          tma_load_3d(sW + PLANE + CHUNK, &tmWl, wfull, 64, 0, l);
+          cur_l = l;
+        }
+        for (int s = 0; s < 4; ++s) {
+          mbar_wait(&empty[stage], phase ^ 1, 11);
+          uint8_t* d = sA + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_3d(d, &tmAh, &full[stage], 0, mt * 128, l * 4 + s);
+          tma_load_3d(d + CHUNK, &tmAh, &full[stage], 64, mt * 128, l * 4 + s);
+          tma_load_3d(d + PLANE, &tmAl, &full[stage], 0, mt * 128, l * 4 + s);
+          tma_load_3d(d + PLANE + CHUNK, &tmAl, &full[stage], 64, mt * 128, l * 4 + s);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+      int stage = 0, cur_l = -1;
+      uint32_t phase = 0, wphase = 0, tphase = 0;
+      const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + PLANE;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int l = t / args.m_tiles;
+        if (l != cur_l) {
+          mbar_wait(wfull, wphase, 12);
+          wphase ^= 1;
+          cur_l = l;
+        }
+        mbar_wait(tempty, tphase ^ 1, 13);
+        tc_fence_after();
+        for (int s = 0; s < 4; ++s) {
+          mbar_wait(&full[stage], phase, 14);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(sA + stage * STAGE_BYTES), a_lo = a_hi + PLANE;
+          const uint32_t d_tmem = tmem_base + s * 128;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t off = (kk >> 2) * CHUNK + (kk & 3) * 32;
+            uint64_t ah = make_sdesc_sw128(a_hi + off, 16, 1024), al = make_sdesc_sw128(a_lo + off, 16, 1024);
+            uint64_t bh = make_sdesc_sw128(w_hi + off, 16, 1024), bl = make_sdesc_sw128(w_lo + off, 16, 1024);
+            umma_f16(d_tmem, al, bh, idesc, kk > 0 ? 1u : 0u);
+            umma_f16(d_tmem, ah, bl, idesc, 1u);
+            umma_f16(d_tmem, ah, bh, idesc, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull);
+        umma_commit(wfree);
+        tphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ewarp = warp - 4, q = ewarp & 3, half = ewarp >> 2;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t tphase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int l = t / args.m_tiles, mt = t % args.m_tiles;
+      const int pt = mt * 128 + q * 32 + lane;
+      mbar_wait(tfull, tphase, 15);
+      tphase ^= 1;
+      tc_fence_after();
+      float u[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int h0 = half * 64 + ch * 16;
+        float z[4][16];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tmem_ld16(tl + s * 128 + h0, z[s]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float zb = z[0][i] + __ldg(args.bias + l * kHidden + h0 + i);
+          act_streams(zb, z[1][i], z[2][i], z[3][i], z[0][i], z[1][i], z[2][i], z[3][i]);
+        }
+        if (kLast) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float w = __ldg(args.W3 + l * kHidden + h0 + i);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) u[s] = fmaf(z[s][i], w, u[s]);
+          }
+        }
+        if (pt < args.P) {
+          if (!kLast) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              long o = (((long)l * 4 + s) * args.P + pt) * kHidden + h0;
+              store_split16(z[s], args.out_hi + o, args.out_lo + o);
+            }
+          }
+          long o = ((long)l * args.Btot + args.p_off + pt) * kHidden + h0;
+          store_split16(z[0], args.sav_hi + o, args.sav_lo + o);
+        }
+      }
+      if (kLast) {
+        const int r = q * 32 + lane;
+        if (half == 1) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s) ubuf[r * 4 + s] = u[s];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && pt < args.P) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s) u[s] += ubuf[r * 4 + s];
+          u[0] += __ldg(args.b3 + l);
+          const long pg = args.p_off + pt;
+          PointGeom g = point_geom(args.x[2 * pg], args.x[2 * pg + 1], args.pb);
+          float f, tf;
+          operator_epilogue(g, args.pb, args.pb.has_exp_mask != 0, args.pb.has_exp_mask ? args.mscales[l] : 1.f,
+                            u[0], u[1], u[2], u[3], f, tf);
+          args.F[pg * args.L + l] = f;
+          args.TF[pg * args.L + l] = tf;
+          args.U0[pg * args.L + l] = u[0];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// S2-bwd: backward of hidden layer i for one copy; tile = (l, 128 points).  One pass over the
+// dZ_i tile produces BOTH
+//   dgrad  D1[pt][k]  = sum_j dZ_i[pt][j] W_i[j][k]      (A K-major, B = W_i^T K-major)
+//   wgrad  D2[j][k]  += sum_pt dZ_i[pt][j] a_{i-1}[pt][k] (the same smem tiles read MN-major)
+// epilogue: dZ_{i-1} = D1 (.) sigma(a_{i-1}) -> hi/lo planes, db_{i-1} column sums; D2 is flushed
+// into dW_i[l] with vector reductions when the CTA leaves copy l.
+// ------------------------------------------------------------------------------------------
+struct HidBwdArgs {
+  int L, P, m_tiles;
+  long Btot, p_off;
+  const __nv_bfloat16 *aprev_hi, *aprev_lo;  // saved value stream of layer i-1: [L][Btot][128]
+  __nv_bfloat16 *dz_hi, *dz_lo;              // out: dZ_{i-1} [L][P][128]
+  float* dW;                                 // (L,128,128) accumulated with reductions
+  float* db_prev;                            // (L,128) accumulated with atomics
+};
+
+__global__ void __launch_bounds__(hid::THREADS, 1)
+hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,
+                  const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                  const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                  const HidBwdArgs args) {
+  using namespace hid;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;                 // W_i^T hi | lo
+  uint8_t* sZ = smem + 2 * PLANE;     // dZ_i hi | lo
+  uint8_t* sA = sZ + 2 * PLANE;       // a_{i-1} hi | lo
+  uint64_t* bars = (uint64_t*)(sA + 2 * PLANE);
+  uint64_t* full = bars;              // dZ + a landed
+  uint64_t* sfree = bars + 1;         // MMAs reading smem retired
+  uint64_t* wfull = bars + 2;
+  uint64_t* tfull = bars + 3;         // [2]
+  uint64_t* tempty = bars + 5;        // [2]
+  uint64_t* w2full = bars + 7;
+  uint64_t* w2empty = bars + 8;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = args.L * args.m_tiles;
+  const int tpc = (T + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * tpc;
+  const int t_end = (t_begin + tpc < T) ? t_begin + tpc : T;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmZh);
+    tma_prefetch_desc(&tmZl);
+    tma_prefetch_desc(&tmAh);
+    tma_prefetch_desc(&tmAl);
+    tma_prefetch_desc(&tmWh);
+    tma_prefetch_desc(&tmWl);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(full, 1);
+    mbar_init(sfree, 1);
+    mbar_init(wfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], EPI_WARPS);
+    }
+    mbar_init(w2full, 1);
+    mbar_init(w2empty, EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d2 = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int cur_l = -1;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int l = t / args.m_tiles, mt = t % args.m_tiles;
+        const int i = t - t_begin;
+        if (i > 0) mbar_wait(sfree, (uint32_t)((i - 1) & 1), 20);
+        if (l != cur_l) {
+          mbar_arrive_expect_tx(wfull, 2 * PLANE);
+          tma_load_3d(sW, &tmWh, wfull, 0, 0, l);
+          tma_load_3d(sW + CHUNK, &tmWh, wfull, 64, 0, l);
+          tma_load_3d(sW + PLANE, &tmWl, wfull, 0, 0, l);
+          tma_load_3d(sW + PLANE + CHUNK, &tmWl, wfull, 64, 0, l);
+          cur_l = l;
+        }
+        mbar_arrive_expect_tx(full, 4 * PLANE);
+        tma_load_3d(sZ, &tmZh, full, 0, mt * 128, l);
+        tma_load_3d(sZ + CHUNK, &tmZh, full, 64, mt * 128, l);
+        tma_load_3d(sZ + PLANE, &tmZl, full, 0, mt * 128, l);
+        tma_load_3d(sZ + PLANE + CHUNK, &tmZl, full, 64, mt * 128, l);
+        tma_load_3d(sA, &tmAh, full, 0, (int)args.p_off + mt * 128, l);
+        tma_load_3d(sA + CHUNK, &tmAh, full, 64, (int)args.p_off + mt * 128, l);
+        tma_load_3d(sA + PLANE, &tmAl, full, 0, (int)args.p_off + mt * 128, l);
+        tma_load_3d(sA + PLANE + CHUNK, &tmAl, full, 64, (int)args.p_off + mt * 128, l);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_d = make_idesc_bf16(128, 128, 0, 0);   // dgrad: K-major operands
+      constexpr uint32_t idesc_w = make_idesc_bf16(128, 128, 1, 1);   // wgrad: MN-major operands
+      const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + PLANE;
+      const uint32_t z_hi = smem_u32(sZ), z_lo = z_hi + PLANE;
+      const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + PLANE;
+      int cur_l = -1, acc = 0, run = -1;
+      uint32_t fphase = 0, wphase = 0, acc_phase = 0;
+      bool first_of_run = true;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int l = t / args.m_tiles;
+        if (l != cur_l) {
+          mbar_wait(wfull, wphase, 21);
+          wphase ^= 1;
+          cur_l = l;
+          first_of_run = true;
+          ++run;
+        }
+        mbar_wait(full, fphase, 22);
+        fphase ^= 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1, 23);
+        tc_fence_after();
+        const uint32_t d1 = tmem_base + acc * 128;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * CHUNK + (kk & 3) * 32;
+          uint64_t ah = make_sdesc_sw128(z_hi + off, 16, 1024), al = make_sdesc_sw128(z_lo + off, 16, 1024);
+          uint64_t bh = make_sdesc_sw128(w_hi + off, 16, 1024), bl = make_sdesc_sw128(w_lo + off, 16, 1024);
+          umma_f16(d1, al, bh, idesc_d, kk > 0 ? 1u : 0u);
+          umma_f16(d1, ah, bl, idesc_d, 1u);
+          umma_f16(d1, ah, bh, idesc_d, 1u);
+        }
+        umma_commit(&tfull[acc]);
+        if (first_of_run && run > 0) {
+          mbar_wait(w2empty, (uint32_t)((run - 1) & 1), 24);  // previous copy's dW flushed out of TMEM
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // K = 128 points, 16 per MMA
+          const uint32_t off = kk * 2048;
+          uint64_t ah = make_sdesc_sw128(z_hi + off, CHUNK, 1024), al = make_sdesc_sw128(z_lo + off, CHUNK, 1024);
+          uint64_t bh = make_sdesc_sw128(a_hi + off, CHUNK, 1024), bl = make_sdesc_sw128(a_lo + off, CHUNK, 1024);
+          umma_f16(tmem_d2, al, bh, idesc_w, (first_of_run && kk == 0) ? 0u : 1u);
+          umma_f16(tmem_d2, ah, bl, idesc_w, 1u);
+          umma_f16(tmem_d2, ah, bh, idesc_w, 1u);
+        }
+        umma_commit(sfree);
+        first_of_run = false;
+        const bool last_of_run = (t + 1 == t_end) || ((t + 1) / args.m_tiles != l);
+        if (last_of_run) umma_commit(w2full);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ewarp = warp - 4, q = ewarp & 3, half = ewarp >> 2;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    int acc = 0, run = -1, cur_l = -1;
+    uint32_t acc_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int l = t / args.m_tiles, mt = t % args.m_tiles;
+      if (l != cur_l) {
+        cur_l = l;
+        ++run;
+      }
+      const int pt = mt * 128 + q * 32 + lane;
+      mbar_wait(&tfull[acc], acc_phase, 25);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int k0 = half * 64 + ch * 16;
+        float v[16], a[16];
+        tmem_ld16(tl + acc * 128 + k0, v);
+        const bool ok = pt < args.P;
+        if (ok) {
+          long o = ((long)l * args.Btot + args.p_off + pt) * kHidden + k0;
+          load_merge16(args.aprev_hi + o, args.aprev_lo + o, a);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = ok ? v[i] * sig_from_softplus(a[i]) : 0.f;
+        if (ok) {
+          long o = ((long)l * args.P + pt) * kHidden + k0;
+          store_split16(v, args.dz_hi + o, args.dz_lo + o);
+        }
+        // db_{i-1}[l][k] += sum over the 32 rows of this warp
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float sres = warp_sum(v[i]);
+          if (lane == i) atomicAdd(args.db_prev + l * kHidden + k0 + i, sres);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      const bool last_of_run = (t + 1 == t_end) || ((t + 1) / args.m_tiles != l);
+      if (last_of_run) {
+        mbar_wait(w2full, (uint32_t)(run & 1), 26);
+        tc_fence_after();
+        const int j = q * 32 + lane;
+        float* drow = args.dW + ((long)l * kHidden + j) * kHidden;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          const int k0 = half * 64 + ch * 16;
+          float v[16];
+          tmem_ld16(tl + 256 + k0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) red_add_v4(drow + k0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(w2empty);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// head backward (SIMT, HBM-bound): du = dF c m rho ; dZ2 = du W3 (.) sigma(a2) -> hi/lo planes ;
+// dW3, db3, db2, dscales accumulated (block partials + atomics).  grid = (point chunks, L)
+// ------------------------------------------------------------------------------------------
+constexpr int kHeadChunk = 128;  // points per block
+__global__ void __launch_bounds__(128)
+head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
+                     const __nv_bfloat16* __restrict__ a2_hi, const __nv_bfloat16* __restrict__ a2_lo,
+                     const float* __restrict__ W3, const float* __restrict__ x, const float* __restrict__ mscales,
+                     nsvd_problem_t pb, __nv_bfloat16* __restrict__ dz_hi, __nv_bfloat16* __restrict__ dz_lo,
+                     float* __restrict__ dW3, float* __restrict__ db3, float* __restrict__ db2,
+                     float* __restrict__ dscales, int P, long Btot, long p_off) {
+  __shared__ float red[4][2 * kHidden + 2];
+  const int l = blockIdx.y, L = pb.n_copies;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p_begin = blockIdx.x * kHeadChunk;
+  const int p_end = p_begin + kHeadChunk < P ? p_begin + kHeadChunk : P;
+  float w3[4], accW[4] = {0, 0, 0, 0}, accB[4] = {0, 0, 0, 0}, acc_b3 = 0.f, acc_s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w3[i] = W3[l * kHidden + lane * 4 + i];
+  float sc = pb.has_exp_mask ? mscales[l] : 1.f;
+  for (int p = p_begin + warp; p < p_end; p += 4) {
+    const long pg = p_off + p;
+    PointGeom g = point_geom(x[2 * pg], x[2 * pg + 1], pb);
+    float m = pb.has_exp_mask ? expf(-g.r / sc) : 1.f;
+    float cm = pb.hard_mul_const * m * g.rho;
+    float du = dF[pg * L + l] * cm;
+    acc_b3 += du;
+    if (pb.has_exp_mask) acc_s += du * U0[pg * L + l] * g.r / (sc * sc);
+    const long oa = ((long)l * Btot + pg) * kHidden + lane * 4;
+    uint2 h = *reinterpret_cast<const uint2*>(a2_hi + oa), lo2 = *reinterpret_cast<const uint2*>(a2_lo + oa);
+    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&h);
+    const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&lo2);
+    float a[4];
+    {
+      float2 t0 = __bfloat1622float2(hh[0]), t1 = __bfloat1622float2(hh[1]);
+      float2 u0 = __bfloat1622float2(ll[0]), u1 = __bfloat1622float2(ll[1]);
+      a[0] = t0.x + u0.x; a[1] = t0.y + u0.y; a[2] = t1.x + u1.x; a[3] = t1.y + u1.y;
+    }
+    float dz[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      dz[i] = du * w3[i] * sig_from_softplus(a[i]);
+      accW[i] = fmaf(du, a[i], accW[i]);
+      accB[i] += dz[i];
+    }
+    uint32_t h01, l01, h23, l23;
+    tc::split_bf16x2(dz[0], dz[1], h01, l01);
+    tc::split_bf16x2(dz[2], dz[3], h23, l23);
+    const long oz = ((long)l * P + p) * kHidden + lane * 4;
+    *reinterpret_cast<uint2*>(dz_hi + oz) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(dz_lo + oz) = make_uint2(l01, l23);
+  }
+  // acc_b3 / acc_s are identical across lanes of a warp (computed redundantly): keep lane 0's
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[warp][lane * 4 + i] = accW[i];
+    red[warp][kHidden + lane * 4 + i] = accB[i];
+  }
+  if (lane == 0) {
+    red[warp][2 * kHidden] = acc_b3;
+    red[warp][2 * kHidden + 1] = acc_s;
+  }
+  __syncthreads();
+  const int tix = threadIdx.x;
+  float sW = red[0][tix] + red[1][tix] + red[2][tix] + red[3][tix];
+  float sB = red[0][kHidden + tix] + red[1][kHidden + tix] + red[2][kHidden + tix] + red[3][kHidden + tix];
+  atomicAdd(dW3 + l * kHidden + tix, sW);
+  atomicAdd(db2 + l * kHidden + tix, sB);
+  if (tix == 0) {
+    atomicAdd(db3 + l, red[0][2 * kHidden] + red[1][2 * kHidden] + red[2][2 * kHidden] + red[3][2 * kHidden]);
+    if (pb.has_exp_mask && dscales)
+      atomicAdd(dscales + l, red[0][2 * kHidden + 1] + red[1][2 * kHidden + 1] + red[2][2 * kHidden + 1] +
+                                 red[3][2 * kHidden + 1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// engine drivers
+// ------------------------------------------------------------------------------------------
+static int tc_micro_batch() {
+  static int mb = 0;
+  if (!mb) {
+    const char* e = getenv("NSVD_TC_MICROBATCH");
+    mb = e ? atoi(e) : 8192;
+    if (mb < 128) mb = 128;
+    mb = (mb + 127) / 128 * 128;
+  }
+  return mb;
+}
+
+struct TcLayout {
+  // saved (whole batch)
+  size_t phi_hi, phi_lo, av_hi[3], av_lo[3], u0, saved_total;
+  // work
+  size_t w0_hi, w0_lo, w_hi[2], w_lo[2], str_hi[2], str_lo[2], dz_hi[2], dz_lo[2], work_total;
+  long P;
+};
+static TcLayout tc_layout(const nsvd_problem_t& pb) {
+  TcLayout t{};
+  const size_t B = pb.n_points, L = pb.n_copies, K0 = 2 * (size_t)pb.n_fourier, H = kHidden;
+  size_t mb = (size_t)tc_micro_batch();
+  t.P = (long)(B < mb ? B : mb);
+  const size_t P = (size_t)t.P;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o += align_up(bytes, 1024);
+    return r;
+  };
+  t.phi_hi = take(B * K0 * 2);
+  t.phi_lo = take(B * K0 * 2);
+  for (int i = 0; i < 3; ++i) {
+    t.av_hi[i] = take(L * B * H * 2);
+    t.av_lo[i] = take(L * B * H * 2);
+  }
+  t.u0 = take(B * L * 4);
+  t.saved_total = o + 1024;
+  o = 0;
+  t.w0_hi = take(L * 512 * K0 * 2);
+  t.w0_lo = take(L * 512 * K0 * 2);
+  for (int i = 0; i < 2; ++i) {
+    t.w_hi[i] = take(L * H * H * 2);
+    t.w_lo[i] = take(L * H * H * 2);
+  }
+  for (int i = 0; i < 2; ++i) {
+    t.str_hi[i] = take(L * 4 * P * H * 2);
+    t.str_lo[i] = take(L * 4 * P * H * 2);
+  }
+  // backward reuses the stream area for the dZ planes (two ping-pong pairs)
+  for (int i = 0; i < 2; ++i) {
+    t.dz_hi[i] = t.str_hi[i];
+    t.dz_lo[i] = t.str_lo[i];
+  }
+  t.work_total = o + 1024;
+  return t;
+}
+
 void tc_scratch_bytes(const nsvd_problem_t& pb, size_t* saved, size_t* work) {
-  *saved = 256;
-  *work = 256;
-  (void)pb;
+  TcLayout t = tc_layout(pb);
+  *saved = t.saved_total;
+  *work = t.work_total;
 }
-int tc_forward(const nsvd_problem_t&, const nsvd_params_t&, const float*, float*, float*, void*, void*, size_t,
-               cudaStream_t) {
-  set_error("tcgen05 engine: forward not built yet");
-  return NSVD_E_BADARG;
+
+static inline uint8_t* align1k(void* p) { return (uint8_t*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023); }
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+template <bool kLast>
+static int launch_hidden_fwd(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh,
+                             const CUtensorMap& wl, const HidFwdArgs& a, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = hidden_fwd_kernel<kLast>;
+  if (!configured) {
+    NSVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hid::SMEM_FWD));
+    configured = true;
+  }
+  int T = a.L * a.m_tiles;
+  int grid = T < 148 ? T : 148;
+  kern<<<grid, hid::THREADS, hid::SMEM_FWD, st>>>(ah, al, wh, wl, a);
+  NSVD_LAUNCH_CHECK();
+  return 0;
 }
-int tc_backward(const nsvd_problem_t&, const nsvd_params_t&, const float*, const float*, const void*, nsvd_grads_t&,
-                void*, size_t, cudaStream_t) {
-  set_error("tcgen05 engine: backward not built yet");
-  return NSVD_E_BADARG;
+
+int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x, float* F, float* TF, void* saved_v,
+               void* work_v, size_t work_bytes, cudaStream_t st) {
+  (void)work_bytes;
+  const long B = pb.n_points, L = pb.n_copies, M = pb.n_fourier, K0 = 2 * M, H = kHidden;
+  TcLayout t = tc_layout(pb);
+  uint8_t* sv = align1k(saved_v);
+  uint8_t* wk = align1k(work_v);
+  int rc;
+  // ---- per-call preparation: features of all points, folded / split weights
+  ProfScope* prep = new ProfScope(KC_PREP, st);
+  features_bf16_kernel<<<cdiv(B * M, 256), 256, 0, st>>>(x, pr.Bff, BF(sv + t.phi_hi), BF(sv + t.phi_lo), B, (int)M);
+  NSVD_LAUNCH_CHECK();
+  fold_w0_kernel<<<cdiv(L * H * M, 256), 256, 0, st>>>(pr.W[0], pr.Bff, BF(wk + t.w0_hi), BF(wk + t.w0_lo), (int)L,
+                                                       (int)M);
+  NSVD_LAUNCH_CHECK();
+  for (int i = 0; i < 2; ++i) {
+    split_w_kernel<<<cdiv(L * H * H, 256), 256, 0, st>>>(pr.W[i + 1], BF(wk + t.w_hi[i]), BF(wk + t.w_lo[i]), (int)L, 0);
+    NSVD_LAUNCH_CHECK();
+  }
+  delete prep;
+  CUtensorMap mW0h, mW0l, mWh[2], mWl[2];
+  if ((rc = make_tmap_bf16_3d(&mW0h, wk + t.w0_hi, K0, 512, L, K0 * 2, 512 * K0 * 2, 64, big::BN))) return rc;
+  if ((rc = make_tmap_bf16_3d(&mW0l, wk + t.w0_lo, K0, 512, L, K0 * 2, 512 * K0 * 2, 64, big::BN))) return rc;
+  for (int i = 0; i < 2; ++i) {
+    if ((rc = make_tmap_bf16_3d(&mWh[i], wk + t.w_hi[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mWl[i], wk + t.w_lo[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
+  }
+  for (long p0 = 0; p0 < B; p0 += t.P) {
+    const int P = (int)((B - p0) < t.P ? (B - p0) : t.P);
+    const int m_tiles = cdiv(P, 128);
+    // ---- layer 0: Z0 = Phi . W0f^T  (S1, K-major) with the softplus-stream epilogue
+    CUtensorMap mPh, mPl;
+    if ((rc = make_tmap_bf16_3d(&mPh, sv + t.phi_hi + p0 * K0 * 2, K0, P, 1, K0 * 2, (uint64_t)P * K0 * 2, 64, big::BM))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mPl, sv + t.phi_lo + p0 * K0 * 2, K0, P, 1, K0 * 2, (uint64_t)P * K0 * 2, 64, big::BM))) return rc;
+    BigShape s{};
+    s.m_tiles = m_tiles;
+    s.n_tiles = 2;
+    s.batches = (int)L;
+    s.k_slices = 1;
+    s.k_chunks_total = cdiv(K0, big::BK);
+    s.k_chunks_per_slice = s.k_chunks_total;
+    s.a_batched = 0;
+    s.b_batched = 1;
+    L0FwdEpi e0{pr.b[0], BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), BF(sv + t.av_hi[0]), BF(sv + t.av_lo[0]), P, B, p0};
+    {
+      ProfScope ps(KC_L0_FWD, st);
+      if ((rc = launch_big<false>(mPh, mPl, mW0h, mW0l, s, e0, st))) return rc;
+    }
+    // ---- hidden layers 1, 2
+    for (int i = 0; i < 2; ++i) {
+      CUtensorMap mAh, mAl;
+      if ((rc = make_tmap_bf16_3d(&mAh, wk + t.str_hi[i], H, P, 4 * L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mAl, wk + t.str_lo[i], H, P, 4 * L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
+      HidFwdArgs a{};
+      a.L = (int)L;
+      a.P = P;
+      a.m_tiles = m_tiles;
+      a.Btot = B;
+      a.p_off = p0;
+      a.bias = pr.b[i + 1];
+      a.sav_hi = BF(sv + t.av_hi[i + 1]);
+      a.sav_lo = BF(sv + t.av_lo[i + 1]);
+      if (i == 0) {
+        a.out_hi = BF(wk + t.str_hi[1]);
+        a.out_lo = BF(wk + t.str_lo[1]);
+        ProfScope ps(KC_HID_FWD, st);
+        if ((rc = launch_hidden_fwd<false>(mAh, mAl, mWh[0], mWl[0], a, st))) return rc;
+      } else {
+        a.W3 = pr.W[3];
+        a.b3 = pr.b[3];
+        a.x = x;
+        a.mscales = pr.mask_scales;
+        a.F = F;
+        a.TF = TF;
+        a.U0 = reinterpret_cast<float*>(sv + t.u0);
+        a.pb = pb;
+        ProfScope ps(KC_HID_FWD, st);
+        if ((rc = launch_hidden_fwd<true>(mAh, mAl, mWh[1], mWl[1], a, st))) return rc;
+      }
+    }
+  }
+  return 0;
+}
+
+int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x, const float* dF,
+                const void* saved_v, nsvd_grads_t& gr, void* work_v, size_t work_bytes, cudaStream_t st) {
+  (void)work_bytes;
+  const long B = pb.n_points, L = pb.n_copies, M = pb.n_fourier, K0 = 2 * M, H = kHidden;
+  TcLayout t = tc_layout(pb);
+  uint8_t* sv = align1k(const_cast<void*>(saved_v));
+  uint8_t* wk = align1k(work_v);
+  int rc;
+  static bool configured = false;
+  if (!configured) {
+    NSVD_CUDA(cudaFuncSetAttribute(hidden_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hid::SMEM_BWD));
+    configured = true;
+  }
+  // gradients are accumulated with reductions: start from zero
+  NSVD_CUDA(cudaMemsetAsync(gr.dW[0], 0, sizeof(float) * L * H * K0, st));
+  NSVD_CUDA(cudaMemsetAsync(gr.dW[1], 0, sizeof(float) * L * H * H, st));
+  NSVD_CUDA(cudaMemsetAsync(gr.dW[2], 0, sizeof(float) * L * H * H, st));
+  NSVD_CUDA(cudaMemsetAsync(gr.dW[3], 0, sizeof(float) * L * H, st));
+  for (int i = 0; i < 3; ++i) NSVD_CUDA(cudaMemsetAsync(gr.db[i], 0, sizeof(float) * L * H, st));
+  NSVD_CUDA(cudaMemsetAsync(gr.db[3], 0, sizeof(float) * L, st));
+  if (pb.has_exp_mask && gr.dmask_scales) NSVD_CUDA(cudaMemsetAsync(gr.dmask_scales, 0, sizeof(float) * L, st));
+  // transposed hidden weights (dgrad B operand, K-major): WT_i[l][k][j] = W_i[l][j][k]
+  CUtensorMap mWh[2], mWl[2];
+  for (int i = 0; i < 2; ++i) {
+    split_w_kernel<<<cdiv(L * H * H, 256), 256, 0, st>>>(pr.W[i + 1], BF(wk + t.w_hi[i]), BF(wk + t.w_lo[i]), (int)L, 1);
+    NSVD_LAUNCH_CHECK();
+    if ((rc = make_tmap_bf16_3d(&mWh[i], wk + t.w_hi[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mWl[i], wk + t.w_lo[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
+  }
+  for (long p0 = 0; p0 < B; p0 += t.P) {
+    const int P = (int)((B - p0) < t.P ? (B - p0) : t.P);
+    const int m_tiles = cdiv(P, 128);
+    // ---- head: dZ2 planes (pair 0), dW3, db3, db2, dscales
+    dim3 hg(cdiv(P, kHeadChunk), (unsigned)L);
+    {
+      ProfScope ps(KC_HEAD_BWD, st);
+      head_bwd_bf16_kernel<<<hg, 128, 0, st>>>(dF, reinterpret_cast<const float*>(sv + t.u0), BF(sv + t.av_hi[2]),
+                                               BF(sv + t.av_lo[2]), pr.W[3], x, pr.mask_scales, pb, BF(wk + t.dz_hi[0]),
+                                               BF(wk + t.dz_lo[0]), gr.dW[3], gr.db[3], gr.db[2], gr.dmask_scales, P, B, p0);
+      NSVD_LAUNCH_CHECK();
+    }
+    // ---- hidden layers 2, 1: dgrad + wgrad in one pass
+    int cur = 0;
+    for (int i = 2; i >= 1; --i) {
+      CUtensorMap mZh, mZl, mAh, mAl;
+      if ((rc = make_tmap_bf16_3d(&mZh, wk + t.dz_hi[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mZl, wk + t.dz_lo[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mAh, sv + t.av_hi[i - 1], H, B, L, H * 2, (uint64_t)B * H * 2, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mAl, sv + t.av_lo[i - 1], H, B, L, H * 2, (uint64_t)B * H * 2, 64, 128))) return rc;
+      HidBwdArgs a{};
+      a.L = (int)L;
+      a.P = P;
+      a.m_tiles = m_tiles;
+      a.Btot = B;
+      a.p_off = p0;
+      a.aprev_hi = BF(sv + t.av_hi[i - 1]);
+      a.aprev_lo = BF(sv + t.av_lo[i - 1]);
+      a.dz_hi = BF(wk + t.dz_hi[cur ^ 1]);
+      a.dz_lo = BF(wk + t.dz_lo[cur ^ 1]);
+      a.dW = gr.dW[i];
+      a.db_prev = gr.db[i - 1];
+      int T = (int)L * m_tiles;
+      int grid = T < 148 ? T : 148;
+      {
+        ProfScope ps(KC_HID_BWD, st);
+        hidden_bwd_kernel<<<grid, hid::THREADS, hid::SMEM_BWD, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], a);
+        NSVD_LAUNCH_CHECK();
+      }
+      cur ^= 1;
+    }
+    // ---- layer 0 weight gradient: dW0[l] += dZ0[l]^T . Phi  (S1, MN-major, K = points in slices)
+    CUtensorMap mZh, mZl, mPh, mPl;
+    if ((rc = make_tmap_bf16_3d(&mZh, wk + t.dz_hi[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 64))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mZl, wk + t.dz_lo[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 64))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mPh, sv + t.phi_hi + p0 * K0 * 2, K0, P, 1, K0 * 2, (uint64_t)P * K0 * 2, 64, 64))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mPl, sv + t.phi_lo + p0 * K0 * 2, K0, P, 1, K0 * 2, (uint64_t)P * K0 * 2, 64, 64))) return rc;
+    BigShape s{};
+    s.m_tiles = 1;
+    s.n_tiles = cdiv(K0, big::BN);
+    s.batches = (int)L;
+    s.k_chunks_total = cdiv(P, big::BK);
+    s.k_chunks_per_slice = 16;  // 1024 points per accumulation (fp32 TMEM accumulation stays short)
+    s.k_slices = cdiv(s.k_chunks_total, s.k_chunks_per_slice);
+    s.a_batched = 1;
+    s.b_batched = 0;
+    L0WgradEpi ew{gr.dW[0], (int)K0};
+    {
+      ProfScope ps(KC_L0_WGRAD, st);
+      if ((rc = launch_big<true>(mZh, mZl, mPh, mPl, s, ew, st))) return rc;
+    }
+  }
+  return 0;
 }
 
 }  // namespace nsvd

@@ -39,7 +39,7 @@ CASES = {
     # configs[2]: hydrogen, B=512, joint, L=16
     "hyd_b512_jnt_L16": dict(cfg=O.PathConfig.hydrogen(), B=512, seed=2),
     # configs[3] shape at reduced B: hydrogen, L=64, joint
-    "hyd_b256_jnt_L64": dict(cfg=O.PathConfig.hydrogen(neigs=64), B=256, seed=3),
+    "hyd_b64_jnt_L64": dict(cfg=O.PathConfig.hydrogen(neigs=64), B=64, seed=3),
     # small cases with full gradients: odd batch (torch.chunk -> 49/48), joint step=2, narrow features
     "hyd_small_odd": dict(cfg=O.PathConfig.hydrogen(neigs=4, fourier_mapping_size=64, step=2), B=97, seed=4),
     "osc_small_seq": dict(cfg=O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64, sequential=True,

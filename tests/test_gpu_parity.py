@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 ENGINES = ["fp32", "bf16x3"]
 PDE_CASES = ["hyd_small_odd", "osc_small_seq", "hyd_b128_seq_L16", "osc_b512_jnt_L16", "hyd_b512_jnt_L16",
-             "hyd_b256_jnt_L64"]
+             "hyd_b64_jnt_L64"]
 
 
 def _step(name, engine):
