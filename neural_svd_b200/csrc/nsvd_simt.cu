@@ -467,6 +467,63 @@ gram_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
   }
 }
 
+// L == 16 specialisation (the benchmark shape): warp-cooperative register tiling.
+//   lane = (ib, jb): 4 x 2 outputs G[4 ib + a][2 jb + c]; per row one 16-byte and one 8-byte load of
+//   the (L1-resident) 64-byte row, 8 FFMA; the operator sum is taken on a coalesced (row pair x 16)
+//   load.  8 warps interleave rows; one smem reduction per block at the end.
+__global__ void __launch_bounds__(256)
+gram16_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
+                     const float* __restrict__ vmask, long row_begin, long row_end, int rows_per_block,
+                     float* __restrict__ partials, int partial_stride, int block_off) {
+  __shared__ float sacc[8][257];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = (lane >> 3) * 4, j0 = (lane & 7) * 2;
+  long r0 = row_begin + (long)blockIdx.x * rows_per_block;
+  long r1 = r0 + rows_per_block < row_end ? r0 + rows_per_block : row_end;
+  float acc[4][2] = {};
+  float ops = 0.f;
+  const float vm = vmask[lane & 15];
+  // each warp takes row pairs (r, r+1): pairs interleaved across the 8 warps
+  for (long r = r0 + 2 * warp; r < r1; r += 16) {
+    const long rr = r + (lane >> 4);
+    if (rr < r1) ops = fmaf(vm * F[rr * 16 + (lane & 15)], TF[rr * 16 + (lane & 15)], ops);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (r + k < r1) {
+        const float* row = F + (r + k) * 16;
+        float4 fi = *reinterpret_cast<const float4*>(row + i0);
+        float2 fj = *reinterpret_cast<const float2*>(row + j0);
+        acc[0][0] = fmaf(fi.x, fj.x, acc[0][0]);
+        acc[0][1] = fmaf(fi.x, fj.y, acc[0][1]);
+        acc[1][0] = fmaf(fi.y, fj.x, acc[1][0]);
+        acc[1][1] = fmaf(fi.y, fj.y, acc[1][1]);
+        acc[2][0] = fmaf(fi.z, fj.x, acc[2][0]);
+        acc[2][1] = fmaf(fi.z, fj.y, acc[2][1]);
+        acc[3][0] = fmaf(fi.w, fj.x, acc[3][0]);
+        acc[3][1] = fmaf(fi.w, fj.y, acc[3][1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) sacc[warp][(i0 + a) * 16 + j0 + c] = acc[a][c];
+  ops = warp_sum(ops);
+  if (lane == 0) sacc[warp][256] = ops;
+  __syncthreads();
+  float* out = partials + (long)(block_off + blockIdx.x) * partial_stride;
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += sacc[w][tid];
+  out[tid] = t;
+  if (tid == 0) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) o += sacc[w][256];
+    out[256] = o;
+  }
+}
+
 // stage 2: out[e] (+)= sum over blocks [b0, b1) of partials[b][src_off + e]
 __global__ void gram_stage2_kernel(const float* __restrict__ partials, int partial_stride, int b0,
                                    int b1, int src_off, int n, float* __restrict__ out,
@@ -514,6 +571,21 @@ static int gram_launch(const float* F, const float* TF, const float* vmask, cons
 static int gram_dispatch(const float* F, const float* TF, const float* vmask, const float* roww, int L,
                          long rb, long re, int cross, float* partials, int stride, int block_off,
                          int* nblocks, cudaStream_t st) {
+  if (L == 16 && !cross && !roww) {
+    long rows = re - rb;
+    if (rows <= 0) {
+      *nblocks = 0;
+      return 0;
+    }
+    int nb = gram_blocks_for(rows);
+    int rpb = (int)((rows + nb - 1) / nb);
+    rpb = (rpb + 15) / 16 * 16;
+    nb = (int)((rows + rpb - 1) / rpb);
+    gram16_stage1_kernel<<<nb, 256, 0, st>>>(F, TF, vmask, rb, re, rpb, partials, stride, block_off);
+    NSVD_LAUNCH_CHECK();
+    *nblocks = nb;
+    return 0;
+  }
   if (L <= 16) return gram_launch<16>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
   if (L <= 32) return gram_launch<32>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
   if (L <= 48) return gram_launch<48>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
@@ -625,9 +697,63 @@ loss_dF_kernel(const float* __restrict__ F, const float* __restrict__ TF,
   }
 }
 
+// L == 16 specialisation: one thread per row; the 16x16 coefficient block of the row's half is read
+// from shared memory as broadcast float4 (all lanes of a warp are in the same half except at b1).
+__global__ void __launch_bounds__(256)
+loss_dF16_kernel(const float* __restrict__ F, const float* __restrict__ TF, const float* __restrict__ vmask,
+                 const float* __restrict__ coef, const float* __restrict__ gscale, int B, int b1, float c4,
+                 float* __restrict__ dF) {
+  __shared__ float4 sC[2][16][4];
+  __shared__ float sV[16];
+  for (int e = threadIdx.x; e < 512; e += blockDim.x) reinterpret_cast<float*>(sC)[e] = coef ? coef[e] : 0.f;
+  if (threadIdx.x < 16) sV[threadIdx.x] = vmask[threadIdx.x];
+  __syncthreads();
+  const float gs = gscale ? gscale[0] : 1.f;
+  for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long)gridDim.x * blockDim.x) {
+    const float4* frow = reinterpret_cast<const float4*>(F + b * 16);
+    float f[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 t = frow[q];
+      f[4 * q] = t.x; f[4 * q + 1] = t.y; f[4 * q + 2] = t.z; f[4 * q + 3] = t.w;
+    }
+    float o[16] = {};
+    const int h = b < b1 ? 0 : 1;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 c = sC[h][l][q];
+        o[4 * q] = fmaf(f[l], c.x, o[4 * q]);
+        o[4 * q + 1] = fmaf(f[l], c.y, o[4 * q + 1]);
+        o[4 * q + 2] = fmaf(f[l], c.z, o[4 * q + 2]);
+        o[4 * q + 3] = fmaf(f[l], c.w, o[4 * q + 3]);
+      }
+    }
+    float4* drow = reinterpret_cast<float4*>(dF + b * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 t = TF ? reinterpret_cast<const float4*>(TF + b * 16)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 r;
+      r.x = gs * (o[4 * q] - c4 * sV[4 * q] * t.x);
+      r.y = gs * (o[4 * q + 1] - c4 * sV[4 * q + 1] * t.y);
+      r.z = gs * (o[4 * q + 2] - c4 * sV[4 * q + 2] * t.z);
+      r.w = gs * (o[4 * q + 3] - c4 * sV[4 * q + 3] * t.w);
+      drow[q] = r;
+    }
+  }
+}
+
 int loss_dF(const float* F, const float* TF, const float* vmask, const float* coef,
             const float* gscale, int B, int L, int b1, long Bg, float* dF, cudaStream_t st) {
   float c4 = (float)(4.0 / (double)Bg);
+  if (L == 16) {
+    int nb16 = cdiv(B, 256);
+    if (nb16 > 148 * 8) nb16 = 148 * 8;
+    loss_dF16_kernel<<<nb16, 256, 0, st>>>(F, TF, vmask, coef, gscale, B, b1, c4, dF);
+    NSVD_LAUNCH_CHECK();
+    return 0;
+  }
   int LT = L <= 16 ? 16 : (L <= 32 ? 32 : (L <= 48 ? 48 : 64));
   if (L > 64) {
     set_error("loss_dF: n_copies %d > 64", L);

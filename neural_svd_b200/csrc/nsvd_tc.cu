@@ -29,7 +29,8 @@ static PFN_encodeTiled get_encode() {
 }
 
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+                      uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1,
+                      int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -40,7 +41,9 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u)",
@@ -347,16 +350,24 @@ int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int
 // ------------------------------------------------------------------------------------------
 // shared epilogue math
 // ------------------------------------------------------------------------------------------
-// softplus on the value stream and its forward-mode derivative streams
+// softplus on the value stream and its forward-mode derivative streams.
+// Epilogue-rate version: 3 MUFU ops (ex2, lg2, rcp) and ~20 FP32 instructions per (point, unit):
+//   e = exp(-|z|), a = max(z,0) + log(1+e), sigma = z>=0 ? 1/(1+e) : e/(1+e).
+// For z > 20: e < 2.1e-9 so 1+e == 1 and a == z, sigma == 1 exactly: torch's threshold=20 branch
+// falls out without a compare.  Absolute error ~1e-7 (below the 2^-17 operand rounding that follows).
 __device__ __forceinline__ void act_streams(float z0, float z1, float z2, float z3, float& a0, float& a1,
                                             float& a2, float& a3) {
-  float a, sg;
-  softplus_sig(z0, a, sg);
-  a0 = a;
+  float e = __expf(-fabsf(z0));
+  float u = 1.f + e;
+  float inv = __frcp_rn(u);
+  float sg = z0 >= 0.f ? inv : e * inv;
+  a0 = fmaxf(z0, 0.f) + __logf(u);
   a1 = sg * z1;
   a2 = sg * z2;
-  a3 = sg * z3 + sg * (1.f - sg) * (z1 * z1 + z2 * z2);
+  a3 = fmaf(sg, z3, sg * (1.f - sg) * fmaf(z1, z1, z2 * z2));
 }
+// sigmoid(z) from a = softplus(z) at epilogue rate: 1 - exp(-a)  (absolute error ~6e-8)
+__device__ __forceinline__ float sig_fast(float a) { return 1.f - __expf(-a); }
 
 // 16 fp32 values -> 16 bf16 hi + 16 bf16 lo, two 16-byte stores each (dst 32-byte aligned)
 __device__ __forceinline__ void store_split16(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo) {
@@ -533,21 +544,24 @@ struct L0WgradEpi {
 // ------------------------------------------------------------------------------------------
 namespace hid {
 constexpr int PLANE = 128 * 128 * 2;  // one bf16 128x128 tile = two 16 KB K-chunks
-constexpr int CHUNK = 16384;
-constexpr int STAGES = 2;
-constexpr int STAGE_BYTES = 2 * PLANE;
+constexpr int CHUNK = 16384;          // [128 rows][128 B]: 64 bf16 along K, 128-byte swizzle
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (4 + EPI_WARPS) * 32;
-constexpr int SMEM_FWD = 2 * PLANE + STAGES * STAGE_BYTES + 1024 + 4096;
-constexpr int SMEM_BWD = 2 * PLANE + 2 * STAGE_BYTES + 1024 + 256;
+// forward kernel
+constexpr int F_STAGES = 3;
+constexpr int F_STAGE_BYTES = 2 * CHUNK;  // hi chunk + lo chunk of one stream
+constexpr int F_BOX = 8192;               // staging box [128 rows][64 B] (32 bf16), 64-byte swizzle
+constexpr int F_STAGING = 8 * F_BOX;      // 4 streams x {hi, lo}
+constexpr int SMEM_FWD = 2 * PLANE + F_STAGES * F_STAGE_BYTES + F_STAGING + 1024 + 1152;
+// backward kernel
+constexpr int STAGE_BYTES = 2 * PLANE;
+constexpr int SMEM_BWD = 2 * PLANE + 2 * STAGE_BYTES + 1024 + 1024;
 }  // namespace hid
 
 struct HidFwdArgs {
   int L, P, m_tiles;
   long Btot, p_off;
   const float* bias;                 // b_i (L,128)
-  __nv_bfloat16 *out_hi, *out_lo;    // next-layer streams [L][4][P][128] (unused when kLast)
-  __nv_bfloat16 *sav_hi, *sav_lo;    // value stream [L][Btot][128]
   // kLast only
   const float* W3;                   // (L,128)
   const float* b3;                   // (L)
@@ -557,26 +571,37 @@ struct HidFwdArgs {
   nsvd_problem_t pb;
 };
 
+// S2-fwd: hidden layer i (128 -> 128) on the 4 streams of one copy; tile = (l, 128 points).
+//   smem : W_i[l] hi/lo resident (64 KB) | ring of 3 x 32 KB (stream, K-chunk) operand stages |
+//          64 KB output staging (8 boxes of 128 rows x 64 B) drained by TMA bulk stores.
+//   TMEM : 4 x 128 columns (one block per stream).
+//   kLast fuses the 128 -> 1 head, the importance / mask product rule, the potential and the
+//   operator scale / shift (F, TF) and only stores the value stream.
 template <bool kLast>
 __global__ void __launch_bounds__(hid::THREADS, 1)
 hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                  const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
+                  const __grid_constant__ CUtensorMap tmSh, const __grid_constant__ CUtensorMap tmSl,
                   const HidFwdArgs args) {
   using namespace hid;
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sW = smem;                       // [hi plane | lo plane]
-  uint8_t* sA = smem + 2 * PLANE;           // stages
-  uint64_t* bars = (uint64_t*)(sA + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;                    // [2]
-  uint64_t* empty = bars + 2;               // [2]
-  uint64_t* wfull = bars + 4;
-  uint64_t* wfree = bars + 5;
-  uint64_t* tfull = bars + 6;
-  uint64_t* tempty = bars + 7;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
-  float* ubuf = (float*)(bars + 16);        // [128][4] partial head sums (kLast)
+  uint8_t* sW = smem;                       // [hi c0 | hi c1 | lo c0 | lo c1]
+  uint8_t* sA = smem + 2 * PLANE;           // ring
+  uint8_t* sO = sA + F_STAGES * F_STAGE_BYTES;  // staging boxes
+  uint64_t* bars = (uint64_t*)(sO + F_STAGING);
+  uint64_t* full = bars;                    // [3]
+  uint64_t* empty = bars + 3;               // [3]
+  uint64_t* wfull = bars + 6;
+  uint64_t* wfree = bars + 7;
+  uint64_t* tfull = bars + 8;
+  uint64_t* tempty = bars + 9;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+  float* bias_s = (float*)(bars + 16);      // [128]
+  float* w3_s = bias_s + 128;               // [128] (kLast)
+  float* ubuf = (float*)(sO + 7 * F_BOX);   // [128][4] head partial sums (kLast: box 7 is unused)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = args.L * args.m_tiles;
@@ -589,9 +614,15 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     tma_prefetch_desc(&tmAl);
     tma_prefetch_desc(&tmWh);
     tma_prefetch_desc(&tmWl);
+    tma_prefetch_desc(&tmSh);
+    tma_prefetch_desc(&tmSl);
+    if (!kLast) {
+      tma_prefetch_desc(&tmOh);
+      tma_prefetch_desc(&tmOl);
+    }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < F_STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -623,15 +654,14 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           tma_load_3d(sW + PLANE + CHUNK, &tmWl, wfull, 64, 0, l);
           cur_l = l;
         }
-        for (int s = 0; s < 4; ++s) {
+        for (int sc = 0; sc < 8; ++sc) {  // (stream, K-chunk)
+          const int s = sc >> 1, c = sc & 1;
           mbar_wait(&empty[stage], phase ^ 1, 11);
-          uint8_t* d = sA + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_3d(d, &tmAh, &full[stage], 0, mt * 128, l * 4 + s);
-          tma_load_3d(d + CHUNK, &tmAh, &full[stage], 64, mt * 128, l * 4 + s);
-          tma_load_3d(d + PLANE, &tmAl, &full[stage], 0, mt * 128, l * 4 + s);
-          tma_load_3d(d + PLANE + CHUNK, &tmAl, &full[stage], 64, mt * 128, l * 4 + s);
-          if (++stage == STAGES) {
+          uint8_t* d = sA + stage * F_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], F_STAGE_BYTES);
+          tma_load_3d(d, &tmAh, &full[stage], 64 * c, mt * 128, l * 4 + s);
+          tma_load_3d(d + CHUNK, &tmAl, &full[stage], 64 * c, mt * 128, l * 4 + s);
+          if (++stage == F_STAGES) {
             stage = 0;
             phase ^= 1;
           }
@@ -653,22 +683,24 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         }
         mbar_wait(tempty, tphase ^ 1, 13);
         tc_fence_after();
-        for (int s = 0; s < 4; ++s) {
+        for (int sc = 0; sc < 8; ++sc) {
+          const int s = sc >> 1, c = sc & 1;
           mbar_wait(&full[stage], phase, 14);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(sA + stage * STAGE_BYTES), a_lo = a_hi + PLANE;
+          const uint32_t a_hi = smem_u32(sA + stage * F_STAGE_BYTES), a_lo = a_hi + CHUNK;
           const uint32_t d_tmem = tmem_base + s * 128;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t off = (kk >> 2) * CHUNK + (kk & 3) * 32;
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t off = kk * 32;
             uint64_t ah = make_sdesc_sw128(a_hi + off, 16, 1024), al = make_sdesc_sw128(a_lo + off, 16, 1024);
-            uint64_t bh = make_sdesc_sw128(w_hi + off, 16, 1024), bl = make_sdesc_sw128(w_lo + off, 16, 1024);
-            umma_f16(d_tmem, al, bh, idesc, kk > 0 ? 1u : 0u);
+            uint64_t bh = make_sdesc_sw128(w_hi + c * CHUNK + off, 16, 1024);
+            uint64_t bl = make_sdesc_sw128(w_lo + c * CHUNK + off, 16, 1024);
+            umma_f16(d_tmem, al, bh, idesc, (c > 0 || kk > 0) ? 1u : 0u);
             umma_f16(d_tmem, ah, bl, idesc, 1u);
             umma_f16(d_tmem, ah, bh, idesc, 1u);
           }
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
+          if (++stage == F_STAGES) {
             stage = 0;
             phase ^= 1;
           }
@@ -680,57 +712,94 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     }
   } else if (warp >= 4) {
     const int ewarp = warp - 4, q = ewarp & 3, half = ewarp >> 2;
+    const int et = threadIdx.x - 128;        // 0..255 among the epilogue threads
+    const int row = q * 32 + lane;           // point row inside the tile == TMEM lane
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    // staging address of this thread's two 16-byte pieces inside a 64-byte swizzled row
+    const uint32_t sw = (uint32_t)((row >> 1) & 3);
+    const uint32_t piece0 = (uint32_t)row * 64 + (((2 * half) ^ sw) << 4);
+    const uint32_t piece1 = (uint32_t)row * 64 + (((2 * half + 1) ^ sw) << 4);
     uint32_t tphase = 0;
+    int cur_l = -1;
     for (int t = t_begin; t < t_end; ++t) {
       const int l = t / args.m_tiles, mt = t % args.m_tiles;
-      const int pt = mt * 128 + q * 32 + lane;
+      const int pt = mt * 128 + row;
+      if (l != cur_l) {  // all epilogue threads are past the previous tile's last staging barrier
+        if (et < 128) {
+          bias_s[et] = args.bias[l * kHidden + et];
+          if (kLast) w3_s[et] = args.W3[l * kHidden + et];
+        }
+        cur_l = l;
+        named_bar_sync(1, 256);
+      }
       mbar_wait(tfull, tphase, 15);
       tphase ^= 1;
       tc_fence_after();
       float u[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        const int h0 = half * 64 + ch * 16;
+      for (int r = 0; r < 4; ++r) {          // h-quarters of 32 hidden units; this warp takes 16 of them
+        const int h0 = r * 32 + half * 16;
         float z[4][16];
 #pragma unroll
         for (int s = 0; s < 4; ++s) tmem_ld16(tl + s * 128 + h0, z[s]);
         tmem_ld_wait();
+        if (r == 3) {                        // last TMEM read of this tile: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty);
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float zb = z[0][i] + __ldg(args.bias + l * kHidden + h0 + i);
+          float zb = z[0][i] + bias_s[h0 + i];
           act_streams(zb, z[1][i], z[2][i], z[3][i], z[0][i], z[1][i], z[2][i], z[3][i]);
         }
         if (kLast) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float w = __ldg(args.W3 + l * kHidden + h0 + i);
+            float w = w3_s[h0 + i];
 #pragma unroll
             for (int s = 0; s < 4; ++s) u[s] = fmaf(z[s][i], w, u[s]);
           }
         }
-        if (pt < args.P) {
+        // previous round's bulk stores must have drained the staging boxes
+        if (et == 0) tma_store_wait_read();
+        named_bar_sync(2, 256);
+#pragma unroll
+        for (int s = 0; s < (kLast ? 1 : 4); ++s) {
+          uint32_t h[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_bf16x2(z[s][2 * i], z[s][2 * i + 1], h[i], lo[i]);
+          uint8_t* bh = sO + (2 * s) * F_BOX;
+          uint8_t* bl = bh + F_BOX;
+          *reinterpret_cast<uint4*>(bh + piece0) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(bh + piece1) = make_uint4(h[4], h[5], h[6], h[7]);
+          *reinterpret_cast<uint4*>(bl + piece0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(bl + piece1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3, 256);
+        if (et == 0) {
           if (!kLast) {
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-              long o = (((long)l * 4 + s) * args.P + pt) * kHidden + h0;
-              store_split16(z[s], args.out_hi + o, args.out_lo + o);
+              tma_store_3d(&tmOh, sO + (2 * s) * F_BOX, r * 32, mt * 128, l * 4 + s);
+              tma_store_3d(&tmOl, sO + (2 * s + 1) * F_BOX, r * 32, mt * 128, l * 4 + s);
             }
           }
-          long o = ((long)l * args.Btot + args.p_off + pt) * kHidden + h0;
-          store_split16(z[0], args.sav_hi + o, args.sav_lo + o);
+          tma_store_3d(&tmSh, sO, r * 32, (int)args.p_off + mt * 128, l);
+          tma_store_3d(&tmSl, sO + F_BOX, r * 32, (int)args.p_off + mt * 128, l);
+          tma_store_commit();
         }
       }
       if (kLast) {
-        const int r = q * 32 + lane;
         if (half == 1) {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) ubuf[r * 4 + s] = u[s];
+          for (int s = 0; s < 4; ++s) ubuf[row * 4 + s] = u[s];
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        named_bar_sync(1, 256);
         if (half == 0 && pt < args.P) {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) u[s] += ubuf[r * 4 + s];
+          for (int s = 0; s < 4; ++s) u[s] += ubuf[row * 4 + s];
           u[0] += __ldg(args.b3 + l);
           const long pg = args.p_off + pt;
           PointGeom g = point_geom(args.x[2 * pg], args.x[2 * pg + 1], args.pb);
@@ -741,11 +810,10 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           args.TF[pg * args.L + l] = tf;
           args.U0[pg * args.L + l] = u[0];
         }
+        named_bar_sync(1, 256);  // ubuf (staging box 7) is free again
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
     }
+    if (et == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -760,39 +828,46 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 // dZ_i tile produces BOTH
 //   dgrad  D1[pt][k]  = sum_j dZ_i[pt][j] W_i[j][k]      (A K-major, B = W_i^T K-major)
 //   wgrad  D2[j][k]  += sum_pt dZ_i[pt][j] a_{i-1}[pt][k] (the same smem tiles read MN-major)
-// epilogue: dZ_{i-1} = D1 (.) sigma(a_{i-1}) -> hi/lo planes, db_{i-1} column sums; D2 is flushed
-// into dW_i[l] with vector reductions when the CTA leaves copy l.
+// epilogue: dZ_{i-1} = D1 (.) sigma(a_{i-1}) with a_{i-1} read back from its smem tile, staged
+// into the (now dead) dZ_i tile and written with TMA bulk stores; db_{i-1} column sums go through
+// shared-memory atomics; D2 / db are flushed with vector reductions when the CTA leaves copy l.
+// The three 64 KB tiles fill shared memory, so load -> MMA -> epilogue run back to back per tile
+// (the next tile is prefetched into L2 meanwhile).
 // ------------------------------------------------------------------------------------------
 struct HidBwdArgs {
   int L, P, m_tiles;
   long Btot, p_off;
-  const __nv_bfloat16 *aprev_hi, *aprev_lo;  // saved value stream of layer i-1: [L][Btot][128]
-  __nv_bfloat16 *dz_hi, *dz_lo;              // out: dZ_{i-1} [L][P][128]
   float* dW;                                 // (L,128,128) accumulated with reductions
   float* db_prev;                            // (L,128) accumulated with atomics
 };
+
+// the two 16-byte pieces holding k0..k0+15 of `row` in a [128][128]-bf16 tile kept as two
+// 128-byte-swizzled K-chunks (the TMA / UMMA K-major layout)
+__device__ __forceinline__ uint32_t tile_piece_off(int row, int k0, int which) {
+  const int c = k0 >> 6, piece = ((k0 & 63) >> 3) + which;
+  return (uint32_t)(c * hid::CHUNK + row * 128 + ((piece ^ (row & 7)) << 4));
+}
 
 __global__ void __launch_bounds__(hid::THREADS, 1)
 hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,
                   const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                  const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
                   const HidBwdArgs args) {
   using namespace hid;
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;                 // W_i^T hi | lo
-  uint8_t* sZ = smem + 2 * PLANE;     // dZ_i hi | lo
+  uint8_t* sZ = smem + 2 * PLANE;     // dZ_i hi | lo   (re-used as the dZ_{i-1} output staging)
   uint8_t* sA = sZ + 2 * PLANE;       // a_{i-1} hi | lo
   uint64_t* bars = (uint64_t*)(sA + 2 * PLANE);
   uint64_t* full = bars;              // dZ + a landed
-  uint64_t* sfree = bars + 1;         // MMAs reading smem retired
-  uint64_t* wfull = bars + 2;
-  uint64_t* tfull = bars + 3;         // [2]
-  uint64_t* tempty = bars + 5;        // [2]
-  uint64_t* w2full = bars + 7;
-  uint64_t* w2empty = bars + 8;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+  uint64_t* mma_done = bars + 1;      // dgrad + wgrad of the tile retired
+  uint64_t* epi_done = bars + 2;      // epilogue finished with TMEM, sZ and sA
+  uint64_t* wfull = bars + 3;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+  float* db_s = (float*)(bars + 6);   // [128] column sums of dZ_{i-1} for the current copy
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = args.L * args.m_tiles;
@@ -807,20 +882,18 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
     tma_prefetch_desc(&tmAl);
     tma_prefetch_desc(&tmWh);
     tma_prefetch_desc(&tmWl);
+    tma_prefetch_desc(&tmOh);
+    tma_prefetch_desc(&tmOl);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(full, 1);
-    mbar_init(sfree, 1);
+    mbar_init(mma_done, 1);
+    mbar_init(epi_done, 1);
     mbar_init(wfull, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], EPI_WARPS);
-    }
-    mbar_init(w2full, 1);
-    mbar_init(w2empty, EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x >= 128 && threadIdx.x < 256) db_s[threadIdx.x - 128] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -833,7 +906,7 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
       for (int t = t_begin; t < t_end; ++t) {
         const int l = t / args.m_tiles, mt = t % args.m_tiles;
         const int i = t - t_begin;
-        if (i > 0) mbar_wait(sfree, (uint32_t)((i - 1) & 1), 20);
+        if (i > 0) mbar_wait(epi_done, (uint32_t)((i - 1) & 1), 20);
         if (l != cur_l) {
           mbar_arrive_expect_tx(wfull, 2 * PLANE);
           tma_load_3d(sW, &tmWh, wfull, 0, 0, l);
@@ -842,15 +915,28 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
           tma_load_3d(sW + PLANE + CHUNK, &tmWl, wfull, 64, 0, l);
           cur_l = l;
         }
+        const int pa = (int)args.p_off + mt * 128;
         mbar_arrive_expect_tx(full, 4 * PLANE);
         tma_load_3d(sZ, &tmZh, full, 0, mt * 128, l);
         tma_load_3d(sZ + CHUNK, &tmZh, full, 64, mt * 128, l);
         tma_load_3d(sZ + PLANE, &tmZl, full, 0, mt * 128, l);
         tma_load_3d(sZ + PLANE + CHUNK, &tmZl, full, 64, mt * 128, l);
-        tma_load_3d(sA, &tmAh, full, 0, (int)args.p_off + mt * 128, l);
-        tma_load_3d(sA + CHUNK, &tmAh, full, 64, (int)args.p_off + mt * 128, l);
-        tma_load_3d(sA + PLANE, &tmAl, full, 0, (int)args.p_off + mt * 128, l);
-        tma_load_3d(sA + PLANE + CHUNK, &tmAl, full, 64, (int)args.p_off + mt * 128, l);
+        tma_load_3d(sA, &tmAh, full, 0, pa, l);
+        tma_load_3d(sA + CHUNK, &tmAh, full, 64, pa, l);
+        tma_load_3d(sA + PLANE, &tmAl, full, 0, pa, l);
+        tma_load_3d(sA + PLANE + CHUNK, &tmAl, full, 64, pa, l);
+        if (t + 1 < t_end) {  // pull the next tile into L2 while this one is processed
+          const int l2 = (t + 1) / args.m_tiles, mt2 = (t + 1) % args.m_tiles;
+          const int pa2 = (int)args.p_off + mt2 * 128;
+          tma_prefetch_3d(&tmZh, 0, mt2 * 128, l2);
+          tma_prefetch_3d(&tmZh, 64, mt2 * 128, l2);
+          tma_prefetch_3d(&tmZl, 0, mt2 * 128, l2);
+          tma_prefetch_3d(&tmZl, 64, mt2 * 128, l2);
+          tma_prefetch_3d(&tmAh, 0, pa2, l2);
+          tma_prefetch_3d(&tmAh, 64, pa2, l2);
+          tma_prefetch_3d(&tmAl, 0, pa2, l2);
+          tma_prefetch_3d(&tmAl, 64, pa2, l2);
+        }
       }
     }
   } else if (warp == 1) {
@@ -860,8 +946,8 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
       const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + PLANE;
       const uint32_t z_hi = smem_u32(sZ), z_lo = z_hi + PLANE;
       const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + PLANE;
-      int cur_l = -1, acc = 0, run = -1;
-      uint32_t fphase = 0, wphase = 0, acc_phase = 0;
+      int cur_l = -1;
+      uint32_t fphase = 0, wphase = 0;
       bool first_of_run = true;
       for (int t = t_begin; t < t_end; ++t) {
         const int l = t / args.m_tiles;
@@ -870,26 +956,18 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
           wphase ^= 1;
           cur_l = l;
           first_of_run = true;
-          ++run;
         }
-        mbar_wait(full, fphase, 22);
+        mbar_wait(full, fphase, 22);  // implies the previous tile's epilogue released TMEM and smem
         fphase ^= 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1, 23);
         tc_fence_after();
-        const uint32_t d1 = tmem_base + acc * 128;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t off = (kk >> 2) * CHUNK + (kk & 3) * 32;
           uint64_t ah = make_sdesc_sw128(z_hi + off, 16, 1024), al = make_sdesc_sw128(z_lo + off, 16, 1024);
           uint64_t bh = make_sdesc_sw128(w_hi + off, 16, 1024), bl = make_sdesc_sw128(w_lo + off, 16, 1024);
-          umma_f16(d1, al, bh, idesc_d, kk > 0 ? 1u : 0u);
-          umma_f16(d1, ah, bl, idesc_d, 1u);
-          umma_f16(d1, ah, bh, idesc_d, 1u);
-        }
-        umma_commit(&tfull[acc]);
-        if (first_of_run && run > 0) {
-          mbar_wait(w2empty, (uint32_t)((run - 1) & 1), 24);  // previous copy's dW flushed out of TMEM
-          tc_fence_after();
+          umma_f16(tmem_base, al, bh, idesc_d, kk > 0 ? 1u : 0u);
+          umma_f16(tmem_base, ah, bl, idesc_d, 1u);
+          umma_f16(tmem_base, ah, bh, idesc_d, 1u);
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // K = 128 points, 16 per MMA
@@ -900,66 +978,84 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
           umma_f16(tmem_d2, ah, bl, idesc_w, 1u);
           umma_f16(tmem_d2, ah, bh, idesc_w, 1u);
         }
-        umma_commit(sfree);
+        umma_commit(mma_done);
         first_of_run = false;
-        const bool last_of_run = (t + 1 == t_end) || ((t + 1) / args.m_tiles != l);
-        if (last_of_run) umma_commit(w2full);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
       }
     }
   } else if (warp >= 4) {
     const int ewarp = warp - 4, q = ewarp & 3, half = ewarp >> 2;
+    const int et = threadIdx.x - 128;
+    const int row = q * 32 + lane;
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-    int acc = 0, run = -1, cur_l = -1;
-    uint32_t acc_phase = 0;
+    uint32_t mphase = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const int l = t / args.m_tiles, mt = t % args.m_tiles;
-      if (l != cur_l) {
-        cur_l = l;
-        ++run;
-      }
-      const int pt = mt * 128 + q * 32 + lane;
-      mbar_wait(&tfull[acc], acc_phase, 25);
+      mbar_wait(mma_done, mphase, 25);
+      mphase ^= 1;
       tc_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         const int k0 = half * 64 + ch * 16;
         float v[16], a[16];
-        tmem_ld16(tl + acc * 128 + k0, v);
-        const bool ok = pt < args.P;
-        if (ok) {
-          long o = ((long)l * args.Btot + args.p_off + pt) * kHidden + k0;
-          load_merge16(args.aprev_hi + o, args.aprev_lo + o, a);
+        tmem_ld16(tl + k0, v);
+        {
+          const uint32_t o0 = tile_piece_off(row, k0, 0), o1 = tile_piece_off(row, k0, 1);
+          uint4 h[2] = {*reinterpret_cast<const uint4*>(sA + o0), *reinterpret_cast<const uint4*>(sA + o1)};
+          uint4 lo[2] = {*reinterpret_cast<const uint4*>(sA + PLANE + o0), *reinterpret_cast<const uint4*>(sA + PLANE + o1)};
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(h);
+          const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(lo);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float2 x0 = __bfloat1622float2(hh[i]), x1 = __bfloat1622float2(ll[i]);
+            a[2 * i] = x0.x + x1.x;
+            a[2 * i + 1] = x0.y + x1.y;
+          }
         }
         tmem_ld_wait();
+        // rows beyond P carry dZ_i = 0 (TMA zero fill), hence D1 = 0 and v = 0 without a mask
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = ok ? v[i] * sig_from_softplus(a[i]) : 0.f;
-        if (ok) {
-          long o = ((long)l * args.P + pt) * kHidden + k0;
-          store_split16(v, args.dz_hi + o, args.dz_lo + o);
+        for (int i = 0; i < 16; ++i) v[i] *= sig_fast(a[i]);
+        {
+          uint32_t h[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], h[i], lo[i]);
+          const uint32_t o0 = tile_piece_off(row, k0, 0), o1 = tile_piece_off(row, k0, 1);
+          *reinterpret_cast<uint4*>(sZ + o0) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(sZ + o1) = make_uint4(h[4], h[5], h[6], h[7]);
+          *reinterpret_cast<uint4*>(sZ + PLANE + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(sZ + PLANE + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
-        // db_{i-1}[l][k] += sum over the 32 rows of this warp
+        // column sums over the 32 rows of this warp: recursive halving (16 shuffles), lane c < 16
+        // ends with column k0 + c
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float sres = warp_sum(v[i]);
-          if (lane == i) atomicAdd(args.db_prev + l * kHidden + k0 + i, sres);
+        for (int w = 8; w >= 1; w >>= 1) {
+          const bool up = (lane & (w * 2)) != 0;  // lanes with this bit keep the upper half
+#pragma unroll
+          for (int i = 0; i < w; ++i) {
+            float send = up ? v[i] : v[i + w];
+            float keep = up ? v[i + w] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w * 2);
+          }
+        }
+        {
+          float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+          // lane bits (16,8,4,2) select the column: col = 8*b16 + 4*b8 + 2*b4 + b2
+          const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          if ((lane & 1) == 0) atomicAdd(&db_s[k0 + col], tot);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
+      fence_proxy_async_smem();
+      named_bar_sync(2, 256);
+      if (et == 0) {
+        tma_store_3d(&tmOh, sZ, 0, mt * 128, l);
+        tma_store_3d(&tmOh, sZ + CHUNK, 64, mt * 128, l);
+        tma_store_3d(&tmOl, sZ + PLANE, 0, mt * 128, l);
+        tma_store_3d(&tmOl, sZ + PLANE + CHUNK, 64, mt * 128, l);
+        tma_store_commit();
       }
       const bool last_of_run = (t + 1 == t_end) || ((t + 1) / args.m_tiles != l);
       if (last_of_run) {
-        mbar_wait(w2full, (uint32_t)(run & 1), 26);
-        tc_fence_after();
-        const int j = q * 32 + lane;
+        const int j = row;
         float* drow = args.dW + ((long)l * kHidden + j) * kHidden;
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
@@ -970,11 +1066,17 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; i += 4) red_add_v4(drow + k0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(w2empty);
+        if (et < 128) {
+          atomicAdd(args.db_prev + l * kHidden + et, db_s[et]);
+          db_s[et] = 0.f;
+        }
       }
+      if (et == 0) tma_store_wait_read();
+      tc_fence_before();
+      named_bar_sync(3, 256);
+      if (et == 0) mbar_arrive(epi_done);
     }
+    if (et == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -1026,7 +1128,7 @@ head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
     float dz[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      dz[i] = du * w3[i] * sig_from_softplus(a[i]);
+      dz[i] = du * w3[i] * sig_fast(a[i]);
       accW[i] = fmaf(du, a[i], accW[i]);
       accB[i] += dz[i];
     }
@@ -1133,7 +1235,8 @@ static inline uint8_t* align1k(void* p) { return (uint8_t*)(((uintptr_t)p + 1023
 
 template <bool kLast>
 static int launch_hidden_fwd(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh,
-                             const CUtensorMap& wl, const HidFwdArgs& a, cudaStream_t st) {
+                             const CUtensorMap& wl, const CUtensorMap& oh, const CUtensorMap& ol,
+                             const CUtensorMap& sh, const CUtensorMap& sl, const HidFwdArgs& a, cudaStream_t st) {
   static bool configured = false;
   auto kern = hidden_fwd_kernel<kLast>;
   if (!configured) {
@@ -1142,7 +1245,7 @@ static int launch_hidden_fwd(const CUtensorMap& ah, const CUtensorMap& al, const
   }
   int T = a.L * a.m_tiles;
   int grid = T < 148 ? T : 148;
-  kern<<<grid, hid::THREADS, hid::SMEM_FWD, st>>>(ah, al, wh, wl, a);
+  kern<<<grid, hid::THREADS, hid::SMEM_FWD, st>>>(ah, al, wh, wl, oh, ol, sh, sl, a);
   NSVD_LAUNCH_CHECK();
   return 0;
 }
@@ -1197,9 +1300,15 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
     }
     // ---- hidden layers 1, 2
     for (int i = 0; i < 2; ++i) {
-      CUtensorMap mAh, mAl;
+      CUtensorMap mAh, mAl, mOh, mOl, mSh, mSl;
       if ((rc = make_tmap_bf16_3d(&mAh, wk + t.str_hi[i], H, P, 4 * L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
       if ((rc = make_tmap_bf16_3d(&mAl, wk + t.str_lo[i], H, P, 4 * L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
+      // bulk-store maps (64-byte swizzle, boxes of 32 hidden units x 128 points)
+      const int o = i == 0 ? 1 : 0;  // layer 2 has no stream output; give it valid (unused) maps
+      if ((rc = make_tmap_bf16_3d(&mOh, wk + t.str_hi[o], H, P, 4 * L, H * 2, (uint64_t)P * H * 2, 32, 128, 64))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mOl, wk + t.str_lo[o], H, P, 4 * L, H * 2, (uint64_t)P * H * 2, 32, 128, 64))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mSh, sv + t.av_hi[i + 1], H, B, L, H * 2, (uint64_t)B * H * 2, 32, 128, 64))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mSl, sv + t.av_lo[i + 1], H, B, L, H * 2, (uint64_t)B * H * 2, 32, 128, 64))) return rc;
       HidFwdArgs a{};
       a.L = (int)L;
       a.P = P;
@@ -1207,13 +1316,9 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
       a.Btot = B;
       a.p_off = p0;
       a.bias = pr.b[i + 1];
-      a.sav_hi = BF(sv + t.av_hi[i + 1]);
-      a.sav_lo = BF(sv + t.av_lo[i + 1]);
+      ProfScope ps(KC_HID_FWD, st);
       if (i == 0) {
-        a.out_hi = BF(wk + t.str_hi[1]);
-        a.out_lo = BF(wk + t.str_lo[1]);
-        ProfScope ps(KC_HID_FWD, st);
-        if ((rc = launch_hidden_fwd<false>(mAh, mAl, mWh[0], mWl[0], a, st))) return rc;
+        if ((rc = launch_hidden_fwd<false>(mAh, mAl, mWh[0], mWl[0], mOh, mOl, mSh, mSl, a, st))) return rc;
       } else {
         a.W3 = pr.W[3];
         a.b3 = pr.b[3];
@@ -1223,8 +1328,7 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
         a.TF = TF;
         a.U0 = reinterpret_cast<float*>(sv + t.u0);
         a.pb = pb;
-        ProfScope ps(KC_HID_FWD, st);
-        if ((rc = launch_hidden_fwd<true>(mAh, mAl, mWh[1], mWl[1], a, st))) return rc;
+        if ((rc = launch_hidden_fwd<true>(mAh, mAl, mWh[1], mWl[1], mOh, mOl, mSh, mSl, a, st))) return rc;
       }
     }
   }
@@ -1280,23 +1384,22 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
       if ((rc = make_tmap_bf16_3d(&mZl, wk + t.dz_lo[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
       if ((rc = make_tmap_bf16_3d(&mAh, sv + t.av_hi[i - 1], H, B, L, H * 2, (uint64_t)B * H * 2, 64, 128))) return rc;
       if ((rc = make_tmap_bf16_3d(&mAl, sv + t.av_lo[i - 1], H, B, L, H * 2, (uint64_t)B * H * 2, 64, 128))) return rc;
+      CUtensorMap mOh, mOl;
+      if ((rc = make_tmap_bf16_3d(&mOh, wk + t.dz_hi[cur ^ 1], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mOl, wk + t.dz_lo[cur ^ 1], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
       HidBwdArgs a{};
       a.L = (int)L;
       a.P = P;
       a.m_tiles = m_tiles;
       a.Btot = B;
       a.p_off = p0;
-      a.aprev_hi = BF(sv + t.av_hi[i - 1]);
-      a.aprev_lo = BF(sv + t.av_lo[i - 1]);
-      a.dz_hi = BF(wk + t.dz_hi[cur ^ 1]);
-      a.dz_lo = BF(wk + t.dz_lo[cur ^ 1]);
       a.dW = gr.dW[i];
       a.db_prev = gr.db[i - 1];
       int T = (int)L * m_tiles;
       int grid = T < 148 ? T : 148;
       {
         ProfScope ps(KC_HID_BWD, st);
-        hidden_bwd_kernel<<<grid, hid::THREADS, hid::SMEM_BWD, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], a);
+        hidden_bwd_kernel<<<grid, hid::THREADS, hid::SMEM_BWD, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], mOh, mOl, a);
         NSVD_LAUNCH_CHECK();
       }
       cur ^= 1;
