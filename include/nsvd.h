@@ -117,9 +117,11 @@ size_t nsvd_gram_partials_bytes(int32_t n_points, int32_t n_copies);
 int nsvd_gram_reduce(const float* F, const float* TF, const float* vector_mask, int32_t n_points,
                      int32_t n_copies, int32_t b1, float* terms, void* partials, void* stream);
 
-/* Full cross Grams for evaluation (methods/spectrum.py:74-75): cov += w^2 F^T F, quad += w^2 F^T TF
- * with optional per-row weight `roww` (sqrt_ws, may be NULL).  Accumulates into cov, quad (L*L). */
-int nsvd_cross_gram(const float* F, const float* TF, const float* roww, int32_t n_points,
+/* Full cross Grams for evaluation (methods/spectrum.py:62-75): with phi = nan_to_num(w F),
+ * Tphi = nan_to_num(w TF) and Tphi rows zeroed where x is the origin (x may be NULL):
+ *   cov += phi^T phi, quad += phi^T Tphi.  `roww` = per-row sqrt weight ratio (may be NULL).
+ * Accumulates into cov, quad (L*L each, caller zero-initialises).                              */
+int nsvd_cross_gram(const float* F, const float* TF, const float* roww, const float* x, int32_t n_points,
                     int32_t n_copies, float* cov, float* quad, void* partials, void* stream);
 
 /* Loss value from (all-reduced) terms: NestedLoRALossFunctionEVD.forward, nestedlora.py:70-94.

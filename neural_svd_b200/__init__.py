@@ -11,5 +11,6 @@ from .operators import (GaussianImportance, NegativeHamiltonian, OperatorWrapper
                         harmonic_oscillator_potential, hydrogen_potential, make_gaussian_sampler)
 from .fused import compute_loss_operator, get_engine, set_engine
 from .dist import PointParallel, shard_points
+from .spectrum import compute_spectrum_evd
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -49,7 +49,7 @@ SIGNATURES = {
     "nsvd_fwd_streams": (C.c_int, [_PB, _PR, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "nsvd_gram_partials_bytes": (_sz, [_i32, _i32]),
     "nsvd_gram_reduce": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "nsvd_cross_gram": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "nsvd_cross_gram": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "nsvd_loss_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
     "nsvd_loss_dF": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp]),
     "nsvd_mlp_bwd": (C.c_int, [_PB, _PR, C.c_int, _vp, _vp, _vp, _sz, _GR, _vp, _sz, _vp]),

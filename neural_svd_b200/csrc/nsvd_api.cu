@@ -156,11 +156,11 @@ int nsvd_gram_reduce(const float* F, const float* TF, const float* vector_mask, 
   return gram_reduce(F, TF, vector_mask, n_points, n_copies, b1, terms, partials, (cudaStream_t)stream);
 }
 
-int nsvd_cross_gram(const float* F, const float* TF, const float* roww, int32_t n_points,
+int nsvd_cross_gram(const float* F, const float* TF, const float* roww, const float* x, int32_t n_points,
                     int32_t n_copies, float* cov, float* quad, void* partials, void* stream) {
   NSVD_CHECK_ARG(F && TF && cov && quad && partials, "NULL buffer");
   NSVD_CHECK_ARG(n_points >= 1 && n_copies >= 1 && n_copies <= 64, "bad shape B=%d L=%d", n_points, n_copies);
-  return cross_gram(F, TF, roww, n_points, n_copies, cov, quad, partials, (cudaStream_t)stream);
+  return cross_gram(F, TF, roww, x, n_points, n_copies, cov, quad, partials, (cudaStream_t)stream);
 }
 
 int nsvd_loss_finalize(const float* terms, const float* matrix_mask, int32_t n_copies, int64_t Bg,

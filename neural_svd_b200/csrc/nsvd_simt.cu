@@ -391,10 +391,17 @@ int simt_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float
 // ------------------------------------------------------------------------------------------
 constexpr int kGramRows = 64;  // rows staged per iteration
 
+__device__ __forceinline__ float nan_to_num_f(float v) {
+  if (isnan(v)) return 0.f;
+  if (isinf(v)) return v > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+  return v;
+}
+
 template <int LT>  // LT = L rounded up to a multiple of 16 (16, 32, 48, 64) ; threads = 256
 __global__ void __launch_bounds__(256)
 gram_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
-                   const float* __restrict__ vmask, const float* __restrict__ roww, int L,
+                   const float* __restrict__ vmask, const float* __restrict__ roww,
+                   const float* __restrict__ xrow, int L,
                    long row_begin, long row_end, int rows_per_block, int cross,
                    float* __restrict__ partials, int partial_stride, int block_off) {
   // thread tile: (LT/16) x (LT/16) outputs; 16x16 threads
@@ -418,6 +425,11 @@ gram_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
         float w = roww ? roww[rb + rr] : 1.f;
         f = F[idx] * w;
         t = TF[idx] * w;
+        if (cross) {  // torch.nan_to_num + zero the T-row at the origin (methods/spectrum.py:71-73)
+          f = nan_to_num_f(f);
+          t = nan_to_num_f(t);
+          if (xrow && fabsf(xrow[2 * (rb + rr)]) <= 1e-8f && fabsf(xrow[2 * (rb + rr) + 1]) <= 1e-8f) t = 0.f;
+        }
         if (!cross) ops += vmask[c] * f * t;
       }
       sF[rr][c] = f;
@@ -550,9 +562,9 @@ size_t gram_partials_bytes(int B, int L) {
 }
 
 template <int LT>
-static int gram_launch(const float* F, const float* TF, const float* vmask, const float* roww, int L,
-                       long rb, long re, int cross, float* partials, int stride, int block_off,
-                       int* nblocks, cudaStream_t st) {
+static int gram_launch(const float* F, const float* TF, const float* vmask, const float* roww,
+                       const float* xrow, int L, long rb, long re, int cross, float* partials, int stride,
+                       int block_off, int* nblocks, cudaStream_t st) {
   long rows = re - rb;
   if (rows <= 0) {
     *nblocks = 0;
@@ -561,16 +573,16 @@ static int gram_launch(const float* F, const float* TF, const float* vmask, cons
   int nb = gram_blocks_for(rows);
   int rpb = (int)((rows + nb - 1) / nb);
   nb = (int)((rows + rpb - 1) / rpb);
-  gram_stage1_kernel<LT><<<nb, 256, 0, st>>>(F, TF, vmask, roww, L, rb, re, rpb, cross, partials,
+  gram_stage1_kernel<LT><<<nb, 256, 0, st>>>(F, TF, vmask, roww, xrow, L, rb, re, rpb, cross, partials,
                                              stride, block_off);
   NSVD_LAUNCH_CHECK();
   *nblocks = nb;
   return 0;
 }
 
-static int gram_dispatch(const float* F, const float* TF, const float* vmask, const float* roww, int L,
-                         long rb, long re, int cross, float* partials, int stride, int block_off,
-                         int* nblocks, cudaStream_t st) {
+static int gram_dispatch(const float* F, const float* TF, const float* vmask, const float* roww,
+                         const float* xrow, int L, long rb, long re, int cross, float* partials, int stride,
+                         int block_off, int* nblocks, cudaStream_t st) {
   if (L == 16 && !cross && !roww) {
     long rows = re - rb;
     if (rows <= 0) {
@@ -586,10 +598,10 @@ static int gram_dispatch(const float* F, const float* TF, const float* vmask, co
     *nblocks = nb;
     return 0;
   }
-  if (L <= 16) return gram_launch<16>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
-  if (L <= 32) return gram_launch<32>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
-  if (L <= 48) return gram_launch<48>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
-  if (L <= 64) return gram_launch<64>(F, TF, vmask, roww, L, rb, re, cross, partials, stride, block_off, nblocks, st);
+  if (L <= 16) return gram_launch<16>(F, TF, vmask, roww, xrow, L, rb, re, cross, partials, stride, block_off, nblocks, st);
+  if (L <= 32) return gram_launch<32>(F, TF, vmask, roww, xrow, L, rb, re, cross, partials, stride, block_off, nblocks, st);
+  if (L <= 48) return gram_launch<48>(F, TF, vmask, roww, xrow, L, rb, re, cross, partials, stride, block_off, nblocks, st);
+  if (L <= 64) return gram_launch<64>(F, TF, vmask, roww, xrow, L, rb, re, cross, partials, stride, block_off, nblocks, st);
   set_error("gram_reduce: n_copies %d > 64 is handled by the CDK path", L);
   return NSVD_E_BADARG;
 }
@@ -598,8 +610,8 @@ int gram_reduce(const float* F, const float* TF, const float* vmask, int B, int 
                 float* terms, void* partials_v, cudaStream_t st) {
   float* partials = (float*)partials_v;
   int stride = 2 * L * L + 1, n1 = 0, n2 = 0, rc;
-  if ((rc = gram_dispatch(F, TF, vmask, nullptr, L, 0, b1, 0, partials, stride, 0, &n1, st))) return rc;
-  if ((rc = gram_dispatch(F, TF, vmask, nullptr, L, b1, B, 0, partials, stride, n1, &n2, st))) return rc;
+  if ((rc = gram_dispatch(F, TF, vmask, nullptr, nullptr, L, 0, b1, 0, partials, stride, 0, &n1, st))) return rc;
+  if ((rc = gram_dispatch(F, TF, vmask, nullptr, nullptr, L, b1, B, 0, partials, stride, n1, &n2, st))) return rc;
   int LL = L * L;
   gram_stage2_kernel<<<cdiv(LL, 128), 128, 0, st>>>(partials, stride, 0, n1, 0, LL, terms, 0);
   NSVD_LAUNCH_CHECK();
@@ -610,11 +622,11 @@ int gram_reduce(const float* F, const float* TF, const float* vmask, int B, int 
   return 0;
 }
 
-int cross_gram(const float* F, const float* TF, const float* roww, int B, int L, float* cov,
+int cross_gram(const float* F, const float* TF, const float* roww, const float* xrow, int B, int L, float* cov,
                float* quad, void* partials_v, cudaStream_t st) {
   float* partials = (float*)partials_v;
   int stride = 2 * L * L + 1, n1 = 0, rc;
-  if ((rc = gram_dispatch(F, TF, nullptr, roww, L, 0, B, 1, partials, stride, 0, &n1, st))) return rc;
+  if ((rc = gram_dispatch(F, TF, nullptr, roww, xrow, L, 0, B, 1, partials, stride, 0, &n1, st))) return rc;
   int LL = L * L;
   gram_stage2_kernel<<<cdiv(LL, 128), 128, 0, st>>>(partials, stride, 0, n1, 0, LL, cov, 1);
   NSVD_LAUNCH_CHECK();

@@ -27,8 +27,8 @@ int simt_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float
 size_t gram_partials_bytes(int B, int L);
 int gram_reduce(const float* F, const float* TF, const float* vmask, int B, int L, int b1, float* terms,
                 void* partials, cudaStream_t st);
-int cross_gram(const float* F, const float* TF, const float* roww, int B, int L, float* cov, float* quad,
-               void* partials, cudaStream_t st);
+int cross_gram(const float* F, const float* TF, const float* roww, const float* xrow, int B, int L, float* cov,
+               float* quad, void* partials, cudaStream_t st);
 int loss_finalize(const float* terms, const float* Mm, int L, long Bg, long B1g, long B2g, float* loss,
                   float* coef, cudaStream_t st);
 int loss_dF(const float* F, const float* TF, const float* vmask, const float* coef, const float* gscale,

@@ -164,3 +164,30 @@ def test_large_batch_properties():
     assert abs(float(loss) - float(loss2)) < 1e-5 * abs(float(loss))
     assert torch.allclose(aux2["f"], aux["f"][perm], rtol=1e-5, atol=1e-6)
     assert rel(method.model.base.ws[0].grad.cpu().numpy(), g0.cpu().numpy()) < 1e-5
+
+
+def test_spectrum_evd_matches_oracle():
+    # methods/spectrum.py:29-102 on a small validation grid that contains the origin (hydrogen: V = -inf there)
+    cfg = O.PathConfig.hydrogen(neigs=4, fourier_mapping_size=64)
+    N.set_engine("fp32")
+    method, operator, importance, _ = build_problem(cfg, 11, "cuda")
+    lim, eps = 4.0, 0.25
+    ax = np.arange(-lim, lim, eps)
+    xx, yy = np.meshgrid(ax, ax)
+    grid = torch.tensor(np.stack([xx.ravel(), yy.ravel()], 1)).float()
+    assert (grid.abs().sum(1) == 0).any()
+
+    def loader():
+        for i in range(0, len(grid), 300):
+            yield grid[i:i + 300], 0.0
+
+    def importance_val(x):
+        return (1 / (2 * lim) ** 2 * torch.ones(x.shape[0], 1)).to(x.device).float()
+
+    out = N.compute_spectrum_evd(method, loader(), operator, importance_train=importance,
+                                 importance_val=importance_val, device="cuda")
+    params = {n: p.detach().cpu().numpy().astype(np.float64) for n, p in method.named_parameters()}
+    ref = O.spectrum_evd(grid.numpy().astype(np.float64), params, cfg, lim, chunk=300)
+    assert rel(out["cov"], ref["cov"]) < TOL and rel(out["quad"], ref["quad"]) < TOL
+    assert rel(out["eigvals"], ref["eigvals"]) < TOL and rel(out["norms"], ref["norms"]) < TOL
+    assert out["eigfuncs"].shape == (len(grid), 4)
