@@ -247,6 +247,195 @@ big_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// S1 on CTA pairs (cta_group::2): the two SMs of a cluster share one 256 x 256 tile.  CTA r owns rows
+// [128 r, 128 r + 128) of the M tile (K-major) or copy 2 b + r (MN-major weight gradient) and loads only
+// half of the B tile (128 of the 256 N rows); the leader issues tcgen05.mma.cta_group::2 (M = 256) which
+// reads A from each CTA's own shared memory and B from both.  Per SM this halves the B-operand shared
+// memory traffic (operand reads 64 B/clk + TMA fills 42 B/clk instead of 96 + 62), which is what
+// limited the single-CTA kernel, and the smaller stage (64 KB) allows a 3-deep ring.
+// ------------------------------------------------------------------------------------------
+namespace big2 {
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 3;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB per plane
+constexpr int BH_BYTES = (BN / 2) * BK * 2;   // 16 KB per plane (this CTA's half of B)
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (4 + EPI_WARPS) * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+}  // namespace big2
+
+template <bool kMN, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(big2::THREADS, 1)
+big2_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                 const BigShape shape, const int batches_valid, const Epi epi) {
+  using namespace big2;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                   // [STAGES]  (the leader's are used)
+  uint64_t* empty = bars + STAGES;         // [STAGES]  (each CTA waits on its own)
+  uint64_t* tfull = bars + 2 * STAGES;     // [2]       (each CTA waits on its own)
+  uint64_t* tempty = tfull + 2;            // [2]       (the leader's are used, 2 x EPI_WARPS arrivals)
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int num_tiles = shape.m_tiles * shape.n_tiles * shape.batches * shape.k_slices;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAh);
+    tma_prefetch_desc(&tmAl);
+    tma_prefetch_desc(&tmBh);
+    tma_prefetch_desc(&tmBl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        TileCoord c = decode_tile(shape, t);
+        const int kc0 = c.ks * shape.k_chunks_per_slice;
+        int kc1 = kc0 + shape.k_chunks_per_slice;
+        if (kc1 > shape.k_chunks_total) kc1 = shape.k_chunks_total;
+        const int bpair = kMN ? 2 * c.b + (int)rank : c.b;
+        const int ab = shape.a_batched ? bpair : 0, bb = shape.b_batched ? c.b : 0;
+        for (int kc = kc0; kc < kc1; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1, 31);
+          uint8_t* sA = smem + stage * STAGE_BYTES;
+          uint8_t* sB = sA + 2 * A_BYTES;
+          const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+          if (!kMN) {
+            const int arow = (2 * c.mt + (int)rank) * BM, brow = c.nt * BN + (int)rank * (BN / 2);
+            tma_load_3d_pair(sA, &tmAh, lead_full, kc * BK, arow, ab);
+            tma_load_3d_pair(sA + A_BYTES, &tmAl, lead_full, kc * BK, arow, ab);
+            tma_load_3d_pair(sB, &tmBh, lead_full, kc * BK, brow, bb);
+            tma_load_3d_pair(sB + BH_BYTES, &tmBl, lead_full, kc * BK, brow, bb);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              tma_load_3d_pair(sA + i * 8192, &tmAh, lead_full, c.mt * BM + i * 64, kc * BK, ab);
+              tma_load_3d_pair(sA + A_BYTES + i * 8192, &tmAl, lead_full, c.mt * BM + i * 64, kc * BK, ab);
+              const int ncol = c.nt * BN + ((int)rank * 2 + i) * 64;
+              tma_load_3d_pair(sB + i * 8192, &tmBh, lead_full, ncol, kc * BK, bb);
+              tma_load_3d_pair(sB + BH_BYTES + i * 8192, &tmBl, lead_full, ncol, kc * BK, bb);
+            }
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, kMN ? 1 : 0, kMN ? 1 : 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        TileCoord c = decode_tile(shape, t);
+        const int kc0 = c.ks * shape.k_chunks_per_slice;
+        int kc1 = kc0 + shape.k_chunks_per_slice;
+        if (kc1 > shape.k_chunks_total) kc1 = shape.k_chunks_total;
+        mbar_wait(&tempty[acc], acc_phase ^ 1, 32);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kc = kc0; kc < kc1; ++kc) {
+          mbar_wait(&full[stage], phase, 33);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sB = sA + 2 * A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            uint64_t ah, al, bh, bl;
+            if (!kMN) {
+              ah = make_sdesc_sw128(sA + kk * 32, 16, 1024);
+              al = make_sdesc_sw128(sA + A_BYTES + kk * 32, 16, 1024);
+              bh = make_sdesc_sw128(sB + kk * 32, 16, 1024);
+              bl = make_sdesc_sw128(sB + BH_BYTES + kk * 32, 16, 1024);
+            } else {
+              ah = make_sdesc_sw128(sA + kk * 2048, 8192, 1024);
+              al = make_sdesc_sw128(sA + A_BYTES + kk * 2048, 8192, 1024);
+              bh = make_sdesc_sw128(sB + kk * 2048, 8192, 1024);
+              bl = make_sdesc_sw128(sB + BH_BYTES + kk * 2048, 8192, 1024);
+            }
+            umma_f16_pair(d_tmem, al, bh, idesc, (kc > kc0 || kk > 0) ? 1u : 0u);
+            umma_f16_pair(d_tmem, ah, bl, idesc, 1u);
+            umma_f16_pair(d_tmem, ah, bh, idesc, 1u);
+          }
+          umma_commit_pair(&empty[stage]);   // frees the stage in both CTAs
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tfull[acc]);       // accumulators of both CTAs complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (both CTAs, own TMEM half) =====================
+    const int ewarp = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      TileCoord c = decode_tile(shape, t);
+      bool valid = true;
+      if (kMN) {
+        c.b = 2 * c.b + (int)rank;
+        valid = c.b < batches_valid;
+      } else {
+        c.mt = 2 * c.mt + (int)rank;
+      }
+      mbar_wait(&tfull[acc], acc_phase, 34);
+      tc_fence_after();
+      if (valid) epi(tmem_base + acc * BN, c, ewarp, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still arrive on our barriers / read our shared memory until here
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // plain epilogue: D[b][row][col] = acc   (self-test / generic GEMM)
 struct StoreEpi {
   float* D;
@@ -305,9 +494,39 @@ static int launch_big(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
   return 0;
 }
 
+template <bool kMN, class Epi>
+static int launch_big2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                       const BigShape& shape, int batches_valid, const Epi& epi, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = big2_gemm_kernel<kMN, Epi>;
+  if (!configured) {
+    NSVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, big2::SMEM_BYTES));
+    configured = true;
+  }
+  int tiles = shape.m_tiles * shape.n_tiles * shape.batches * shape.k_slices;
+  if (tiles <= 0) return 0;
+  int clusters = tiles < 74 ? tiles : 74;
+  kern<<<2 * clusters, big2::THREADS, big2::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, batches_valid, epi);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// CTA pairs are the default for the two layer-0 GEMMs; NSVD_TC_PAIR=0 selects the single-CTA kernel.
+static bool tc_use_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NSVD_TC_PAIR");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int K, int a_kmajor, int b_kmajor,
                      void* work, size_t work_bytes, cudaStream_t st) {
   NSVD_CHECK_ARG(a_kmajor == b_kmajor, "selftest: both operands must share the major mode");
+  const bool pair = a_kmajor >= 2;   // 2 / 3 = MN- / K-major on the CTA-pair kernel
+  a_kmajor &= 1;
+  b_kmajor &= 1;
   NSVD_CHECK_ARG(M % 8 == 0 && N % 8 == 0 && K % 8 == 0, "selftest: M, N, K must be multiples of 8");
   size_t na = (size_t)M * K, nb = (size_t)N * K;
   size_t need = 2 * (na + nb) * sizeof(__nv_bfloat16) + 1024;
@@ -337,6 +556,12 @@ int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int
     if ((rc = make_tmap_bf16_3d(&mah, ah, K, M, 1, (uint64_t)K * 2, (uint64_t)M * K * 2, 64, big::BM))) return rc;
     if ((rc = make_tmap_bf16_3d(&mal, al, K, M, 1, (uint64_t)K * 2, (uint64_t)M * K * 2, 64, big::BM))) return rc;
     if ((rc = make_tmap_bf16_3d(&mbh, bh, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN))) return rc;
+    if (pair) {
+      if ((rc = make_tmap_bf16_3d(&mbh, bh, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN / 2))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mbl, bl, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN / 2))) return rc;
+      s.m_tiles = cdiv(M, 2 * big::BM);
+      return launch_big2<false>(mah, mal, mbh, mbl, s, 1, epi, st);
+    }
     if ((rc = make_tmap_bf16_3d(&mbl, bl, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN))) return rc;
     return launch_big<false>(mah, mal, mbh, mbl, s, epi, st);
   }
@@ -344,6 +569,12 @@ int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int
   if ((rc = make_tmap_bf16_3d(&mal, al, M, K, 1, (uint64_t)M * 2, (uint64_t)M * K * 2, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&mbh, bh, N, K, 1, (uint64_t)N * 2, (uint64_t)N * K * 2, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&mbl, bl, N, K, 1, (uint64_t)N * 2, (uint64_t)N * K * 2, 64, 64))) return rc;
+  if (pair) {   // MN-major pair kernel stacks two batches along M: here batch 1 does not exist (zero fill, skipped)
+    s.m_tiles = cdiv(M, big::BM);
+    s.a_batched = 1;
+    NSVD_CHECK_ARG(M <= big::BM, "selftest: MN-major pair mode takes M <= 128");
+    return launch_big2<true>(mah, mal, mbh, mbl, s, 1, epi, st);
+  }
   return launch_big<true>(mah, mal, mbh, mbl, s, epi, st);
 }
 
@@ -1271,8 +1502,10 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
   }
   delete prep;
   CUtensorMap mW0h, mW0l, mWh[2], mWl[2];
-  if ((rc = make_tmap_bf16_3d(&mW0h, wk + t.w0_hi, K0, 512, L, K0 * 2, 512 * K0 * 2, 64, big::BN))) return rc;
-  if ((rc = make_tmap_bf16_3d(&mW0l, wk + t.w0_lo, K0, 512, L, K0 * 2, 512 * K0 * 2, 64, big::BN))) return rc;
+  const bool pair = tc_use_pair();
+  const uint32_t w0_box = pair ? big::BN / 2 : big::BN;   // a CTA of a pair loads half of the 256 W' rows
+  if ((rc = make_tmap_bf16_3d(&mW0h, wk + t.w0_hi, K0, 512, L, K0 * 2, 512 * K0 * 2, 64, w0_box))) return rc;
+  if ((rc = make_tmap_bf16_3d(&mW0l, wk + t.w0_lo, K0, 512, L, K0 * 2, 512 * K0 * 2, 64, w0_box))) return rc;
   for (int i = 0; i < 2; ++i) {
     if ((rc = make_tmap_bf16_3d(&mWh[i], wk + t.w_hi[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
     if ((rc = make_tmap_bf16_3d(&mWl[i], wk + t.w_lo[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
@@ -1296,7 +1529,12 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
     L0FwdEpi e0{pr.b[0], BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), BF(sv + t.av_hi[0]), BF(sv + t.av_lo[0]), P, B, p0};
     {
       ProfScope ps(KC_L0_FWD, st);
-      if ((rc = launch_big<false>(mPh, mPl, mW0h, mW0l, s, e0, st))) return rc;
+      if (pair) {
+        s.m_tiles = cdiv(P, 2 * big::BM);
+        if ((rc = launch_big2<false>(mPh, mPl, mW0h, mW0l, s, (int)L, e0, st))) return rc;
+      } else {
+        if ((rc = launch_big<false>(mPh, mPl, mW0h, mW0l, s, e0, st))) return rc;
+      }
     }
     // ---- hidden layers 1, 2
     for (int i = 0; i < 2; ++i) {
@@ -1422,7 +1660,12 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
     L0WgradEpi ew{gr.dW[0], (int)K0};
     {
       ProfScope ps(KC_L0_WGRAD, st);
-      if ((rc = launch_big<true>(mZh, mZl, mPh, mPl, s, ew, st))) return rc;
+      if (tc_use_pair()) {
+        s.batches = cdiv(L, 2);   // a CTA pair stacks two copies along M
+        if ((rc = launch_big2<true>(mZh, mZl, mPh, mPl, s, (int)L, ew, st))) return rc;
+      } else {
+        if ((rc = launch_big<true>(mZh, mZl, mPh, mPl, s, ew, st))) return rc;
+      }
     }
   }
   return 0;

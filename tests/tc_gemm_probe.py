@@ -4,7 +4,9 @@ import ctypes as C
 import subprocess
 import sys
 
-CASES = [  # M, N, K, kmajor
+CASES = [  # M, N, K, mode: 1 = K-major, 0 = MN-major, 3 / 2 = the same on the CTA-pair (cta_group::2) kernel
+    (256, 256, 64, 3), (256, 512, 2048, 3), (200, 264, 72, 3), (1024, 1024, 512, 3), (2048, 4096, 2048, 3),
+    (128, 256, 64, 2), (128, 2048, 1024, 2), (128, 264, 200, 2), (128, 512, 4096, 2),
     (128, 256, 64, 1), (128, 256, 256, 1), (256, 512, 2048, 1), (200, 264, 72, 1), (1024, 1024, 512, 1),
     (128, 256, 64, 0), (128, 256, 256, 0), (128, 2048, 1024, 0), (128, 264, 200, 0), (256, 512, 4096, 0),
 ]
@@ -19,21 +21,23 @@ def run_case(M, N, K, kmajor):
     A = torch.randn(M, K, generator=g)
     B = torch.randn(N, K, generator=g)
     ref = (A.double() @ B.double().T)
+    mode = kmajor
+    kmajor = mode & 1
     Ad = (A if kmajor else A.T.contiguous()).cuda()
     Bd = (B if kmajor else B.T.contiguous()).cuda()
     D = torch.full((M, N), float("nan"), device="cuda")
     work = torch.empty(4 * (M * K + N * K) + 4096, dtype=torch.uint8, device="cuda")
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    rc = lib.nsvd_tc_gemm_selftest(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(D), M, N, K, kmajor, kmajor, _lib.ptr(work),
+    rc = lib.nsvd_tc_gemm_selftest(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(D), M, N, K, mode, mode, _lib.ptr(work),
                                    work.numel(), st)
     if rc:
-        print(f"case {M}x{N}x{K} kmajor={kmajor}: rc={rc} {lib.nsvd_last_error()}")
+        print(f"case {M}x{N}x{K} mode={mode}: rc={rc} {lib.nsvd_last_error()}")
         return
     torch.cuda.synchronize()
     Dh = D.cpu().double()
     err = (Dh - ref).norm() / ref.norm()
     nan = int(torch.isnan(Dh).sum())
-    print(f"case {M}x{N}x{K} kmajor={kmajor}: rel_err={err:.3e} nans={nan}")
+    print(f"case {M}x{N}x{K} mode={mode}: rel_err={err:.3e} nans={nan}")
     if not (err < 1e-4):
         Dh = torch.nan_to_num(Dh)
         e = (Dh - ref).abs()
