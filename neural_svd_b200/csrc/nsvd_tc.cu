@@ -70,17 +70,42 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barrier
 }  // namespace big
 
 struct BigShape {
-  int m_tiles, n_tiles, batches, k_slices;  // tile index: mt fastest, then ks, nt, batch
+  int m_tiles, n_tiles, batches, k_slices;  // tile index: mt (inside an m-group) fastest, then ks, nt, batch, m-group
   int k_chunks_per_slice, k_chunks_total;
   int a_batched, b_batched;                 // third TMA coordinate = batch index or 0
+  int m_group;                              // m-tiles per group (0 = all): keeps the A rows of a group L2-resident
+                                            // while every (batch, n-tile) of B sweeps over them
+  int k_group;                              // k-slices per group (0 = off): same idea for the weight-gradient GEMM,
+                                            // whose long dimension is K (points)
 };
 struct TileCoord {
   int b, nt, ks, mt;
 };
 __device__ __forceinline__ TileCoord decode_tile(const BigShape& s, int t) {
   TileCoord c;
-  c.mt = t % s.m_tiles;
-  t /= s.m_tiles;
+  if (s.k_group > 0) {   // k-slice groups outermost; inside a group: ks fastest, then mt, nt, batch
+    const int G = s.k_group;
+    const int per_group_full = G * s.m_tiles * s.n_tiles * s.batches;
+    const int g = t / per_group_full;
+    t -= g * per_group_full;
+    const int k0 = g * G;
+    const int gk = (s.k_slices - k0) < G ? (s.k_slices - k0) : G;
+    c.ks = k0 + t % gk;
+    t /= gk;
+    c.mt = t % s.m_tiles;
+    t /= s.m_tiles;
+    c.nt = t % s.n_tiles;
+    c.b = t / s.n_tiles;
+    return c;
+  }
+  const int G = s.m_group > 0 ? s.m_group : s.m_tiles;
+  const int per_group_full = G * s.k_slices * s.n_tiles * s.batches;
+  const int g = t / per_group_full;
+  t -= g * per_group_full;
+  const int m0 = g * G;
+  const int gm = (s.m_tiles - m0) < G ? (s.m_tiles - m0) : G;   // tiles in this (possibly last, smaller) group
+  c.mt = m0 + t % gm;
+  t /= gm;
   c.ks = t % s.k_slices;
   t /= s.k_slices;
   c.nt = t % s.n_tiles;
@@ -1401,7 +1426,7 @@ static int tc_micro_batch() {
   static int mb = 0;
   if (!mb) {
     const char* e = getenv("NSVD_TC_MICROBATCH");
-    mb = e ? atoi(e) : 8192;
+    mb = e ? atoi(e) : 65536;
     if (mb < 128) mb = 128;
     mb = (mb + 127) / 128 * 128;
   }
@@ -1526,6 +1551,7 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
     s.k_chunks_per_slice = s.k_chunks_total;
     s.a_batched = 0;
     s.b_batched = 1;
+    s.m_group = pair ? 16 : 32;   // 4096 points x 8 KB of Phi per group
     L0FwdEpi e0{pr.b[0], BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), BF(sv + t.av_hi[0]), BF(sv + t.av_lo[0]), P, B, p0};
     {
       ProfScope ps(KC_L0_FWD, st);
@@ -1657,6 +1683,7 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
     s.k_slices = cdiv(s.k_chunks_total, s.k_chunks_per_slice);
     s.a_batched = 1;
     s.b_batched = 0;
+    s.k_group = 4;   // 4096 points per group: dZ0 (all copies) + Phi of a group stay in L2
     L0WgradEpi ew{gr.dW[0], (int)K0};
     {
       ProfScope ps(KC_L0_WGRAD, st);
