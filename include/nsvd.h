@@ -150,18 +150,22 @@ int nsvd_mlp_bwd(const nsvd_problem_t* pb, const nsvd_params_t* pr, int engine, 
  *   fwd: terms = [Fp^T Fp | Gp^T Gp | sum v f g] un-normalised (all-reducible), then
  *   nsvd_cdk_finalize -> losses[3] = {loss, loss_operator, loss_metric}, coef (2*Lp*Lp);
  *   bwd: grad_f, grad_g (B, L).  rs_joint (B) = diag(Fp Gp^T) is produced by fwd when non-NULL;
- *   nsvd_cdk_offdiag writes off_diagonal(Fp Gp^T) (B*B-B) on request (methods/utils.py:16-22). */
-size_t nsvd_cdk_work_bytes(int32_t n_rows, int32_t n_feat, int32_t first_const);
+ *   nsvd_cdk_offdiag writes off_diagonal(Fp Gp^T) (B*B-B) on request (methods/utils.py:16-22).
+ *   With NSVD_ENGINE_BF16X3_TC the Grams (MN-major operands, K = rows), the backward GEMMs and
+ *   Fp Gp^T run on the tcgen05 GEMM block; the row dots stay exact fp32.                        */
+size_t nsvd_cdk_work_bytes(int32_t n_rows, int32_t n_feat, int32_t first_const, int engine);
 int nsvd_cdk_fwd(const float* f, const float* g, const float* vector_mask, int32_t n_rows,
-                 int32_t n_feat, int32_t first_const, float* terms, float* rs_joint, void* work,
-                 size_t work_bytes, void* stream);
+                 int32_t n_feat, int32_t first_const, int engine, float* terms, float* rs_joint,
+                 void* work, size_t work_bytes, void* stream);
 int nsvd_cdk_finalize(const float* terms, const float* matrix_mask, int32_t Lp, int64_t Bg,
                       float* losses, float* coef, void* stream);
 int nsvd_cdk_bwd(const float* f, const float* g, const float* vector_mask, const float* coef,
                  const float* grad_scale, int32_t n_rows, int32_t n_feat, int32_t first_const,
-                 int64_t Bg, float* grad_f, float* grad_g, void* stream);
+                 int64_t Bg, int engine, float* grad_f, float* grad_g, void* work, size_t work_bytes,
+                 void* stream);
 int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_feat,
-                     int32_t first_const, float* rs_indep, void* stream);
+                     int32_t first_const, int engine, float* rs_indep, void* work, size_t work_bytes,
+                     void* stream);
 
 /* Self-test hooks for the tcgen05 building block (tests/test_gpu_tc_gemm.py):
  *   D (M,N) fp32 = A . B^T with bf16x3 splitting; A (M,K), B (N,K) fp32 when *_kmajor = 1,

@@ -53,11 +53,11 @@ SIGNATURES = {
     "nsvd_loss_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
     "nsvd_loss_dF": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp]),
     "nsvd_mlp_bwd": (C.c_int, [_PB, _PR, C.c_int, _vp, _vp, _vp, _sz, _GR, _vp, _sz, _vp]),
-    "nsvd_cdk_work_bytes": (_sz, [_i32, _i32, _i32]),
-    "nsvd_cdk_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "nsvd_cdk_work_bytes": (_sz, [_i32, _i32, _i32, C.c_int]),
+    "nsvd_cdk_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, C.c_int, _vp, _vp, _vp, _sz, _vp]),
     "nsvd_cdk_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
-    "nsvd_cdk_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp]),
-    "nsvd_cdk_offdiag": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "nsvd_cdk_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, C.c_int, _vp, _vp, _vp, _sz, _vp]),
+    "nsvd_cdk_offdiag": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_int, _vp, _vp, _sz, _vp]),
     "nsvd_tc_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
 }
 

@@ -180,18 +180,28 @@ int nsvd_loss_dF(const float* F, const float* TF, const float* vector_mask, cons
   return loss_dF(F, TF, vector_mask, coef, grad_scale, n_points, n_copies, b1, Bg, dF, (cudaStream_t)stream);
 }
 
-size_t nsvd_cdk_work_bytes(int32_t n_rows, int32_t n_feat, int32_t first_const) {
-  return cdk_work_bytes(n_rows, n_feat, first_const);
+size_t nsvd_cdk_work_bytes(int32_t n_rows, int32_t n_feat, int32_t first_const, int engine) {
+  return engine == NSVD_ENGINE_BF16X3_TC ? tc_cdk_work_bytes(n_rows, n_feat, first_const)
+                                         : cdk_work_bytes(n_rows, n_feat, first_const);
 }
-int nsvd_cdk_fwd(const float* f, const float* g, const float* vector_mask, int32_t n_rows, int32_t n_feat,
-                 int32_t first_const, float* terms, float* rs_joint, void* work, size_t work_bytes,
-                 void* stream) {
-  NSVD_CHECK_ARG(f && g && vector_mask && terms && work, "NULL buffer");
-  NSVD_CHECK_ARG(n_rows >= 1 && n_feat >= 1 && (first_const == 0 || first_const == 1), "bad shape");
-  if (work_bytes < cdk_work_bytes(n_rows, n_feat, first_const)) {
-    set_error("cdk work too small");
+static int cdk_check(int engine, const void* work, size_t work_bytes, int n_rows, int n_feat, int fc) {
+  NSVD_CHECK_ARG(engine == NSVD_ENGINE_FP32_SIMT || engine == NSVD_ENGINE_BF16X3_TC, "unknown engine %d", engine);
+  NSVD_CHECK_ARG(n_rows >= 2 && n_feat >= 1 && (fc == 0 || fc == 1), "bad shape");
+  NSVD_CHECK_ARG(work != nullptr, "work is NULL");
+  if (work_bytes < nsvd_cdk_work_bytes(n_rows, n_feat, fc, engine)) {
+    set_error("cdk work too small: %zu < %zu", work_bytes, nsvd_cdk_work_bytes(n_rows, n_feat, fc, engine));
     return NSVD_E_WORKSPACE;
   }
+  return 0;
+}
+int nsvd_cdk_fwd(const float* f, const float* g, const float* vector_mask, int32_t n_rows, int32_t n_feat,
+                 int32_t first_const, int engine, float* terms, float* rs_joint, void* work, size_t work_bytes,
+                 void* stream) {
+  NSVD_CHECK_ARG(f && g && vector_mask && terms, "NULL buffer");
+  int rc = cdk_check(engine, work, work_bytes, n_rows, n_feat, first_const);
+  if (rc) return rc;
+  if (engine == NSVD_ENGINE_BF16X3_TC)
+    return tc_cdk_fwd(f, g, vector_mask, n_rows, n_feat, first_const, terms, rs_joint, work, (cudaStream_t)stream);
   return cdk_fwd(f, g, vector_mask, n_rows, n_feat, first_const, terms, rs_joint, work, (cudaStream_t)stream);
 }
 int nsvd_cdk_finalize(const float* terms, const float* matrix_mask, int32_t Lp, int64_t Bg, float* losses,
@@ -200,15 +210,24 @@ int nsvd_cdk_finalize(const float* terms, const float* matrix_mask, int32_t Lp, 
   return cdk_finalize(terms, matrix_mask, Lp, Bg, losses, coef, (cudaStream_t)stream);
 }
 int nsvd_cdk_bwd(const float* f, const float* g, const float* vector_mask, const float* coef,
-                 const float* grad_scale, int32_t n_rows, int32_t n_feat, int32_t first_const, int64_t Bg,
-                 float* grad_f, float* grad_g, void* stream) {
+                 const float* grad_scale, int32_t n_rows, int32_t n_feat, int32_t first_const, int64_t Bg, int engine,
+                 float* grad_f, float* grad_g, void* work, size_t work_bytes, void* stream) {
   NSVD_CHECK_ARG(f && g && vector_mask && coef && grad_f && grad_g, "NULL buffer");
+  int rc = cdk_check(engine, work, work_bytes, n_rows, n_feat, first_const);
+  if (rc) return rc;
+  if (engine == NSVD_ENGINE_BF16X3_TC)
+    return tc_cdk_bwd(f, g, vector_mask, coef, grad_scale, n_rows, n_feat, first_const, Bg, grad_f, grad_g, work,
+                      (cudaStream_t)stream);
   return cdk_bwd(f, g, vector_mask, coef, grad_scale, n_rows, n_feat, first_const, Bg, grad_f, grad_g,
                  (cudaStream_t)stream);
 }
-int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_feat, int32_t first_const,
-                     float* rs_indep, void* stream) {
-  NSVD_CHECK_ARG(f && g && rs_indep && n_rows >= 2, "bad args");
+int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_feat, int32_t first_const, int engine,
+                     float* rs_indep, void* work, size_t work_bytes, void* stream) {
+  NSVD_CHECK_ARG(f && g && rs_indep, "NULL buffer");
+  int rc = cdk_check(engine, work, work_bytes, n_rows, n_feat, first_const);
+  if (rc) return rc;
+  if (engine == NSVD_ENGINE_BF16X3_TC)
+    return tc_cdk_offdiag(f, g, n_rows, n_feat, first_const, rs_indep, work, (cudaStream_t)stream);
   return cdk_offdiag(f, g, n_rows, n_feat, first_const, rs_indep, (cudaStream_t)stream);
 }
 

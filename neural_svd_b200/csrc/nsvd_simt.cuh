@@ -35,6 +35,8 @@ int loss_dF(const float* F, const float* TF, const float* vmask, const float* co
             int B, int L, int b1, long Bg, float* dF, cudaStream_t st);
 
 size_t cdk_work_bytes(int B, int L, int fc);
+int cdk_pad_rowdots(const float* f, const float* g, const float* v, int B, int L, int fc, float* fp, float* gp,
+                    float* opdot, float* rs_joint, cudaStream_t st);
 int cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int fc, float* terms,
             float* rs_joint, void* work, cudaStream_t st);
 int cdk_finalize(const float* terms, const float* Mm, int Lp, long Bg, float* losses, float* coef,
@@ -49,6 +51,12 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
                void* saved, void* work, size_t work_bytes, cudaStream_t st);
 int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x, const float* dF,
                 const void* saved, nsvd_grads_t& gr, void* work, size_t work_bytes, cudaStream_t st);
+size_t tc_cdk_work_bytes(int B, int L, int fc);
+int tc_cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int fc, float* terms, float* rs_joint,
+               void* work, cudaStream_t st);
+int tc_cdk_bwd(const float* f, const float* g, const float* v, const float* coef, const float* gscale, int B, int L,
+               int fc, long Bg, float* grad_f, float* grad_g, void* work, cudaStream_t st);
+int tc_cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* out, void* work, cudaStream_t st);
 int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int K, int a_kmajor,
                      int b_kmajor, void* work, size_t work_bytes, cudaStream_t st);
 

@@ -1698,4 +1698,237 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// CDK loss on the tcgen05 GEMM block (methods/nestedlora.py:270-332; BASELINE config 5:
+// B = 4096, L = 512 (+1 constant mode)).  Operand planes are [rows][Lpad] bf16 hi/lo with the
+// constant-1 column in front and zero padding up to a multiple of 8 columns (TMA stride rule).
+// ------------------------------------------------------------------------------------------
+static inline long cdk_lpad(int Lp) { return (Lp + 7) / 8 * 8; }
+
+// planes of the padded inputs: out[b][c] = (fc && c == 0) ? 1 : in[b][c - fc] ; zero for c >= Lp
+__global__ void cdk_planes_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long B, int L, int fc, int Lpad) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Lpad) return;
+  long b = i / Lpad;
+  int c = (int)(i % Lpad);
+  float v = 0.f;
+  if (c < L + fc) v = (fc && c == 0) ? 1.f : in[b * L + c - fc];
+  __nv_bfloat16 a, d;
+  tc::split_bf16(v, a, d);
+  hi[i] = a;
+  lo[i] = d;
+}
+// transposed coefficient planes: out[which][c][i] = coef[which][i][c]  (K-major B operand of the backward GEMM)
+__global__ void cdk_coefT_planes_kernel(const float* __restrict__ coef, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo, int Lp, int Lpad) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n = 2L * Lp * Lpad;
+  if (i >= n) return;
+  int k = (int)(i % Lpad);
+  int c = (int)((i / Lpad) % Lp);
+  int w = (int)(i / ((long)Lpad * Lp));
+  float v = k < Lp ? coef[(long)w * Lp * Lp + (long)k * Lp + c] : 0.f;
+  __nv_bfloat16 a, d;
+  tc::split_bf16(v, a, d);
+  hi[i] = a;
+  lo[i] = d;
+}
+
+// grad[b][c - fc] = gs * ( acc[b][c] - c2 v[c] other[b][c - fc] )
+struct CdkBwdEpi {
+  float* grad;
+  const float* other;
+  const float* v;
+  const float* gscale;
+  int B, L, fc;
+  float c2;
+  __device__ __forceinline__ void operator()(uint32_t tmem_acc, const TileCoord& c, int ewarp, int lane) const {
+    const int q = ewarp & 3, half = ewarp >> 2;
+    const int b = c.mt * big::BM + q * 32 + lane;
+    const float gs = gscale ? gscale[0] : 1.f;
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ++ch) {
+      const int col0 = half * 128 + ch * 16;
+      float a[16];
+      tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, a);
+      tc::tmem_ld_wait();
+      if (b < B) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          int cc = c.nt * big::BN + col0 + i;
+          if (cc >= fc && cc < L + fc) {
+            long o = (long)b * L + cc - fc;
+            grad[o] = gs * (a[i] - c2 * v[cc] * other[o]);
+          }
+        }
+      }
+    }
+  }
+};
+
+// off_diagonal(Fp Gp^T): out[i (B-1) + j - (j > i)] = acc[i][j], i != j   (methods/utils.py:16-22)
+struct CdkOffdiagEpi {
+  float* out;
+  int B;
+  __device__ __forceinline__ void operator()(uint32_t tmem_acc, const TileCoord& c, int ewarp, int lane) const {
+    const int q = ewarp & 3, half = ewarp >> 2;
+    const int i = c.mt * big::BM + q * 32 + lane;
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ++ch) {
+      const int col0 = half * 128 + ch * 16;
+      float a[16];
+      tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, a);
+      tc::tmem_ld_wait();
+      if (i < B) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          int j = c.nt * big::BN + col0 + k;
+          if (j < B && j != i) out[(long)i * (B - 1) + j - (j > i ? 1 : 0)] = a[k];
+        }
+      }
+    }
+  }
+};
+
+struct CdkLayout {
+  size_t fp32_f, fp32_g, opdot, f_hi, f_lo, g_hi, g_lo, c_hi, c_lo, total;
+};
+static CdkLayout cdk_layout(long B, int L, int fc) {
+  CdkLayout t{};
+  const long Lp = L + fc, Lpad = cdk_lpad((int)Lp);
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o += align_up(bytes, 1024);
+    return r;
+  };
+  t.fp32_f = take(B * Lp * 4);
+  t.fp32_g = take(B * Lp * 4);
+  t.opdot = take(B * 4);
+  t.f_hi = take(B * Lpad * 2);
+  t.f_lo = take(B * Lpad * 2);
+  t.g_hi = take(B * Lpad * 2);
+  t.g_lo = take(B * Lpad * 2);
+  t.c_hi = take(2 * Lp * Lpad * 2);
+  t.c_lo = take(2 * Lp * Lpad * 2);
+  t.total = o + 1024;
+  return t;
+}
+size_t tc_cdk_work_bytes(int B, int L, int fc) { return cdk_layout(B, L, fc).total; }
+
+static int cdk_make_planes(const float* f, const float* g, long B, int L, int fc, uint8_t* wk, const CdkLayout& t,
+                           cudaStream_t st) {
+  const int Lpad = (int)cdk_lpad(L + fc);
+  long n = B * Lpad;
+  cdk_planes_kernel<<<cdiv(n, 256), 256, 0, st>>>(f, BF(wk + t.f_hi), BF(wk + t.f_lo), B, L, fc, Lpad);
+  NSVD_LAUNCH_CHECK();
+  cdk_planes_kernel<<<cdiv(n, 256), 256, 0, st>>>(g, BF(wk + t.g_hi), BF(wk + t.g_lo), B, L, fc, Lpad);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc_cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int fc, float* terms, float* rs_joint,
+               void* work, cudaStream_t st) {
+  const int Lp = L + fc, Lpad = (int)cdk_lpad(Lp);
+  CdkLayout t = cdk_layout(B, L, fc);
+  uint8_t* wk = align1k(work);
+  int rc;
+  // exact fp32 row dots (operator term, diag(Fp Gp^T)) on the padded fp32 copies
+  float* fp = reinterpret_cast<float*>(wk + t.fp32_f);
+  float* gp = reinterpret_cast<float*>(wk + t.fp32_g);
+  float* opdot = reinterpret_cast<float*>(wk + t.opdot);
+  if ((rc = cdk_pad_rowdots(f, g, v, B, L, fc, fp, gp, opdot, rs_joint, st))) return rc;
+  // Grams: X^T X with both operands MN-major straight from the [B][Lpad] planes, K = rows in slices
+  if ((rc = cdk_make_planes(f, g, B, L, fc, wk, t, st))) return rc;
+  NSVD_CUDA(cudaMemsetAsync(terms, 0, sizeof(float) * 2L * Lp * Lp, st));
+  if ((rc = colsum(opdot, terms + 2L * Lp * Lp, B, 1, 1, 0, 0, st))) return rc;
+  for (int which = 0; which < 2; ++which) {
+    const uint8_t* ph = wk + (which ? t.g_hi : t.f_hi);
+    const uint8_t* pl = wk + (which ? t.g_lo : t.f_lo);
+    CUtensorMap mh, ml;
+    if ((rc = make_tmap_bf16_3d(&mh, ph, Lpad, B, 1, (uint64_t)Lpad * 2, (uint64_t)B * Lpad * 2, 64, 64))) return rc;
+    if ((rc = make_tmap_bf16_3d(&ml, pl, Lpad, B, 1, (uint64_t)Lpad * 2, (uint64_t)B * Lpad * 2, 64, 64))) return rc;
+    BigShape s{};
+    s.m_tiles = cdiv(Lp, big::BM);
+    s.n_tiles = cdiv(Lp, big::BN);
+    s.batches = 1;
+    s.k_chunks_total = cdiv(B, big::BK);
+    s.k_chunks_per_slice = 8;
+    s.k_slices = cdiv(s.k_chunks_total, s.k_chunks_per_slice);
+    StoreEpi epi{terms + (long)which * Lp * Lp, Lp, Lp, 0, 1};
+    if ((rc = launch_big<true>(mh, ml, mh, ml, s, epi, st))) return rc;
+  }
+  return 0;
+}
+
+int tc_cdk_bwd(const float* f, const float* g, const float* v, const float* coef, const float* gscale, int B, int L,
+               int fc, long Bg, float* grad_f, float* grad_g, void* work, cudaStream_t st) {
+  const int Lp = L + fc, Lpad = (int)cdk_lpad(Lp);
+  CdkLayout t = cdk_layout(B, L, fc);
+  uint8_t* wk = align1k(work);
+  int rc;
+  if ((rc = cdk_make_planes(f, g, B, L, fc, wk, t, st))) return rc;
+  long nc = 2L * Lp * Lpad;
+  cdk_coefT_planes_kernel<<<cdiv(nc, 256), 256, 0, st>>>(coef, BF(wk + t.c_hi), BF(wk + t.c_lo), Lp, Lpad);
+  NSVD_LAUNCH_CHECK();
+  const bool pair = tc_use_pair();
+  const float c2 = (float)(2.0 / (double)Bg);
+  for (int which = 0; which < 2; ++which) {
+    const uint8_t* xh = wk + (which ? t.g_hi : t.f_hi);
+    const uint8_t* xl = wk + (which ? t.g_lo : t.f_lo);
+    const uint8_t* ch = wk + t.c_hi + (size_t)which * Lp * Lpad * 2;
+    const uint8_t* cl = wk + t.c_lo + (size_t)which * Lp * Lpad * 2;
+    CUtensorMap mah, mal, mbh, mbl;
+    const uint32_t bbox = pair ? big::BN / 2 : big::BN;
+    if ((rc = make_tmap_bf16_3d(&mah, xh, Lpad, B, 1, (uint64_t)Lpad * 2, (uint64_t)B * Lpad * 2, 64, big::BM))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mal, xl, Lpad, B, 1, (uint64_t)Lpad * 2, (uint64_t)B * Lpad * 2, 64, big::BM))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mbh, ch, Lpad, Lp, 1, (uint64_t)Lpad * 2, (uint64_t)Lp * Lpad * 2, 64, bbox))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mbl, cl, Lpad, Lp, 1, (uint64_t)Lpad * 2, (uint64_t)Lp * Lpad * 2, 64, bbox))) return rc;
+    BigShape s{};
+    s.n_tiles = cdiv(Lp, big::BN);
+    s.batches = 1;
+    s.k_slices = 1;
+    s.k_chunks_total = cdiv(Lpad, big::BK);
+    s.k_chunks_per_slice = s.k_chunks_total;
+    CdkBwdEpi epi{which ? grad_g : grad_f, which ? f : g, v, gscale, B, L, fc, c2};
+    if (pair) {
+      s.m_tiles = cdiv(B, 2 * big::BM);
+      if ((rc = launch_big2<false>(mah, mal, mbh, mbl, s, 1, epi, st))) return rc;
+    } else {
+      s.m_tiles = cdiv(B, big::BM);
+      if ((rc = launch_big<false>(mah, mal, mbh, mbl, s, epi, st))) return rc;
+    }
+  }
+  return 0;
+}
+
+int tc_cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* out, void* work, cudaStream_t st) {
+  const int Lp = L + fc, Lpad = (int)cdk_lpad(Lp);
+  CdkLayout t = cdk_layout(B, L, fc);
+  uint8_t* wk = align1k(work);
+  int rc;
+  if ((rc = cdk_make_planes(f, g, B, L, fc, wk, t, st))) return rc;
+  const bool pair = tc_use_pair();
+  const uint32_t bbox = pair ? big::BN / 2 : big::BN;
+  CUtensorMap mah, mal, mbh, mbl;
+  if ((rc = make_tmap_bf16_3d(&mah, wk + t.f_hi, Lpad, B, 1, (uint64_t)Lpad * 2, (uint64_t)B * Lpad * 2, 64, big::BM))) return rc;
+  if ((rc = make_tmap_bf16_3d(&mal, wk + t.f_lo, Lpad, B, 1, (uint64_t)Lpad * 2, (uint64_t)B * Lpad * 2, 64, big::BM))) return rc;
+  if ((rc = make_tmap_bf16_3d(&mbh, wk + t.g_hi, Lpad, B, 1, (uint64_t)Lpad * 2, (uint64_t)B * Lpad * 2, 64, bbox))) return rc;
+  if ((rc = make_tmap_bf16_3d(&mbl, wk + t.g_lo, Lpad, B, 1, (uint64_t)Lpad * 2, (uint64_t)B * Lpad * 2, 64, bbox))) return rc;
+  BigShape s{};
+  s.n_tiles = cdiv(B, big::BN);
+  s.batches = 1;
+  s.k_slices = 1;
+  s.k_chunks_total = cdiv(Lpad, big::BK);
+  s.k_chunks_per_slice = s.k_chunks_total;
+  CdkOffdiagEpi epi{out, B};
+  if (pair) {
+    s.m_tiles = cdiv(B, 2 * big::BM);
+    return launch_big2<false>(mah, mal, mbh, mbl, s, 1, epi, st);
+  }
+  s.m_tiles = cdiv(B, big::BM);
+  return launch_big<false>(mah, mal, mbh, mbl, s, epi, st);
+}
+
 }  // namespace nsvd

@@ -176,9 +176,10 @@ class NestedLoRALossFunctionForCDK(torch.autograd.Function):
         st = _stream(dev)
         terms = torch.empty(2 * Lp * Lp + 1, dtype=torch.float32, device=dev)
         rs_joint = torch.empty(B, dtype=torch.float32, device=dev)
-        nwork = lib.nsvd_cdk_work_bytes(B, L, fc)
+        engine = _lib.ENGINES[fused.get_engine()]
+        nwork = lib.nsvd_cdk_work_bytes(B, L, fc, engine)
         work = torch.empty(nwork, dtype=torch.uint8, device=dev)
-        _lib.check(lib.nsvd_cdk_fwd(_lib.ptr(fd), _lib.ptr(gd), _lib.ptr(v), B, L, fc, _lib.ptr(terms),
+        _lib.check(lib.nsvd_cdk_fwd(_lib.ptr(fd), _lib.ptr(gd), _lib.ptr(v), B, L, fc, engine, _lib.ptr(terms),
                                     _lib.ptr(rs_joint), _lib.ptr(work), nwork, st), "nsvd_cdk_fwd")
         Bg = B
         if dp is not None:
@@ -189,12 +190,12 @@ class NestedLoRALossFunctionForCDK(torch.autograd.Function):
                    "nsvd_cdk_finalize")
         if diagnostics:
             rs_indep = torch.empty(B * B - B, dtype=torch.float32, device=dev)
-            _lib.check(lib.nsvd_cdk_offdiag(_lib.ptr(fd), _lib.ptr(gd), B, L, fc, _lib.ptr(rs_indep), st),
-                       "nsvd_cdk_offdiag")
+            _lib.check(lib.nsvd_cdk_offdiag(_lib.ptr(fd), _lib.ptr(gd), B, L, fc, engine, _lib.ptr(rs_indep),
+                                            _lib.ptr(work), nwork, st), "nsvd_cdk_offdiag")
         else:
             rs_indep = torch.empty(0, dtype=torch.float32, device=dev)
         ctx.save_for_backward(fd, gd, v, coef)
-        ctx.fc, ctx.Bg = fc, Bg
+        ctx.fc, ctx.Bg, ctx.engine, ctx.work = fc, Bg, engine, work
         ctx.mark_non_differentiable(rs_joint, rs_indep)
         return losses[0], losses[1], losses[2], rs_joint, rs_indep
 
@@ -207,7 +208,8 @@ class NestedLoRALossFunctionForCDK(torch.autograd.Function):
         gl = _dev_f32(grad_output, dev)
         gf, gg = torch.empty_like(fd), torch.empty_like(gd)
         _lib.check(lib.nsvd_cdk_bwd(_lib.ptr(fd), _lib.ptr(gd), _lib.ptr(v), _lib.ptr(coef), _lib.ptr(gl), B, L,
-                                    ctx.fc, ctx.Bg, _lib.ptr(gf), _lib.ptr(gg), _stream(dev)), "nsvd_cdk_bwd")
+                                    ctx.fc, ctx.Bg, ctx.engine, _lib.ptr(gf), _lib.ptr(gg), _lib.ptr(ctx.work),
+                                    ctx.work.numel(), _stream(dev)), "nsvd_cdk_bwd")
         return gf, gg, None, None, None, None, None, None
 
 

@@ -112,9 +112,11 @@ def test_standalone_loss_function_matches_oracle(B, L, seq):
     assert rel(fc.grad.cpu().numpy(), dF_o) < 1e-5
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", ["cdk_small_seq", "cdk_small_noconst"])
-def test_cdk_matches_reference_golden(name):
+def test_cdk_matches_reference_golden(name, engine):
     d, _ = load_golden(name)
+    N.set_engine(engine)
     m = N.NestedLoRAForCDK(None, int(d["L"]), step=1, sequential=bool(d["sequential"]),
                            set_first_mode_const=bool(d["const"]))
     f = torch.from_numpy(d["f"]).cuda().requires_grad_()
@@ -129,8 +131,10 @@ def test_cdk_matches_reference_golden(name):
     assert rsi.shape == (f.shape[0] ** 2 - f.shape[0],)
 
 
-def test_cdk_full_size_config5():
+@pytest.mark.parametrize("engine", ENGINES)
+def test_cdk_full_size_config5(engine):
     d, _ = load_golden("cdk_b4096_L512")
+    N.set_engine(engine)
     g = torch.Generator().manual_seed(int(d["seed"]))
     f = torch.randn(int(d["B"]), int(d["L"]), generator=g).cuda().requires_grad_()
     gg = torch.randn(int(d["B"]), int(d["L"]), generator=g).cuda().requires_grad_()
