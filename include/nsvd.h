@@ -167,6 +167,21 @@ int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_f
                      int32_t first_const, int engine, float* rs_indep, void* work, size_t work_bytes,
                      void* stream);
 
+/* ---- "next" rows of the scope table ------------------------------------------
+ * Fused optimizer step for up to 16 tensors in one launch: RMSprop with momentum 0 / weight decay 0
+ * (examples/utils.py:48-57: lr, alpha = rmsprop_decay, eps = 1e-10) followed by the torch_ema shadow
+ * update used by the loop (examples/operator/__init__.py:36,73):
+ *   sq = alpha sq + (1-alpha) g^2 ; p -= lr g / (sqrt(sq) + eps) ; ema -= w (ema - p), w = 1 - decay_t.
+ * The pointer tables are HOST arrays of device pointers; `ema` may be NULL.  The cosine learning-rate
+ * schedule (operator/__init__.py:35,71-72) is evaluated by the caller and passed as `lr`.        */
+int nsvd_rmsprop_ema_step(int32_t n_tensors, float* const* params, const float* const* grads,
+                          float* const* square_avg, float* const* ema, const int64_t* sizes, float lr,
+                          float alpha, float eps, float ema_one_minus_decay, void* stream);
+/* On-device Gaussian sampler x (n_points, 2) = sigma * N(0, I) (main_pde.py:92-93 draws on the CPU;
+ * that stays the RNG-parity mode).  Counter-based: reproducible for (seed, offset).               */
+int nsvd_sample_gaussian(float* x, int64_t n_points, float sigma, uint64_t seed, uint64_t offset,
+                         void* stream);
+
 /* Self-test hooks for the tcgen05 building block (tests/test_gpu_tc_gemm.py):
  *   D (M,N) fp32 = A . B^T with bf16x3 splitting; A (M,K), B (N,K) fp32 when *_kmajor = 1,
  *   A (K,M) / B (K,N) when 0 (MN-major operands, as the weight-gradient GEMMs use them).       */

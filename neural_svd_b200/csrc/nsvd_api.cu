@@ -231,6 +231,29 @@ int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_f
   return cdk_offdiag(f, g, n_rows, n_feat, first_const, rs_indep, (cudaStream_t)stream);
 }
 
+int nsvd_rmsprop_ema_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* square_avg,
+                          float* const* ema, const int64_t* sizes, float lr, float alpha, float eps,
+                          float ema_one_minus_decay, void* stream) {
+  NSVD_CHECK_ARG(n_tensors >= 1 && n_tensors <= 16, "n_tensors must be in [1,16] (got %d)", n_tensors);
+  NSVD_CHECK_ARG(params && grads && square_avg && sizes, "NULL table");
+  OptTensors t{};
+  t.n = n_tensors;
+  for (int i = 0; i < n_tensors; ++i) {
+    NSVD_CHECK_ARG(params[i] && grads[i] && square_avg[i] && sizes[i] >= 0, "tensor %d: NULL pointer or negative size", i);
+    t.p[i] = params[i];
+    t.g[i] = grads[i];
+    t.sq[i] = square_avg[i];
+    t.ema[i] = ema ? ema[i] : nullptr;
+    t.size[i] = sizes[i];
+  }
+  return rmsprop_ema_step(t, lr, alpha, eps, ema_one_minus_decay, (cudaStream_t)stream);
+}
+
+int nsvd_sample_gaussian(float* x, int64_t n_points, float sigma, uint64_t seed, uint64_t offset, void* stream) {
+  NSVD_CHECK_ARG(x && n_points >= 0 && sigma > 0.f, "bad args");
+  return sample_gaussian2(x, n_points, sigma, seed, offset, (cudaStream_t)stream);
+}
+
 int nsvd_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K,
                           int32_t a_kmajor, int32_t b_kmajor, void* work, size_t work_bytes, void* stream) {
   NSVD_CHECK_ARG(A && B && D && work, "NULL buffer");

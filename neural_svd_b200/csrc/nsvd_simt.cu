@@ -479,24 +479,28 @@ gram_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
   }
 }
 
-// L == 16 specialisation (the benchmark shape): warp-cooperative register tiling.
-//   lane = (ib, jb): 4 x 2 outputs G[4 ib + a][2 jb + c]; per row one 16-byte and one 8-byte load of
-//   the (L1-resident) 64-byte row, 8 FFMA; the operator sum is taken on a coalesced (row pair x 16)
-//   load.  8 warps interleave rows; one smem reduction per block at the end.
+// L == 16 specialisation (the benchmark shape): ONE launch for the whole K2.
+//   warp-cooperative register tiling: lane = (ib, jb) owns the 4 x 2 block G[4 ib + a][2 jb + c]; per row
+//   one 16-byte and one 8-byte load of the (L1-resident) 64-byte row and 8 FFMA; the operator sum is
+//   taken on a coalesced (row pair x 16) load.  Blocks [0, nb1) cover the first half of the rows, the
+//   rest the second half.  Each block writes a 257-float partial; the last block to finish (ticket
+//   counter) adds the partials in block order, so the result is deterministic.
 __global__ void __launch_bounds__(256)
-gram16_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
-                     const float* __restrict__ vmask, long row_begin, long row_end, int rows_per_block,
-                     float* __restrict__ partials, int partial_stride, int block_off) {
+gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, const float* __restrict__ vmask,
+                    long B, long b1, int rows_per_block, int nb1, float* __restrict__ partials,
+                    unsigned int* __restrict__ counter, float* __restrict__ terms) {
   __shared__ float sacc[8][257];
+  __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int i0 = (lane >> 3) * 4, j0 = (lane & 7) * 2;
-  long r0 = row_begin + (long)blockIdx.x * rows_per_block;
-  long r1 = r0 + rows_per_block < row_end ? r0 + rows_per_block : row_end;
+  const bool second = (int)blockIdx.x >= nb1;
+  const long hb = second ? b1 : 0, he = second ? B : b1;
+  long r0 = hb + (long)(second ? blockIdx.x - nb1 : blockIdx.x) * rows_per_block;
+  long r1 = r0 + rows_per_block < he ? r0 + rows_per_block : he;
   float acc[4][2] = {};
   float ops = 0.f;
   const float vm = vmask[lane & 15];
-  // each warp takes row pairs (r, r+1): pairs interleaved across the 8 warps
-  for (long r = r0 + 2 * warp; r < r1; r += 16) {
+  for (long r = r0 + 2 * warp; r < r1; r += 16) {   // row pairs interleaved across the 8 warps
     const long rr = r + (lane >> 4);
     if (rr < r1) ops = fmaf(vm * F[rr * 16 + (lane & 15)], TF[rr * 16 + (lane & 15)], ops);
 #pragma unroll
@@ -523,7 +527,7 @@ gram16_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
   ops = warp_sum(ops);
   if (lane == 0) sacc[warp][256] = ops;
   __syncthreads();
-  float* out = partials + (long)(block_off + blockIdx.x) * partial_stride;
+  float* out = partials + (long)blockIdx.x * 257;
   float t = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) t += sacc[w][tid];
@@ -533,6 +537,25 @@ gram16_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
 #pragma unroll
     for (int w = 0; w < 8; ++w) o += sacc[w][256];
     out[256] = o;
+  }
+  // ---- last block reduces all partials in fixed order
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nb = gridDim.x;
+  float g1 = 0.f, g2 = 0.f;
+  for (int bb = 0; bb < nb1; ++bb) g1 += __ldcg(partials + (long)bb * 257 + tid);
+  for (int bb = nb1; bb < nb; ++bb) g2 += __ldcg(partials + (long)bb * 257 + tid);
+  terms[tid] = g1;
+  terms[256 + tid] = g2;
+  if (tid == 0) {
+    float o = 0.f;
+    for (int bb = 0; bb < nb; ++bb) o += __ldcg(partials + (long)bb * 257 + 256);
+    terms[512] = o;
+    *counter = 0u;
   }
 }
 
@@ -583,21 +606,6 @@ static int gram_launch(const float* F, const float* TF, const float* vmask, cons
 static int gram_dispatch(const float* F, const float* TF, const float* vmask, const float* roww,
                          const float* xrow, int L, long rb, long re, int cross, float* partials, int stride,
                          int block_off, int* nblocks, cudaStream_t st) {
-  if (L == 16 && !cross && !roww) {
-    long rows = re - rb;
-    if (rows <= 0) {
-      *nblocks = 0;
-      return 0;
-    }
-    int nb = gram_blocks_for(rows);
-    int rpb = (int)((rows + nb - 1) / nb);
-    rpb = (rpb + 15) / 16 * 16;
-    nb = (int)((rows + rpb - 1) / rpb);
-    gram16_stage1_kernel<<<nb, 256, 0, st>>>(F, TF, vmask, rb, re, rpb, partials, stride, block_off);
-    NSVD_LAUNCH_CHECK();
-    *nblocks = nb;
-    return 0;
-  }
   if (L <= 16) return gram_launch<16>(F, TF, vmask, roww, xrow, L, rb, re, cross, partials, stride, block_off, nblocks, st);
   if (L <= 32) return gram_launch<32>(F, TF, vmask, roww, xrow, L, rb, re, cross, partials, stride, block_off, nblocks, st);
   if (L <= 48) return gram_launch<48>(F, TF, vmask, roww, xrow, L, rb, re, cross, partials, stride, block_off, nblocks, st);
@@ -609,6 +617,22 @@ static int gram_dispatch(const float* F, const float* TF, const float* vmask, co
 int gram_reduce(const float* F, const float* TF, const float* vmask, int B, int L, int b1,
                 float* terms, void* partials_v, cudaStream_t st) {
   float* partials = (float*)partials_v;
+  if (L == 16) {
+    // blocks sized for >= 512 rows each, at most 4 x 148 blocks, split between the halves in proportion
+    long rows_max = b1 > B - b1 ? b1 : B - b1;
+    int per_half = (int)((rows_max + 511) / 512);
+    if (per_half > 296) per_half = 296;
+    if (per_half < 1) per_half = 1;
+    int rpb = (int)((rows_max + per_half - 1) / per_half);
+    rpb = (rpb + 15) / 16 * 16;
+    int nb1 = (int)((b1 + rpb - 1) / rpb), nb2 = (int)((B - b1 + rpb - 1) / rpb);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(partials + (long)(nb1 + nb2) * 257);
+    NSVD_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    if (nb1 + nb2 == 0) return 0;
+    gram16_fused_kernel<<<nb1 + nb2, 256, 0, st>>>(F, TF, vmask, B, b1, rpb, nb1, partials, counter, terms);
+    NSVD_LAUNCH_CHECK();
+    return 0;
+  }
   int stride = 2 * L * L + 1, n1 = 0, n2 = 0, rc;
   if ((rc = gram_dispatch(F, TF, vmask, nullptr, nullptr, L, 0, b1, 0, partials, stride, 0, &n1, st))) return rc;
   if ((rc = gram_dispatch(F, TF, vmask, nullptr, nullptr, L, b1, B, 0, partials, stride, n1, &n2, st))) return rc;
@@ -962,6 +986,77 @@ __global__ void cdk_offdiag_kernel(const float* __restrict__ f, const float* __r
 int cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* out, cudaStream_t st) {
   dim3 grid(cdiv(B, 32), cdiv(B, 32));
   cdk_offdiag_kernel<<<grid, dim3(32, 32), 0, st>>>(f, g, B, L, fc, out);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// "next" rows: fused optimizer step and on-device sampler
+// ------------------------------------------------------------------------------------------
+// RMSprop (momentum 0, weight decay 0: examples/utils.py:48-57) + EMA shadow update (torch_ema) for up to
+// 16 tensors in one launch:  sq = alpha sq + (1-alpha) g^2 ; p -= lr g / (sqrt(sq) + eps) ;
+//                            ema -= ema_w (ema - p)        (ema_w = 1 - decay_t ; skipped when ema == NULL)
+__global__ void rmsprop_ema_kernel(OptTensors t, float lr, float alpha, float eps, float ema_w) {
+  const int ti = blockIdx.y;
+  if (ti >= t.n) return;
+  float* __restrict__ p = t.p[ti];
+  const float* __restrict__ g = t.g[ti];
+  float* __restrict__ sq = t.sq[ti];
+  float* __restrict__ em = t.ema[ti];
+  const long n = t.size[ti];
+  const float oma = 1.f - alpha;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    float s = sq[i] * alpha;
+    s = s + oma * gi * gi;
+    sq[i] = s;
+    float pi = p[i] - lr * (gi / (sqrtf(s) + eps));
+    p[i] = pi;
+    if (em) {
+      float e = em[i];
+      em[i] = e - ema_w * (e - pi);
+    }
+  }
+}
+
+int rmsprop_ema_step(const OptTensors& t, float lr, float alpha, float eps, float ema_w, cudaStream_t st) {
+  long mx = 0;
+  for (int i = 0; i < t.n; ++i) mx = t.size[i] > mx ? t.size[i] : mx;
+  if (t.n <= 0 || mx <= 0) return 0;
+  int gx = cdiv(mx, 1024);
+  if (gx > 148 * 4) gx = 148 * 4;
+  rmsprop_ema_kernel<<<dim3(gx, t.n), 256, 0, st>>>(t, lr, alpha, eps, ema_w);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// x[b][d] = sigma * N(0,1): counter-based (Philox-style mixing of (seed, index)) + Box-Muller; one thread
+// per point (2 coordinates).  Reproducible for a given (seed, offset); NOT the torch CPU stream
+// (main_pde.py:92-93 stays the parity mode).
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {   // splitmix64 finaliser, upper bits
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+__global__ void sample_gaussian2_kernel(float* __restrict__ x, long n, float sigma, uint64_t seed, uint64_t offset) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t ctr = (offset + (uint64_t)i) * 2ull;
+  uint32_t a = mix32(seed ^ (ctr * 0xD1342543DE82EF95ull));
+  uint32_t b = mix32((seed + 0x632BE59BD9B4E019ull) ^ ((ctr + 1ull) * 0xD1342543DE82EF95ull));
+  float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+  float u2 = (float)b * 2.3283064365386963e-10f;            // [0, 1)
+  float r = sigma * sqrtf(-2.f * logf(u1));
+  float sn, cs;
+  sincospif(2.f * u2, &sn, &cs);
+  x[2 * i] = r * cs;
+  x[2 * i + 1] = r * sn;
+}
+int sample_gaussian2(float* x, long n, float sigma, uint64_t seed, uint64_t offset, cudaStream_t st) {
+  if (n <= 0) return 0;
+  sample_gaussian2_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, n, sigma, seed, offset);
   NSVD_LAUNCH_CHECK();
   return 0;
 }

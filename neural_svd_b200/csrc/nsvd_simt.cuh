@@ -45,6 +45,17 @@ int cdk_bwd(const float* f, const float* g, const float* v, const float* coef, c
             int L, int fc, long Bg, float* grad_f, float* grad_g, cudaStream_t st);
 int cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* out, cudaStream_t st);
 
+struct OptTensors {
+  int n;
+  float* p[16];
+  const float* g[16];
+  float* sq[16];
+  float* ema[16];
+  long size[16];
+};
+int rmsprop_ema_step(const OptTensors& t, float lr, float alpha, float eps, float ema_w, cudaStream_t st);
+int sample_gaussian2(float* x, long n, float sigma, uint64_t seed, uint64_t offset, cudaStream_t st);
+
 // tcgen05 engine (nsvd_tc.cu)
 void tc_scratch_bytes(const nsvd_problem_t& pb, size_t* saved, size_t* work);
 int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x, float* F, float* TF,

@@ -195,3 +195,45 @@ def test_spectrum_evd_matches_oracle():
     assert rel(out["cov"], ref["cov"]) < TOL and rel(out["quad"], ref["quad"]) < TOL
     assert rel(out["eigvals"], ref["eigvals"]) < TOL and rel(out["norms"], ref["norms"]) < TOL
     assert out["eigfuncs"].shape == (len(grid), 4)
+
+
+def test_fused_rmsprop_ema_matches_torch():
+    # examples/utils.py:48-57 + CosineAnnealingLR + torch_ema semantics (operator/__init__.py:34-36,69-73)
+    g = torch.Generator().manual_seed(0)
+    shapes = [(16, 128, 64), (16, 128, 1), (16,), (3, 5, 7)]
+    p_ref = [torch.randn(s, generator=g).cuda().requires_grad_() for s in shapes]
+    p_our = [p.detach().clone().requires_grad_() for p in p_ref]
+    S, decay = 25, 0.995
+    opt = torch.optim.RMSprop(p_ref, lr=1e-3, alpha=0.999, eps=1e-10, weight_decay=0, momentum=0.0)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, S)
+    shadow = [p.detach().clone() for p in p_ref]
+    ours = N.FusedRMSpropEMA(p_our, lr=1e-3, alpha=0.999, eps=1e-10, ema_decay=decay, num_iters=S)
+    for it in range(S):
+        grads = [torch.randn(s, generator=g).cuda() * (10.0 ** ((it % 5) - 3)) for s in shapes]
+        for p, q, gr in zip(p_ref, p_our, grads):
+            p.grad, q.grad = gr.clone(), gr.clone()
+        opt.step()
+        sched.step()
+        d = min(decay, (1 + it + 1) / (10 + it + 1))
+        with torch.no_grad():
+            for sh, p in zip(shadow, p_ref):
+                sh.sub_((1 - d) * (sh - p))
+        ours.step()
+    for p, q, sh, sq in zip(p_ref, p_our, shadow, ours.shadow):
+        assert rel(q.detach().cpu().numpy(), p.detach().cpu().numpy()) < 1e-6
+        assert rel(sq.cpu().numpy(), sh.cpu().numpy()) < 1e-6
+
+
+def test_device_sampler_statistics_and_reproducibility():
+    x = N.sample_gaussian(1 << 20, 16.0, seed=5)
+    y = N.sample_gaussian(1 << 20, 16.0, seed=5)
+    z = N.sample_gaussian(1 << 20, 16.0, seed=6)
+    assert torch.equal(x, y) and not torch.equal(x, z)
+    tail = N.sample_gaussian(1 << 10, 16.0, seed=5, offset=(1 << 20) - (1 << 10))
+    assert torch.equal(tail, x[-(1 << 10):])                       # counter-based: offset continues the stream
+    xs = x.double().cpu().numpy() / 16.0
+    assert abs(xs.mean()) < 5e-3 and abs(xs.std() - 1) < 5e-3
+    assert abs((xs[:, 0] * xs[:, 1]).mean()) < 5e-3                # coordinates uncorrelated
+    assert abs((xs ** 4).mean() - 3.0) < 0.05                      # kurtosis of a normal
+    r2 = (xs ** 2).sum(1)
+    assert abs(np.mean(r2 < 2 * np.log(2)) - 0.5) < 5e-3           # chi^2_2 median

@@ -1,0 +1,60 @@
+"""North-star acceptance check: learned eigenvalue estimates after a fixed-seed, fixed-step training
+run agree with the reference within 1e-3 relative.
+
+Fixture `run_hyd_b128_seq_L16.npz` (oracle/make_golden_run.py): the unmodified reference on CPU, exact
+Laplacian, hydrogen B=128 sequential L=16, 200 steps of RMSprop(1e-4, alpha .999, eps 1e-10) + cosine LR,
+in fp64 (truth) and fp32 (what a user of the reference gets; their gap is the reference's self-noise).
+Estimators on a fixed batch of 8192 points: norms_l = mean f_l^2 (NestedLoRA's eigenvalue estimator,
+methods/spectrum.py:87) and Rayleigh quotients sum f Tf / sum f^2 (spectrum.py:86).
+"""
+import numpy as np
+import pytest
+import torch
+
+import neural_svd_b200 as N
+from conftest import build_problem, load_golden
+from oracle import nsvd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("engine", ["bf16x3", "fp32"])
+def test_fixed_seed_training_run_matches_reference(engine):
+    d, _ = load_golden("run_hyd_b128_seq_L16")
+    S, B, seed = int(d["steps"]), int(d["B"]), int(d["seed"])
+    cfg = O.PathConfig.hydrogen(sequential=True)
+    N.set_engine(engine)
+    method, operator, importance, _ = build_problem(cfg, seed, "cuda")
+    opt = torch.optim.RMSprop(method.parameters(), lr=1e-4, alpha=0.999, eps=1e-10, weight_decay=0, momentum=0.0)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, S)
+    g = torch.Generator().manual_seed(4242)
+    losses = []
+    for _ in range(S):
+        x = (cfg.sampling_scale * torch.randn((B, 1, cfg.ndim), generator=g)).reshape(B, -1)
+        opt.zero_grad()
+        loss, _ = method.compute_loss_operator(operator, x.cuda(), importance=importance)
+        loss.backward()
+        opt.step()
+        sched.step()
+        losses.append(loss.detach())
+    losses = torch.stack(losses).cpu().numpy()
+    ge = torch.Generator().manual_seed(777)
+    xe = (cfg.sampling_scale * torch.randn((8192, 1, cfg.ndim), generator=ge)).reshape(8192, -1)
+    params = {n: p.detach().cpu().numpy().astype(np.float64) for n, p in method.named_parameters()}
+    x64 = xe.numpy().astype(np.float64)
+    u = O.forward_streams(x64, params, cfg)
+    Tf, f, _ = O.operator_apply(x64, u, params, cfg)
+    norms, ray = (f * f).mean(0), (f * Tf).sum(0) / (f * f).sum(0)
+    e_norm = np.abs(norms / d["norms64"] - 1)
+    e_ray = np.abs(ray / d["rayleigh64"] - 1)
+    self_norm = np.abs(d["norms32"] / d["norms64"] - 1)
+    self_ray = np.abs(d["rayleigh32"] / d["rayleigh64"] - 1)
+    print(f"[{engine}] norms   : ours max {e_norm.max():.2e}  reference fp32-vs-fp64 max {self_norm.max():.2e}")
+    print(f"[{engine}] rayleigh: ours max {e_ray.max():.2e}  reference fp32-vs-fp64 max {self_ray.max():.2e}")
+    print(f"[{engine}] loss traj rel diff step1 {abs(losses[0] / d['loss64'][0] - 1):.2e} "
+          f"last {abs(losses[-1] / d['loss64'][-1] - 1):.2e}")
+    assert abs(losses[0] / d["loss64"][0] - 1) < 1e-4
+    # eigenvalue estimator of the method (norms): 1e-3 relative on every mode
+    assert e_norm.max() < 1e-3, e_norm
+    # Rayleigh quotients are noisier for the reference itself; allow its own self-noise on top
+    assert np.all(e_ray < 1e-3 + 2 * self_ray), (e_ray, self_ray)
