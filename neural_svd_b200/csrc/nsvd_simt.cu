@@ -485,11 +485,11 @@ gram_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
 //   taken on a coalesced (row pair x 16) load.  Blocks [0, nb1) cover the first half of the rows, the
 //   rest the second half.  Each block writes a 257-float partial; the last block to finish (ticket
 //   counter) adds the partials in block order, so the result is deterministic.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, const float* __restrict__ vmask,
                     long B, long b1, int rows_per_block, int nb1, float* __restrict__ partials,
                     unsigned int* __restrict__ counter, float* __restrict__ terms) {
-  __shared__ float sacc[8][257];
+  __shared__ float sacc[32][257];
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int i0 = (lane >> 3) * 4, j0 = (lane & 7) * 2;
@@ -500,24 +500,52 @@ gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, c
   float acc[4][2] = {};
   float ops = 0.f;
   const float vm = vmask[lane & 15];
-  for (long r = r0 + 2 * warp; r < r1; r += 16) {   // row pairs interleaved across the 8 warps
-    const long rr = r + (lane >> 4);
-    if (rr < r1) ops = fmaf(vm * F[rr * 16 + (lane & 15)], TF[rr * 16 + (lane & 15)], ops);
+  // each of the 32 warps owns row pairs (r, r+1), r = r0 + 2 warp (mod 64); 4 pairs are loaded before use
+  // (memory-level parallelism: 4 x 256 B per warp in flight, 32 KB per SM)
+  // One coalesced 128-byte load per row pair and array; the Gram operands are taken from it by shuffles.
+  // 8 row pairs per iteration and the next iteration's loads are issued before the current one is consumed
+  // (software pipeline): ~4 KB per warp = 128 KB per SM in flight, enough to cover HBM latency.
+  constexpr int U = 8;
+  float fo[U], to[U], fn[U], tn[U];
+  auto load8 = [&](long r, float* f8, float* t8) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (r + k < r1) {
-        const float* row = F + (r + k) * 16;
-        float4 fi = *reinterpret_cast<const float4*>(row + i0);
-        float2 fj = *reinterpret_cast<const float2*>(row + j0);
-        acc[0][0] = fmaf(fi.x, fj.x, acc[0][0]);
-        acc[0][1] = fmaf(fi.x, fj.y, acc[0][1]);
-        acc[1][0] = fmaf(fi.y, fj.x, acc[1][0]);
-        acc[1][1] = fmaf(fi.y, fj.y, acc[1][1]);
-        acc[2][0] = fmaf(fi.z, fj.x, acc[2][0]);
-        acc[2][1] = fmaf(fi.z, fj.y, acc[2][1]);
-        acc[3][0] = fmaf(fi.w, fj.x, acc[3][0]);
-        acc[3][1] = fmaf(fi.w, fj.y, acc[3][1]);
+    for (int u = 0; u < U; ++u) {
+      const long rr = r + 64 * u + (lane >> 4);
+      const bool okr = rr < r1;
+      f8[u] = okr ? F[rr * 16 + (lane & 15)] : 0.f;
+      t8[u] = okr ? TF[rr * 16 + (lane & 15)] : 0.f;
+    }
+  };
+  long r = r0 + 2 * warp;
+  load8(r, fo, to);
+  for (; r < r1; r += 64 * U) {
+    load8(r + 64 * U, fn, tn);   // rows beyond r1 load as zeros
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ops = fmaf(vm * fo[u], to[u], ops);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int src = 16 * k;
+        const float ax = __shfl_sync(0xffffffffu, fo[u], src + i0);
+        const float ay = __shfl_sync(0xffffffffu, fo[u], src + i0 + 1);
+        const float az = __shfl_sync(0xffffffffu, fo[u], src + i0 + 2);
+        const float aw = __shfl_sync(0xffffffffu, fo[u], src + i0 + 3);
+        const float cx = __shfl_sync(0xffffffffu, fo[u], src + j0);
+        const float cy = __shfl_sync(0xffffffffu, fo[u], src + j0 + 1);
+        acc[0][0] = fmaf(ax, cx, acc[0][0]);
+        acc[0][1] = fmaf(ax, cy, acc[0][1]);
+        acc[1][0] = fmaf(ay, cx, acc[1][0]);
+        acc[1][1] = fmaf(ay, cy, acc[1][1]);
+        acc[2][0] = fmaf(az, cx, acc[2][0]);
+        acc[2][1] = fmaf(az, cy, acc[2][1]);
+        acc[3][0] = fmaf(aw, cx, acc[3][0]);
+        acc[3][1] = fmaf(aw, cy, acc[3][1]);
       }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      fo[u] = fn[u];
+      to[u] = tn[u];
     }
   }
 #pragma unroll
@@ -528,17 +556,13 @@ gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, c
   if (lane == 0) sacc[warp][256] = ops;
   __syncthreads();
   float* out = partials + (long)blockIdx.x * 257;
-  float t = 0.f;
+  if (tid < 257) {
+    float t = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) t += sacc[w][tid];
-  out[tid] = t;
-  if (tid == 0) {
-    float o = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) o += sacc[w][256];
-    out[256] = o;
+    for (int w = 0; w < 32; ++w) t += sacc[w][tid];
+    out[tid] = t;
   }
-  // ---- last block reduces all partials in fixed order
+  // ---- the last block to finish adds all partials (fixed order => deterministic result)
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
@@ -546,17 +570,48 @@ gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, c
   if (!s_last) return;
   __threadfence();
   const int nb = gridDim.x;
-  float g1 = 0.f, g2 = 0.f;
-  for (int bb = 0; bb < nb1; ++bb) g1 += __ldcg(partials + (long)bb * 257 + tid);
-  for (int bb = nb1; bb < nb; ++bb) g2 += __ldcg(partials + (long)bb * 257 + tid);
-  terms[tid] = g1;
-  terms[256 + tid] = g2;
-  if (tid == 0) {
-    float o = 0.f;
-    for (int bb = 0; bb < nb; ++bb) o += __ldcg(partials + (long)bb * 257 + 256);
-    terms[512] = o;
-    *counter = 0u;
+  // warp w sums partial rows w, w+32, ... of each half; lane handles columns lane + 32 c; 4 rows in flight
+  for (int halfsel = 0; halfsel < 2; ++halfsel) {
+    const int pb = halfsel ? nb1 : 0, pe = halfsel ? nb : nb1;
+    float a8[8] = {}, a_ops = 0.f;
+    for (int bb = pb + warp; bb < pe; bb += 128) {
+      float v[4][8], vo[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b2 = bb + 32 * u;
+        const bool ok = b2 < pe;
+        const float* prow = partials + (long)(ok ? b2 : pb) * 257;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[u][c] = ok ? __ldcg(prow + lane + 32 * c) : 0.f;
+        vo[u] = (ok && lane == 0) ? __ldcg(prow + 256) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a8[c] += v[u][c];
+        a_ops += vo[u];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sacc[warp][lane + 32 * c] = a8[c];
+    if (lane == 0) sacc[warp][256] = a_ops;
+    __syncthreads();
+    if (tid < 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 32; ++w) t += sacc[w][tid];
+      terms[halfsel * 256 + tid] = t;
+    }
+    if (tid == 256) {
+      float o = 0.f;
+#pragma unroll
+      for (int w = 0; w < 32; ++w) o += sacc[w][256];
+      if (halfsel == 0) terms[512] = o;
+      else terms[512] += o;
+    }
   }
+  if (tid == 0) *counter = 0u;
 }
 
 // stage 2: out[e] (+)= sum over blocks [b0, b1) of partials[b][src_off + e]
@@ -620,16 +675,16 @@ int gram_reduce(const float* F, const float* TF, const float* vmask, int B, int 
   if (L == 16) {
     // blocks sized for >= 512 rows each, at most 4 x 148 blocks, split between the halves in proportion
     long rows_max = b1 > B - b1 ? b1 : B - b1;
-    int per_half = (int)((rows_max + 511) / 512);
-    if (per_half > 296) per_half = 296;
+    int per_half = (int)((rows_max + 1023) / 1024);
+    if (per_half > 74) per_half = 74;   // 148 blocks of 1024 threads: one per SM
     if (per_half < 1) per_half = 1;
     int rpb = (int)((rows_max + per_half - 1) / per_half);
-    rpb = (rpb + 15) / 16 * 16;
+    rpb = (rpb + 511) / 512 * 512;
     int nb1 = (int)((b1 + rpb - 1) / rpb), nb2 = (int)((B - b1 + rpb - 1) / rpb);
     unsigned int* counter = reinterpret_cast<unsigned int*>(partials + (long)(nb1 + nb2) * 257);
     NSVD_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     if (nb1 + nb2 == 0) return 0;
-    gram16_fused_kernel<<<nb1 + nb2, 256, 0, st>>>(F, TF, vmask, B, b1, rpb, nb1, partials, counter, terms);
+    gram16_fused_kernel<<<nb1 + nb2, 1024, 0, st>>>(F, TF, vmask, B, b1, rpb, nb1, partials, counter, terms);
     NSVD_LAUNCH_CHECK();
     return 0;
   }
@@ -733,28 +788,42 @@ loss_dF_kernel(const float* __restrict__ F, const float* __restrict__ TF,
   }
 }
 
-// L == 16 specialisation: one thread per row; the 16x16 coefficient block of the row's half is read
-// from shared memory as broadcast float4 (all lanes of a warp are in the same half except at b1).
+// L == 16 specialisation: one thread per row.  Rows are staged through shared memory so that every
+// global access is a fully coalesced 16-byte-per-lane transfer (256 rows x 64 B per block and array); the
+// 16x16 coefficient block of the row's half is read from shared memory as broadcast float4.
 __global__ void __launch_bounds__(256)
 loss_dF16_kernel(const float* __restrict__ F, const float* __restrict__ TF, const float* __restrict__ vmask,
                  const float* __restrict__ coef, const float* __restrict__ gscale, int B, int b1, float c4,
                  float* __restrict__ dF) {
   __shared__ float4 sC[2][16][4];
   __shared__ float sV[16];
-  for (int e = threadIdx.x; e < 512; e += blockDim.x) reinterpret_cast<float*>(sC)[e] = coef ? coef[e] : 0.f;
-  if (threadIdx.x < 16) sV[threadIdx.x] = vmask[threadIdx.x];
-  __syncthreads();
+  __shared__ float sF[256][17];
+  __shared__ float sT[256][17];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 512; e += 256) reinterpret_cast<float*>(sC)[e] = coef ? coef[e] : 0.f;
+  if (tid < 16) sV[tid] = vmask[tid];
   const float gs = gscale ? gscale[0] : 1.f;
-  for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long)gridDim.x * blockDim.x) {
-    const float4* frow = reinterpret_cast<const float4*>(F + b * 16);
-    float f[16];
+  for (long base = (long)blockIdx.x * 256; base < B; base += (long)gridDim.x * 256) {
+    __syncthreads();
+    const long nrow = (B - base) < 256 ? (B - base) : 256;
+    // coalesced loads: 256 rows x 4 float4
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 t = frow[q];
-      f[4 * q] = t.x; f[4 * q + 1] = t.y; f[4 * q + 2] = t.z; f[4 * q + 3] = t.w;
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i;          // float4 index inside the 256 x 16 block
+      const int r = e >> 2, q = e & 3;
+      float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f), t4 = f4;
+      if (r < nrow) {
+        f4 = reinterpret_cast<const float4*>(F + base * 16)[e];
+        if (TF) t4 = reinterpret_cast<const float4*>(TF + base * 16)[e];
+      }
+      sF[r][4 * q] = f4.x; sF[r][4 * q + 1] = f4.y; sF[r][4 * q + 2] = f4.z; sF[r][4 * q + 3] = f4.w;
+      sT[r][4 * q] = t4.x; sT[r][4 * q + 1] = t4.y; sT[r][4 * q + 2] = t4.z; sT[r][4 * q + 3] = t4.w;
     }
-    float o[16] = {};
-    const int h = b < b1 ? 0 : 1;
+    __syncthreads();
+    float f[16], o[16] = {};
+#pragma unroll
+    for (int l = 0; l < 16; ++l) f[l] = sF[tid][l];
+    const int h = (base + tid) < b1 ? 0 : 1;
 #pragma unroll
     for (int l = 0; l < 16; ++l) {
 #pragma unroll
@@ -766,16 +835,16 @@ loss_dF16_kernel(const float* __restrict__ F, const float* __restrict__ TF, cons
         o[4 * q + 3] = fmaf(f[l], c.w, o[4 * q + 3]);
       }
     }
-    float4* drow = reinterpret_cast<float4*>(dF + b * 16);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 t = TF ? reinterpret_cast<const float4*>(TF + b * 16)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 r;
-      r.x = gs * (o[4 * q] - c4 * sV[4 * q] * t.x);
-      r.y = gs * (o[4 * q + 1] - c4 * sV[4 * q + 1] * t.y);
-      r.z = gs * (o[4 * q + 2] - c4 * sV[4 * q + 2] * t.z);
-      r.w = gs * (o[4 * q + 3] - c4 * sV[4 * q + 3] * t.w);
-      drow[q] = r;
+    for (int m = 0; m < 16; ++m) sF[tid][m] = gs * (o[m] - c4 * sV[m] * sT[tid][m]);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i;
+      const int r = e >> 2, q = e & 3;
+      if (r < nrow)
+        reinterpret_cast<float4*>(dF + base * 16)[e] =
+            make_float4(sF[r][4 * q], sF[r][4 * q + 1], sF[r][4 * q + 2], sF[r][4 * q + 3]);
     }
   }
 }
@@ -785,7 +854,7 @@ int loss_dF(const float* F, const float* TF, const float* vmask, const float* co
   float c4 = (float)(4.0 / (double)Bg);
   if (L == 16) {
     int nb16 = cdiv(B, 256);
-    if (nb16 > 148 * 8) nb16 = 148 * 8;
+    if (nb16 > 148 * 6) nb16 = 148 * 6;
     loss_dF16_kernel<<<nb16, 256, 0, st>>>(F, TF, vmask, coef, gscale, B, b1, c4, dF);
     NSVD_LAUNCH_CHECK();
     return 0;
