@@ -163,8 +163,8 @@ def run_reference_arm(args):
     r = cpu_reference_run(cfg, budget_s=60.0, steps=max(args.steps, 2), warmup=max(args.warmup, 1))
     v = r["value"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": 1e3 * 512 / v if r.get("kind") == "reference" else 1e3 * 2048 / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"2D hydrogen, joint nesting, L={args.neigs}, CPU sample (see cpu_baseline.sample)"},
             "cpu_baseline": r, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
@@ -296,9 +296,17 @@ def run_ours(args):
         roof = None
         if l0_n:
             ach = flops_l0 / (l0_ms * 1e-3) / 1e12
-            roof = {"kernel": "big_gemm_kernel<K-major, L0FwdEpi> (layer-0 4-stream forward GEMM, tcgen05 bf16x3)",
+            # DRAM traffic of this kernel from the committed ncu capture (profiles/r1_ncu_full.csv: 1.772 GB read +
+            # 1.307 GB written by one launch over 32768 points), scaled to the points one launch covers here
+            pts_per_launch = P * args.steps / l0_n
+            traffic = (1.771712e9 + 1.307366e9) / 32768 * pts_per_launch
+            roof = {"kernel": "big2_gemm_kernel<K-major, L0FwdEpi> (layer-0 4-stream forward GEMM, tcgen05 cta_group::2, bf16x3)",
                     "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                    "frac": ach / pk["tf_sust"], "traffic": traffic,
+                    "traffic_note": "bytes per launch = ncu dram read+write per point (93.97 KB, profiles/r1_ncu_full.csv) x "
+                                    "points per launch; algorithmic bytes are 8 KB (Phi) + 32.5 KB (activation streams "
+                                    "out) per point + 67 MB of folded weights per launch",
+                    "peak_source": pk["src"] + " bf16 sustained",
                     "issued_frac": 3 * ach / pk["tf_sust"], "launches": l0_n, "avg_launch_ms": l0_ms / l0_n,
                     "note": "achieved = ALGORITHMIC fp32-equivalent FLOPs; every MAC is issued as 3 bf16 MMAs "
                             "(hi*hi + hi*lo + lo*hi), so tensor-pipe issue rate = issued_frac of the bf16 peak"}
