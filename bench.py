@@ -179,8 +179,7 @@ def run_ours(args):
     import torch.distributed as dist
     import neural_svd_b200 as N
     from neural_svd_b200 import _lib
-    from conftest import build_problem
-    from oracle import nsvd_oracle as O   # PathConfig only (hyper-parameter container) + cpu_baseline leg
+    from types import SimpleNamespace
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -196,9 +195,19 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
         dp = N.PointParallel()
 
-    cfg = O.PathConfig.hydrogen(neigs=args.neigs)
+    # scripts/exps/pde/hydrogen.sh hyper-parameters with BASELINE's L (the product API only: no oracle, no test code)
+    cfg = SimpleNamespace(
+        problem="sch", potential_type="hydrogen", ndim=2, neigs=args.neigs, charge=1.0, laplacian_eps=0.0,
+        operator_scale=100.0, operator_shift=0.0, lim=50.0, use_fourier_feature=True, fourier_mapping_size=1024,
+        fourier_scale=0.1, fourier_deterministic=False, fourier_append_raw=False, mlp_hidden_dims="128,128,128",
+        nonlinearity="softplus", parallel=True, apply_boundary=False, boundary_mode="dir_box_sqrt",
+        apply_exp_mask=False, exp_mask_init_scale=100.0, hard_mul_const=1.0, sampling_scale=16.0)
     N.set_engine(args.engine)
-    method, operator, importance, _ = build_problem(cfg, 0, dev)
+    torch.manual_seed(0)
+    operator, _gt = N.get_problem(cfg)
+    model = N.get_wavefunctions(cfg)
+    method = N.NestedLoRA(model=model, neigs=cfg.neigs, step=1, sort=False, sequential=False).to(dev)
+    importance = N.GaussianImportance(cfg.sampling_scale, cfg.ndim)
     method.data_parallel = dp
     P = args.points
     g = torch.Generator().manual_seed(100 + rank)
@@ -337,7 +346,8 @@ def run_ours(args):
                 "roofline": roof, "kernels": kernels,
                 "step_tflops_algorithmic": flop_pt * value / 1e12}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_run(cfg, args.cpu_seconds)
+            from oracle import nsvd_oracle as O        # cpu_baseline leg only
+            line["cpu_baseline"] = cpu_reference_run(O.PathConfig.hydrogen(neigs=args.neigs), args.cpu_seconds)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -13,5 +13,6 @@ from .fused import compute_loss_operator, get_engine, set_engine
 from .dist import PointParallel, shard_points
 from .spectrum import compute_spectrum_evd
 from .optim import FusedRMSpropEMA, sample_gaussian
+from .graphs import GraphedOperatorStep
 
 __all__ = [n for n in dir() if not n.startswith("_")]

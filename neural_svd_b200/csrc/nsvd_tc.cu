@@ -702,24 +702,42 @@ __global__ void split_w_kernel(const float* __restrict__ W, __nv_bfloat16* __res
 }
 
 // Phi = [sin(x B), cos(x B)] as bf16 hi/lo planes (B, 2M)   (examples/utils.py:139-140)
+// One thread = 4 consecutive features of one point (8-byte stores).  The phase p = x.B is formed in fp32 exactly
+// like the reference; a two-constant Cody-Waite step (k = rint(p / 2pi), r = p - k 2pi_hi - k 2pi_lo with FMAs,
+// 3.5e-8 rms error) brings it to [-pi, pi], and sincospif(r / pi) evaluates it without any large-argument path
+// (total ~1e-7).  Reducing in turns (p / 2pi in fp32) was measured to add 5e-7..1.2e-6 rms per feature, i.e. as much
+// as the bf16 hi/lo rounding itself, and is not used.
 __global__ void features_bf16_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long P,
                                      int M) {
+  const int M4 = M >> 2;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * M) return;
-  long p = i / M;
-  int j = (int)(i % M);
-  float ph = fmaf(x[2 * p + 1], Bff[M + j], x[2 * p] * Bff[j]);
-  float s, c;
-  sincosf(ph, &s, &c);
-  long o = p * 2L * M;
-  __nv_bfloat16 a, b;
-  tc::split_bf16(s, a, b);
-  hi[o + j] = a;
-  lo[o + j] = b;
-  tc::split_bf16(c, a, b);
-  hi[o + M + j] = a;
-  lo[o + M + j] = b;
+  if (i >= P * M4) return;
+  long p = i / M4;
+  int j = (int)(i % M4) * 4;
+  const float x0 = x[2 * p], x1 = x[2 * p + 1];
+  const float4 b0 = *reinterpret_cast<const float4*>(Bff + j);
+  const float4 b1 = *reinterpret_cast<const float4*>(Bff + M + j);
+  const float bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+  float sn[4], cs[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float ph = fmaf(x1, bb1[k], x0 * bb0[k]);
+    float kq = rintf(ph * 0.15915494309189535f);
+    float r = fmaf(-kq, 6.2831855f, ph);          // 2pi_hi = fl(2 pi)
+    r = fmaf(-kq, -1.7484555e-07f, r);            // 2pi_lo = 2 pi - 2pi_hi
+    sincospif(r * 0.3183098861837907f, &sn[k], &cs[k]);
+  }
+  uint32_t h0, l0, h1, l1;
+  long o = p * 2L * M + j;
+  tc::split_bf16x2(sn[0], sn[1], h0, l0);
+  tc::split_bf16x2(sn[2], sn[3], h1, l1);
+  *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(lo + o) = make_uint2(l0, l1);
+  tc::split_bf16x2(cs[0], cs[1], h0, l0);
+  tc::split_bf16x2(cs[2], cs[3], h1, l1);
+  *reinterpret_cast<uint2*>(hi + o + M) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(lo + o + M) = make_uint2(l0, l1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1516,7 +1534,7 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
   int rc;
   // ---- per-call preparation: features of all points, folded / split weights
   ProfScope* prep = new ProfScope(KC_PREP, st);
-  features_bf16_kernel<<<cdiv(B * M, 256), 256, 0, st>>>(x, pr.Bff, BF(sv + t.phi_hi), BF(sv + t.phi_lo), B, (int)M);
+  features_bf16_kernel<<<cdiv(B * (M / 4), 256), 256, 0, st>>>(x, pr.Bff, BF(sv + t.phi_hi), BF(sv + t.phi_lo), B, (int)M);
   NSVD_LAUNCH_CHECK();
   fold_w0_kernel<<<cdiv(L * H * M, 256), 256, 0, st>>>(pr.W[0], pr.Bff, BF(wk + t.w0_hi), BF(wk + t.w0_lo), (int)L,
                                                        (int)M);

@@ -14,3 +14,24 @@ for pts in (128, 512, 4096):
                   f"e2e points/s {d['e2e']['value']:.0f}  launches/step {d['gpu_launches'] / 50:.1f}")
         except Exception as e:
             print(pts, eng, "failed", e, r.stderr[-300:])
+
+# CUDA-graph step (GraphedOperatorStep) vs the eager sequence, B = 128 / 512
+import os, time, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+import neural_svd_b200 as N
+from conftest import build_problem
+from oracle import nsvd_oracle as O
+for pts in (128, 512, 4096):
+    cfg = O.PathConfig.hydrogen()
+    N.set_engine("bf16x3")
+    method, operator, importance, _ = build_problem(cfg, 0, "cuda")
+    step = N.GraphedOperatorStep(method, operator, importance, pts)
+    x = (cfg.sampling_scale * torch.randn(pts, 2)).pin_memory()
+    for _ in range(10):
+        float(step(x))
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(200):
+        float(step(x))
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 200
+    print(f"B={pts:5d} bf16x3 graphed e2e ms/step {dt * 1e3:.4f}  points/s {pts / dt:.0f}")

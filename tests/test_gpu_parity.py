@@ -237,3 +237,26 @@ def test_device_sampler_statistics_and_reproducibility():
     assert abs((xs ** 4).mean() - 3.0) < 0.05                      # kurtosis of a normal
     r2 = (xs ** 2).sum(1)
     assert abs(np.mean(r2 < 2 * np.log(2)) - 0.5) < 5e-3           # chi^2_2 median
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_graphed_step_equals_eager_step(engine):
+    d, cfg = load_golden("osc_b512_jnt_L16")
+    N.set_engine(engine)
+    method, operator, importance, _ = build_problem(cfg, int(d["seed"]), "cuda")
+    x = torch.from_numpy(d["x"]).cuda()
+    step = N.GraphedOperatorStep(method, operator, importance, batch_size=x.shape[0])
+    for rep in range(2):                                        # replay twice: buffers are reused correctly
+        loss = step(x)
+        grads_g = {n: p.grad.clone() for n, p in method.named_parameters() if p.grad is not None}
+        assert abs(float(loss) - float(d["loss64"])) <= TOL * abs(float(d["loss64"]))
+        errs = golden_grad_errors(d, list(grads_g), {k: v.cpu().numpy() for k, v in grads_g.items()})
+        assert max(errs.values()) < TOL, errs
+    method.zero_grad(set_to_none=True)
+    loss_e, aux = method.compute_loss_operator(operator, x, importance=importance)
+    loss_e.backward()
+    assert abs(float(loss) - float(loss_e)) < 1e-5 * abs(float(loss_e))
+    for n, p in method.named_parameters():
+        if p.grad is not None:
+            assert rel(grads_g[n].cpu().numpy(), p.grad.cpu().numpy()) < 2e-5, n
+    assert rel(step.aux["Tf"].cpu().numpy(), aux["Tf"].cpu().numpy()) < 1e-6
