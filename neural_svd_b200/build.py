@@ -14,12 +14,25 @@ NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,c
               "-lineinfo", "-O3", "-std=c++17", "-diag-suppress", "550"]
 
 
+HASHFILE = LIB + ".srchash"
+
+
+def _source_hash() -> str:
+    """sha256 over the sources, the header and the flags (content-based: file times do not survive copies)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "nsvd.h")]
+    for d in deps:
+        if os.path.isfile(d):
+            h.update(os.path.basename(d).encode())
+            h.update(open(d, "rb").read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.isfile(LIB):
+    if not os.path.isfile(LIB) or not os.path.isfile(HASHFILE):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "nsvd.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+    return open(HASHFILE).read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -31,13 +44,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if os.path.isfile(LIB):
             return LIB          # prebuilt library travelled with the tree (GPU box without nvcc)
         raise RuntimeError("nvcc not found and no prebuilt libnsvd.so in the tree")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + SOURCES
-    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    os.replace(LIB + ".tmp", LIB)
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:       # one builder at a time (torchrun starts N ranks at once)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():
+            return LIB
+        tmp = f"{LIB}.tmp.{os.getpid()}"
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+        r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if verbose:
+            sys.stderr.write(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, LIB)
+        with open(HASHFILE, "w") as f:
+            f.write(_source_hash())
     return LIB
 
 

@@ -42,10 +42,12 @@ def test_step_matches_reference_golden(name, engine):
     assert max(errs.values()) < TOL, errs
 
 
+@pytest.mark.parametrize("neigs", [6, 5])
 @pytest.mark.parametrize("engine", ENGINES)
-def test_step_matches_oracle_on_fresh_inputs(engine):
-    # seeded inputs that are in no fixture, at a ragged size (B not a multiple of the 128-row tile)
-    cfg = O.PathConfig.oscillator(neigs=6, fourier_mapping_size=40, sequential=False, step=2)
+def test_step_matches_oracle_on_fresh_inputs(engine, neigs):
+    # seeded inputs that are in no fixture, at a ragged size (B not a multiple of the 128-row tile); an odd number
+    # of copies exercises the zero-filled second copy of the last CTA pair in the weight-gradient GEMM
+    cfg = O.PathConfig.oscillator(neigs=neigs, fourier_mapping_size=40, sequential=False, step=2)
     N.set_engine(engine)
     method, operator, importance, _ = build_problem(cfg, 77, "cuda")
     g = torch.Generator().manual_seed(5)
@@ -54,7 +56,7 @@ def test_step_matches_oracle_on_fresh_inputs(engine):
     with torch.no_grad():
         for i, b in enumerate(method.model.base.bs):
             b.add_(0.1 * torch.randn(b.shape, generator=g).to(b.device))
-        method.model.boundary_mask.scales.mul_(1 + 0.2 * torch.rand(6, generator=g).to("cuda"))
+        method.model.boundary_mask.scales.mul_(1 + 0.2 * torch.rand(neigs, generator=g).to("cuda"))
     params = {n: p.detach().cpu().numpy().astype(np.float64) for n, p in method.named_parameters()}
     r = O.train_step(x.numpy().astype(np.float64), params, cfg)
     loss, aux = method.compute_loss_operator(operator, x.cuda(), importance=importance)
