@@ -822,6 +822,8 @@ constexpr int CHUNK = 16384;          // [128 rows][128 B]: 64 bf16 along K, 128
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (4 + EPI_WARPS) * 32;
 // forward kernel
+constexpr int F_EPI_WARPS = 16;
+constexpr int F_THREADS = (4 + F_EPI_WARPS) * 32;
 constexpr int F_STAGES = 3;
 constexpr int F_STAGE_BYTES = 2 * CHUNK;  // hi chunk + lo chunk of one stream
 constexpr int F_BOX = 8192;               // staging box [128 rows][64 B] (32 bf16), 64-byte swizzle
@@ -852,7 +854,7 @@ struct HidFwdArgs {
 //   kLast fuses the 128 -> 1 head, the importance / mask product rule, the potential and the
 //   operator scale / shift (F, TF) and only stores the value stream.
 template <bool kLast>
-__global__ void __launch_bounds__(hid::THREADS, 1)
+__global__ void __launch_bounds__(hid::F_THREADS, 1)
 hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                   const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
@@ -875,7 +877,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
   uint32_t* tmem_slot = (uint32_t*)(bars + 10);
   float* bias_s = (float*)(bars + 16);      // [128]
   float* w3_s = bias_s + 128;               // [128] (kLast)
-  float* ubuf = (float*)(sO + 7 * F_BOX);   // [128][4] head partial sums (kLast: box 7 is unused)
+  float* ubuf = (float*)(sO + 6 * F_BOX);   // [128][3][4] head partial sums (kLast: boxes 2..7 are unused)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = args.L * args.m_tiles;
@@ -903,7 +905,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     mbar_init(wfull, 1);
     mbar_init(wfree, 1);
     mbar_init(tfull, 1);
-    mbar_init(tempty, EPI_WARPS);
+    mbar_init(tempty, F_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -985,14 +987,15 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    const int ewarp = warp - 4, q = ewarp & 3, half = ewarp >> 2;
-    const int et = threadIdx.x - 128;        // 0..255 among the epilogue threads
+    // 16 epilogue warps: 4 per TMEM lane quarter, each owning 8 of the 32 hidden units of a round (4 warps per
+    // scheduler keep the SFU / conversion latency of the activation math hidden)
+    const int ewarp = warp - 4, q = ewarp & 3, sub = ewarp >> 2;
+    const int et = threadIdx.x - 128;        // 0..511 among the epilogue threads
     const int row = q * 32 + lane;           // point row inside the tile == TMEM lane
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-    // staging address of this thread's two 16-byte pieces inside a 64-byte swizzled row
+    // staging address of this thread's 16-byte piece inside a 64-byte swizzled row
     const uint32_t sw = (uint32_t)((row >> 1) & 3);
-    const uint32_t piece0 = (uint32_t)row * 64 + (((2 * half) ^ sw) << 4);
-    const uint32_t piece1 = (uint32_t)row * 64 + (((2 * half + 1) ^ sw) << 4);
+    const uint32_t piece0 = (uint32_t)row * 64 + (((uint32_t)sub ^ sw) << 4);
     uint32_t tphase = 0;
     int cur_l = -1;
     for (int t = t_begin; t < t_end; ++t) {
@@ -1004,18 +1007,18 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           if (kLast) w3_s[et] = args.W3[l * kHidden + et];
         }
         cur_l = l;
-        named_bar_sync(1, 256);
+        named_bar_sync(1, F_EPI_WARPS * 32);
       }
       mbar_wait(tfull, tphase, 15);
       tphase ^= 1;
       tc_fence_after();
       float u[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int r = 0; r < 4; ++r) {          // h-quarters of 32 hidden units; this warp takes 16 of them
-        const int h0 = r * 32 + half * 16;
-        float z[4][16];
+      for (int r = 0; r < 4; ++r) {          // h-quarters of 32 hidden units; this warp takes 8 of them
+        const int h0 = r * 32 + sub * 8;
+        float z[4][8];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) tmem_ld16(tl + s * 128 + h0, z[s]);
+        for (int s = 0; s < 4; ++s) tmem_ld8(tl + s * 128 + h0, z[s]);
         tmem_ld_wait();
         if (r == 3) {                        // last TMEM read of this tile: hand the accumulator back
           tc_fence_before();
@@ -1023,13 +1026,13 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           if (lane == 0) mbar_arrive(tempty);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           float zb = z[0][i] + bias_s[h0 + i];
           act_streams(zb, z[1][i], z[2][i], z[3][i], z[0][i], z[1][i], z[2][i], z[3][i]);
         }
         if (kLast) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 8; ++i) {
             float w = w3_s[h0 + i];
 #pragma unroll
             for (int s = 0; s < 4; ++s) u[s] = fmaf(z[s][i], w, u[s]);
@@ -1037,21 +1040,19 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         }
         // previous round's bulk stores must have drained the staging boxes
         if (et == 0) tma_store_wait_read();
-        named_bar_sync(2, 256);
+        named_bar_sync(2, F_EPI_WARPS * 32);
 #pragma unroll
         for (int s = 0; s < (kLast ? 1 : 4); ++s) {
-          uint32_t h[8], lo[8];
+          uint32_t h[4], lo[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) split_bf16x2(z[s][2 * i], z[s][2 * i + 1], h[i], lo[i]);
+          for (int i = 0; i < 4; ++i) split_bf16x2(z[s][2 * i], z[s][2 * i + 1], h[i], lo[i]);
           uint8_t* bh = sO + (2 * s) * F_BOX;
           uint8_t* bl = bh + F_BOX;
           *reinterpret_cast<uint4*>(bh + piece0) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(bh + piece1) = make_uint4(h[4], h[5], h[6], h[7]);
           *reinterpret_cast<uint4*>(bl + piece0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(bl + piece1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
         fence_proxy_async_smem();
-        named_bar_sync(3, 256);
+        named_bar_sync(3, F_EPI_WARPS * 32);
         if (et == 0) {
           if (!kLast) {
 #pragma unroll
@@ -1066,14 +1067,16 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         }
       }
       if (kLast) {
-        if (half == 1) {
+        if (sub != 0) {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) ubuf[row * 4 + s] = u[s];
+          for (int s = 0; s < 4; ++s) ubuf[(row * 3 + sub - 1) * 4 + s] = u[s];
         }
-        named_bar_sync(1, 256);
-        if (half == 0 && pt < args.P) {
+        named_bar_sync(1, F_EPI_WARPS * 32);
+        if (sub == 0 && pt < args.P) {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) u[s] += ubuf[row * 4 + s];
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) u[s] += ubuf[(row * 3 + j) * 4 + s];
           u[0] += __ldg(args.b3 + l);
           const long pg = args.p_off + pt;
           PointGeom g = point_geom(args.x[2 * pg], args.x[2 * pg + 1], args.pb);
@@ -1084,7 +1087,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           args.TF[pg * args.L + l] = tf;
           args.U0[pg * args.L + l] = u[0];
         }
-        named_bar_sync(1, 256);  // ubuf (staging box 7) is free again
+        named_bar_sync(1, F_EPI_WARPS * 32);  // ubuf (staging boxes 6-7) is free again
       }
     }
     if (et == 0) tma_store_wait_all();
@@ -1122,7 +1125,7 @@ __device__ __forceinline__ uint32_t tile_piece_off(int row, int k0, int which) {
   return (uint32_t)(c * hid::CHUNK + row * 128 + ((piece ^ (row & 7)) << 4));
 }
 
-__global__ void __launch_bounds__(hid::THREADS, 1)
+__global__ void __launch_bounds__(hid::F_THREADS, 1)
 hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,
                   const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
@@ -1257,10 +1260,12 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    const int ewarp = warp - 4, q = ewarp & 3, half = ewarp >> 2;
+    // 16 epilogue warps: 4 per TMEM lane quarter, each owning 32 of the 128 columns (4 chunks of 8)
+    const int ewarp = warp - 4, q = ewarp & 3, sub = ewarp >> 2;
     const int et = threadIdx.x - 128;
     const int row = q * 32 + lane;
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int NEPI = F_EPI_WARPS * 32;
     uint32_t mphase = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const int l = t / args.m_tiles, mt = t % args.m_tiles;
@@ -1269,17 +1274,17 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
       tc_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
-        const int k0 = half * 64 + ch * 16;
-        float v[16], a[16];
-        tmem_ld16(tl + k0, v);
+        const int k0 = sub * 32 + ch * 8;
+        float v[8], a[8];
+        tmem_ld8(tl + k0, v);
+        const uint32_t o0 = (uint32_t)((k0 >> 6) * CHUNK + row * 128 + ((((k0 & 63) >> 3) ^ (row & 7)) << 4));
         {
-          const uint32_t o0 = tile_piece_off(row, k0, 0), o1 = tile_piece_off(row, k0, 1);
-          uint4 h[2] = {*reinterpret_cast<const uint4*>(sA + o0), *reinterpret_cast<const uint4*>(sA + o1)};
-          uint4 lo[2] = {*reinterpret_cast<const uint4*>(sA + PLANE + o0), *reinterpret_cast<const uint4*>(sA + PLANE + o1)};
-          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(h);
-          const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(lo);
+          uint4 h = *reinterpret_cast<const uint4*>(sA + o0);
+          uint4 lo = *reinterpret_cast<const uint4*>(sA + PLANE + o0);
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&h);
+          const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&lo);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             float2 x0 = __bfloat1622float2(hh[i]), x1 = __bfloat1622float2(ll[i]);
             a[2 * i] = x0.x + x1.x;
             a[2 * i + 1] = x0.y + x1.y;
@@ -1288,38 +1293,34 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
         tmem_ld_wait();
         // rows beyond P carry dZ_i = 0 (TMA zero fill), hence D1 = 0 and v = 0 without a mask
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= sig_fast(a[i]);
+        for (int i = 0; i < 8; ++i) v[i] *= sig_fast(a[i]);
         {
-          uint32_t h[8], lo[8];
+          uint32_t h[4], lo[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], h[i], lo[i]);
-          const uint32_t o0 = tile_piece_off(row, k0, 0), o1 = tile_piece_off(row, k0, 1);
+          for (int i = 0; i < 4; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], h[i], lo[i]);
           *reinterpret_cast<uint4*>(sZ + o0) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(sZ + o1) = make_uint4(h[4], h[5], h[6], h[7]);
           *reinterpret_cast<uint4*>(sZ + PLANE + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(sZ + PLANE + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         }
-        // column sums over the 32 rows of this warp: recursive halving (16 shuffles), lane c < 16
-        // ends with column k0 + c
+        // column sums over the 32 rows of this warp: recursive halving, then two full butterflies
 #pragma unroll
-        for (int w = 8; w >= 1; w >>= 1) {
-          const bool up = (lane & (w * 2)) != 0;  // lanes with this bit keep the upper half
+        for (int w = 4; w >= 1; w >>= 1) {
+          const bool up = (lane & (w * 4)) != 0;   // lane bits 16, 8, 4 select the upper half
 #pragma unroll
           for (int i = 0; i < w; ++i) {
             float send = up ? v[i] : v[i + w];
             float keep = up ? v[i + w] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w * 2);
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w * 4);
           }
         }
         {
-          float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-          // lane bits (16,8,4,2) select the column: col = 8*b16 + 4*b8 + 2*b4 + b2
-          const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          if ((lane & 1) == 0) atomicAdd(&db_s[k0 + col], tot);
+          float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 2);
+          tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+          const int col = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+          if ((lane & 3) == 0) atomicAdd(&db_s[k0 + col], tot);
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(2, 256);
+      named_bar_sync(2, NEPI);
       if (et == 0) {
         tma_store_3d(&tmOh, sZ, 0, mt * 128, l);
         tma_store_3d(&tmOh, sZ + CHUNK, 64, mt * 128, l);
@@ -1333,12 +1334,12 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
         float* drow = args.dW + ((long)l * kHidden + j) * kHidden;
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
-          const int k0 = half * 64 + ch * 16;
-          float v[16];
-          tmem_ld16(tl + 256 + k0, v);
+          const int k0 = sub * 32 + ch * 8;
+          float v[8];
+          tmem_ld8(tl + 256 + k0, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) red_add_v4(drow + k0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+          red_add_v4(drow + k0, v[0], v[1], v[2], v[3]);
+          red_add_v4(drow + k0 + 4, v[4], v[5], v[6], v[7]);
         }
         if (et < 128) {
           atomicAdd(args.db_prev + l * kHidden + et, db_s[et]);
@@ -1347,7 +1348,7 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
       }
       if (et == 0) tma_store_wait_read();
       tc_fence_before();
-      named_bar_sync(3, 256);
+      named_bar_sync(3, NEPI);
       if (et == 0) mbar_arrive(epi_done);
     }
     if (et == 0) tma_store_wait_all();
@@ -1519,7 +1520,7 @@ static int launch_hidden_fwd(const CUtensorMap& ah, const CUtensorMap& al, const
   }
   int T = a.L * a.m_tiles;
   int grid = T < 148 ? T : 148;
-  kern<<<grid, hid::THREADS, hid::SMEM_FWD, st>>>(ah, al, wh, wl, oh, ol, sh, sl, a);
+  kern<<<grid, hid::F_THREADS, hid::SMEM_FWD, st>>>(ah, al, wh, wl, oh, ol, sh, sl, a);
   NSVD_LAUNCH_CHECK();
   return 0;
 }
@@ -1681,7 +1682,7 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
       int grid = T < 148 ? T : 148;
       {
         ProfScope ps(KC_HID_BWD, st);
-        hidden_bwd_kernel<<<grid, hid::THREADS, hid::SMEM_BWD, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], mOh, mOl, a);
+        hidden_bwd_kernel<<<grid, hid::F_THREADS, hid::SMEM_BWD, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], mOh, mOl, a);
         NSVD_LAUNCH_CHECK();
       }
       cur ^= 1;
