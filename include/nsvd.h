@@ -92,6 +92,10 @@ const char* nsvd_last_error(void);
 /* 0 when device `dev` is an sm_100 part this library can run on. */
 int nsvd_device_ok(int dev);
 
+/* Points per micro-batch of the tcgen05 engine (rounded up to a multiple of 128; default 65536 or the
+ * NSVD_TC_MICROBATCH environment variable).  Sets the size of `work`; call before nsvd_scratch_bytes.  */
+void nsvd_set_tc_microbatch(int32_t points);
+
 /* Scratch sizes for nsvd_fwd_streams / nsvd_mlp_bwd.  `saved_bytes`: value-stream activations
  * kept from forward to backward (whole batch).  `work_bytes`: micro-batch scratch, reusable. */
 int nsvd_scratch_bytes(const nsvd_problem_t* pb, int engine, size_t* saved_bytes, size_t* work_bytes);

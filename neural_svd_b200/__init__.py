@@ -9,7 +9,7 @@ from .nestedlora import (NestedLoRA, NestedLoRAForCDK, NestedLoRALossFunctionEVD
                          get_joint_nesting_masks, get_sequential_nesting_masks)
 from .operators import (GaussianImportance, NegativeHamiltonian, OperatorWrapper, get_problem,
                         harmonic_oscillator_potential, hydrogen_potential, make_gaussian_sampler)
-from .fused import compute_loss_operator, get_engine, set_engine
+from .fused import compute_loss_operator, get_engine, set_engine, set_microbatch
 from .dist import PointParallel, shard_points
 from .spectrum import compute_spectrum_evd
 from .optim import FusedRMSpropEMA, sample_gaussian

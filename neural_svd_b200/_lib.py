@@ -42,6 +42,7 @@ SIGNATURES = {
     "nsvd_abi_version": (C.c_int, []),
     "nsvd_last_error": (C.c_char_p, []),
     "nsvd_launch_count": (C.c_long, []),
+    "nsvd_set_tc_microbatch": (None, [C.c_int32]),
     "nsvd_profile_enable": (None, [C.c_int]),
     "nsvd_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int, C.c_int]),
     "nsvd_device_ok": (C.c_int, [C.c_int]),

@@ -52,6 +52,7 @@ extern "C" {
 
 int nsvd_abi_version(void) { return NSVD_ABI_VERSION; }
 long nsvd_launch_count(void) { return g_launches; }
+void nsvd_set_tc_microbatch(int32_t points) { tc_set_micro_batch(points); }
 void nsvd_profile_enable(int on) { g_prof_on = on != 0; }
 int nsvd_profile_read(double* ms_per_class, long* launches_per_class, int n_classes, int reset) {
   for (int i = 0; i < n_classes; ++i) {

@@ -57,6 +57,7 @@ int rmsprop_ema_step(const OptTensors& t, float lr, float alpha, float eps, floa
 int sample_gaussian2(float* x, long n, float sigma, uint64_t seed, uint64_t offset, cudaStream_t st);
 
 // tcgen05 engine (nsvd_tc.cu)
+void tc_set_micro_batch(int points);
 void tc_scratch_bytes(const nsvd_problem_t& pb, size_t* saved, size_t* work);
 int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x, float* F, float* TF,
                void* saved, void* work, size_t work_bytes, cudaStream_t st);

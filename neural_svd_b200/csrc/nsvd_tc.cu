@@ -1382,39 +1382,61 @@ head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
 #pragma unroll
   for (int i = 0; i < 4; ++i) w3[i] = W3[l * kHidden + lane * 4 + i];
   float sc = pb.has_exp_mask ? mscales[l] : 1.f;
-  for (int p = p_begin + warp; p < p_end; p += 4) {
-    const long pg = p_off + p;
-    PointGeom g = point_geom(x[2 * pg], x[2 * pg + 1], pb);
-    float m = pb.has_exp_mask ? expf(-g.r / sc) : 1.f;
-    float cm = pb.hard_mul_const * m * g.rho;
-    float du = dF[pg * L + l] * cm;
-    acc_b3 += du;
-    if (pb.has_exp_mask) acc_s += du * U0[pg * L + l] * g.r / (sc * sc);
-    const long oa = ((long)l * Btot + pg) * kHidden + lane * 4;
-    uint2 h = *reinterpret_cast<const uint2*>(a2_hi + oa), lo2 = *reinterpret_cast<const uint2*>(a2_lo + oa);
-    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&h);
-    const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&lo2);
-    float a[4];
-    {
-      float2 t0 = __bfloat1622float2(hh[0]), t1 = __bfloat1622float2(hh[1]);
-      float2 u0 = __bfloat1622float2(ll[0]), u1 = __bfloat1622float2(ll[1]);
-      a[0] = t0.x + u0.x; a[1] = t0.y + u0.y; a[2] = t1.x + u1.x; a[3] = t1.y + u1.y;
+  // each warp owns 32 consecutive points: lane i evaluates the per-point factor du of point i once, then the
+  // warp walks the 32 points with 4 rows of a2 in flight (lane = 4 hidden units)
+  {
+    const int pw = p_begin + warp * 32;
+    const int pmine = pw + lane;
+    float du_l = 0.f;
+    if (pmine < p_end) {
+      const long pg = p_off + pmine;
+      PointGeom g = point_geom(x[2 * pg], x[2 * pg + 1], pb);
+      float m = pb.has_exp_mask ? expf(-g.r / sc) : 1.f;
+      float cm = pb.hard_mul_const * m * g.rho;
+      du_l = dF[pg * L + l] * cm;
+      acc_b3 = du_l;
+      if (pb.has_exp_mask) acc_s = du_l * U0[pg * L + l] * g.r / (sc * sc);
     }
-    float dz[4];
+    for (int j0 = 0; j0 < 32 && pw + j0 < p_end; j0 += 4) {
+      uint2 h[4], lo2[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      dz[i] = du * w3[i] * sig_fast(a[i]);
-      accW[i] = fmaf(du, a[i], accW[i]);
-      accB[i] += dz[i];
+      for (int u = 0; u < 4; ++u) {
+        const int p = pw + j0 + u;
+        const long oa = ((long)l * Btot + p_off + (p < p_end ? p : pw)) * kHidden + lane * 4;
+        h[u] = *reinterpret_cast<const uint2*>(a2_hi + oa);
+        lo2[u] = *reinterpret_cast<const uint2*>(a2_lo + oa);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = pw + j0 + u;
+        const float du = __shfl_sync(0xffffffffu, du_l, j0 + u);
+        if (p >= p_end) continue;
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&h[u]);
+        const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&lo2[u]);
+        float a[4];
+        {
+          float2 t0 = __bfloat1622float2(hh[0]), t1 = __bfloat1622float2(hh[1]);
+          float2 u0 = __bfloat1622float2(ll[0]), u1 = __bfloat1622float2(ll[1]);
+          a[0] = t0.x + u0.x; a[1] = t0.y + u0.y; a[2] = t1.x + u1.x; a[3] = t1.y + u1.y;
+        }
+        float dz[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dz[i] = du * w3[i] * sig_fast(a[i]);
+          accW[i] = fmaf(du, a[i], accW[i]);
+          accB[i] += dz[i];
+        }
+        uint32_t h01, l01, h23, l23;
+        tc::split_bf16x2(dz[0], dz[1], h01, l01);
+        tc::split_bf16x2(dz[2], dz[3], h23, l23);
+        const long oz = ((long)l * P + p) * kHidden + lane * 4;
+        *reinterpret_cast<uint2*>(dz_hi + oz) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(dz_lo + oz) = make_uint2(l01, l23);
+      }
     }
-    uint32_t h01, l01, h23, l23;
-    tc::split_bf16x2(dz[0], dz[1], h01, l01);
-    tc::split_bf16x2(dz[2], dz[3], h23, l23);
-    const long oz = ((long)l * P + p) * kHidden + lane * 4;
-    *reinterpret_cast<uint2*>(dz_hi + oz) = make_uint2(h01, h23);
-    *reinterpret_cast<uint2*>(dz_lo + oz) = make_uint2(l01, l23);
+    acc_b3 = warp_sum(acc_b3);
+    acc_s = warp_sum(acc_s);
   }
-  // acc_b3 / acc_s are identical across lanes of a warp (computed redundantly): keep lane 0's
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     red[warp][lane * 4 + i] = accW[i];
@@ -1441,15 +1463,17 @@ head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
 // ------------------------------------------------------------------------------------------
 // engine drivers
 // ------------------------------------------------------------------------------------------
+static int g_tc_micro_batch = 0;   // 0 = not initialised yet
+void tc_set_micro_batch(int points) {
+  if (points < 128) points = 128;
+  g_tc_micro_batch = (points + 127) / 128 * 128;
+}
 static int tc_micro_batch() {
-  static int mb = 0;
-  if (!mb) {
+  if (!g_tc_micro_batch) {
     const char* e = getenv("NSVD_TC_MICROBATCH");
-    mb = e ? atoi(e) : 65536;
-    if (mb < 128) mb = 128;
-    mb = (mb + 127) / 128 * 128;
+    tc_set_micro_batch(e ? atoi(e) : 65536);
   }
-  return mb;
+  return g_tc_micro_batch;
 }
 
 struct TcLayout {
@@ -1505,6 +1529,10 @@ void tc_scratch_bytes(const nsvd_problem_t& pb, size_t* saved, size_t* work) {
   *work = t.work_total;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 static inline uint8_t* align1k(void* p) { return (uint8_t*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023); }
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 
@@ -1570,7 +1598,8 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
     s.k_chunks_per_slice = s.k_chunks_total;
     s.a_batched = 0;
     s.b_batched = 1;
-    s.m_group = pair ? 16 : 32;   // 4096 points x 8 KB of Phi per group
+    static const int mgroup = env_int("NSVD_L0_MGROUP", 16);
+    s.m_group = pair ? mgroup : 2 * mgroup;   // 4096 points x 8 KB of Phi per group
     L0FwdEpi e0{pr.b[0], BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), BF(sv + t.av_hi[0]), BF(sv + t.av_lo[0]), P, B, p0};
     {
       ProfScope ps(KC_L0_FWD, st);
@@ -1698,11 +1727,12 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
     s.n_tiles = cdiv(K0, big::BN);
     s.batches = (int)L;
     s.k_chunks_total = cdiv(P, big::BK);
-    s.k_chunks_per_slice = 16;  // 1024 points per accumulation (fp32 TMEM accumulation stays short)
+    static const int kslice = env_int("NSVD_WGRAD_KSLICE", 16), kgroup = env_int("NSVD_WGRAD_KGROUP", 4);
+    s.k_chunks_per_slice = kslice;  // 1024 points per accumulation (fp32 TMEM accumulation stays short)
     s.k_slices = cdiv(s.k_chunks_total, s.k_chunks_per_slice);
     s.a_batched = 1;
     s.b_batched = 0;
-    s.k_group = 4;   // 4096 points per group: dZ0 (all copies) + Phi of a group stay in L2
+    s.k_group = kgroup;   // 4096 points per group: dZ0 (all copies) + Phi of a group stay in L2
     L0WgradEpi ew{gr.dW[0], (int)K0};
     {
       ProfScope ps(KC_L0_WGRAD, st);

@@ -32,6 +32,11 @@ def get_engine() -> str:
     return _ENGINE
 
 
+def set_microbatch(points: int):
+    """Points per micro-batch of the tensor-core engine (bounds the size of the stream scratch buffers)."""
+    _lib.load().nsvd_set_tc_microbatch(int(points))
+
+
 def _require_cuda(dev: torch.device):
     if dev.type != "cuda":
         raise RuntimeError("neural_svd_b200 has no CPU path: parameters and inputs must live on a CUDA (sm_100) device")
@@ -121,10 +126,10 @@ class _Scratch:
         self.version = 0
 
     def ensure(self, lib, pb: _lib.Problem, engine: int, dev):
-        key = (pb.n_points, pb.n_copies, pb.n_fourier, engine, str(dev))
+        ns, nw = C.c_size_t(), C.c_size_t()
+        _lib.check(lib.nsvd_scratch_bytes(C.byref(pb), engine, C.byref(ns), C.byref(nw)), "nsvd_scratch_bytes")
+        key = (pb.n_points, pb.n_copies, pb.n_fourier, engine, str(dev), ns.value, nw.value)
         if key != self.key:
-            ns, nw = C.c_size_t(), C.c_size_t()
-            _lib.check(lib.nsvd_scratch_bytes(C.byref(pb), engine, C.byref(ns), C.byref(nw)), "nsvd_scratch_bytes")
             self.saved = torch.empty(ns.value, dtype=torch.uint8, device=dev)
             self.work = torch.empty(nw.value, dtype=torch.uint8, device=dev)
             npart = lib.nsvd_gram_partials_bytes(pb.n_points, pb.n_copies)

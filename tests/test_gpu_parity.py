@@ -262,3 +262,28 @@ def test_graphed_step_equals_eager_step(engine):
         if p.grad is not None:
             assert rel(grads_g[n].cpu().numpy(), p.grad.cpu().numpy()) < 2e-5, n
     assert rel(step.aux["Tf"].cpu().numpy(), aux["Tf"].cpu().numpy()) < 1e-6
+
+
+def test_micro_batch_boundaries():
+    # several micro-batches with a ragged tail (p_off handling in every kernel): B = 1000 in micro-batches of 256,
+    # and B = 65536 + 300 with the default micro-batch, tensor-core engine against the fp32 engine
+    d, cfg = load_golden("hyd_small_odd")
+    g = torch.Generator().manual_seed(3)
+    try:
+        for B, mb in ((1000, 256), (65536 + 300, 65536)):
+            x = (cfg.sampling_scale * torch.randn(B, 2, generator=g)).cuda()
+            res = {}
+            for engine in ("fp32", "bf16x3"):
+                N.set_engine(engine)
+                N.set_microbatch(mb)
+                method, operator, importance, _ = build_problem(cfg, 21, "cuda")
+                loss, aux = method.compute_loss_operator(operator, x, importance=importance)
+                loss.backward()
+                res[engine] = (float(loss.detach()), aux["Tf"].cpu().numpy(),
+                               {n: p.grad.cpu().numpy() for n, p in method.named_parameters() if p.grad is not None})
+            assert abs(res["bf16x3"][0] - res["fp32"][0]) < TOL * abs(res["fp32"][0])
+            assert rel(res["bf16x3"][1], res["fp32"][1]) < TOL
+            for n in res["fp32"][2]:
+                assert rel(res["bf16x3"][2][n], res["fp32"][2][n]) < TOL, (B, n)
+    finally:
+        N.set_microbatch(65536)
