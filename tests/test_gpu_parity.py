@@ -287,3 +287,46 @@ def test_micro_batch_boundaries():
                 assert rel(res["bf16x3"][2][n], res["fp32"][2][n]) < TOL, (B, n)
     finally:
         N.set_microbatch(65536)
+
+
+def test_config4_shape_L64_engines_agree():
+    # BASELINE configs[3] shape (hydrogen, L=64, M_ff=1024) at a batch the fp32 engine finishes quickly:
+    # tensor-core engine against the fp32 engine (itself pinned to the L=64 golden fixture above)
+    cfg = O.PathConfig.hydrogen(neigs=64)
+    g = torch.Generator().manual_seed(64)
+    x = (cfg.sampling_scale * torch.randn(3000, 2, generator=g)).cuda()
+    res = {}
+    for engine in ("fp32", "bf16x3"):
+        N.set_engine(engine)
+        method, operator, importance, _ = build_problem(cfg, 8, "cuda")
+        loss, aux = method.compute_loss_operator(operator, x, importance=importance)
+        loss.backward()
+        res[engine] = (float(loss.detach()), aux["f"].cpu().numpy(), aux["Tf"].cpu().numpy(),
+                       {n: p.grad.cpu().numpy() for n, p in method.named_parameters() if p.grad is not None})
+        del method
+        torch.cuda.empty_cache()
+    assert abs(res["bf16x3"][0] - res["fp32"][0]) < TOL * abs(res["fp32"][0])
+    assert rel(res["bf16x3"][1], res["fp32"][1]) < TOL and rel(res["bf16x3"][2], res["fp32"][2]) < TOL
+    for n in res["fp32"][3]:
+        assert rel(res["bf16x3"][3][n], res["fp32"][3][n]) < TOL, n
+
+
+def test_no_grad_and_double_backward_calls():
+    d, cfg = load_golden("hyd_small_odd")
+    N.set_engine("bf16x3")
+    method, operator, importance, _ = build_problem(cfg, int(d["seed"]), "cuda")
+    x = torch.from_numpy(d["x"]).cuda()
+    with torch.no_grad():
+        loss0, aux0 = method.compute_loss_operator(operator, x, importance=importance)
+    assert not loss0.requires_grad and abs(float(loss0) - float(d["loss64"])) < TOL * abs(float(d["loss64"]))
+    loss, _ = method.compute_loss_operator(operator, x, importance=importance)
+    loss.backward(retain_graph=True)
+    g1 = method.model.base.ws[2].grad.clone()
+    loss.backward()                                   # second backward through the same graph accumulates
+    assert rel(method.model.base.ws[2].grad.cpu().numpy(), 2 * g1.cpu().numpy()) < 1e-5
+    # a second forward invalidates the scratch of the first: its backward must refuse rather than use stale data
+    l1, _ = method.compute_loss_operator(operator, x, importance=importance)
+    l2, _ = method.compute_loss_operator(operator, x, importance=importance)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        l1.backward()
+    l2.backward()
