@@ -263,11 +263,11 @@ def run_ours(args):
 
     # ---- end to end: host x (pinned) -> H2D -> step -> loss.item(); wall clock, max over ranks
     for i in range(2):
-        float(step(xs_host[i % 4]))
+        step(xs_host[i % 4]).detach().item()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        float(step(xs_host[i % 4]))     # .to(device) inside compute_loss_operator; .item() reads the loss back
+        step(xs_host[i % 4]).detach().item()     # .to(device) inside compute_loss_operator; .item() reads the loss back
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
