@@ -4,7 +4,8 @@
 // cores as  A_hi B_hi + A_lo B_hi + A_hi B_lo  (bf16 operands, fp32 accumulation in TMEM), where
 // v = v_hi + v_lo is the two-term bf16 split (16 significant bits).  Kernels are persistent and
 // warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
-// allocator, warps 4..11 = epilogue (TMEM -> registers -> fused math -> global).
+// allocator, warps 4.. = epilogue (TMEM -> registers -> fused math -> global / staged TMA stores):
+// 8 epilogue warps in the layer-0 GEMMs (MMA-bound), 16 in the hidden-layer kernels (epilogue-bound).
 #include "nsvd_simt.cuh"
 #include "nsvd_tc.cuh"
 
@@ -1562,7 +1563,8 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
   uint8_t* wk = align1k(work_v);
   int rc;
   // ---- per-call preparation: features of all points, folded / split weights
-  ProfScope* prep = new ProfScope(KC_PREP, st);
+  {
+  ProfScope prep(KC_PREP, st);
   features_bf16_kernel<<<cdiv(B * (M / 4), 256), 256, 0, st>>>(x, pr.Bff, BF(sv + t.phi_hi), BF(sv + t.phi_lo), B, (int)M);
   NSVD_LAUNCH_CHECK();
   fold_w0_kernel<<<cdiv(L * H * M, 256), 256, 0, st>>>(pr.W[0], pr.Bff, BF(wk + t.w0_hi), BF(wk + t.w0_lo), (int)L,
@@ -1572,7 +1574,7 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
     split_w_kernel<<<cdiv(L * H * H, 256), 256, 0, st>>>(pr.W[i + 1], BF(wk + t.w_hi[i]), BF(wk + t.w_lo[i]), (int)L, 0);
     NSVD_LAUNCH_CHECK();
   }
-  delete prep;
+  }
   CUtensorMap mW0h, mW0l, mWh[2], mWl[2];
   const bool pair = tc_use_pair();
   const uint32_t w0_box = pair ? big::BN / 2 : big::BN;   // a CTA of a pair loads half of the 256 W' rows
