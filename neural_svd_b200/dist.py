@@ -21,8 +21,13 @@ class PointParallel:
         self.rank = dist.get_rank(group)
         self._counts_cache = {}
 
+    def reset_counts(self):
+        """Forget the cached global counts (call on every rank if ANY rank changes its local batch size)."""
+        self._counts_cache = {}
+
     def global_counts(self, n_local: int, b1_local: int, device):
-        """(B, B1, B2) summed over ranks. Cached per (n_local, b1_local): counts are static in training."""
+        """(B, B1, B2) summed over ranks.  Cached per (n_local, b1_local) of this rank — batch sizes are static in
+        the reference's training loop — so the steady state has no host synchronisation; see reset_counts()."""
         key = (n_local, b1_local)
         if key not in self._counts_cache:
             c = torch.tensor([n_local, b1_local], dtype=torch.int64, device=device)
