@@ -1115,8 +1115,12 @@ __global__ void sample_gaussian2_kernel(float* __restrict__ x, long n, float sig
   uint64_t ctr = (offset + (uint64_t)i) * 2ull;
   uint32_t a = mix32(seed ^ (ctr * 0xD1342543DE82EF95ull));
   uint32_t b = mix32((seed + 0x632BE59BD9B4E019ull) ^ ((ctr + 1ull) * 0xD1342543DE82EF95ull));
-  float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
-  float u2 = (float)b * 2.3283064365386963e-10f;            // [0, 1)
+  // u1 strictly inside (0, 1): u1 == 1 would give r == 0, i.e. a point exactly at the origin where the hydrogen
+  // potential is infinite (a (float)a + 1 construction rounds to 1.0 with probability 3e-8 per sample; a soak run
+  // of 2e7 samples hit it).  23-bit mid-point grid (k + 0.5 is exact in fp32 for k < 2^23): u1 <= 1 - 2^-24,
+  // r in [3.5e-4, 5.8] sigma.
+  float u1 = ((float)(a >> 9) + 0.5f) * 1.1920928955078125e-07f;
+  float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;     // [0, 1)
   float r = sigma * sqrtf(-2.f * logf(u1));
   float sn, cs;
   sincospif(2.f * u2, &sn, &cs);

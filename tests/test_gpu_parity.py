@@ -239,6 +239,9 @@ def test_device_sampler_statistics_and_reproducibility():
     assert abs((xs ** 4).mean() - 3.0) < 0.05                      # kurtosis of a normal
     r2 = (xs ** 2).sum(1)
     assert abs(np.mean(r2 < 2 * np.log(2)) - 0.5) < 5e-3           # chi^2_2 median
+    # never exactly at the origin (V = -1/r): the radius grid starts at 2.4e-4 sigma
+    big = N.sample_gaussian(1 << 26, 1.0, seed=11)
+    assert float((big ** 2).sum(1).min()) > 1e-8
 
 
 @pytest.mark.parametrize("engine", ENGINES)
