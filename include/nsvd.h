@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NSVD_ABI_VERSION 1
+#define NSVD_ABI_VERSION 2
 
 enum {
   NSVD_E_BADARG = 10001,   /* shape / enum / alignment violation */
@@ -37,8 +37,18 @@ enum {
   NSVD_E_WORKSPACE = 10003 /* workspace too small */
 };
 
-/* potentials: examples/operator/pde/schrodinger/potentials.py:5-8 and :24-27 */
-enum { NSVD_POT_HYDROGEN = 0, NSVD_POT_HARMONIC = 1 };
+/* potentials (examples/operator/pde/schrodinger/potentials.py): hydrogen :5-8 (pot_coef = charge Z), harmonic
+ * oscillator :24-27 (pot_coef = k), H2+ ion :11-17 (pot_coef = nuclear charge, pot_coef2 = R, nuclei at (0, +-R)),
+ * infinite well :20-21 (V = 0), cosine :30-31 (pot_coef, pot_coef2 = cs[0], cs[1]). */
+enum { NSVD_POT_HYDROGEN = 0, NSVD_POT_HARMONIC = 1, NSVD_POT_HYDROGEN_MOL_ION = 2, NSVD_POT_INFINITE_WELL = 3,
+       NSVD_POT_COSINE = 4 };
+
+/* importance density w(x) of the sampler (examples/operator/pde/main_pde.py:89-118); sampling_sigma is its scale.
+ * NONE = the operator is applied without re-weighting (importance=None, diff_ops.py:10-11). */
+enum { NSVD_IMP_GAUSSIAN = 0, NSVD_IMP_LAPLACE = 1, NSVD_IMP_UNIFORM = 2, NSVD_IMP_NONE = 3 };
+
+/* DirichletBoundaryMaskBox modes (examples/operator/pde/boundary.py:16-37) */
+enum { NSVD_BOX_NONE = 0, NSVD_BOX_SQRT = 1, NSVD_BOX_EXP = 2 };
 
 /* arithmetic engines for the dense contractions.
  *   FP32_SIMT   : CUDA-core fp32 FMA. Reference-grade accuracy; validation and tiny batches.
@@ -56,12 +66,16 @@ typedef struct nsvd_problem {
   int32_t hidden;          /* hidden width of the 3 hidden layers; must be 128                  */
   int32_t potential;       /* NSVD_POT_*                                                        */
   int32_t has_exp_mask;    /* ExponentialMask present (pde/boundary.py:39-53)                   */
-  float pot_coef;          /* charge Z (hydrogen) or k (harmonic)                               */
+  float pot_coef;          /* first potential coefficient (see NSVD_POT_*)                      */
   float scale_kinetic;     /* kappa, problems.py:28 (1.0 for single-particle problems)          */
   float op_scale;          /* OperatorWrapper.scale  (examples/__init__.py:2-9)                 */
   float op_shift;          /* OperatorWrapper.shift                                             */
-  float sampling_sigma;    /* sigma of the Gaussian importance density (main_pde.py:94-100)     */
+  float sampling_sigma;    /* scale of the importance density: sigma / b / half-width           */
   float hard_mul_const;    /* WaveFunctions.hard_mul_const (pde/__init__.py:9-16)               */
+  int32_t importance;      /* NSVD_IMP_*  (ABI 2)                                               */
+  int32_t box_mask;        /* NSVD_BOX_*: Dirichlet box mask multiplying every eigenfunction    */
+  float pot_coef2;         /* second potential coefficient                                      */
+  float box_lim;           /* half-width `lim` of the Dirichlet box                             */
 } nsvd_problem_t;
 
 /* Parameters in the reference's own layout (ParallelMLP, mlp.py:181-199):

@@ -17,7 +17,9 @@ class Problem(C.Structure):
     _fields_ = [("n_points", C.c_int32), ("n_copies", C.c_int32), ("n_fourier", C.c_int32),
                 ("hidden", C.c_int32), ("potential", C.c_int32), ("has_exp_mask", C.c_int32),
                 ("pot_coef", C.c_float), ("scale_kinetic", C.c_float), ("op_scale", C.c_float),
-                ("op_shift", C.c_float), ("sampling_sigma", C.c_float), ("hard_mul_const", C.c_float)]
+                ("op_shift", C.c_float), ("sampling_sigma", C.c_float), ("hard_mul_const", C.c_float),
+                ("importance", C.c_int32), ("box_mask", C.c_int32), ("pot_coef2", C.c_float),
+                ("box_lim", C.c_float)]
 
 
 class Params(C.Structure):
@@ -29,7 +31,9 @@ class Grads(C.Structure):
     _fields_ = [("dW", C.c_void_p * 4), ("db", C.c_void_p * 4), ("dmask_scales", C.c_void_p)]
 
 
-POT_HYDROGEN, POT_HARMONIC = 0, 1
+POT_HYDROGEN, POT_HARMONIC, POT_HYDROGEN_MOL_ION, POT_INFINITE_WELL, POT_COSINE = 0, 1, 2, 3, 4
+IMP_GAUSSIAN, IMP_LAPLACE, IMP_UNIFORM, IMP_NONE = 0, 1, 2, 3
+BOX_NONE, BOX_SQRT, BOX_EXP = 0, 1, 2
 ENGINE_FP32_SIMT, ENGINE_BF16X3_TC = 0, 1
 ENGINES = {"fp32": ENGINE_FP32_SIMT, "fp32_simt": ENGINE_FP32_SIMT, "bf16x3": ENGINE_BF16X3_TC,
            "tc": ENGINE_BF16X3_TC}
@@ -83,7 +87,7 @@ def load():
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)        # AttributeError if a declared symbol is missing
                 fn.restype, fn.argtypes = res, args
-            if lib.nsvd_abi_version() != 1:
+            if lib.nsvd_abi_version() != 2:
                 raise RuntimeError("libnsvd.so ABI version mismatch")
             _lib = lib
     return _lib

@@ -34,8 +34,11 @@ static int check_problem(const nsvd_problem_t* pb) {
   NSVD_CHECK_ARG(pb->n_copies >= 1 && pb->n_copies <= 64, "n_copies must be in [1,64] (got %d)", pb->n_copies);
   NSVD_CHECK_ARG(pb->hidden == kHidden, "hidden must be %d (got %d)", kHidden, pb->hidden);
   NSVD_CHECK_ARG(pb->n_fourier >= 8 && pb->n_fourier % 8 == 0, "n_fourier must be a positive multiple of 8 (got %d)", pb->n_fourier);
-  NSVD_CHECK_ARG(pb->potential == NSVD_POT_HYDROGEN || pb->potential == NSVD_POT_HARMONIC, "unknown potential %d", pb->potential);
-  NSVD_CHECK_ARG(pb->sampling_sigma > 0.f, "sampling_sigma must be > 0");
+  NSVD_CHECK_ARG(pb->potential >= NSVD_POT_HYDROGEN && pb->potential <= NSVD_POT_COSINE, "unknown potential %d", pb->potential);
+  NSVD_CHECK_ARG(pb->importance >= NSVD_IMP_GAUSSIAN && pb->importance <= NSVD_IMP_NONE, "unknown importance %d", pb->importance);
+  NSVD_CHECK_ARG(pb->importance == NSVD_IMP_NONE || pb->sampling_sigma > 0.f, "sampling_sigma must be > 0");
+  NSVD_CHECK_ARG(pb->box_mask >= NSVD_BOX_NONE && pb->box_mask <= NSVD_BOX_EXP, "unknown box mask mode %d", pb->box_mask);
+  NSVD_CHECK_ARG(pb->box_mask == NSVD_BOX_NONE || pb->box_lim > 0.f, "box_lim must be > 0");
   return 0;
 }
 static int check_params(const nsvd_problem_t* pb, const nsvd_params_t* pr) {

@@ -72,8 +72,31 @@ __device__ __forceinline__ float sig_from_softplus(float a) { return -expm1f(-a)
 // Per-point quantities of the operator epilogue: shared by forward and backward.
 struct PointGeom {
   float x0, x1, r, rho, V;
-  float gq0, gq1, lapq;  // grad/laplacian of ln sqrt(w)   (mask part added per copy)
+  float gq0, gq1, lapq;            // grad / Laplacian of ln sqrt(w)   (exp-mask part added per copy)
+  float mb, gmb0, gmb1, lapmb;     // Dirichlet box mask and its derivatives (1, 0, 0, 0 without one)
 };
+
+__device__ __forceinline__ float sgnf(float v) { return (v > 0.f) - (v < 0.f); }   // torch.sign / d|x|/dx
+
+// one factor of DirichletBoundaryMaskBox (pde/boundary.py:16-37): value, first and second derivative as autograd
+// sees them (clamp and maximum pass no gradient outside the box)
+__device__ __forceinline__ void box_factor(float x, float lim, int mode, float& m, float& d1, float& d2) {
+  const bool inside = x >= -lim && x <= lim;
+  const float xc = fminf(fmaxf(x, -lim), lim);
+  if (mode == NSVD_BOX_SQRT) {           // max((sqrt(2 lim^2 - x^2) - lim) / lim, 0)
+    const float q = 2.f * lim * lim - xc * xc, sq = sqrtf(q);
+    const float t = (sq - lim) / lim;
+    const bool on = inside && t > 0.f;
+    m = fmaxf(t, 0.f);
+    d1 = on ? -xc / (lim * sq) : 0.f;
+    d2 = on ? -2.f * lim / (q * sq) : 0.f;
+  } else {                               // (1 - exp(-(lim - x))) (1 - exp(-(x + lim)))
+    const float a = expf(xc - lim), b = expf(-xc - lim);
+    m = (1.f - a) * (1.f - b);
+    d1 = inside ? b - a : 0.f;
+    d2 = inside ? -(a + b) : 0.f;
+  }
+}
 
 __device__ __forceinline__ PointGeom point_geom(float x0, float x1, const nsvd_problem_t& pb) {
   PointGeom g;
@@ -81,20 +104,64 @@ __device__ __forceinline__ PointGeom point_geom(float x0, float x1, const nsvd_p
   g.x1 = x1;
   float r2 = x0 * x0 + x1 * x1;
   g.r = sqrtf(r2);
-  float s2 = pb.sampling_sigma * pb.sampling_sigma;
-  // w = N(x; 0, sigma^2 I_2) through log_prob().exp() as main_pde.py:97-100
-  float logw = -r2 / (2.f * s2) - logf(6.283185307179586f * s2);
-  float sw = sqrtf(expf(logw));
-  g.rho = sw / fmaxf(sw, 1e-5f);  // diff_ops.py:15-18
-  float inv = -1.f / (2.f * s2);
-  g.gq0 = x0 * inv;
-  g.gq1 = x1 * inv;
-  g.lapq = 2.f * inv;  // -D/(2 sigma^2), D = 2
-  g.V = pb.potential == NSVD_POT_HYDROGEN ? -(pb.pot_coef / g.r) : pb.pot_coef * (g.r * g.r);
+  const float sg = pb.sampling_sigma;
+  if (pb.importance == NSVD_IMP_GAUSSIAN) {
+    // w = N(x; 0, sigma^2 I_2) through log_prob().exp() as main_pde.py:97-100
+    float s2 = sg * sg;
+    float logw = -r2 / (2.f * s2) - logf(6.283185307179586f * s2);
+    float sw = sqrtf(expf(logw));
+    g.rho = sw / fmaxf(sw, 1e-5f);  // diff_ops.py:15-18
+    float inv = -1.f / (2.f * s2);
+    g.gq0 = x0 * inv;
+    g.gq1 = x1 * inv;
+    g.lapq = 2.f * inv;  // -D/(2 sigma^2), D = 2
+  } else if (pb.importance == NSVD_IMP_LAPLACE) {
+    // w = prod_i exp(-|x_i|/b) / (2b)  (main_pde.py:101-112); d|x|/dx = sign(x), second derivative 0
+    float logw = -(fabsf(x0) + fabsf(x1)) / sg - 2.f * logf(2.f * sg);
+    float sw = sqrtf(expf(logw));
+    g.rho = sw / fmaxf(sw, 1e-5f);
+    g.gq0 = -sgnf(x0) / (2.f * sg);
+    g.gq1 = -sgnf(x1) / (2.f * sg);
+    g.lapq = 0.f;
+  } else {
+    // uniform on [-s, s]^2: w = (2s)^-2 (main_pde.py:113-118); NSVD_IMP_NONE: no re-weighting at all
+    float sw = pb.importance == NSVD_IMP_UNIFORM ? sqrtf(1.f / (4.f * sg * sg)) : 1.f;
+    g.rho = sw / fmaxf(sw, pb.importance == NSVD_IMP_UNIFORM ? 1e-5f : 0.f);
+    g.gq0 = g.gq1 = g.lapq = 0.f;
+  }
+  switch (pb.potential) {                                   // schrodinger/potentials.py
+    case NSVD_POT_HYDROGEN: g.V = -(pb.pot_coef / g.r); break;                      // :5-8
+    case NSVD_POT_HARMONIC: g.V = pb.pot_coef * (g.r * g.r); break;                 // :24-27
+    case NSVD_POT_HYDROGEN_MOL_ION: {                                               // :11-17, nuclei at (0, +-R)
+      float ym = x1 - pb.pot_coef2, yp = x1 + pb.pot_coef2;
+      g.V = -(pb.pot_coef / sqrtf(x0 * x0 + ym * ym)) - (pb.pot_coef / sqrtf(x0 * x0 + yp * yp));
+      break;
+    }
+    case NSVD_POT_COSINE: g.V = pb.pot_coef * cosf(x0) + pb.pot_coef2 * cosf(x1); break;   // :30-31
+    default: g.V = 0.f; break;                                                      // infinite well, :20-21
+  }
+  g.mb = 1.f;
+  g.gmb0 = g.gmb1 = g.lapmb = 0.f;
+  if (pb.box_mask != NSVD_BOX_NONE) {
+    float m0, m1, a0, a1, c0, c1;
+    box_factor(x0, pb.box_lim, pb.box_mask, m0, a0, c0);
+    box_factor(x1, pb.box_lim, pb.box_mask, m1, a1, c1);
+    g.mb = m0 * m1;
+    g.gmb0 = a0 * m1;
+    g.gmb1 = m0 * a1;
+    g.lapmb = c0 * m1 + m0 * c1;
+  }
   return g;
 }
 
-// (F, TF) of one (point, copy) from the raw network streams u = (value, d1, d2, lap).
+// value-stream factor f = cm * u0 (and df/du0 in the backward): hard_mul_const * exp mask * box mask * rho
+__device__ __forceinline__ float head_factor(const PointGeom& g, const nsvd_problem_t& pb, float mexp) {
+  return pb.hard_mul_const * mexp * g.rho * g.mb;
+}
+
+// (F, TF) of one (point, copy) from the raw network streams u = (value, d1, d2, lap): product rule on
+// q u with q = sqrt(w) * exp-mask_l * box-mask, written with Q = ln(sqrt(w) exp-mask) and the box mask explicit
+// (it may vanish).
 __device__ __forceinline__ void operator_epilogue(const PointGeom& g, const nsvd_problem_t& pb,
                                                   bool has_mask, float mscale, float u0, float u1,
                                                   float u2, float u3, float& f, float& tf) {
@@ -106,9 +173,11 @@ __device__ __forceinline__ void operator_epilogue(const PointGeom& g, const nsvd
     gq1 -= g.x1 * irs;
     lapq -= irs;                      // (D-1)/(r s), D = 2
   }
-  float cm = pb.hard_mul_const * m * g.rho;
-  float lap = cm * (u3 + 2.f * (gq0 * u1 + gq1 * u2) + u0 * (lapq + gq0 * gq0 + gq1 * gq1));
-  f = cm * u0;
+  float ce = pb.hard_mul_const * m * g.rho;
+  float inner = u3 + 2.f * (gq0 * u1 + gq1 * u2) + u0 * (lapq + gq0 * gq0 + gq1 * gq1);
+  inner = g.mb * inner + 2.f * (g.gmb0 * (u1 + u0 * gq0) + g.gmb1 * (u2 + u0 * gq1)) + u0 * g.lapmb;
+  float lap = ce * inner;
+  f = ce * g.mb * u0;
   float negH = pb.scale_kinetic * lap - g.V * f;   // schrodinger/__init__.py:19-22
   tf = pb.op_scale * negH + pb.op_shift * f;       // examples/__init__.py:9
 }

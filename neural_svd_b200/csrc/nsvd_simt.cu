@@ -219,7 +219,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ dF, const float* __res
     sc = mscales[l];
     m = expf(-g.r / sc);
   }
-  float cm = pb.hard_mul_const * m * g.rho;
+  float cm = head_factor(g, pb, m);
   float df = dF[pg * L + l];
   float du = df * cm;
   if (lane == 0) {

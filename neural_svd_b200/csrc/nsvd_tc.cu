@@ -118,7 +118,7 @@ template <bool kMN, class Epi>
 __global__ void __launch_bounds__(big::THREADS, 1)
 big_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                const BigShape shape, const Epi epi) {
+                const BigShape shape, const tc::MmaDescs md, const Epi epi) {
   using namespace big;
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
@@ -199,7 +199,6 @@ big_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, kMN ? 1 : 0, kMN ? 1 : 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -229,9 +228,10 @@ big_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
               bh = make_sdesc_sw128(sB + kk * 2048, 8192, 1024);
               bl = make_sdesc_sw128(sB + B_BYTES + kk * 2048, 8192, 1024);
             }
-            umma_f16(d_tmem, al, bh, idesc, (kc > kc0 || kk > 0) ? 1u : 0u);
-            umma_f16(d_tmem, ah, bl, idesc, 1u);
-            umma_f16(d_tmem, ah, bh, idesc, 1u);
+            umma_f16(d_tmem, al, bh, md.lh, (kc > kc0 || kk > 0) ? 1u : 0u);
+            umma_f16(d_tmem, ah, bl, md.hl, 1u);
+            if (md.four) umma_f16(d_tmem, al, bl, md.ll, 1u);
+            umma_f16(d_tmem, ah, bh, md.hh, 1u);
           }
           umma_commit(&empty[stage]);  // frees the smem stage when these MMAs retire
           if (++stage == STAGES) {
@@ -295,7 +295,7 @@ template <bool kMN, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(big2::THREADS, 1)
 big2_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                 const BigShape shape, const int batches_valid, const Epi epi) {
+                 const BigShape shape, const int batches_valid, const tc::MmaDescs md, const Epi epi) {
   using namespace big2;
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
@@ -380,7 +380,6 @@ big2_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, kMN ? 1 : 0, kMN ? 1 : 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -410,9 +409,10 @@ big2_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
               bh = make_sdesc_sw128(sB + kk * 2048, 8192, 1024);
               bl = make_sdesc_sw128(sB + BH_BYTES + kk * 2048, 8192, 1024);
             }
-            umma_f16_pair(d_tmem, al, bh, idesc, (kc > kc0 || kk > 0) ? 1u : 0u);
-            umma_f16_pair(d_tmem, ah, bl, idesc, 1u);
-            umma_f16_pair(d_tmem, ah, bh, idesc, 1u);
+            umma_f16_pair(d_tmem, al, bh, md.lh, (kc > kc0 || kk > 0) ? 1u : 0u);
+            umma_f16_pair(d_tmem, ah, bl, md.hl, 1u);
+            if (md.four) umma_f16_pair(d_tmem, al, bl, md.ll, 1u);
+            umma_f16_pair(d_tmem, ah, bh, md.hh, 1u);
           }
           umma_commit_pair(&empty[stage]);   // frees the stage in both CTAs
           if (++stage == STAGES) {
@@ -494,18 +494,21 @@ struct StoreEpi {
 
 // fp32 -> bf16 hi/lo planes (optionally transposing nothing: same layout)
 __global__ void split_planes_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo, long n) {
+                                    __nv_bfloat16* __restrict__ lo, long n, int fmt) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  __nv_bfloat16 h, l;
-  tc::split_bf16(src[i], h, l);
-  hi[i] = h;
-  lo[i] = l;
+  uint16_t h, l;
+  if (fmt == tc::PF_BB) tc::split1<tc::PF_BB>(src[i], h, l);
+  else if (fmt == tc::PF_BH) tc::split1<tc::PF_BH>(src[i], h, l);
+  else tc::split1<tc::PF_HH>(src[i], h, l);
+  reinterpret_cast<uint16_t*>(hi)[i] = h;
+  reinterpret_cast<uint16_t*>(lo)[i] = l;
 }
 
 template <bool kMN, class Epi>
 static int launch_big(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                      const BigShape& shape, const Epi& epi, cudaStream_t st) {
+                      const BigShape& shape, const Epi& epi, cudaStream_t st, int fa = tc::PF_BB, int fb = tc::PF_BB,
+                      int four = 0) {
   static bool configured = false;
   auto kern = big_gemm_kernel<kMN, Epi>;
   if (!configured) {
@@ -515,14 +518,16 @@ static int launch_big(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
   int tiles = shape.m_tiles * shape.n_tiles * shape.batches * shape.k_slices;
   if (tiles <= 0) return 0;
   int grid = tiles < 148 ? tiles : 148;
-  kern<<<grid, big::THREADS, big::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, epi);
+  const tc::MmaDescs md = tc::make_descs(big::BM, big::BN, kMN ? 1 : 0, kMN ? 1 : 0, fa, fb, four);
+  kern<<<grid, big::THREADS, big::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, md, epi);
   NSVD_LAUNCH_CHECK();
   return 0;
 }
 
 template <bool kMN, class Epi>
 static int launch_big2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                       const BigShape& shape, int batches_valid, const Epi& epi, cudaStream_t st) {
+                       const BigShape& shape, int batches_valid, const Epi& epi, cudaStream_t st,
+                       int fa = tc::PF_BB, int fb = tc::PF_BB, int four = 0) {
   static bool configured = false;
   auto kern = big2_gemm_kernel<kMN, Epi>;
   if (!configured) {
@@ -532,7 +537,8 @@ static int launch_big2(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   int tiles = shape.m_tiles * shape.n_tiles * shape.batches * shape.k_slices;
   if (tiles <= 0) return 0;
   int clusters = tiles < 74 ? tiles : 74;
-  kern<<<2 * clusters, big2::THREADS, big2::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, batches_valid, epi);
+  const tc::MmaDescs md = tc::make_descs(2 * big2::BM, big2::BN, kMN ? 1 : 0, kMN ? 1 : 0, fa, fb, four);
+  kern<<<2 * clusters, big2::THREADS, big2::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, batches_valid, md, epi);
   NSVD_LAUNCH_CHECK();
   return 0;
 }
@@ -550,7 +556,10 @@ static bool tc_use_pair() {
 int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int K, int a_kmajor, int b_kmajor,
                      void* work, size_t work_bytes, cudaStream_t st) {
   NSVD_CHECK_ARG(a_kmajor == b_kmajor, "selftest: both operands must share the major mode");
-  const bool pair = a_kmajor >= 2;   // 2 / 3 = MN- / K-major on the CTA-pair kernel
+  // mode bits: 0 = K-major, 1 = CTA-pair kernel, 4-5 = plane format of A, 6-7 = plane format of B, 8 = add lo*lo
+  const int fa = (a_kmajor >> 4) & 3, fb = (a_kmajor >> 6) & 3, four = (a_kmajor >> 8) & 1;
+  NSVD_CHECK_ARG(fa <= tc::PF_HH && fb <= tc::PF_HH, "selftest: unknown plane format");
+  const bool pair = (a_kmajor & 2) != 0;
   a_kmajor &= 1;
   b_kmajor &= 1;
   NSVD_CHECK_ARG(M % 8 == 0 && N % 8 == 0 && K % 8 == 0, "selftest: M, N, K must be multiples of 8");
@@ -564,9 +573,9 @@ int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int
   __nv_bfloat16* al = ah + na;
   __nv_bfloat16* bh = al + na;
   __nv_bfloat16* bl = bh + nb;
-  split_planes_kernel<<<cdiv((long)na, 256), 256, 0, st>>>(A, ah, al, (long)na);
+  split_planes_kernel<<<cdiv((long)na, 256), 256, 0, st>>>(A, ah, al, (long)na, fa);
   NSVD_LAUNCH_CHECK();
-  split_planes_kernel<<<cdiv((long)nb, 256), 256, 0, st>>>(B, bh, bl, (long)nb);
+  split_planes_kernel<<<cdiv((long)nb, 256), 256, 0, st>>>(B, bh, bl, (long)nb, fb);
   NSVD_LAUNCH_CHECK();
   CUtensorMap mah, mal, mbh, mbl;
   int rc;
@@ -586,10 +595,10 @@ int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int
       if ((rc = make_tmap_bf16_3d(&mbh, bh, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN / 2))) return rc;
       if ((rc = make_tmap_bf16_3d(&mbl, bl, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN / 2))) return rc;
       s.m_tiles = cdiv(M, 2 * big::BM);
-      return launch_big2<false>(mah, mal, mbh, mbl, s, 1, epi, st);
+      return launch_big2<false>(mah, mal, mbh, mbl, s, 1, epi, st, fa, fb, four);
     }
     if ((rc = make_tmap_bf16_3d(&mbl, bl, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN))) return rc;
-    return launch_big<false>(mah, mal, mbh, mbl, s, epi, st);
+    return launch_big<false>(mah, mal, mbh, mbl, s, epi, st, fa, fb, four);
   }
   if ((rc = make_tmap_bf16_3d(&mah, ah, M, K, 1, (uint64_t)M * 2, (uint64_t)M * K * 2, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&mal, al, M, K, 1, (uint64_t)M * 2, (uint64_t)M * K * 2, 64, 64))) return rc;
@@ -599,9 +608,9 @@ int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int
     s.m_tiles = cdiv(M, big::BM);
     s.a_batched = 1;
     NSVD_CHECK_ARG(M <= big::BM, "selftest: MN-major pair mode takes M <= 128");
-    return launch_big2<true>(mah, mal, mbh, mbl, s, 1, epi, st);
+    return launch_big2<true>(mah, mal, mbh, mbl, s, 1, epi, st, fa, fb, four);
   }
-  return launch_big<true>(mah, mal, mbh, mbl, s, epi, st);
+  return launch_big<true>(mah, mal, mbh, mbl, s, epi, st, fa, fb, four);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1393,7 +1402,7 @@ head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
       const long pg = p_off + pmine;
       PointGeom g = point_geom(x[2 * pg], x[2 * pg + 1], pb);
       float m = pb.has_exp_mask ? expf(-g.r / sc) : 1.f;
-      float cm = pb.hard_mul_const * m * g.rho;
+      float cm = head_factor(g, pb, m);
       du_l = dF[pg * L + l] * cm;
       acc_b3 = du_l;
       if (pb.has_exp_mask) acc_s = du_l * U0[pg * L + l] * g.r / (sc * sc);

@@ -3,6 +3,7 @@
 // tcgen05 matrix/instruction descriptor tables.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "nsvd_common.cuh"
 
 namespace nsvd {
@@ -207,6 +208,34 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          | ((uint32_t)(M >> 4) << 24);   // M / 16
 }
 
+// Two-plane operand formats.  Every fp32 operand v is stored as hi + lo (two 16-bit planes):
+//   PF_BB  hi = bf16(v),  lo = bf16(v - hi)   16 significant bits, bf16 range in both planes
+//   PF_BH  hi = bf16(v),  lo = fp16(v - hi)   19 bits (8 + 11); hi keeps the bf16 range, lo is 2^-9 |v| and must stay
+//                                             inside the fp16 range (gradients are pre-scaled by a power of two)
+//   PF_HH  hi = fp16(v),  lo = fp16(v - hi)   22 bits; only for tensors whose magnitude is known (features in [-1,1],
+//                                             weights scaled by a power of two taken from their exact maximum)
+// kind::f16 MMAs take the A and B formats independently from the instruction descriptor, so each of the
+// three (or four) partial products uses the formats of the two planes it multiplies.
+enum PlaneFmt : int { PF_BB = 0, PF_BH = 1, PF_HH = 2 };
+__host__ __device__ constexpr bool pf_hi_bf16(int f) { return f != PF_HH; }
+__host__ __device__ constexpr bool pf_lo_bf16(int f) { return f == PF_BB; }
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major, bool a_bf16,
+                                                      bool b_bf16) {
+  return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// instruction descriptors of the partial products  lo*hi, hi*lo, hi*hi (and lo*lo when `four`)
+struct MmaDescs {
+  uint32_t lh, hl, hh, ll;
+  int four;
+};
+__host__ __device__ constexpr MmaDescs make_descs(int M, int N, int a_mn, int b_mn, int fa, int fb, int four = 0) {
+  return MmaDescs{make_idesc_f16(M, N, a_mn, b_mn, pf_lo_bf16(fa), pf_hi_bf16(fb)),
+                  make_idesc_f16(M, N, a_mn, b_mn, pf_hi_bf16(fa), pf_lo_bf16(fb)),
+                  make_idesc_f16(M, N, a_mn, b_mn, pf_hi_bf16(fa), pf_hi_bf16(fb)),
+                  make_idesc_f16(M, N, a_mn, b_mn, pf_lo_bf16(fa), pf_lo_bf16(fb)), four};
+}
+
 // shared-memory matrix descriptor, 128-byte swizzle.
 //   K-major : rows of 128 B (64 bf16 along K), 8-row groups 1024 B apart (SBO); LBO unused.
 //   MN-major: rows of 128 B (64 bf16 along M/N), one row per k; 8-k groups SBO apart, next 64 MN
@@ -233,6 +262,44 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi2, ui
   __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
   hi2 = *reinterpret_cast<uint32_t*>(&h);
   lo2 = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// ---- format-generic splits (16-bit payloads; the planes are typed __nv_bfloat16* only as "16-bit storage")
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {   // {lo16 = a, hi16 = b}, saturating
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+template <int F>
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  if (F == PF_BB) {
+    split_bf16x2(a, b, hi2, lo2);
+  } else if (F == PF_BH) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    float2 hf = __bfloat1622float2(h);
+    hi2 = *reinterpret_cast<uint32_t*>(&h);
+    lo2 = pack_f16x2_sat(a - hf.x, b - hf.y);
+  } else {
+    hi2 = pack_f16x2_sat(a, b);
+    float2 hf = unpack_f16x2(hi2);
+    lo2 = pack_f16x2_sat(a - hf.x, b - hf.y);
+  }
+}
+template <int F>
+__device__ __forceinline__ float2 merge2(uint32_t hi2, uint32_t lo2) {
+  float2 h = pf_hi_bf16(F) ? __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&hi2)) : unpack_f16x2(hi2);
+  float2 l = pf_lo_bf16(F) ? __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&lo2)) : unpack_f16x2(lo2);
+  return make_float2(h.x + l.x, h.y + l.y);
+}
+template <int F>
+__device__ __forceinline__ void split1(float v, uint16_t& hi, uint16_t& lo) {
+  uint32_t h2, l2;
+  split2<F>(v, 0.f, h2, l2);
+  hi = (uint16_t)(h2 & 0xFFFF);
+  lo = (uint16_t)(l2 & 0xFFFF);
 }
 
 }  // namespace tc

@@ -52,14 +52,16 @@ def describe_model(model):
     if base is None or not hasattr(base, "ws") or not hasattr(base, "bs"):
         raise NotImplementedError("fused path needs WaveFunctions(base=ParallelMLP(...)) (--parallel 1)")
     fm = getattr(base, "feature_map", None)
-    if fm is None or not hasattr(fm, "_B") or getattr(fm, "append_raw", False) or getattr(fm, "deterministic", False):
-        raise NotImplementedError("fused path needs the Gaussian Fourier feature map without raw append")
+    if fm is None or not hasattr(fm, "_B") or getattr(fm, "append_raw", False):
+        raise NotImplementedError("fused path needs the Fourier feature map without raw append")
     if getattr(base, "weight_normalization", False) or not getattr(base, "bias", True):
         raise NotImplementedError("weight_normalization / bias=False are not supported")
     ws, bs = list(base.ws), list(base.bs)
     if len(ws) != 4 or len(bs) != 4:
         raise NotImplementedError("fused path is built for 3 hidden layers (mlp_hidden_dims='128,128,128')")
-    Bff = fm._B
+    Bff = fm._B.detach()
+    if not Bff.is_contiguous():          # the deterministic map is built as a transposed view (utils.py:108-111)
+        Bff = Bff.contiguous()
     if Bff.shape[0] != 2:
         raise NotImplementedError("fused path is built for ndim=2, n_particles=1")
     L, H, K0 = ws[0].shape
@@ -71,36 +73,40 @@ def describe_model(model):
         raise NotImplementedError("unexpected ParallelMLP parameter shapes for the fused path")
     mask = getattr(m, "boundary_mask", None)
     scales = getattr(mask, "scales", None)
-    if scales is None:
-        try:
-            unit = mask is None or float(mask(None)) == 1.0
-        except Exception:
-            unit = False
-        if not unit:
-            raise NotImplementedError("only ExponentialMask or no boundary mask")
-    elif getattr(mask, "boundary_mask", None) is not None:
-        inner = mask.boundary_mask
-        try:
-            unit = float(inner(None)) == 1.0
-        except Exception:
-            unit = False
-        if not unit:
-            raise NotImplementedError("ExponentialMask over a Dirichlet box mask is out of scope")
+    box = mask if scales is None else getattr(mask, "boundary_mask", None)
+    box_mode, box_lim = _describe_box(box)
     params = [Bff] + ws + bs + ([scales] if scales is not None else [])
     for p in params:
         if p.dtype != torch.float32:
             raise NotImplementedError("fused path is fp32 (reference default, --use_amp off)")
         if not p.is_contiguous():
             raise RuntimeError("parameters must be contiguous")
-    return dict(Bff=Bff, ws=ws, bs=bs, scales=scales, L=L, Mff=Mff,
+    return dict(Bff=Bff, ws=ws, bs=bs, scales=scales, L=L, Mff=Mff, box_mode=box_mode, box_lim=box_lim,
                 hard_mul_const=float(getattr(m, "hard_mul_const", 1.0)))
 
 
-def _problem(md, od, sigma, B) -> _lib.Problem:
+def _describe_box(box):
+    """(mode, lim) of a DirichletBoundaryMaskBox (pde/boundary.py:16-37), (BOX_NONE, 0) for `lambda x: 1.`."""
+    if box is None:
+        return _lib.BOX_NONE, 0.0
+    mode, lim = getattr(box, "mode", None), getattr(box, "lim", None)
+    if mode in ("dir_box_sqrt", "dir_box_exp") and lim is not None:
+        return (_lib.BOX_SQRT if mode == "dir_box_sqrt" else _lib.BOX_EXP), float(lim)
+    try:
+        if float(box(None)) == 1.0:
+            return _lib.BOX_NONE, 0.0
+    except Exception:
+        pass
+    raise NotImplementedError("boundary mask must be ExponentialMask, DirichletBoundaryMaskBox, both, or none")
+
+
+def _problem(md, od, imp, B) -> _lib.Problem:
     return _lib.Problem(n_points=B, n_copies=md["L"], n_fourier=md["Mff"], hidden=128,
                         potential=od["potential"], has_exp_mask=int(md["scales"] is not None),
                         pot_coef=od["pot_coef"], scale_kinetic=od["scale_kinetic"], op_scale=od["op_scale"],
-                        op_shift=od["op_shift"], sampling_sigma=sigma, hard_mul_const=md["hard_mul_const"])
+                        op_shift=od["op_shift"], sampling_sigma=imp["sigma"], hard_mul_const=md["hard_mul_const"],
+                        importance=imp["importance"], box_mask=md["box_mode"], pot_coef2=od.get("pot_coef2", 0.0),
+                        box_lim=md["box_lim"])
 
 
 def _params_struct(md) -> _lib.Params:
@@ -154,12 +160,12 @@ def _prep_x(x, dev):
     return x.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
 
 
-def _forward_kernels(lib, owner, md, od, sigma, x, engine):
+def _forward_kernels(lib, owner, md, od, imp, x, engine):
     dev = md["Bff"].device
     _require_cuda(dev)
     x = _prep_x(x, dev)
     B, L = x.shape[0], md["L"]
-    pb = _problem(md, od, sigma, B)
+    pb = _problem(md, od, imp, B)
     sc = _scratch_of(owner).ensure(lib, pb, engine, dev)
     sc.version += 1
     F = torch.empty((B, L), dtype=torch.float32, device=dev)
@@ -175,9 +181,9 @@ def apply_operator(model, operator, x, importance):
     """`operator(model, x, importance) -> (Tf, f)` on the fused forward kernel (no autograd graph)."""
     lib = _lib.load()
     md, od = describe_model(model), describe_operator(operator)
-    sigma = describe_importance(importance)
+    imp = describe_importance(importance)
     with torch.no_grad():
-        _, _, _, _, F, TF = _forward_kernels(lib, getattr(model, "model", model), md, od, sigma, x,
+        _, _, _, _, F, TF = _forward_kernels(lib, getattr(model, "model", model), md, od, imp, x,
                                              _lib.ENGINES[_ENGINE])
     return TF, F
 
@@ -186,10 +192,10 @@ def model_values(model, x):
     """hard_mul_const * base(x) * mask(x), shape (B, L) (WaveFunctions.forward, pde/__init__.py:15-16)."""
     lib = _lib.load()
     md = describe_model(model)
-    od = dict(potential=_lib.POT_HARMONIC, pot_coef=0.0, scale_kinetic=1.0, op_scale=1.0, op_shift=0.0)
-    # sigma = 1e3 keeps sqrt(w) above the 1e-5 clamp for |x| < 3.8e3, so rho == 1 and F == c * m * u.
+    od = dict(potential=_lib.POT_INFINITE_WELL, pot_coef=0.0, scale_kinetic=1.0, op_scale=1.0, op_shift=0.0)
     with torch.no_grad():
-        _, _, _, _, F, _ = _forward_kernels(lib, getattr(model, "model", model), md, od, 1.0e3, x,
+        _, _, _, _, F, _ = _forward_kernels(lib, getattr(model, "model", model), md, od,
+                                            dict(importance=_lib.IMP_NONE, sigma=1.0), x,
                                             _lib.ENGINES[_ENGINE])
     return F
 
@@ -202,9 +208,9 @@ class _FusedOperatorStep(torch.autograd.Function):
     def forward(ctx, method, operator, importance, x, dp, *params):
         lib = _lib.load()
         md, od = describe_model(method), describe_operator(operator)
-        sigma = describe_importance(importance)
+        imp = describe_importance(importance)
         engine = _lib.ENGINES[_ENGINE]
-        x, pb, pr, sc, F, TF = _forward_kernels(lib, method, md, od, sigma, x, engine)
+        x, pb, pr, sc, F, TF = _forward_kernels(lib, method, md, od, imp, x, engine)
         dev = F.device
         B, L = F.shape
         b1 = (B + 1) // 2                                     # torch.chunk(f, 2), nestedlora.py:263

@@ -25,7 +25,7 @@ class GraphedOperatorStep:
         self.method = method
         md = self.md = fused.describe_model(method)
         od = describe_operator(operator)
-        sigma = describe_importance(importance)
+        imp = describe_importance(importance)
         if getattr(method, "data_parallel", None) is not None:
             raise NotImplementedError("GraphedOperatorStep is single-GPU; use compute_loss_operator with data_parallel")
         dev = self.dev = md["Bff"].device
@@ -33,7 +33,7 @@ class GraphedOperatorStep:
         B, L = batch_size, md["L"]
         self.B, self.L = B, L
         self.engine = _lib.ENGINES[fused.get_engine()]
-        self.pb = fused._problem(md, od, sigma, B)
+        self.pb = fused._problem(md, od, imp, B)
         ns, nw = C.c_size_t(), C.c_size_t()
         _lib.check(lib.nsvd_scratch_bytes(C.byref(self.pb), self.engine, C.byref(ns), C.byref(nw)), "nsvd_scratch_bytes")
         f32 = dict(dtype=torch.float32, device=dev)

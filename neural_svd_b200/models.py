@@ -5,6 +5,7 @@ reference, so `state_dict()` round-trips (`model.base.ws.{i}`, `model.base.bs.{i
 `model.base.feature_map._B`, `model.boundary_mask.scales`):
   GaussianFourierFeatureTransform  examples/utils.py:90-143
   ParallelMLP                      examples/models/mlp.py:167-221
+  DirichletBoundaryMaskBox         examples/operator/pde/boundary.py:16-37
   ExponentialMask                  examples/operator/pde/boundary.py:39-53
   WaveFunctions / get_wavefunctions examples/operator/pde/__init__.py:8-55
 
@@ -26,18 +27,25 @@ def parse_str(dims_str: str):
 
 
 class GaussianFourierFeatureTransform(nn.Module):
-    """phi(x) = [sin(x B), cos(x B)], B = 2 pi scale randn(D, M), frozen (utils.py:102-124)."""
+    """phi(x) = [sin(x B), cos(x B)], frozen B (utils.py:102-124): 2 pi scale randn(D, M), or the deterministic
+    integer modulation scale [1 I, 2 I, ..., M I] of shape (D, D M)."""
 
     def __init__(self, input_dim, mapping_size=256, scale=10, deterministic=False, append_raw=False):
         super().__init__()
-        if deterministic or append_raw:
-            raise NotImplementedError("fused path supports the Gaussian random projection without raw append only")
+        if append_raw:
+            raise NotImplementedError("fused path supports Fourier features without raw append only")
         self.input_dim = input_dim
-        self.deterministic = False
-        self._B = nn.Parameter(2 * torch.pi * scale * torch.randn((input_dim, mapping_size)).float(),
-                               requires_grad=False)
-        self._mapping_size = mapping_size
-        self.feature_dim = 2 * mapping_size
+        self.deterministic = deterministic
+        if deterministic:
+            self._B = nn.Parameter(
+                scale * torch.cat([i * torch.eye(input_dim) for i in range(1, mapping_size + 1)], dim=0).T,
+                requires_grad=False)
+            self._mapping_size = input_dim * mapping_size
+        else:
+            self._B = nn.Parameter(2 * torch.pi * scale * torch.randn((input_dim, mapping_size)).float(),
+                                   requires_grad=False)
+            self._mapping_size = mapping_size
+        self.feature_dim = 2 * self._mapping_size
         self.append_raw = False
 
     def forward(self, x):
@@ -81,16 +89,27 @@ class ParallelMLP(nn.Module):
         raise RuntimeError("ParallelMLP is evaluated inside the fused kernel (WaveFunctions.forward)")
 
 
+class DirichletBoundaryMaskBox(nn.Module):
+    """Zero Dirichlet condition on the box [-lim, lim]^D (boundary.py:16-37); evaluated inside the fused kernel."""
+
+    def __init__(self, lim, mode="dir_box_sqrt"):
+        super().__init__()
+        assert mode in ["dir_box_sqrt", "dir_box_exp"]
+        self.lim = lim
+        self.mode = mode
+
+
 class ExponentialMask(nn.Module):
-    """mask_l(x) = exp(-|x| / s_l), s trainable (boundary.py:39-53)."""
+    """mask_l(x) = exp(-|x| / s_l), s trainable, optionally times a box mask (boundary.py:39-53)."""
 
     def __init__(self, output_dim, init_scale=1000, boundary_mask=None):
         super().__init__()
-        if boundary_mask is not None and not _is_unit_mask(boundary_mask):
-            raise NotImplementedError("Dirichlet box masks are out of scope (apply_boundary=0 in the scripts)")
+        if boundary_mask is not None and not isinstance(boundary_mask, DirichletBoundaryMaskBox) \
+                and not _is_unit_mask(boundary_mask):
+            raise NotImplementedError("ExponentialMask takes a DirichletBoundaryMaskBox or no inner mask")
         self.output_dim = output_dim
         self.scales = nn.Parameter(init_scale * torch.ones(output_dim))
-        self.boundary_mask = None
+        self.boundary_mask = boundary_mask if isinstance(boundary_mask, DirichletBoundaryMaskBox) else None
 
 
 def _is_unit_mask(m) -> bool:
@@ -106,8 +125,9 @@ class WaveFunctions(nn.Module):
     def __init__(self, base, boundary_mask, hard_mul_const=1.0):
         super().__init__()
         self.base = base
-        if not isinstance(boundary_mask, ExponentialMask) and not _is_unit_mask(boundary_mask):
-            raise NotImplementedError("only ExponentialMask or no mask")
+        if not isinstance(boundary_mask, (ExponentialMask, DirichletBoundaryMaskBox)) \
+                and not _is_unit_mask(boundary_mask):
+            raise NotImplementedError("only ExponentialMask, DirichletBoundaryMaskBox or no mask")
         self.boundary_mask = boundary_mask
         self.hard_mul_const = hard_mul_const
 
@@ -131,8 +151,6 @@ def get_wavefunctions(args):
     """pde/__init__.py:19-55 for the configurations the fused path covers."""
     if not args.use_fourier_feature:
         raise NotImplementedError("use_fourier_feature=0")
-    if getattr(args, "apply_boundary", False):
-        raise NotImplementedError("apply_boundary=1 (Dirichlet box) is out of scope")
     n_particles = getattr(args, "n_particles", 1)
     feature_map = GaussianFourierFeatureTransform(
         input_dim=args.ndim * n_particles, mapping_size=args.fourier_mapping_size, scale=args.fourier_scale,
@@ -140,7 +158,11 @@ def get_wavefunctions(args):
     base = get_mlp_eigfuncs(input_dim=args.ndim * n_particles, neigs=args.neigs,
                             mlp_hidden_dims=args.mlp_hidden_dims, nonlinearity=args.nonlinearity,
                             parallel=args.parallel, feature_map=feature_map)
-    boundary_mask = lambda x: 1.0  # noqa: E731
+    if getattr(args, "apply_boundary", False):
+        assert args.boundary_mode in ["dir_box_sqrt", "dir_box_exp"]
+        boundary_mask = DirichletBoundaryMaskBox(lim=args.lim, mode=args.boundary_mode)
+    else:
+        boundary_mask = lambda x: 1.0  # noqa: E731
     if args.apply_exp_mask:
         boundary_mask = ExponentialMask(output_dim=args.neigs, init_scale=args.exp_mask_init_scale,
                                         boundary_mask=boundary_mask)

@@ -1,10 +1,11 @@
 """Host-side mirror of the reference's operator objects for the hot path.
 
-  hydrogen_potential / harmonic_oscillator_potential  pde/schrodinger/potentials.py:5-8,24-27
+  hydrogen / harmonic_oscillator / hydrogen_mol_ion / infinite_well / cosine potentials
+                                                       pde/schrodinger/potentials.py:5-31
   NegativeHamiltonian                                  pde/schrodinger/__init__.py:4-22
   OperatorWrapper                                      examples/__init__.py:1-9
-  GaussianImportance  (the closure of)                 pde/main_pde.py:94-100
-  get_problem                                          pde/problems.py:23-130 (sch / hydrogen, oscillator)
+  GaussianImportance / LaplaceImportance / UniformImportance  (the closures of)  pde/main_pde.py:89-118
+  get_problem                                          pde/problems.py:23-130 (problem 'sch', ndim 2, one particle)
 
 `operator(method, x, importance) -> (Tf, f)` keeps the reference's callable protocol; the work is
 done by the fused forward-mode kernel (exact Laplacian, no autograd double backward).
@@ -29,6 +30,22 @@ def harmonic_oscillator_potential(x, k=1.0):
     return (k * x.norm(dim=1, p=2) ** 2).reshape(-1, 1)
 
 
+def hydrogen_mol_ion_potential(x, R, charge=2.0):
+    """H2+ ion, nuclei at (0, ..., +-R) on the last axis (potentials.py:11-17)."""
+    x = x.reshape(x.shape[0], -1)
+    e = torch.zeros((x.shape[-1],), device=x.device, dtype=x.dtype)
+    e[-1] = 1.0
+    return hydrogen_potential(x - R * e, charge) + hydrogen_potential(x + R * e, charge)
+
+
+def infinite_well_potential(x):
+    return torch.zeros((x.shape[0],), device=x.device)
+
+
+def cosine_potential(x, cs):
+    return (torch.cos(x.view(x.shape[0], -1)) * torch.tensor(cs, device=x.device).view(1, -1)).sum(-1)
+
+
 class GaussianImportance:
     """w(x) = N(x; 0, sigma^2 I).  Callable like the reference's `importance_train` closure."""
 
@@ -41,6 +58,32 @@ class GaussianImportance:
         s2 = self.sampling_scale ** 2
         logw = -(x ** 2).sum(1) / (2 * s2) - 0.5 * self.dim * math.log(2 * math.pi * s2)
         return logw.exp().view(-1, 1)
+
+
+class LaplaceImportance:
+    """w(x) = prod_i exp(-|x_i|/b) / (2b)  (sampling_mode='laplacian', main_pde.py:101-112)."""
+    sampling_mode = "laplacian"
+
+    def __init__(self, sampling_scale: float, dim: int = 2):
+        self.sampling_scale = float(sampling_scale)
+        self.dim = dim
+
+    def __call__(self, x):
+        x = x.reshape(x.shape[0], -1)
+        b = self.sampling_scale
+        return (-(x.abs().sum(1)) / b - self.dim * math.log(2 * b)).exp().view(-1, 1)
+
+
+class UniformImportance:
+    """w(x) = (2s)^-D on [-s, s]^D  (sampling_mode='uniform', main_pde.py:113-118)."""
+    sampling_mode = "uniform"
+
+    def __init__(self, sampling_scale: float, dim: int = 2):
+        self.sampling_scale = float(sampling_scale)
+        self.dim = dim
+
+    def __call__(self, x):
+        return torch.full((x.shape[0], 1), 1.0 / (2 * self.sampling_scale) ** self.dim, device=x.device)
 
 
 def make_gaussian_sampler(batch_size, sampling_scale, ndim=2, n_particles=1, generator=None):
@@ -95,28 +138,46 @@ def describe_operator(operator):
     func = pot.func if isinstance(pot, partial) else pot
     kw = pot.keywords if isinstance(pot, partial) else {}
     name = getattr(func, "__name__", "")
+    coef2 = 0.0
     if name == "hydrogen_potential":
         kind, coef = 0, float(kw.get("charge", 1.0))
     elif name == "harmonic_oscillator_potential":
         kind, coef = 1, float(kw.get("k", 1.0))
+    elif name == "hydrogen_mol_ion_potential":
+        if "R" not in kw:
+            raise NotImplementedError("hydrogen_mol_ion_potential needs R bound with functools.partial")
+        kind, coef, coef2 = 2, float(kw.get("charge", 2.0)), float(kw["R"])
+    elif name == "infinite_well_potential":
+        kind, coef = 3, 0.0
+    elif name == "cosine_potential":
+        cs = list(kw.get("cs", ()))
+        if len(cs) != 2:
+            raise NotImplementedError("cosine_potential: the fused path is 2D (two coefficients)")
+        kind, coef, coef2 = 4, float(cs[0]), float(cs[1])
     else:
-        raise NotImplementedError(f"unsupported potential {name!r}: only hydrogen / harmonic_oscillator")
+        raise NotImplementedError(f"unsupported potential {name!r}")
     eps = getattr(inner, "laplacian_eps", 0.0)
     if eps is not None and eps > 0 and not _FD_WARNED:
         _FD_WARNED = True
         warnings.warn(f"laplacian_eps={eps}: the fused kernel evaluates the EXACT Laplacian in forward mode "
                       "(the limit the reference's finite difference approximates; see DESIGN.md)")
-    return dict(potential=kind, pot_coef=coef, scale_kinetic=float(inner.scale_kinetic),
+    return dict(potential=kind, pot_coef=coef, pot_coef2=coef2, scale_kinetic=float(inner.scale_kinetic),
                 op_scale=float(operator.scale), op_shift=float(operator.shift))
 
 
-def describe_importance(importance, dim=2) -> float:
-    """sigma of a Gaussian importance density; accepts GaussianImportance or the reference's closure
-    over a zero-mean isotropic MultivariateNormal (main_pde.py:94-100)."""
+_IMP_CODES = {"gaussian": 0, "laplacian": 1, "uniform": 2}
+
+
+def describe_importance(importance, dim=2) -> dict:
+    """{importance: NSVD_IMP_* code, sigma: scale} of the sampler's density.  Accepts the classes above, `None`
+    (no re-weighting, diff_ops.py:10-11) and the reference's own `importance_train` closures: over a zero-mean
+    isotropic MultivariateNormal (main_pde.py:94-100) or over `args` with sampling_mode laplacian / uniform
+    (main_pde.py:101-118)."""
     if importance is None:
-        raise NotImplementedError("fused path needs the Gaussian importance density (sampling_mode='gaussian')")
+        return dict(importance=3, sigma=1.0)
     if hasattr(importance, "sampling_scale"):
-        return float(importance.sampling_scale)
+        mode = getattr(importance, "sampling_mode", "gaussian")
+        return dict(importance=_IMP_CODES[mode], sigma=float(importance.sampling_scale))
     for cell in (getattr(importance, "__closure__", None) or ()):
         obj = cell.cell_contents
         cov = getattr(obj, "covariance_matrix", None)
@@ -126,8 +187,19 @@ def describe_importance(importance, dim=2) -> float:
             d = cov.shape[0]
             if d != dim or loc.abs().max() != 0 or not torch.allclose(cov, cov[0, 0] * torch.eye(d, dtype=cov.dtype)):
                 raise NotImplementedError("importance must be a zero-mean isotropic Gaussian in 2D")
-            return float(cov[0, 0].sqrt())
-    raise NotImplementedError("cannot recognise the importance density; pass neural_svd_b200.GaussianImportance(sigma)")
+            return dict(importance=0, sigma=float(cov[0, 0].sqrt()))
+        if type(obj).__name__ == "Laplace" and hasattr(obj, "loc") and hasattr(obj, "scale"):
+            loc, sc = obj.loc.detach().cpu().double().reshape(-1), obj.scale.detach().cpu().double().reshape(-1)
+            if loc.numel() != dim or loc.abs().max() != 0 or (sc != sc[0]).any():
+                raise NotImplementedError("importance must be a zero-mean Laplace density with one scale in 2D")
+            return dict(importance=1, sigma=float(sc[0]))
+        mode = getattr(obj, "sampling_mode", None)          # the `args` namespace the closure reads
+        if mode in ("laplacian", "uniform") and hasattr(obj, "sampling_scale"):
+            if getattr(obj, "ndim", dim) != dim or getattr(obj, "n_particles", 1) != 1:
+                raise NotImplementedError("importance must be over one particle in 2D")
+            return dict(importance=_IMP_CODES[mode], sigma=float(obj.sampling_scale))
+    raise NotImplementedError("cannot recognise the importance density; pass neural_svd_b200.GaussianImportance / "
+                              "LaplaceImportance / UniformImportance")
 
 
 def hydrogen2d_eigvals(neigs, charge=1.0):
@@ -149,19 +221,44 @@ def oscillator2d_eigvals(neigs, k=1.0):
     return np.array(out[:neigs])
 
 
+def infinite_well2d_eigvals(neigs, L=1.0):
+    """(nx^2 + ny^2) pi^2 / L^2, sorted (ground_truths.py:40-59)."""
+    vals = sorted(nx ** 2 + ny ** 2 for nx in range(1, neigs + 1) for ny in range(1, neigs + 1))[:neigs]
+    return np.array(vals) * np.pi ** 2 / L ** 2
+
+
+# eigenvalues of -Lap + cs . cos(x) on the 2D torus quoted by the reference (problems.py:48-60)
+_COSINE_2D = [-0.591624518674115, 0.623365592493771, 0.662887867122419, 0.891545971509540, 0.982541637674317,
+              1.877877978290306, 2.146058357306075, 2.197531748842203, 2.465712127857973, 3.699555061533076,
+              3.701057706578779, 3.756708397099993, 3.758994296902169, 4.954067447329610, 4.955570092375313,
+              4.971698508267879, 4.973984408070056, 5.239878887283648, 5.242164787085825, 5.273721217881508,
+              5.275223862927211, 8.047887977307184, 8.049390622352888, 8.050173877109360, 8.051676522155063]
+
+
 def get_problem(args, device=None):
-    """pde/problems.py:23-130 for problem='sch', potential_type in {hydrogen, harmonic_oscillator}, ndim=2."""
+    """pde/problems.py:23-130 for problem='sch', ndim=2, one particle."""
     if args.problem != "sch" or args.ndim != 2:
         raise NotImplementedError("fused path covers the 2D Schroedinger problems")
     args.n_particles = 1
+    gt = None
     if args.potential_type == "hydrogen":
         pot = partial(hydrogen_potential, charge=args.charge)
         gt = -hydrogen2d_eigvals(args.neigs, args.charge)
     elif args.potential_type == "harmonic_oscillator":
         pot = partial(harmonic_oscillator_potential, k=1.0)
         gt = -oscillator2d_eigvals(args.neigs, 1.0)
+    elif args.potential_type == "infinite_well":
+        pot = infinite_well_potential
+        gt = -infinite_well2d_eigvals(args.neigs, L=2 * args.lim)
+    elif args.potential_type == "cosine":
+        assert args.lim == np.pi and not args.apply_boundary and args.fourier_deterministic
+        assert args.neigs <= 25
+        pot = partial(cosine_potential, cs=[0.814723686393179, 0.905791937075619])
+        gt = -np.array(_COSINE_2D[:args.neigs])
+    elif args.potential_type == "hydrogen_mol_ion":
+        pot = partial(hydrogen_mol_ion_potential, R=args.hydrogen_mol_ion_R, charge=2 * args.charge)
     else:
         raise NotImplementedError(args.potential_type)
     op = NegativeHamiltonian(pot, scale_kinetic=1.0, laplacian_eps=args.laplacian_eps, n_particles=1)
     op = OperatorWrapper(op, scale=args.operator_scale, shift=args.operator_shift)
-    return op, args.operator_scale * gt + args.operator_shift
+    return op, (args.operator_scale * gt + args.operator_shift if gt is not None else None)

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import dataclasses
 import json
+import math
 import os
 import sys
 
@@ -44,6 +45,26 @@ CASES = {
     "hyd_small_odd": dict(cfg=O.PathConfig.hydrogen(neigs=4, fourier_mapping_size=64, step=2), B=97, seed=4),
     "osc_small_seq": dict(cfg=O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64, sequential=True,
                                                       hard_mul_const=0.5), B=64, seed=5),
+    # the other single-particle 2D problems of pde/problems.py, samplers of main_pde.py:89-118 and the
+    # Dirichlet box masks of pde/boundary.py (small shapes, full gradients)
+    "well_uniform_boxsqrt": dict(cfg=O.PathConfig(potential="infinite_well", neigs=4, fourier_mapping_size=64,
+                                                  fourier_scale=0.5, operator_scale=1.0, sampling_mode="uniform",
+                                                  sampling_scale=2.0, lim=2.0, apply_boundary=True,
+                                                  boundary_mode="dir_box_sqrt"), B=96, seed=6),
+    "cosine_uniform_detff": dict(cfg=O.PathConfig(potential="cosine", neigs=4, fourier_mapping_size=32,
+                                                  fourier_scale=1.0, fourier_deterministic=True, operator_scale=1.0,
+                                                  operator_shift=2.0, sampling_mode="uniform",
+                                                  sampling_scale=math.pi, lim=math.pi, sequential=True),
+                                 B=80, seed=7),
+    "molion_laplace_boxexp_mask": dict(cfg=O.PathConfig(potential="hydrogen_mol_ion", neigs=4,
+                                                        fourier_mapping_size=64, fourier_scale=0.2,
+                                                        operator_scale=10.0, sampling_mode="laplacian",
+                                                        sampling_scale=3.0, lim=12.0, apply_boundary=True,
+                                                        boundary_mode="dir_box_exp", apply_exp_mask=True,
+                                                        exp_mask_init_scale=8.0, hydrogen_mol_ion_R=1.5,
+                                                        hard_mul_const=2.0), B=101, seed=8),
+    "osc_no_importance": dict(cfg=O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64, sampling_mode="none"),
+                              B=64, seed=9),
 }
 
 CDK_CASES = {
@@ -74,7 +95,13 @@ def run_reference(ref, cfg, seed, x32, dtype):
 def make_case(ref, name, spec):
     cfg, B, seed = spec["cfg"], spec["B"], spec["seed"]
     g = torch.Generator().manual_seed(1000 + seed)
-    x32 = (cfg.sampling_scale * torch.randn((B, 1, cfg.ndim), generator=g)).reshape(B, -1).numpy()
+    if cfg.sampling_mode == "uniform":                              # main_pde.py:114-115
+        x32 = (cfg.sampling_scale * (2 * torch.rand((B, 1, cfg.ndim), generator=g) - 1)).reshape(B, -1).numpy()
+    elif cfg.sampling_mode == "laplacian":                          # main_pde.py:102-106
+        u = torch.rand((B, 1, cfg.ndim), generator=g, dtype=torch.float64) - 0.5
+        x32 = (-cfg.sampling_scale * u.sign() * torch.log1p(-2 * u.abs())).float().reshape(B, -1).numpy()
+    else:                                                           # main_pde.py:92-93
+        x32 = (cfg.sampling_scale * torch.randn((B, 1, cfg.ndim), generator=g)).reshape(B, -1).numpy()
     r64 = run_reference(ref, cfg, seed, x32, torch.float64)
     r32 = run_reference(ref, cfg, seed, x32, torch.float32)
     mine = O.init_params_like_reference(cfg, seed)

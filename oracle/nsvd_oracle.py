@@ -37,7 +37,7 @@ class PathConfig:
     `get_wavefunctions` (examples/operator/pde/__init__.py:19-55) and the Gaussian
     sampler/importance (examples/operator/pde/main_pde.py:89-100).
     """
-    potential: str = "hydrogen"          # 'hydrogen' | 'harmonic_oscillator'
+    potential: str = "hydrogen"          # 'hydrogen' | 'harmonic_oscillator' | 'hydrogen_mol_ion' | 'infinite_well' | 'cosine'
     ndim: int = 2
     neigs: int = 16
     charge: float = 1.0                  # potentials.py:5-8
@@ -54,6 +54,12 @@ class PathConfig:
     exp_mask_init_scale: float = 100.0
     sequential: bool = False             # nestedlora.py:183-192
     step: int = 1
+    sampling_mode: str = "gaussian"      # 'gaussian' | 'laplacian' | 'uniform' | 'none'  (main_pde.py:89-118)
+    apply_boundary: bool = False         # DirichletBoundaryMaskBox(lim, boundary_mode), pde/boundary.py:16-37
+    boundary_mode: str = "dir_box_sqrt"
+    lim: float = 50.0
+    fourier_deterministic: bool = False  # utils.py:106-113
+    hydrogen_mol_ion_R: float = 1.0      # problems.py:71
 
     @staticmethod
     def hydrogen(**kw) -> "PathConfig":
@@ -169,6 +175,55 @@ def forward_streams(x: np.ndarray, params: Dict[str, np.ndarray], cfg: PathConfi
     return u
 
 
+COSINE_CS_2D = (0.814723686393179, 0.905791937075619)          # problems.py:46
+
+
+def importance_terms(x: np.ndarray, cfg: PathConfig):
+    """(w, grad ln sqrt(w), Lap ln sqrt(w)) of the sampler's density (main_pde.py:89-118); `none` = no re-weighting
+    (importance=None, diff_ops.py:10-11).  d|x|/dx = sign(x) with a vanishing second derivative, as autograd has it."""
+    B, D = x.shape
+    s = cfg.sampling_scale
+    if cfg.sampling_mode == "gaussian":
+        return importance_gaussian(x, s), -x / (2 * s ** 2), np.full((B,), -D / (2 * s ** 2), x.dtype)
+    if cfg.sampling_mode == "laplacian":
+        w = np.exp(-np.abs(x).sum(1) / s - D * math.log(2 * s)).astype(x.dtype)
+        return w, -np.sign(x) / (2 * s), np.zeros((B,), x.dtype)
+    if cfg.sampling_mode == "uniform":
+        return np.full((B,), 1.0 / (2 * s) ** D, x.dtype), np.zeros_like(x), np.zeros((B,), x.dtype)
+    if cfg.sampling_mode == "none":
+        return None, np.zeros_like(x), np.zeros((B,), x.dtype)
+    raise NotImplementedError(cfg.sampling_mode)
+
+
+def box_mask_terms(x: np.ndarray, cfg: PathConfig):
+    """DirichletBoundaryMaskBox (pde/boundary.py:16-37): mask (B,), its gradient (B,D) and Laplacian (B,) as autograd
+    differentiates it (clamp / maximum pass no gradient outside the box)."""
+    B, D = x.shape
+    if not cfg.apply_boundary:
+        return np.ones((B,), x.dtype), np.zeros_like(x), np.zeros((B,), x.dtype)
+    lim = cfg.lim
+    inside = (x >= -lim) & (x <= lim)
+    xc = np.clip(x, -lim, lim)
+    if cfg.boundary_mode == "dir_box_sqrt":
+        q = 2 * lim ** 2 - xc ** 2
+        t = (np.sqrt(q) - lim) / lim
+        on = inside & (t > 0)
+        m = np.maximum(t, 0.0)
+        d1 = np.where(on, -xc / (lim * np.sqrt(q)), 0.0)
+        d2 = np.where(on, -2 * lim / (q * np.sqrt(q)), 0.0)
+    elif cfg.boundary_mode == "dir_box_exp":
+        a, b = np.exp(xc - lim), np.exp(-xc - lim)
+        m = (1 - a) * (1 - b)
+        d1 = np.where(inside, b - a, 0.0)
+        d2 = np.where(inside, -(a + b), 0.0)
+    else:
+        raise NotImplementedError(cfg.boundary_mode)
+    mask = m.prod(1)
+    grad = np.stack([d1[:, i] * np.delete(m, i, 1).prod(1) for i in range(D)], 1)
+    lap = sum(d2[:, i] * np.delete(m, i, 1).prod(1) for i in range(D))
+    return mask.astype(x.dtype), grad.astype(x.dtype), lap.astype(x.dtype)
+
+
 def importance_gaussian(x: np.ndarray, sigma: float) -> np.ndarray:
     """N(x; 0, sigma^2 I) as MultivariateNormal.log_prob().exp() (main_pde.py:94-100)."""
     D = x.shape[1]
@@ -182,6 +237,16 @@ def potential(x: np.ndarray, cfg: PathConfig) -> np.ndarray:
         return -(cfg.charge / r)                                   # potentials.py:5-8
     if cfg.potential == "harmonic_oscillator":
         return cfg.k * r ** 2                                       # potentials.py:24-27
+    if cfg.potential == "hydrogen_mol_ion":                         # potentials.py:11-17, charge = 2 * args.charge
+        e = np.zeros((x.shape[1],), x.dtype)
+        e[-1] = cfg.hydrogen_mol_ion_R
+        Z = 2 * cfg.charge
+        return -Z / np.sqrt(((x - e) ** 2).sum(1)) - Z / np.sqrt(((x + e) ** 2).sum(1))
+    if cfg.potential == "infinite_well":
+        return np.zeros((x.shape[0],), x.dtype)                     # potentials.py:20-21
+    if cfg.potential == "cosine":
+        cs = np.asarray(COSINE_CS_2D, np.float32).astype(x.dtype)   # torch.tensor(cs) is fp32 whatever x is
+        return (np.cos(x) * cs[None, :]).sum(1)                     # potentials.py:30-31
     raise NotImplementedError(cfg.potential)
 
 
@@ -196,25 +261,33 @@ def operator_apply(x: np.ndarray, u: np.ndarray, params: Dict[str, np.ndarray], 
     """
     dt = x.dtype
     D = cfg.ndim
-    sig = cfg.sampling_scale
+    B, L = x.shape[0], cfg.neigs
     r = np.sqrt((x ** 2).sum(1))[:, None]                           # (B,1)
-    w = importance_gaussian(x, sig)[:, None]
-    sqrt_w = np.sqrt(w)
-    rho = sqrt_w / np.maximum(sqrt_w, 1e-5)                         # diff_ops.py:15-18
-    gradQ = -x[:, None, :] / (2 * sig ** 2) * np.ones((1, cfg.neigs, 1), dt)   # (B,L,D)
-    lapQ = -D / (2 * sig ** 2) * np.ones((x.shape[0], cfg.neigs), dt)
+    w, gq, lq = importance_terms(x, cfg)
+    if w is None:
+        rho = np.ones((B, 1), dt)
+    else:
+        sqrt_w = np.sqrt(w)[:, None]
+        rho = sqrt_w / np.maximum(sqrt_w, 1e-5)                     # diff_ops.py:15-18
+    gradQ = gq[:, None, :] * np.ones((1, L, 1), dt)                 # (B,L,D)
+    lapQ = lq[:, None] * np.ones((1, L), dt)
     if cfg.apply_exp_mask:
         sc = params["model.boundary_mask.scales"].astype(dt)[None, :]            # (1,L)
         m = np.exp(-r / sc)                                         # boundary.py:48-49
         gradQ = gradQ - x[:, None, :] / (r * sc)[:, :, None]
         lapQ = lapQ - (D - 1) / (r * sc)
     else:
-        m = np.ones((x.shape[0], cfg.neigs), dt)
-    cm = cfg.hard_mul_const * m * rho
+        m = np.ones((B, L), dt)
+    mb, gmb, lmb = box_mask_terms(x, cfg)                           # boundary.py:16-37 (and :50-51 under the exp mask)
+    ce = cfg.hard_mul_const * m * rho
     uv = u[0]
     gu = np.stack([u[1 + d] for d in range(D)], -1)                 # (B,L,D)
-    lap = cm * (u[D + 1] + 2 * (gradQ * gu).sum(-1) + uv * (lapQ + (gradQ ** 2).sum(-1)))
-    f = cm * uv
+    inner = u[D + 1] + 2 * (gradQ * gu).sum(-1) + uv * (lapQ + (gradQ ** 2).sum(-1))
+    inner = (mb[:, None] * inner + 2 * (gmb[:, None, :] * (gu + uv[..., None] * gradQ)).sum(-1)
+             + uv * lmb[:, None])
+    lap = ce * inner
+    m = m * mb[:, None]                                             # total mask (backward: df/du = c m rho)
+    f = ce * mb[:, None] * uv
     V = potential(x, cfg)[:, None]
     negH = cfg.scale_kinetic * lap - V * f                          # schrodinger/__init__.py:19-22
     Tf = cfg.operator_scale * negH + cfg.operator_shift * f         # examples/__init__.py:9
@@ -378,8 +451,13 @@ def init_params_like_reference(cfg: PathConfig, seed: int) -> Dict[str, np.ndarr
     g = torch.Generator().manual_seed(seed)
     D, M = cfg.ndim, cfg.fourier_mapping_size
     out = {}
-    out["model.base.feature_map._B"] = (2 * torch.pi * cfg.fourier_scale *
-                                        torch.randn((D, M), generator=g).float()).numpy()
+    if cfg.fourier_deterministic:                                   # utils.py:106-113 (no RNG draw)
+        out["model.base.feature_map._B"] = (cfg.fourier_scale * torch.cat(
+            [i * torch.eye(D) for i in range(1, M + 1)], dim=0).T).numpy()
+        M = D * M
+    else:
+        out["model.base.feature_map._B"] = (2 * torch.pi * cfg.fourier_scale *
+                                            torch.randn((D, M), generator=g).float()).numpy()
     prev = 2 * M
     dims = list(cfg.hidden) + [1]
     for i, h in enumerate(dims):

@@ -60,11 +60,13 @@ def reference_args(cfg, laplacian_eps: float = 0.0):
     return SimpleNamespace(
         problem="sch", potential_type=cfg.potential, ndim=cfg.ndim, neigs=cfg.neigs, charge=cfg.charge,
         laplacian_eps=laplacian_eps, operator_scale=cfg.operator_scale, operator_shift=cfg.operator_shift,
-        lim=50.0, use_fourier_feature=True, fourier_mapping_size=cfg.fourier_mapping_size,
-        fourier_scale=cfg.fourier_scale, fourier_deterministic=False, fourier_append_raw=False,
+        lim=cfg.lim, use_fourier_feature=True, fourier_mapping_size=cfg.fourier_mapping_size,
+        fourier_scale=cfg.fourier_scale, fourier_deterministic=cfg.fourier_deterministic, fourier_append_raw=False,
         mlp_hidden_dims=",".join(str(h) for h in cfg.hidden), nonlinearity="softplus", parallel=True,
-        apply_boundary=False, boundary_mode="dir_box_sqrt", apply_exp_mask=cfg.apply_exp_mask,
-        exp_mask_init_scale=cfg.exp_mask_init_scale, hard_mul_const=cfg.hard_mul_const)
+        apply_boundary=cfg.apply_boundary, boundary_mode=cfg.boundary_mode, apply_exp_mask=cfg.apply_exp_mask,
+        exp_mask_init_scale=cfg.exp_mask_init_scale, hard_mul_const=cfg.hard_mul_const,
+        hydrogen_mol_ion_R=cfg.hydrogen_mol_ion_R, sampling_mode=cfg.sampling_mode,
+        sampling_scale=cfg.sampling_scale, use_gaussian_sampling=cfg.sampling_mode == "gaussian", n_particles=1)
 
 
 def build_reference_problem(ref, cfg, seed: int, laplacian_eps: float = 0.0, dtype=None):
@@ -83,10 +85,24 @@ def build_reference_problem(ref, cfg, seed: int, laplacian_eps: float = 0.0, dty
         method.vector_mask = method.vector_mask.to(dtype)
         method.matrix_mask = method.matrix_mask.to(dtype)
     n = cfg.ndim
-    mvn = MultivariateNormal(loc=torch.zeros(n, dtype=dtype),
-                             covariance_matrix=cfg.sampling_scale ** 2 * torch.eye(n, dtype=dtype))
+    if cfg.sampling_mode == "gaussian":
+        mvn = MultivariateNormal(loc=torch.zeros(n, dtype=dtype),
+                                 covariance_matrix=cfg.sampling_scale ** 2 * torch.eye(n, dtype=dtype))
 
-    def importance(x):                                             # main_pde.py:97-100
-        return mvn.log_prob(x.view(x.shape[0], -1)).exp().view(-1, 1)
+        def importance(x):                                         # main_pde.py:97-100
+            return mvn.log_prob(x.view(x.shape[0], -1)).exp().view(-1, 1)
+    elif cfg.sampling_mode == "laplacian":
+        from torch.distributions import Laplace
+        lap = Laplace(torch.zeros(n, dtype=dtype), cfg.sampling_scale * torch.ones(n, dtype=dtype))
+
+        def importance(x):                                         # main_pde.py:107-112
+            return lap.log_prob(x.view(x.shape[0], -1)).sum(-1).exp().view(-1, 1)
+    elif cfg.sampling_mode == "uniform":
+        def importance(x):                                         # main_pde.py:116-118
+            return (1 / (2 * cfg.sampling_scale) ** cfg.ndim * torch.ones(x.shape[0], 1)).to(dtype)
+    elif cfg.sampling_mode == "none":
+        importance = None
+    else:
+        raise NotImplementedError(cfg.sampling_mode)
 
     return method, operator, importance, gt

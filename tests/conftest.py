@@ -40,12 +40,14 @@ def ref_args(cfg):
     from types import SimpleNamespace
     return SimpleNamespace(
         problem="sch", potential_type=cfg.potential, ndim=cfg.ndim, neigs=cfg.neigs, charge=cfg.charge,
-        laplacian_eps=0.0, operator_scale=cfg.operator_scale, operator_shift=cfg.operator_shift, lim=50.0,
+        laplacian_eps=0.0, operator_scale=cfg.operator_scale, operator_shift=cfg.operator_shift, lim=cfg.lim,
         use_fourier_feature=True, fourier_mapping_size=cfg.fourier_mapping_size, fourier_scale=cfg.fourier_scale,
-        fourier_deterministic=False, fourier_append_raw=False,
+        fourier_deterministic=cfg.fourier_deterministic, fourier_append_raw=False,
         mlp_hidden_dims=",".join(str(h) for h in cfg.hidden), nonlinearity="softplus", parallel=True,
-        apply_boundary=False, boundary_mode="dir_box_sqrt", apply_exp_mask=cfg.apply_exp_mask,
-        exp_mask_init_scale=cfg.exp_mask_init_scale, hard_mul_const=cfg.hard_mul_const)
+        apply_boundary=cfg.apply_boundary, boundary_mode=cfg.boundary_mode, apply_exp_mask=cfg.apply_exp_mask,
+        exp_mask_init_scale=cfg.exp_mask_init_scale, hard_mul_const=cfg.hard_mul_const,
+        hydrogen_mol_ion_R=cfg.hydrogen_mol_ion_R, sampling_mode=cfg.sampling_mode,
+        sampling_scale=cfg.sampling_scale)
 
 
 def build_problem(cfg, seed, device="cpu"):
@@ -58,7 +60,9 @@ def build_problem(cfg, seed, device="cpu"):
     model = N.get_wavefunctions(args)
     method = N.NestedLoRA(model=model, neigs=cfg.neigs, step=cfg.step, sort=False, sequential=cfg.sequential)
     method = method.to(device)
-    return method, operator, N.GaussianImportance(cfg.sampling_scale, cfg.ndim), gt
+    importance = {"gaussian": N.GaussianImportance, "laplacian": N.LaplaceImportance, "uniform": N.UniformImportance,
+                  "none": lambda *a: None}[cfg.sampling_mode](cfg.sampling_scale, cfg.ndim)
+    return method, operator, importance, gt
 
 
 def rel(a, b):

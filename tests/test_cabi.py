@@ -21,7 +21,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), n
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.nsvd_abi_version() == 1
+    assert lib.nsvd_abi_version() == 2
 
 
 def test_library_is_sm100a_and_has_no_torch_dependency():

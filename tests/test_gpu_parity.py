@@ -13,7 +13,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 ENGINES = ["fp32", "bf16x3"]
 PDE_CASES = ["hyd_small_odd", "osc_small_seq", "hyd_b128_seq_L16", "osc_b512_jnt_L16", "hyd_b512_jnt_L16",
-             "hyd_b64_jnt_L64"]
+             "hyd_b64_jnt_L64",
+             # infinite well / cosine / H2+ potentials, uniform / Laplace / no importance,
+             # Dirichlet box masks (sqrt, exp; alone and under the exp mask), deterministic Fourier features
+             "well_uniform_boxsqrt", "cosine_uniform_detff", "molion_laplace_boxexp_mask", "osc_no_importance"]
 
 
 def _step(name, engine):

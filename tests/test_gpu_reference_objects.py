@@ -7,23 +7,31 @@ import pytest
 import torch
 
 import neural_svd_b200 as N
-from conftest import rel
+from conftest import load_golden, rel
 from oracle import nsvd_oracle as O
 from oracle import ref_bootstrap as RB
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("which", ["hydrogen", "oscillator"])
+@pytest.mark.parametrize("which", ["hydrogen", "oscillator", "well_uniform_boxsqrt", "molion_laplace_boxexp_mask",
+                                   "cosine_uniform_detff"])
 def test_reference_objects_run_on_the_fused_kernels(which):
     root = RB.find_reference()
     if root is None:
         pytest.skip("no copy of the reference (baseline/_ref) on this machine")
     ref = RB.import_reference(root)
-    cfg = (O.PathConfig.hydrogen(neigs=4, fourier_mapping_size=64, sequential=True) if which == "hydrogen"
-           else O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64))
+    if which == "hydrogen":
+        cfg = O.PathConfig.hydrogen(neigs=4, fourier_mapping_size=64, sequential=True)
+    elif which == "oscillator":
+        cfg = O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64)
+    else:                                  # the f-4 families: configuration of the fixture of that name
+        cfg = load_golden(which)[1]
     g = torch.Generator().manual_seed(0)
-    x = (cfg.sampling_scale * torch.randn(200, 1, 2, generator=g)).reshape(200, -1)
+    if cfg.sampling_mode == "uniform":
+        x = (cfg.sampling_scale * (2 * torch.rand(200, 1, 2, generator=g) - 1)).reshape(200, -1)
+    else:
+        x = (cfg.sampling_scale * torch.randn(200, 1, 2, generator=g)).reshape(200, -1)
     # the reference, on the CPU, exact Laplacian
     m_cpu, op_cpu, imp_cpu, _ = RB.build_reference_problem(ref, cfg, 31, 0.0)
     loss_ref, aux_ref = m_cpu.compute_loss_operator(op_cpu, x, importance=imp_cpu)

@@ -45,24 +45,59 @@ def test_describe_operator_and_importance():
     d, cfg = load_golden("osc_small_seq")
     method, operator, importance, _ = build_problem(cfg, 0)
     od = operators.describe_operator(operator)
-    assert od == dict(potential=1, pot_coef=1.0, scale_kinetic=1.0, op_scale=1.0, op_shift=16.0)
-    assert operators.describe_importance(importance) == 4.0
+    assert od == dict(potential=1, pot_coef=1.0, pot_coef2=0.0, scale_kinetic=1.0, op_scale=1.0, op_shift=16.0)
+    assert operators.describe_importance(importance) == dict(importance=0, sigma=4.0)
     md = fused.describe_model(method)
     assert md["L"] == 4 and md["Mff"] == 64 and md["scales"] is not None and md["hard_mul_const"] == 0.5
     # the reference's importance is a closure over a MultivariateNormal (main_pde.py:94-100)
     from torch.distributions import MultivariateNormal
     mvn = MultivariateNormal(loc=torch.zeros(2), covariance_matrix=16.0 ** 2 * torch.eye(2))
     closure = lambda x: mvn.log_prob(x.view(x.shape[0], -1)).exp().view(-1, 1)  # noqa: E731
-    assert operators.describe_importance(closure) == 16.0
+    assert operators.describe_importance(closure) == dict(importance=0, sigma=16.0)
     x = 16 * torch.randn(8, 2)
     assert torch.allclose(N.GaussianImportance(16.0)(x), closure(x), rtol=1e-5)
+    # importance=None is the reference's un-weighted operator call (diff_ops.py:10-11)
+    assert operators.describe_importance(None)["importance"] == 3
+
+
+def test_other_samplers_potentials_and_masks_are_recognised():
+    """main_pde.py:101-118 closures read `args`; problems.py:30-73 potentials; boundary.py:16-37."""
+    from types import SimpleNamespace
+    from torch.distributions import Laplace
+    args = SimpleNamespace(sampling_mode="laplacian", sampling_scale=3.0, ndim=2, n_particles=1)
+
+    def importance_train(x):
+        return Laplace(torch.zeros(2), args.sampling_scale * torch.ones(2)).log_prob(x).sum(-1).exp().view(-1, 1)
+    assert operators.describe_importance(importance_train) == dict(importance=1, sigma=3.0)
+    x = 3 * torch.randn(8, 2)
+    assert torch.allclose(N.LaplaceImportance(3.0)(x), importance_train(x), rtol=1e-5)
+    args.sampling_mode = "uniform"
+    assert operators.describe_importance(importance_train) == dict(importance=2, sigma=3.0)
+    assert torch.allclose(N.UniformImportance(3.0)(x), torch.full((8, 1), 1 / 36.0))
+
+    d, cfg = load_golden("molion_laplace_boxexp_mask")
+    method, operator, importance, gt = build_problem(cfg, int(d["seed"]))
+    assert gt is None
+    od = operators.describe_operator(operator)
+    assert (od["potential"], od["pot_coef"], od["pot_coef2"]) == (2, 2.0, 1.5)
+    md = fused.describe_model(method)
+    assert md["scales"] is not None and (md["box_mode"], md["box_lim"]) == (2, 12.0)
+    d, cfg = load_golden("cosine_uniform_detff")
+    method, operator, importance, gt = build_problem(cfg, int(d["seed"]))
+    assert np.allclose(gt, d["gt"]) and fused.describe_model(method)["Mff"] == 64
+    assert operators.describe_operator(operator)["potential"] == 4
+    d, cfg = load_golden("well_uniform_boxsqrt")
+    method, operator, importance, gt = build_problem(cfg, int(d["seed"]))
+    assert np.allclose(gt, d["gt"]) and fused.describe_model(method)["box_mode"] == 1
+    xx = torch.tensor([[0.3, -1.2]])
+    assert torch.allclose(N.hydrogen_mol_ion_potential(xx, R=1.5, charge=2.0),
+                          N.hydrogen_potential(xx - torch.tensor([0.0, 1.5]), 2.0)
+                          + N.hydrogen_potential(xx + torch.tensor([0.0, 1.5]), 2.0))
 
 
 def test_unsupported_configurations_raise():
     with pytest.raises(NotImplementedError):
         operators.describe_operator(N.OperatorWrapper(N.NegativeHamiltonian(lambda x: x), 1.0, 0.0))
-    with pytest.raises(NotImplementedError):
-        operators.describe_importance(None)
     with pytest.raises(NotImplementedError):
         operators.describe_importance(lambda x: x)
     a = ref_args(O.PathConfig.hydrogen(neigs=2, fourier_mapping_size=8))

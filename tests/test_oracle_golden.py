@@ -6,7 +6,9 @@ import pytest
 from conftest import golden_grad_errors, load_golden, rel
 from oracle import nsvd_oracle as O
 
-PDE_SMALL = ["hyd_small_odd", "osc_small_seq"]
+PDE_SMALL = ["hyd_small_odd", "osc_small_seq",
+             # other potentials, samplers, Dirichlet box masks, deterministic features
+             "well_uniform_boxsqrt", "cosine_uniform_detff", "molion_laplace_boxexp_mask", "osc_no_importance"]
 PDE_FULL = ["hyd_b128_seq_L16", "osc_b512_jnt_L16", "hyd_b512_jnt_L16"]
 
 
