@@ -114,13 +114,17 @@ __device__ __forceinline__ TileCoord decode_tile(const BigShape& s, int t) {
   return c;
 }
 
-template <bool kMN, class Epi>
+// FMT = plane format of A | plane format of B << 2 | (add the lo*lo product) << 4, compile-time so that the
+// instruction descriptors stay immediates in the MMA issue loop (as kernel arguments they cost 5-6 % of the
+// layer-0 GEMMs: the single issuing thread is on the critical path at 98 % tensor-pipe utilisation).
+template <bool kMN, class Epi, int FMT = 0>
 __global__ void __launch_bounds__(big::THREADS, 1)
 big_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                const BigShape shape, const tc::MmaDescs md, const Epi epi) {
+                const BigShape shape, const Epi epi) {
   using namespace big;
   using namespace tc;
+  constexpr MmaDescs md = make_descs(BM, BN, kMN ? 1 : 0, kMN ? 1 : 0, FMT & 3, (FMT >> 2) & 3, (FMT >> 4) & 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -291,13 +295,14 @@ constexpr int THREADS = (4 + EPI_WARPS) * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 }  // namespace big2
 
-template <bool kMN, class Epi>
+template <bool kMN, class Epi, int FMT = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(big2::THREADS, 1)
 big2_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                 const BigShape shape, const int batches_valid, const tc::MmaDescs md, const Epi epi) {
+                 const BigShape shape, const int batches_valid, const Epi epi) {
   using namespace big2;
   using namespace tc;
+  constexpr MmaDescs md = make_descs(2 * BM, BN, kMN ? 1 : 0, kMN ? 1 : 0, FMT & 3, (FMT >> 2) & 3, (FMT >> 4) & 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -505,12 +510,11 @@ __global__ void split_planes_kernel(const float* __restrict__ src, __nv_bfloat16
   reinterpret_cast<uint16_t*>(lo)[i] = l;
 }
 
-template <bool kMN, class Epi>
+template <bool kMN, class Epi, int FMT = 0>
 static int launch_big(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                      const BigShape& shape, const Epi& epi, cudaStream_t st, int fa = tc::PF_BB, int fb = tc::PF_BB,
-                      int four = 0) {
+                      const BigShape& shape, const Epi& epi, cudaStream_t st) {
   static bool configured = false;
-  auto kern = big_gemm_kernel<kMN, Epi>;
+  auto kern = big_gemm_kernel<kMN, Epi, FMT>;
   if (!configured) {
     NSVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, big::SMEM_BYTES));
     configured = true;
@@ -518,18 +522,16 @@ static int launch_big(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
   int tiles = shape.m_tiles * shape.n_tiles * shape.batches * shape.k_slices;
   if (tiles <= 0) return 0;
   int grid = tiles < 148 ? tiles : 148;
-  const tc::MmaDescs md = tc::make_descs(big::BM, big::BN, kMN ? 1 : 0, kMN ? 1 : 0, fa, fb, four);
-  kern<<<grid, big::THREADS, big::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, md, epi);
+  kern<<<grid, big::THREADS, big::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, epi);
   NSVD_LAUNCH_CHECK();
   return 0;
 }
 
-template <bool kMN, class Epi>
+template <bool kMN, class Epi, int FMT = 0>
 static int launch_big2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                       const BigShape& shape, int batches_valid, const Epi& epi, cudaStream_t st,
-                       int fa = tc::PF_BB, int fb = tc::PF_BB, int four = 0) {
+                       const BigShape& shape, int batches_valid, const Epi& epi, cudaStream_t st) {
   static bool configured = false;
-  auto kern = big2_gemm_kernel<kMN, Epi>;
+  auto kern = big2_gemm_kernel<kMN, Epi, FMT>;
   if (!configured) {
     NSVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, big2::SMEM_BYTES));
     configured = true;
@@ -537,8 +539,7 @@ static int launch_big2(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   int tiles = shape.m_tiles * shape.n_tiles * shape.batches * shape.k_slices;
   if (tiles <= 0) return 0;
   int clusters = tiles < 74 ? tiles : 74;
-  const tc::MmaDescs md = tc::make_descs(2 * big2::BM, big2::BN, kMN ? 1 : 0, kMN ? 1 : 0, fa, fb, four);
-  kern<<<2 * clusters, big2::THREADS, big2::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, batches_valid, md, epi);
+  kern<<<2 * clusters, big2::THREADS, big2::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, batches_valid, epi);
   NSVD_LAUNCH_CHECK();
   return 0;
 }
@@ -559,6 +560,9 @@ int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int
   // mode bits: 0 = K-major, 1 = CTA-pair kernel, 4-5 = plane format of A, 6-7 = plane format of B, 8 = add lo*lo
   const int fa = (a_kmajor >> 4) & 3, fb = (a_kmajor >> 6) & 3, four = (a_kmajor >> 8) & 1;
   NSVD_CHECK_ARG(fa <= tc::PF_HH && fb <= tc::PF_HH, "selftest: unknown plane format");
+  const int fmt = fa | (fb << 2) | (four << 4);
+  // non-default formats exist on the single-CTA K-major kernel only (profiles/format_probe.py)
+  NSVD_CHECK_ARG(fmt == 0 || ((a_kmajor & 3) == 1), "selftest: plane formats other than bf16+bf16 need mode 1");
   const bool pair = (a_kmajor & 2) != 0;
   a_kmajor &= 1;
   b_kmajor &= 1;
@@ -595,10 +599,19 @@ int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int
       if ((rc = make_tmap_bf16_3d(&mbh, bh, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN / 2))) return rc;
       if ((rc = make_tmap_bf16_3d(&mbl, bl, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN / 2))) return rc;
       s.m_tiles = cdiv(M, 2 * big::BM);
-      return launch_big2<false>(mah, mal, mbh, mbl, s, 1, epi, st, fa, fb, four);
+      return launch_big2<false>(mah, mal, mbh, mbl, s, 1, epi, st);
     }
     if ((rc = make_tmap_bf16_3d(&mbl, bl, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN))) return rc;
-    return launch_big<false>(mah, mal, mbh, mbl, s, epi, st, fa, fb, four);
+    switch (fmt) {
+      case 0: return launch_big<false>(mah, mal, mbh, mbl, s, epi, st);
+      case 16: return launch_big<false, StoreEpi, 16>(mah, mal, mbh, mbl, s, epi, st);            // bf16 planes, 4 products
+      case 10: return launch_big<false, StoreEpi, 10>(mah, mal, mbh, mbl, s, epi, st);            // fp16+fp16 both
+      case 9: return launch_big<false, StoreEpi, 9>(mah, mal, mbh, mbl, s, epi, st);              // A bf16+fp16, B fp16+fp16
+      case 25: return launch_big<false, StoreEpi, 25>(mah, mal, mbh, mbl, s, epi, st);
+      case 5: return launch_big<false, StoreEpi, 5>(mah, mal, mbh, mbl, s, epi, st);              // bf16+fp16 both
+      case 21: return launch_big<false, StoreEpi, 21>(mah, mal, mbh, mbl, s, epi, st);
+      default: set_error("selftest: plane format combination %d not instantiated", fmt); return NSVD_E_BADARG;
+    }
   }
   if ((rc = make_tmap_bf16_3d(&mah, ah, M, K, 1, (uint64_t)M * 2, (uint64_t)M * K * 2, 64, 64))) return rc;
   if ((rc = make_tmap_bf16_3d(&mal, al, M, K, 1, (uint64_t)M * 2, (uint64_t)M * K * 2, 64, 64))) return rc;
@@ -608,9 +621,9 @@ int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int
     s.m_tiles = cdiv(M, big::BM);
     s.a_batched = 1;
     NSVD_CHECK_ARG(M <= big::BM, "selftest: MN-major pair mode takes M <= 128");
-    return launch_big2<true>(mah, mal, mbh, mbl, s, 1, epi, st, fa, fb, four);
+    return launch_big2<true>(mah, mal, mbh, mbl, s, 1, epi, st);
   }
-  return launch_big<true>(mah, mal, mbh, mbl, s, epi, st, fa, fb, four);
+  return launch_big<true>(mah, mal, mbh, mbl, s, epi, st);
 }
 
 // ------------------------------------------------------------------------------------------

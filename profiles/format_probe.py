@@ -45,10 +45,10 @@ if __name__ == "__main__":
     if len(sys.argv) >= 5:
         run_case(sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), *(int(v) for v in sys.argv[5:]))
     else:
-        cases = [(a, b, f, base) for base in (3, 2, 1) for (a, b, f) in
+        cases = [(a, b, f, base) for base in (1,) for (a, b, f) in
                  [("BB", "BB", 0), ("BB", "BB", 1), ("HH", "HH", 0), ("BH", "HH", 0), ("BH", "HH", 1),
                   ("BH", "BH", 0), ("BH", "BH", 1), ("BH-small", "HH", 1), ("BH-small", "BH", 1)]]
-        cases += [("HH", "HH", 0, 3, 128), ("HH", "HH", 0, 3, 512), ("HH", "HH", 0, 3, 8192), ("BB", "BB", 1, 3, 128)]
+        cases += [("HH", "HH", 0, 1, 128), ("HH", "HH", 0, 1, 512), ("HH", "HH", 0, 1, 8192), ("BB", "BB", 1, 1, 128)]
         for c in cases:
             r = subprocess.run([sys.executable, __file__] + [str(v) for v in c], capture_output=True, text=True,
                                timeout=120)
