@@ -855,6 +855,12 @@ constexpr int SMEM_FWD = 2 * PLANE + F_STAGES * F_STAGE_BYTES + F_STAGING + 1024
 // backward kernel
 constexpr int STAGE_BYTES = 2 * PLANE;
 constexpr int SMEM_BWD = 2 * PLANE + 2 * STAGE_BYTES + 1024 + 1024;
+// pipelined backward kernel: half tiles of 64 points in a 2-stage ring
+constexpr int HROWS = 64;
+constexpr int HCHUNK = HROWS * 128;       // [64 rows][128 B]
+constexpr int HPLANE = 2 * HCHUNK;        // one 64 x 128 bf16 plane
+constexpr int B2_STAGE = 4 * HPLANE;      // dZ hi | dZ lo | a hi | a lo  = 64 KB
+constexpr int SMEM_BWD2 = 2 * PLANE + 2 * B2_STAGE + 1024 + 1024;
 }  // namespace hid
 
 struct HidFwdArgs {
@@ -1385,6 +1391,229 @@ hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
+// S2-bwd, pipelined version (default): the same dgrad + wgrad fusion on HALF tiles of 64 points in a 2-stage
+// ring, so the loads of half tile j+1 overlap the MMAs, epilogue and stores of half tile j.
+//   smem : W_i^T hi/lo resident (64 KB) | 2 stages x 64 KB (dZ_i hi/lo, a_{i-1} hi/lo of 64 points).
+//   dgrad is issued transposed, D1[k][p] = sum_j W_i^T[k][j] dZ_i[p][j]  (M = 128 units, N = 64 points), so the
+//   accumulator keeps the full 128-lane datapath busy; TMEM lane = unit k, column = point.  Epilogue thread (k, 16
+//   points): dZ_{i-1} = D1 (.) sigma(a_{i-1}) with a read from the stage, written back as hi/lo over the dead dZ_i
+//   half tile (2-byte accesses, conflict-free: a warp covers 64 contiguous bytes of one row), db_{i-1} is a
+//   per-thread running sum.  Warp 3 drains the staged half tile with TMA stores and releases the stage.
+//   wgrad D2[j][k] += dZ_i^T a_{i-1} accumulates in TMEM over the half tiles of a copy (K = 64 points each).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(hid::F_THREADS, 1)
+hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,
+                   const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                   const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
+                   const HidBwdArgs args) {
+  using namespace hid;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;                 // W_i^T hi | lo  (128 rows k, K = j)
+  uint8_t* sS = smem + 2 * PLANE;     // 2 stages
+  uint64_t* bars = (uint64_t*)(sS + 2 * B2_STAGE);
+  uint64_t* full = bars;              // [2] stage landed
+  uint64_t* mma_done = bars + 2;      // [2] dgrad + wgrad of the stage retired
+  uint64_t* empty = bars + 4;         // [2] stage drained (stores have read it), TMEM buffer free
+  uint64_t* wfull = bars + 6;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 7);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h_tiles = args.m_tiles;   // half tiles (64 points) per copy
+  const int T = args.L * h_tiles;
+  const int tpc = (T + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * tpc;
+  const int t_end = (t_begin + tpc < T) ? t_begin + tpc : T;
+  constexpr int NBAR = F_EPI_WARPS * 32 + 32;   // epilogue threads arrive, the store warp syncs
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmZh);
+    tma_prefetch_desc(&tmZl);
+    tma_prefetch_desc(&tmAh);
+    tma_prefetch_desc(&tmAl);
+    tma_prefetch_desc(&tmWh);
+    tma_prefetch_desc(&tmWl);
+    tma_prefetch_desc(&tmOh);
+    tma_prefetch_desc(&tmOl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&mma_done[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;       // columns [0,64) and [64,128): dgrad buffers; [128,256): wgrad
+  const uint32_t tmem_d2 = tmem_base + 128;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int cur_l = -1;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int j = t - t_begin, s = j & 1, u = j >> 1;
+        const int l = t / h_tiles, ht = t % h_tiles;
+        if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1), 40);
+        if (l != cur_l) {
+          // every MMA that reads the resident weights has retired once the previous half tile is drained
+          if (j > 0) mbar_wait(&empty[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1), 41);
+          mbar_arrive_expect_tx(wfull, 2 * PLANE);
+          tma_load_3d(sW, &tmWh, wfull, 0, 0, l);
+          tma_load_3d(sW + CHUNK, &tmWh, wfull, 64, 0, l);
+          tma_load_3d(sW + PLANE, &tmWl, wfull, 0, 0, l);
+          tma_load_3d(sW + PLANE + CHUNK, &tmWl, wfull, 64, 0, l);
+          cur_l = l;
+        }
+        uint8_t* st = sS + s * B2_STAGE;
+        const int pz = ht * HROWS, pa = (int)args.p_off + pz;
+        mbar_arrive_expect_tx(&full[s], B2_STAGE);
+        tma_load_3d(st, &tmZh, &full[s], 0, pz, l);
+        tma_load_3d(st + HCHUNK, &tmZh, &full[s], 64, pz, l);
+        tma_load_3d(st + HPLANE, &tmZl, &full[s], 0, pz, l);
+        tma_load_3d(st + HPLANE + HCHUNK, &tmZl, &full[s], 64, pz, l);
+        tma_load_3d(st + 2 * HPLANE, &tmAh, &full[s], 0, pa, l);
+        tma_load_3d(st + 2 * HPLANE + HCHUNK, &tmAh, &full[s], 64, pa, l);
+        tma_load_3d(st + 3 * HPLANE, &tmAl, &full[s], 0, pa, l);
+        tma_load_3d(st + 3 * HPLANE + HCHUNK, &tmAl, &full[s], 64, pa, l);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_d = make_idesc_bf16(128, HROWS, 0, 0);  // dgrad: K-major, M = units, N = points
+      constexpr uint32_t idesc_w = make_idesc_bf16(128, 128, 1, 1);    // wgrad: MN-major operands
+      const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + PLANE;
+      int cur_l = -1;
+      uint32_t wphase = 0;
+      bool first_of_run = true;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int j = t - t_begin, s = j & 1, u = j >> 1;
+        const int l = t / h_tiles;
+        if (l != cur_l) {
+          mbar_wait(wfull, wphase, 42);
+          wphase ^= 1;
+          cur_l = l;
+          first_of_run = true;
+        }
+        mbar_wait(&full[s], (uint32_t)(u & 1), 43);   // implies stage s and TMEM buffer s were released
+        tc_fence_after();
+        const uint32_t z_hi = smem_u32(sS + s * B2_STAGE), z_lo = z_hi + HPLANE;
+        const uint32_t a_hi = z_hi + 2 * HPLANE, a_lo = z_hi + 3 * HPLANE;
+        const uint32_t acc = tmem_base + (uint32_t)s * HROWS;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t ow = (kk >> 2) * CHUNK + (kk & 3) * 32, oz = (kk >> 2) * HCHUNK + (kk & 3) * 32;
+          uint64_t ah = make_sdesc_sw128(w_hi + ow, 16, 1024), al = make_sdesc_sw128(w_lo + ow, 16, 1024);
+          uint64_t bh = make_sdesc_sw128(z_hi + oz, 16, 1024), bl = make_sdesc_sw128(z_lo + oz, 16, 1024);
+          umma_f16(acc, al, bh, idesc_d, kk > 0 ? 1u : 0u);
+          umma_f16(acc, ah, bl, idesc_d, 1u);
+          umma_f16(acc, ah, bh, idesc_d, 1u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < HROWS / 16; ++kk) {   // K = 64 points, 16 per MMA
+          const uint32_t off = kk * 2048;
+          uint64_t ah = make_sdesc_sw128(z_hi + off, HCHUNK, 1024), al = make_sdesc_sw128(z_lo + off, HCHUNK, 1024);
+          uint64_t bh = make_sdesc_sw128(a_hi + off, HCHUNK, 1024), bl = make_sdesc_sw128(a_lo + off, HCHUNK, 1024);
+          umma_f16(tmem_d2, al, bh, idesc_w, (first_of_run && kk == 0) ? 0u : 1u);
+          umma_f16(tmem_d2, ah, bl, idesc_w, 1u);
+          umma_f16(tmem_d2, ah, bh, idesc_w, 1u);
+        }
+        umma_commit(&mma_done[s]);
+        first_of_run = false;
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== store warp: drain the staged half tile, release the stage =====================
+    for (int t = t_begin; t < t_end; ++t) {
+      const int j = t - t_begin, s = j & 1;
+      const int l = t / h_tiles, ht = t % h_tiles;
+      named_bar_sync(2 + s, NBAR);
+      if (lane == 0) {
+        const uint8_t* st = sS + s * B2_STAGE;
+        tma_store_3d(&tmOh, st, 0, ht * HROWS, l);
+        tma_store_3d(&tmOh, st + HCHUNK, 64, ht * HROWS, l);
+        tma_store_3d(&tmOl, st + HPLANE, 0, ht * HROWS, l);
+        tma_store_3d(&tmOl, st + HPLANE + HCHUNK, 64, ht * HROWS, l);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) tma_store_wait_all();
+  } else if (warp >= 4) {
+    // ===================== 16 epilogue warps: lane quarter q (32 units) x point group cg (16 points) ==========
+    const int ewarp = warp - 4, q = ewarp & 3, cg = ewarp >> 2;
+    const int k = q * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t koff = (uint32_t)((k >> 6) * HCHUNK + (k & 7) * 2);
+    const int piece = (k & 63) >> 3;
+    float dbacc = 0.f;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int j = t - t_begin, s = j & 1, u = j >> 1;
+      const int l = t / h_tiles;
+      mbar_wait(&mma_done[s], (uint32_t)(u & 1), 45);
+      tc_fence_after();
+      float v[16];
+      tmem_ld16(tl + (uint32_t)(s * HROWS + cg * 16), v);
+      uint8_t* st = sS + s * B2_STAGE;
+      tmem_ld_wait();
+      // rows beyond P carry dZ_i = 0 (TMA zero fill), hence D1 = 0 and the product is 0 without a mask
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int pt = cg * 16 + i;
+        const uint32_t off = koff + (uint32_t)(pt * 128 + ((piece ^ (pt & 7)) << 4));
+        const uint32_t ahb = *reinterpret_cast<const uint16_t*>(st + 2 * HPLANE + off);
+        const uint32_t alb = *reinterpret_cast<const uint16_t*>(st + 3 * HPLANE + off);
+        const float a = __uint_as_float(ahb << 16) + __uint_as_float(alb << 16);
+        const float val = v[i] * sig_fast(a);
+        dbacc += val;
+        const __nv_bfloat16 h = __float2bfloat16_rn(val);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(h));
+        *reinterpret_cast<__nv_bfloat16*>(st + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(st + HPLANE + off) = lo;
+      }
+      const bool last_of_run = (t + 1 == t_end) || ((t + 1) / h_tiles != l);
+      if (last_of_run) {
+        float* drow = args.dW + ((long)l * kHidden + k) * kHidden;   // wgrad accumulator: lane = row j of dW
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          const int k0 = cg * 32 + ch * 16;
+          float w[16];
+          tmem_ld16(tl + 128 + k0, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) red_add_v4(drow + k0 + 4 * i, w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        }
+        atomicAdd(args.db_prev + l * kHidden + k, dbacc);
+        dbacc = 0.f;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_arrive(2 + s, NBAR);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // head backward (SIMT, HBM-bound): du = dF c m rho ; dZ2 = du W3 (.) sigma(a2) -> hi/lo planes ;
 // dW3, db3, db2, dscales accumulated (block partials + atomics).  grid = (point chunks, L)
 // ------------------------------------------------------------------------------------------
@@ -1682,8 +1911,10 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
   static bool configured = false;
   if (!configured) {
     NSVD_CUDA(cudaFuncSetAttribute(hidden_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hid::SMEM_BWD));
+    NSVD_CUDA(cudaFuncSetAttribute(hidden_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hid::SMEM_BWD2));
     configured = true;
   }
+  static const int hidbwd_v1 = env_int("NSVD_HIDBWD_V1", 0);   // 1 = the unpipelined 128-point kernel
   // gradients are accumulated with reductions: start from zero
   NSVD_CUDA(cudaMemsetAsync(gr.dW[0], 0, sizeof(float) * L * H * K0, st));
   NSVD_CUDA(cudaMemsetAsync(gr.dW[1], 0, sizeof(float) * L * H * H, st));
@@ -1716,26 +1947,30 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
     int cur = 0;
     for (int i = 2; i >= 1; --i) {
       CUtensorMap mZh, mZl, mAh, mAl;
-      if ((rc = make_tmap_bf16_3d(&mZh, wk + t.dz_hi[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
-      if ((rc = make_tmap_bf16_3d(&mZl, wk + t.dz_lo[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
-      if ((rc = make_tmap_bf16_3d(&mAh, sv + t.av_hi[i - 1], H, B, L, H * 2, (uint64_t)B * H * 2, 64, 128))) return rc;
-      if ((rc = make_tmap_bf16_3d(&mAl, sv + t.av_lo[i - 1], H, B, L, H * 2, (uint64_t)B * H * 2, 64, 128))) return rc;
+      const int rows = hidbwd_v1 ? 128 : hid::HROWS;   // points per (half) tile = TMA box height
+      if ((rc = make_tmap_bf16_3d(&mZh, wk + t.dz_hi[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, rows))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mZl, wk + t.dz_lo[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, rows))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mAh, sv + t.av_hi[i - 1], H, B, L, H * 2, (uint64_t)B * H * 2, 64, rows))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mAl, sv + t.av_lo[i - 1], H, B, L, H * 2, (uint64_t)B * H * 2, 64, rows))) return rc;
       CUtensorMap mOh, mOl;
-      if ((rc = make_tmap_bf16_3d(&mOh, wk + t.dz_hi[cur ^ 1], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
-      if ((rc = make_tmap_bf16_3d(&mOl, wk + t.dz_lo[cur ^ 1], H, P, L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mOh, wk + t.dz_hi[cur ^ 1], H, P, L, H * 2, (uint64_t)P * H * 2, 64, rows))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mOl, wk + t.dz_lo[cur ^ 1], H, P, L, H * 2, (uint64_t)P * H * 2, 64, rows))) return rc;
       HidBwdArgs a{};
       a.L = (int)L;
       a.P = P;
-      a.m_tiles = m_tiles;
+      a.m_tiles = cdiv(P, rows);
       a.Btot = B;
       a.p_off = p0;
       a.dW = gr.dW[i];
       a.db_prev = gr.db[i - 1];
-      int T = (int)L * m_tiles;
+      int T = (int)L * a.m_tiles;
       int grid = T < 148 ? T : 148;
       {
         ProfScope ps(KC_HID_BWD, st);
-        hidden_bwd_kernel<<<grid, hid::F_THREADS, hid::SMEM_BWD, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], mOh, mOl, a);
+        if (hidbwd_v1)
+          hidden_bwd_kernel<<<grid, hid::F_THREADS, hid::SMEM_BWD, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], mOh, mOl, a);
+        else
+          hidden_bwd2_kernel<<<grid, hid::F_THREADS, hid::SMEM_BWD2, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], mOh, mOl, a);
         NSVD_LAUNCH_CHECK();
       }
       cur ^= 1;
