@@ -72,3 +72,32 @@ def test_oscillator_spectrum_emerges_from_training():
     # measured: 13.95 11.89 11.91 9.93 9.91 (0.4-0.9 % off); later modes are still sorting themselves out
     assert np.all(np.abs(rayleigh[:5] / gt[:5] - 1) < 0.03)
     assert np.all(rayleigh[5:10] > 5.0) and np.all(rayleigh[5:10] < 10.5)
+
+
+def test_infinite_well_spectrum_emerges_from_training():
+    # SURVEY §8 f-4 families end to end: infinite well on [-1, 1]^2 (problems.py:30-33), uniform sampler and importance
+    # (main_pde.py:113-118), Dirichlet box mask 'dir_box_sqrt' (boundary.py:29-31), shifted operator 40 - H.
+    # Analytic (ground_truths.py:40-59, L = 2): 40 - (nx^2 + ny^2) pi^2 / 4 -> 35.07, 27.66 x2, 20.26, 15.33 x2, ...
+    cfg = O.PathConfig(potential="infinite_well", neigs=8, fourier_mapping_size=256, fourier_scale=0.5,
+                       operator_scale=1.0, operator_shift=40.0, sampling_mode="uniform", sampling_scale=1.0, lim=1.0,
+                       apply_boundary=True, boundary_mode="dir_box_sqrt", sequential=True)
+    steps, B = 2000, 16384
+    N.set_engine("bf16x3")
+    method, operator, importance, gt = build_problem(cfg, 0, "cuda")
+    assert np.allclose(gt[:4], 40 - np.array([2, 5, 5, 8]) * np.pi ** 2 / 4)
+    opt = N.FusedRMSpropEMA(method.parameters(), lr=1e-3, alpha=0.999, eps=1e-10, ema_decay=0.995, num_iters=steps)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for it in range(steps):
+        x = cfg.sampling_scale * (2 * torch.rand(B, 2, device="cuda", generator=g) - 1)
+        opt.zero_grad()
+        loss, _ = method.compute_loss_operator(operator, x, importance=importance)
+        loss.backward()
+        opt.step()
+    assert np.isfinite(float(loss.detach()))
+    xe = cfg.sampling_scale * (2 * torch.rand(1 << 18, 2, device="cuda", generator=g) - 1)
+    Tf, f = operator(method, xe, importance=importance)
+    rayleigh = ((f.double() * Tf.double()).sum(0) / (f.double() ** 2).sum(0)).cpu().numpy()
+    print("ground truth:", np.round(gt, 2))
+    print("rayleigh    :", np.round(rayleigh, 2))
+    # measured: 35.07 27.66 27.66 20.25 15.33 15.32 7.92 7.87
+    assert np.all(np.abs(rayleigh / gt - 1) < 0.02)
