@@ -16,5 +16,6 @@ from .dist import PointParallel, shard_points
 from .spectrum import compute_spectrum_evd
 from .optim import FusedRMSpropEMA, sample_gaussian
 from .graphs import GraphedOperatorStep
+from .siam import HeteroNetwork, get_mlp, get_sketchy_encoder, normalize
 
 __all__ = [n for n in dir() if not n.startswith("_")]
