@@ -199,6 +199,11 @@ int nsvd_rmsprop_ema_step(int32_t n_tensors, float* const* params, const float* 
  * that stays the RNG-parity mode).  Counter-based: reproducible for (seed, offset).               */
 int nsvd_sample_gaussian(float* x, int64_t n_points, float sigma, uint64_t seed, uint64_t offset,
                          void* stream);
+/* The other samplers of main_pde.py:101-118 on the device, same counter scheme: `importance` = NSVD_IMP_LAPLACE
+ * (x_i ~ Laplace(0, scale), inverse CDF) or NSVD_IMP_UNIFORM (x_i ~ U[-scale, scale)); NSVD_IMP_GAUSSIAN forwards
+ * to nsvd_sample_gaussian.                                                                          */
+int nsvd_sample_points(float* x, int64_t n_points, int32_t importance, float scale, uint64_t seed, uint64_t offset,
+                       void* stream);
 
 /* Self-test hooks for the tcgen05 building block (tests/test_gpu_tc_gemm.py):
  *   D (M,N) fp32 = A . B^T with bf16x3 splitting; A (M,K), B (N,K) fp32 when *_kmajor = 1,

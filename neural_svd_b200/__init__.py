@@ -14,7 +14,7 @@ from .operators import (GaussianImportance, LaplaceImportance, NegativeHamiltoni
 from .fused import compute_loss_operator, get_engine, set_engine, set_microbatch
 from .dist import PointParallel, shard_points
 from .spectrum import compute_spectrum_evd
-from .optim import FusedRMSpropEMA, sample_gaussian
+from .optim import FusedRMSpropEMA, sample_gaussian, sample_points
 from .graphs import GraphedOperatorStep
 from .siam import HeteroNetwork, get_mlp, get_sketchy_encoder, normalize
 

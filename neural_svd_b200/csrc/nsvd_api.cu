@@ -258,6 +258,15 @@ int nsvd_sample_gaussian(float* x, int64_t n_points, float sigma, uint64_t seed,
   return sample_gaussian2(x, n_points, sigma, seed, offset, (cudaStream_t)stream);
 }
 
+int nsvd_sample_points(float* x, int64_t n_points, int32_t importance, float scale, uint64_t seed, uint64_t offset,
+                       void* stream) {
+  NSVD_CHECK_ARG(x && n_points >= 0 && scale > 0.f, "bad args");
+  if (importance == NSVD_IMP_GAUSSIAN) return sample_gaussian2(x, n_points, scale, seed, offset, (cudaStream_t)stream);
+  NSVD_CHECK_ARG(importance == NSVD_IMP_LAPLACE || importance == NSVD_IMP_UNIFORM, "no sampler for importance %d",
+                 importance);
+  return sample_other2(x, n_points, importance == NSVD_IMP_LAPLACE, scale, seed, offset, (cudaStream_t)stream);
+}
+
 int nsvd_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K,
                           int32_t a_kmajor, int32_t b_kmajor, void* work, size_t work_bytes, void* stream) {
   NSVD_CHECK_ARG(A && B && D && work, "NULL buffer");

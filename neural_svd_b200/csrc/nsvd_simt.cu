@@ -1127,6 +1127,36 @@ __global__ void sample_gaussian2_kernel(float* __restrict__ x, long n, float sig
   x[2 * i] = r * cs;
   x[2 * i + 1] = r * sn;
 }
+// Laplace (inverse CDF: x = -b sign(u) ln(1 - 2|u|), u in (-1/2, 1/2)) and uniform [-s, s) samplers
+// (main_pde.py:101-118), one thread per point, same (seed, offset) counter scheme as the Gaussian one.
+__global__ void sample_other2_kernel(float* __restrict__ x, long n, int laplace, float scale, uint64_t seed,
+                                     uint64_t offset) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t ctr = (offset + (uint64_t)i) * 2ull;
+  uint32_t r[2] = {mix32(seed ^ (ctr * 0xD1342543DE82EF95ull)),
+                   mix32((seed + 0x632BE59BD9B4E019ull) ^ ((ctr + 1ull) * 0xD1342543DE82EF95ull))};
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    // 23-bit mid-point grid: u in [2^-24, 1 - 2^-24], never 0 or 1
+    float u = ((float)(r[d] >> 9) + 0.5f) * 1.1920928955078125e-07f;
+    float v;
+    if (laplace) {
+      float c = u - 0.5f;                                  // (-1/2, 1/2)
+      v = -scale * copysignf(1.f, c) * log1pf(-2.f * fabsf(c));
+    } else {
+      v = scale * (2.f * u - 1.f);
+    }
+    x[2 * i + d] = v;
+  }
+}
+int sample_other2(float* x, long n, int laplace, float scale, uint64_t seed, uint64_t offset, cudaStream_t st) {
+  if (n <= 0) return 0;
+  sample_other2_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, n, laplace, scale, seed, offset);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
 int sample_gaussian2(float* x, long n, float sigma, uint64_t seed, uint64_t offset, cudaStream_t st) {
   if (n <= 0) return 0;
   sample_gaussian2_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, n, sigma, seed, offset);

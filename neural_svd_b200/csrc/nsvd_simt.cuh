@@ -55,6 +55,7 @@ struct OptTensors {
 };
 int rmsprop_ema_step(const OptTensors& t, float lr, float alpha, float eps, float ema_w, cudaStream_t st);
 int sample_gaussian2(float* x, long n, float sigma, uint64_t seed, uint64_t offset, cudaStream_t st);
+int sample_other2(float* x, long n, int laplace, float scale, uint64_t seed, uint64_t offset, cudaStream_t st);
 
 // tcgen05 engine (nsvd_tc.cu)
 void tc_set_micro_batch(int points);

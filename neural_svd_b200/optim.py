@@ -78,3 +78,17 @@ def sample_gaussian(n_points: int, sigma: float, seed: int, offset: int = 0, dev
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(lib.nsvd_sample_gaussian(_lib.ptr(x), n_points, sigma, seed, offset, st), "nsvd_sample_gaussian")
     return x
+
+
+def sample_points(n_points: int, sampling_mode: str, scale: float, seed: int, offset: int = 0, device="cuda"):
+    """x (n_points, 2) from the sampler of `sampling_mode` in {'gaussian', 'laplacian', 'uniform'} (main_pde.py:89-118),
+    generated on the device; pairs with GaussianImportance / LaplaceImportance / UniformImportance."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("sample_points has no CPU path")
+    code = {"gaussian": _lib.IMP_GAUSSIAN, "laplacian": _lib.IMP_LAPLACE, "uniform": _lib.IMP_UNIFORM}[sampling_mode]
+    x = torch.empty((n_points, 2), dtype=torch.float32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(lib.nsvd_sample_points(_lib.ptr(x), n_points, code, scale, seed, offset, st), "nsvd_sample_points")
+    return x

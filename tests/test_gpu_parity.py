@@ -247,6 +247,23 @@ def test_device_sampler_statistics_and_reproducibility():
     assert float((big ** 2).sum(1).min()) > 1e-8
 
 
+def test_device_samplers_of_the_other_importance_modes():
+    # main_pde.py:101-118 on the device: Laplace(0, b) per coordinate, uniform on [-s, s)^2
+    n = 1 << 20
+    lap = N.sample_points(n, "laplacian", 3.0, seed=5)
+    assert torch.equal(lap, N.sample_points(n, "laplacian", 3.0, seed=5))
+    assert torch.equal(N.sample_points(1 << 10, "laplacian", 3.0, seed=5, offset=n - (1 << 10)), lap[-(1 << 10):])
+    v = lap.double().cpu().numpy() / 3.0
+    assert abs(v.mean()) < 5e-3 and abs(np.abs(v).mean() - 1) < 5e-3 and abs((v ** 2).mean() - 2) < 2e-2
+    assert abs(np.mean(np.abs(v) < np.log(2)) - 0.5) < 5e-3        # median of |x|/b
+    assert np.isfinite(v).all() and abs((v[:, 0] * v[:, 1]).mean()) < 1e-2
+    uni = N.sample_points(n, "uniform", 2.0, seed=7).double().cpu().numpy() / 2.0
+    assert uni.min() > -1 and uni.max() < 1
+    assert abs(uni.mean()) < 3e-3 and abs((uni ** 2).mean() - 1 / 3) < 3e-3 and abs((uni[:, 0] * uni[:, 1]).mean()) < 3e-3
+    g1, g2 = N.sample_points(4096, "gaussian", 16.0, seed=5), N.sample_gaussian(4096, 16.0, seed=5)
+    assert torch.equal(g1, g2)
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_graphed_step_equals_eager_step(engine):
     d, cfg = load_golden("osc_b512_jnt_L16")
