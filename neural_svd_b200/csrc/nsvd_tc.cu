@@ -793,8 +793,10 @@ struct L0FwdEpi {
         act_streams(zb, z[1][i], z[2][i], z[3][i], z[0][i], z[1][i], z[2][i], z[3][i]);
       }
       if (pt < P) {
+        // the value stream lives only in `saved` (the next layer and the backward both read it there);
+        // the derivative streams go to the micro-batch stream buffer
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 1; s < 4; ++s) {
           long o = (((long)l * 4 + s) * P + pt) * kHidden + h0;
           store_split16(z[s], str_hi + o, str_lo + o);
         }
@@ -888,6 +890,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                   const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
                   const __grid_constant__ CUtensorMap tmSh, const __grid_constant__ CUtensorMap tmSl,
+                  const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
                   const HidFwdArgs args) {
   using namespace hid;
   using namespace tc;
@@ -921,6 +924,8 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     tma_prefetch_desc(&tmWl);
     tma_prefetch_desc(&tmSh);
     tma_prefetch_desc(&tmSl);
+    tma_prefetch_desc(&tmVh);
+    tma_prefetch_desc(&tmVl);
     if (!kLast) {
       tma_prefetch_desc(&tmOh);
       tma_prefetch_desc(&tmOl);
@@ -964,8 +969,13 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           mbar_wait(&empty[stage], phase ^ 1, 11);
           uint8_t* d = sA + stage * F_STAGE_BYTES;
           mbar_arrive_expect_tx(&full[stage], F_STAGE_BYTES);
-          tma_load_3d(d, &tmAh, &full[stage], 64 * c, mt * 128, l * 4 + s);
-          tma_load_3d(d + CHUNK, &tmAl, &full[stage], 64 * c, mt * 128, l * 4 + s);
+          if (s == 0) {   // input value stream: from `saved` (whole-batch rows), not duplicated in the stream buffer
+            tma_load_3d(d, &tmVh, &full[stage], 64 * c, (int)args.p_off + mt * 128, l);
+            tma_load_3d(d + CHUNK, &tmVl, &full[stage], 64 * c, (int)args.p_off + mt * 128, l);
+          } else {
+            tma_load_3d(d, &tmAh, &full[stage], 64 * c, mt * 128, l * 4 + s);
+            tma_load_3d(d + CHUNK, &tmAl, &full[stage], 64 * c, mt * 128, l * 4 + s);
+          }
           if (++stage == F_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -1085,7 +1095,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         if (et == 0) {
           if (!kLast) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
+            for (int s = 1; s < 4; ++s) {
               tma_store_3d(&tmOh, sO + (2 * s) * F_BOX, r * 32, mt * 128, l * 4 + s);
               tma_store_3d(&tmOl, sO + (2 * s + 1) * F_BOX, r * 32, mt * 128, l * 4 + s);
             }
@@ -1791,7 +1801,8 @@ static inline uint8_t* align1k(void* p) { return (uint8_t*)(((uintptr_t)p + 1023
 template <bool kLast>
 static int launch_hidden_fwd(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh,
                              const CUtensorMap& wl, const CUtensorMap& oh, const CUtensorMap& ol,
-                             const CUtensorMap& sh, const CUtensorMap& sl, const HidFwdArgs& a, cudaStream_t st) {
+                             const CUtensorMap& sh, const CUtensorMap& sl, const CUtensorMap& vh, const CUtensorMap& vl,
+                             const HidFwdArgs& a, cudaStream_t st) {
   static bool configured = false;
   auto kern = hidden_fwd_kernel<kLast>;
   if (!configured) {
@@ -1800,7 +1811,7 @@ static int launch_hidden_fwd(const CUtensorMap& ah, const CUtensorMap& al, const
   }
   int T = a.L * a.m_tiles;
   int grid = T < 148 ? T : 148;
-  kern<<<grid, hid::F_THREADS, hid::SMEM_FWD, st>>>(ah, al, wh, wl, oh, ol, sh, sl, a);
+  kern<<<grid, hid::F_THREADS, hid::SMEM_FWD, st>>>(ah, al, wh, wl, oh, ol, sh, sl, vh, vl, a);
   NSVD_LAUNCH_CHECK();
   return 0;
 }
@@ -1874,6 +1885,10 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
       if ((rc = make_tmap_bf16_3d(&mOl, wk + t.str_lo[o], H, P, 4 * L, H * 2, (uint64_t)P * H * 2, 32, 128, 64))) return rc;
       if ((rc = make_tmap_bf16_3d(&mSh, sv + t.av_hi[i + 1], H, B, L, H * 2, (uint64_t)B * H * 2, 32, 128, 64))) return rc;
       if ((rc = make_tmap_bf16_3d(&mSl, sv + t.av_lo[i + 1], H, B, L, H * 2, (uint64_t)B * H * 2, 32, 128, 64))) return rc;
+      // input value stream a_i of this layer, as saved by the previous one (rows = points of the whole batch)
+      CUtensorMap mVh, mVl;
+      if ((rc = make_tmap_bf16_3d(&mVh, sv + t.av_hi[i], H, B, L, H * 2, (uint64_t)B * H * 2, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&mVl, sv + t.av_lo[i], H, B, L, H * 2, (uint64_t)B * H * 2, 64, 128))) return rc;
       HidFwdArgs a{};
       a.L = (int)L;
       a.P = P;
@@ -1883,7 +1898,7 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
       a.bias = pr.b[i + 1];
       ProfScope ps(KC_HID_FWD, st);
       if (i == 0) {
-        if ((rc = launch_hidden_fwd<false>(mAh, mAl, mWh[0], mWl[0], mOh, mOl, mSh, mSl, a, st))) return rc;
+        if ((rc = launch_hidden_fwd<false>(mAh, mAl, mWh[0], mWl[0], mOh, mOl, mSh, mSl, mVh, mVl, a, st))) return rc;
       } else {
         a.W3 = pr.W[3];
         a.b3 = pr.b[3];
@@ -1893,7 +1908,7 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
         a.TF = TF;
         a.U0 = reinterpret_cast<float*>(sv + t.u0);
         a.pb = pb;
-        if ((rc = launch_hidden_fwd<true>(mAh, mAl, mWh[1], mWl[1], mOh, mOl, mSh, mSl, a, st))) return rc;
+        if ((rc = launch_hidden_fwd<true>(mAh, mAl, mWh[1], mWl[1], mOh, mOl, mSh, mSl, mVh, mVl, a, st))) return rc;
       }
     }
   }
