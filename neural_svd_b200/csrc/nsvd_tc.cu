@@ -865,6 +865,18 @@ constexpr int B2_STAGE = 4 * HPLANE;      // dZ hi | dZ lo | a hi | a lo  = 64 K
 constexpr int SMEM_BWD2 = 2 * PLANE + 2 * B2_STAGE + 1024 + 1024;
 }  // namespace hid
 
+// Optional phase timeline of block 0 (development builds: nvcc -DNSVD_TIMELINE; see profiles/timeline_probe.py)
+#ifdef NSVD_TIMELINE
+__device__ long long g_timeline[64 * 8];
+#define NSVD_TL(tile, slot) \
+  do { if (blockIdx.x == 0 && (tile) < 64) g_timeline[(tile) * 8 + (slot)] = clock64(); } while (0)
+extern "C" int nsvd_debug_timeline(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 64 * 8);
+}
+#else
+#define NSVD_TL(tile, slot) do {} while (0)
+#endif
+
 struct HidFwdArgs {
   int L, P, m_tiles;
   long Btot, p_off;
@@ -981,6 +993,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             phase ^= 1;
           }
         }
+        NSVD_TL(i, 6);   // all loads of the tile issued
       }
     }
   } else if (warp == 1) {
@@ -998,10 +1011,13 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         }
         mbar_wait(tempty, tphase ^ 1, 13);
         tc_fence_after();
+        NSVD_TL(t - t_begin, 0);   // accumulators handed back
         for (int sc = 0; sc < 8; ++sc) {
           const int s = sc >> 1, c = sc & 1;
           mbar_wait(&full[stage], phase, 14);
           tc_fence_after();
+          if (sc == 0) NSVD_TL(t - t_begin, 1);   // first operand stage present
+          if (sc == 7) NSVD_TL(t - t_begin, 2);   // last operand stage present
           const uint32_t a_hi = smem_u32(sA + stage * F_STAGE_BYTES), a_lo = a_hi + CHUNK;
           const uint32_t d_tmem = tmem_base + s * 128;
 #pragma unroll
@@ -1051,6 +1067,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       mbar_wait(tfull, tphase, 15);
       tphase ^= 1;
       tc_fence_after();
+      if (et == 0) NSVD_TL(t - t_begin, 3);       // MMAs of the tile retired
       float u[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int r = 0; r < 4; ++r) {          // h-quarters of 32 hidden units; this warp takes 8 of them
@@ -1063,6 +1080,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty);
+          if (et == 0) NSVD_TL(t - t_begin, 4);   // last TMEM read of the tile
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -1128,6 +1146,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         }
         named_bar_sync(1, F_EPI_WARPS * 32);  // ubuf (staging boxes 6-7) is free again
       }
+      if (et == 0) NSVD_TL(t - t_begin, 5);       // epilogue of the tile done
     }
     if (et == 0) tma_store_wait_all();
   }
