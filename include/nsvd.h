@@ -95,6 +95,9 @@ typedef struct nsvd_grads {
 } nsvd_grads_t;
 
 int nsvd_abi_version(void);
+/* sizeof(nsvd_problem_t) / sizeof(nsvd_params_t) / sizeof(nsvd_grads_t) as compiled (which = 0, 1, 2): lets a
+ * binding written in another language check its struct layout at load time.                            */
+size_t nsvd_struct_size(int32_t which);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
 long nsvd_launch_count(void);
 /* Optional per-kernel-class timing with CUDA events on the launch stream (bench.py roofline).

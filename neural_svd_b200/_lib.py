@@ -44,6 +44,7 @@ _PB, _PR, _GR = C.POINTER(Problem), C.POINTER(Params), C.POINTER(Grads)
 # name -> (restype, argtypes); every symbol declared in include/nsvd.h
 SIGNATURES = {
     "nsvd_abi_version": (C.c_int, []),
+    "nsvd_struct_size": (C.c_size_t, [C.c_int32]),
     "nsvd_last_error": (C.c_char_p, []),
     "nsvd_launch_count": (C.c_long, []),
     "nsvd_set_tc_microbatch": (None, [C.c_int32]),
@@ -90,6 +91,9 @@ def load():
                 fn.restype, fn.argtypes = res, args
             if lib.nsvd_abi_version() != 2:
                 raise RuntimeError("libnsvd.so ABI version mismatch")
+            for which, cls in enumerate((Problem, Params, Grads)):
+                if lib.nsvd_struct_size(which) != C.sizeof(cls):
+                    raise RuntimeError(f"libnsvd.so struct layout mismatch for {cls.__name__}")
             _lib = lib
     return _lib
 

@@ -54,6 +54,9 @@ using namespace nsvd;
 extern "C" {
 
 int nsvd_abi_version(void) { return NSVD_ABI_VERSION; }
+size_t nsvd_struct_size(int32_t which) {
+  return which == 0 ? sizeof(nsvd_problem_t) : which == 1 ? sizeof(nsvd_params_t) : which == 2 ? sizeof(nsvd_grads_t) : 0;
+}
 long nsvd_launch_count(void) { return g_launches; }
 void nsvd_set_tc_microbatch(int32_t points) { tc_set_micro_batch(points); }
 void nsvd_profile_enable(int on) { g_prof_on = on != 0; }
