@@ -301,19 +301,24 @@ def run_ours(args):
     graphed = None
     if world == 1:
         method.zero_grad(set_to_none=True)
-        gstep = N.GraphedOperatorStep(method, operator, importance, P)
-        for i in range(2):
-            gstep(xs_dev[i % 4])
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for i in range(args.steps):
-            gstep(xs_dev[i % 4])
-        g1.record()
-        barrier()
-        gms = g0.elapsed_time(g1) / args.steps
-        graphed = {"value": P / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms,
-                   "what": "loss+grad step replayed as one CUDA graph (no L2 flush between steps)"}
+        try:
+            gstep = N.GraphedOperatorStep(method, operator, importance, P)     # owns a second set of scratch buffers
+        except torch.OutOfMemoryError:
+            gstep = None
+            graphed = {"skipped": "a second set of scratch buffers does not fit next to the eager one at this size"}
+        if gstep is not None:
+            for i in range(2):
+                gstep(xs_dev[i % 4])
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for i in range(args.steps):
+                gstep(xs_dev[i % 4])
+            g1.record()
+            barrier()
+            gms = g0.elapsed_time(g1) / args.steps
+            graphed = {"value": P / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms,
+                       "what": "loss+grad step replayed as one CUDA graph (no L2 flush between steps)"}
 
     if rank == 0:
         pk = peaks()
