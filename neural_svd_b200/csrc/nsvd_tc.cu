@@ -854,9 +854,6 @@ constexpr int F_STAGE_BYTES = 2 * CHUNK;  // hi chunk + lo chunk of one stream
 constexpr int F_BOX = 8192;               // staging box [128 rows][64 B] (32 bf16), 64-byte swizzle
 constexpr int F_STAGING = 8 * F_BOX;      // 4 streams x {hi, lo}
 constexpr int SMEM_FWD = 2 * PLANE + F_STAGES * F_STAGE_BYTES + F_STAGING + 1024 + 1152;
-// backward kernel
-constexpr int STAGE_BYTES = 2 * PLANE;
-constexpr int SMEM_BWD = 2 * PLANE + 2 * STAGE_BYTES + 1024 + 1024;
 // pipelined backward kernel: half tiles of 64 points in a 2-stage ring
 constexpr int HROWS = 64;
 constexpr int HCHUNK = HROWS * 128;       // [64 rows][128 B]
@@ -1158,17 +1155,6 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// S2-bwd: backward of hidden layer i for one copy; tile = (l, 128 points).  One pass over the
-// dZ_i tile produces BOTH
-//   dgrad  D1[pt][k]  = sum_j dZ_i[pt][j] W_i[j][k]      (A K-major, B = W_i^T K-major)
-//   wgrad  D2[j][k]  += sum_pt dZ_i[pt][j] a_{i-1}[pt][k] (the same smem tiles read MN-major)
-// epilogue: dZ_{i-1} = D1 (.) sigma(a_{i-1}) with a_{i-1} read back from its smem tile, staged
-// into the (now dead) dZ_i tile and written with TMA bulk stores; db_{i-1} column sums go through
-// shared-memory atomics; D2 / db are flushed with vector reductions when the CTA leaves copy l.
-// The three 64 KB tiles fill shared memory, so load -> MMA -> epilogue run back to back per tile
-// (the next tile is prefetched into L2 meanwhile).
-// ------------------------------------------------------------------------------------------
 struct HidBwdArgs {
   int L, P, m_tiles;
   long Btot, p_off;
@@ -1176,252 +1162,11 @@ struct HidBwdArgs {
   float* db_prev;                            // (L,128) accumulated with atomics
 };
 
-// the two 16-byte pieces holding k0..k0+15 of `row` in a [128][128]-bf16 tile kept as two
-// 128-byte-swizzled K-chunks (the TMA / UMMA K-major layout)
-__device__ __forceinline__ uint32_t tile_piece_off(int row, int k0, int which) {
-  const int c = k0 >> 6, piece = ((k0 & 63) >> 3) + which;
-  return (uint32_t)(c * hid::CHUNK + row * 128 + ((piece ^ (row & 7)) << 4));
-}
-
-__global__ void __launch_bounds__(hid::F_THREADS, 1)
-hidden_bwd_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant__ CUtensorMap tmZl,
-                  const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                  const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
-                  const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
-                  const HidBwdArgs args) {
-  using namespace hid;
-  using namespace tc;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sW = smem;                 // W_i^T hi | lo
-  uint8_t* sZ = smem + 2 * PLANE;     // dZ_i hi | lo   (re-used as the dZ_{i-1} output staging)
-  uint8_t* sA = sZ + 2 * PLANE;       // a_{i-1} hi | lo
-  uint64_t* bars = (uint64_t*)(sA + 2 * PLANE);
-  uint64_t* full = bars;              // dZ + a landed
-  uint64_t* mma_done = bars + 1;      // dgrad + wgrad of the tile retired
-  uint64_t* epi_done = bars + 2;      // epilogue finished with TMEM, sZ and sA
-  uint64_t* wfull = bars + 3;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 4);
-  float* db_s = (float*)(bars + 6);   // [128] column sums of dZ_{i-1} for the current copy
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = args.L * args.m_tiles;
-  const int tpc = (T + gridDim.x - 1) / gridDim.x;
-  const int t_begin = blockIdx.x * tpc;
-  const int t_end = (t_begin + tpc < T) ? t_begin + tpc : T;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmZh);
-    tma_prefetch_desc(&tmZl);
-    tma_prefetch_desc(&tmAh);
-    tma_prefetch_desc(&tmAl);
-    tma_prefetch_desc(&tmWh);
-    tma_prefetch_desc(&tmWl);
-    tma_prefetch_desc(&tmOh);
-    tma_prefetch_desc(&tmOl);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(full, 1);
-    mbar_init(mma_done, 1);
-    mbar_init(epi_done, 1);
-    mbar_init(wfull, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
-  if (threadIdx.x >= 128 && threadIdx.x < 256) db_s[threadIdx.x - 128] = 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d2 = tmem_base + 256;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int cur_l = -1;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int l = t / args.m_tiles, mt = t % args.m_tiles;
-        const int i = t - t_begin;
-        if (i > 0) mbar_wait(epi_done, (uint32_t)((i - 1) & 1), 20);
-        if (l != cur_l) {
-          mbar_arrive_expect_tx(wfull, 2 * PLANE);
-          tma_load_3d(sW, &tmWh, wfull, 0, 0, l);
-          tma_load_3d(sW + CHUNK, &tmWh, wfull, 64, 0, l);
-          tma_load_3d(sW + PLANE, &tmWl, wfull, 0, 0, l);
-          tma_load_3d(sW + PLANE + CHUNK, &tmWl, wfull, 64, 0, l);
-          cur_l = l;
-        }
-        const int pa = (int)args.p_off + mt * 128;
-        mbar_arrive_expect_tx(full, 4 * PLANE);
-        tma_load_3d(sZ, &tmZh, full, 0, mt * 128, l);
-        tma_load_3d(sZ + CHUNK, &tmZh, full, 64, mt * 128, l);
-        tma_load_3d(sZ + PLANE, &tmZl, full, 0, mt * 128, l);
-        tma_load_3d(sZ + PLANE + CHUNK, &tmZl, full, 64, mt * 128, l);
-        tma_load_3d(sA, &tmAh, full, 0, pa, l);
-        tma_load_3d(sA + CHUNK, &tmAh, full, 64, pa, l);
-        tma_load_3d(sA + PLANE, &tmAl, full, 0, pa, l);
-        tma_load_3d(sA + PLANE + CHUNK, &tmAl, full, 64, pa, l);
-        if (t + 1 < t_end) {  // pull the next tile into L2 while this one is processed
-          const int l2 = (t + 1) / args.m_tiles, mt2 = (t + 1) % args.m_tiles;
-          const int pa2 = (int)args.p_off + mt2 * 128;
-          tma_prefetch_3d(&tmZh, 0, mt2 * 128, l2);
-          tma_prefetch_3d(&tmZh, 64, mt2 * 128, l2);
-          tma_prefetch_3d(&tmZl, 0, mt2 * 128, l2);
-          tma_prefetch_3d(&tmZl, 64, mt2 * 128, l2);
-          tma_prefetch_3d(&tmAh, 0, pa2, l2);
-          tma_prefetch_3d(&tmAh, 64, pa2, l2);
-          tma_prefetch_3d(&tmAl, 0, pa2, l2);
-          tma_prefetch_3d(&tmAl, 64, pa2, l2);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_d = make_idesc_bf16(128, 128, 0, 0);   // dgrad: K-major operands
-      constexpr uint32_t idesc_w = make_idesc_bf16(128, 128, 1, 1);   // wgrad: MN-major operands
-      const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + PLANE;
-      const uint32_t z_hi = smem_u32(sZ), z_lo = z_hi + PLANE;
-      const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + PLANE;
-      int cur_l = -1;
-      uint32_t fphase = 0, wphase = 0;
-      bool first_of_run = true;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int l = t / args.m_tiles;
-        if (l != cur_l) {
-          mbar_wait(wfull, wphase, 21);
-          wphase ^= 1;
-          cur_l = l;
-          first_of_run = true;
-        }
-        mbar_wait(full, fphase, 22);  // implies the previous tile's epilogue released TMEM and smem
-        fphase ^= 1;
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = (kk >> 2) * CHUNK + (kk & 3) * 32;
-          uint64_t ah = make_sdesc_sw128(z_hi + off, 16, 1024), al = make_sdesc_sw128(z_lo + off, 16, 1024);
-          uint64_t bh = make_sdesc_sw128(w_hi + off, 16, 1024), bl = make_sdesc_sw128(w_lo + off, 16, 1024);
-          umma_f16(tmem_base, al, bh, idesc_d, kk > 0 ? 1u : 0u);
-          umma_f16(tmem_base, ah, bl, idesc_d, 1u);
-          umma_f16(tmem_base, ah, bh, idesc_d, 1u);
-        }
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // K = 128 points, 16 per MMA
-          const uint32_t off = kk * 2048;
-          uint64_t ah = make_sdesc_sw128(z_hi + off, CHUNK, 1024), al = make_sdesc_sw128(z_lo + off, CHUNK, 1024);
-          uint64_t bh = make_sdesc_sw128(a_hi + off, CHUNK, 1024), bl = make_sdesc_sw128(a_lo + off, CHUNK, 1024);
-          umma_f16(tmem_d2, al, bh, idesc_w, (first_of_run && kk == 0) ? 0u : 1u);
-          umma_f16(tmem_d2, ah, bl, idesc_w, 1u);
-          umma_f16(tmem_d2, ah, bh, idesc_w, 1u);
-        }
-        umma_commit(mma_done);
-        first_of_run = false;
-      }
-    }
-  } else if (warp >= 4) {
-    // 16 epilogue warps: 4 per TMEM lane quarter, each owning 32 of the 128 columns (4 chunks of 8)
-    const int ewarp = warp - 4, q = ewarp & 3, sub = ewarp >> 2;
-    const int et = threadIdx.x - 128;
-    const int row = q * 32 + lane;
-    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int NEPI = F_EPI_WARPS * 32;
-    uint32_t mphase = 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      const int l = t / args.m_tiles, mt = t % args.m_tiles;
-      mbar_wait(mma_done, mphase, 25);
-      mphase ^= 1;
-      tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        const int k0 = sub * 32 + ch * 8;
-        float v[8], a[8];
-        tmem_ld8(tl + k0, v);
-        const uint32_t o0 = (uint32_t)((k0 >> 6) * CHUNK + row * 128 + ((((k0 & 63) >> 3) ^ (row & 7)) << 4));
-        {
-          uint4 h = *reinterpret_cast<const uint4*>(sA + o0);
-          uint4 lo = *reinterpret_cast<const uint4*>(sA + PLANE + o0);
-          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&h);
-          const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&lo);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float2 x0 = __bfloat1622float2(hh[i]), x1 = __bfloat1622float2(ll[i]);
-            a[2 * i] = x0.x + x1.x;
-            a[2 * i + 1] = x0.y + x1.y;
-          }
-        }
-        tmem_ld_wait();
-        // rows beyond P carry dZ_i = 0 (TMA zero fill), hence D1 = 0 and v = 0 without a mask
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] *= sig_fast(a[i]);
-        {
-          uint32_t h[4], lo[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], h[i], lo[i]);
-          *reinterpret_cast<uint4*>(sZ + o0) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(sZ + PLANE + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        // column sums over the 32 rows of this warp: recursive halving, then two full butterflies
-#pragma unroll
-        for (int w = 4; w >= 1; w >>= 1) {
-          const bool up = (lane & (w * 4)) != 0;   // lane bits 16, 8, 4 select the upper half
-#pragma unroll
-          for (int i = 0; i < w; ++i) {
-            float send = up ? v[i] : v[i + w];
-            float keep = up ? v[i + w] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w * 4);
-          }
-        }
-        {
-          float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 2);
-          tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-          const int col = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-          if ((lane & 3) == 0) atomicAdd(&db_s[k0 + col], tot);
-        }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(2, NEPI);
-      if (et == 0) {
-        tma_store_3d(&tmOh, sZ, 0, mt * 128, l);
-        tma_store_3d(&tmOh, sZ + CHUNK, 64, mt * 128, l);
-        tma_store_3d(&tmOl, sZ + PLANE, 0, mt * 128, l);
-        tma_store_3d(&tmOl, sZ + PLANE + CHUNK, 64, mt * 128, l);
-        tma_store_commit();
-      }
-      const bool last_of_run = (t + 1 == t_end) || ((t + 1) / args.m_tiles != l);
-      if (last_of_run) {
-        const int j = row;
-        float* drow = args.dW + ((long)l * kHidden + j) * kHidden;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          const int k0 = sub * 32 + ch * 8;
-          float v[8];
-          tmem_ld8(tl + 256 + k0, v);
-          tmem_ld_wait();
-          red_add_v4(drow + k0, v[0], v[1], v[2], v[3]);
-          red_add_v4(drow + k0 + 4, v[4], v[5], v[6], v[7]);
-        }
-        if (et < 128) {
-          atomicAdd(args.db_prev + l * kHidden + et, db_s[et]);
-          db_s[et] = 0.f;
-        }
-      }
-      if (et == 0) tma_store_wait_read();
-      tc_fence_before();
-      named_bar_sync(3, NEPI);
-      if (et == 0) mbar_arrive(epi_done);
-    }
-    if (et == 0) tma_store_wait_all();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // ------------------------------------------------------------------------------------------
-// S2-bwd, pipelined version (default): the same dgrad + wgrad fusion on HALF tiles of 64 points in a 2-stage
-// ring, so the loads of half tile j+1 overlap the MMAs, epilogue and stores of half tile j.
+// S2-bwd: backward of hidden layer i for one copy.  One pass over dZ_i produces BOTH the input gradient
+//   dgrad  D1 = dZ_i W_i  (then dZ_{i-1} = D1 (.) sigma(a_{i-1}))  and the weight gradient  wgrad  D2 = dZ_i^T a_{i-1},
+// on HALF tiles of 64 points in a 2-stage ring, so the loads of half tile j+1 overlap the MMAs, epilogue and stores
+// of half tile j (an earlier version kept three 64 KB tiles resident and ran load -> MMA -> epilogue back to back).
 //   smem : W_i^T hi/lo resident (64 KB) | 2 stages x 64 KB (dZ_i hi/lo, a_{i-1} hi/lo of 64 points).
 //   dgrad is issued transposed, D1[k][p] = sum_j W_i^T[k][j] dZ_i[p][j]  (M = 128 units, N = 64 points), so the
 //   accumulator keeps the full 128-lane datapath busy; TMEM lane = unit k, column = point.  Epilogue thread (k, 16
@@ -1944,11 +1689,9 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
   int rc;
   static bool configured = false;
   if (!configured) {
-    NSVD_CUDA(cudaFuncSetAttribute(hidden_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hid::SMEM_BWD));
     NSVD_CUDA(cudaFuncSetAttribute(hidden_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hid::SMEM_BWD2));
     configured = true;
   }
-  static const int hidbwd_v1 = env_int("NSVD_HIDBWD_V1", 0);   // 1 = the unpipelined 128-point kernel
   // gradients are accumulated with reductions: start from zero
   NSVD_CUDA(cudaMemsetAsync(gr.dW[0], 0, sizeof(float) * L * H * K0, st));
   NSVD_CUDA(cudaMemsetAsync(gr.dW[1], 0, sizeof(float) * L * H * H, st));
@@ -1981,7 +1724,7 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
     int cur = 0;
     for (int i = 2; i >= 1; --i) {
       CUtensorMap mZh, mZl, mAh, mAl;
-      const int rows = hidbwd_v1 ? 128 : hid::HROWS;   // points per (half) tile = TMA box height
+      const int rows = hid::HROWS;   // points per half tile = TMA box height
       if ((rc = make_tmap_bf16_3d(&mZh, wk + t.dz_hi[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, rows))) return rc;
       if ((rc = make_tmap_bf16_3d(&mZl, wk + t.dz_lo[cur], H, P, L, H * 2, (uint64_t)P * H * 2, 64, rows))) return rc;
       if ((rc = make_tmap_bf16_3d(&mAh, sv + t.av_hi[i - 1], H, B, L, H * 2, (uint64_t)B * H * 2, 64, rows))) return rc;
@@ -2001,10 +1744,7 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
       int grid = T < 148 ? T : 148;
       {
         ProfScope ps(KC_HID_BWD, st);
-        if (hidbwd_v1)
-          hidden_bwd_kernel<<<grid, hid::F_THREADS, hid::SMEM_BWD, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], mOh, mOl, a);
-        else
-          hidden_bwd2_kernel<<<grid, hid::F_THREADS, hid::SMEM_BWD2, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], mOh, mOl, a);
+        hidden_bwd2_kernel<<<grid, hid::F_THREADS, hid::SMEM_BWD2, st>>>(mZh, mZl, mAh, mAl, mWh[i - 1], mWl[i - 1], mOh, mOl, a);
         NSVD_LAUNCH_CHECK();
       }
       cur ^= 1;
