@@ -122,7 +122,7 @@ def cpu_reference_run(cfg, budget_s, steps=None, warmup=1):
                 method.zero_grad()
                 loss, _ = method.compute_loss_operator(operator, x, importance=importance)
                 loss.backward()
-                float(loss)
+                float(loss.detach())
                 dt = time.perf_counter() - t0
                 if n >= warmup:
                     ts.append(dt)

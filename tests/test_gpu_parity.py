@@ -27,7 +27,7 @@ def _step(name, engine):
     loss, aux = method.compute_loss_operator(operator, x, importance=importance)
     loss.backward()
     grads = {n: p.grad.detach().cpu().numpy() for n, p in method.named_parameters() if p.grad is not None}
-    return d, cfg, method, float(loss), aux, grads
+    return d, cfg, method, float(loss.detach()), aux, grads
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -64,7 +64,7 @@ def test_step_matches_oracle_on_fresh_inputs(engine, neigs):
     r = O.train_step(x.numpy().astype(np.float64), params, cfg)
     loss, aux = method.compute_loss_operator(operator, x.cuda(), importance=importance)
     loss.backward()
-    assert abs(float(loss) - r["loss"]) <= TOL * abs(r["loss"])
+    assert abs(float(loss.detach()) - r["loss"]) <= TOL * abs(r["loss"])
     assert rel(aux["Tf"].cpu().numpy(), r["Tf"]) < TOL
     for n, p in method.named_parameters():
         if p.grad is not None:
@@ -113,7 +113,7 @@ def test_standalone_loss_function_matches_oracle(B, L, seq):
     f1, f2 = torch.chunk(fc, 2)
     loss = N.NestedLoRALossFunctionEVD.apply(fc, Tf.cuda(), f1, f2, torch.from_numpy(v), torch.from_numpy(M))
     loss.backward()
-    assert abs(float(loss) - loss_o) < 1e-5 * abs(loss_o)
+    assert abs(float(loss.detach()) - loss_o) < 1e-5 * abs(loss_o)
     assert rel(fc.grad.cpu().numpy(), dF_o) < 1e-5
 
 
@@ -128,7 +128,7 @@ def test_cdk_matches_reference_golden(name, engine):
     g = torch.from_numpy(d["g"]).cuda().requires_grad_()
     loss, lop, lmet, rsj, rsi = m.compute_loss(f, g)
     loss.backward()
-    assert abs(float(loss) - float(d["loss64"])) < TOL * abs(float(d["loss64"]))
+    assert abs(float(loss.detach()) - float(d["loss64"])) < TOL * abs(float(d["loss64"]))
     assert abs(float(lop) - float(d["lop64"])) < TOL * abs(float(d["lop64"]))
     assert abs(float(lmet) - float(d["lmet64"])) < TOL * abs(float(d["lmet64"]))
     assert rel(f.grad.cpu().numpy(), d["gf64"]) < TOL and rel(g.grad.cpu().numpy(), d["gg64"]) < TOL
@@ -146,7 +146,7 @@ def test_cdk_full_size_config5(engine):
     m = N.NestedLoRAForCDK(None, int(d["L"]))
     loss, lop, lmet, rsj, rsi = m.compute_loss(f, gg)
     loss.backward()
-    assert abs(float(loss) - float(d["loss64"])) < TOL * abs(float(d["loss64"]))
+    assert abs(float(loss.detach()) - float(d["loss64"])) < TOL * abs(float(d["loss64"]))
     assert rel(f.grad.cpu().numpy().reshape(-1)[d["gidx"]], d["gfval"]) < TOL
     assert rel(gg.grad.cpu().numpy().reshape(-1)[d["gidx"]], d["ggval"]) < TOL
     assert rel(rsj.cpu().numpy(), d["rsj64"]) < TOL
@@ -170,7 +170,7 @@ def test_large_batch_properties():
     perm = torch.cat([torch.randperm(B // 2, generator=g), B // 2 + torch.randperm(B // 2, generator=g)]).cuda()
     loss2, aux2 = method.compute_loss_operator(operator, x[perm], importance=importance)
     loss2.backward()
-    assert abs(float(loss) - float(loss2)) < 1e-5 * abs(float(loss))
+    assert abs(float(loss.detach()) - float(loss2)) < 1e-5 * abs(float(loss.detach()))
     assert torch.allclose(aux2["f"], aux["f"][perm], rtol=1e-5, atol=1e-6)
     assert rel(method.model.base.ws[0].grad.cpu().numpy(), g0.cpu().numpy()) < 1e-5
 
@@ -274,13 +274,13 @@ def test_graphed_step_equals_eager_step(engine):
     for rep in range(2):                                        # replay twice: buffers are reused correctly
         loss = step(x)
         grads_g = {n: p.grad.clone() for n, p in method.named_parameters() if p.grad is not None}
-        assert abs(float(loss) - float(d["loss64"])) <= TOL * abs(float(d["loss64"]))
+        assert abs(float(loss.detach()) - float(d["loss64"])) <= TOL * abs(float(d["loss64"]))
         errs = golden_grad_errors(d, list(grads_g), {k: v.cpu().numpy() for k, v in grads_g.items()})
         assert max(errs.values()) < TOL, errs
     method.zero_grad(set_to_none=True)
     loss_e, aux = method.compute_loss_operator(operator, x, importance=importance)
     loss_e.backward()
-    assert abs(float(loss) - float(loss_e)) < 1e-5 * abs(float(loss_e))
+    assert abs(float(loss.detach()) - float(loss_e)) < 1e-5 * abs(float(loss_e))
     for n, p in method.named_parameters():
         if p.grad is not None:
             assert rel(grads_g[n].cpu().numpy(), p.grad.cpu().numpy()) < 2e-5, n
