@@ -55,7 +55,7 @@ def _cpu_worker(rank, world, port, xg, seed, q):
     flat = torch.from_numpy(np.concatenate([grads[k].ravel() for k in names]))
     dp.allreduce_grads(flat)                                            # all-reduce #2
     if rank == 0:
-        q.put((float(loss.detach()), flat.numpy(), (Bg, B1g, B2g)))
+        q.put((float(loss), flat.numpy(), (Bg, B1g, B2g)))
     dist.destroy_process_group()
 
 
