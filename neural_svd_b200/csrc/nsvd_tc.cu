@@ -727,8 +727,8 @@ __global__ void split_w_kernel(const float* __restrict__ W, __nv_bfloat16* __res
 // Phi = [sin(x B), cos(x B)] as bf16 hi/lo planes (B, 2M)   (examples/utils.py:139-140)
 // One thread = 4 consecutive features of one point (8-byte stores).  The phase p = x.B is formed in fp32 exactly
 // like the reference; a two-constant Cody-Waite step (k = rint(p / 2pi), r = p - k 2pi_hi - k 2pi_lo with FMAs,
-// 3.5e-8 rms error) brings it to [-pi, pi], and sincospif(r / pi) evaluates it without any large-argument path
-// (total ~1e-7).  Reducing in turns (p / 2pi in fp32) was measured to add 5e-7..1.2e-6 rms per feature, i.e. as much
+// 3.5e-8 rms error) brings it to [-pi, pi], where the MUFU sine / cosine are accurate to 5e-7 absolute (the accurate
+// sincospif path cost 0.14 ms/step more for an error that the hi/lo rounding hides).  Reducing in turns (p / 2pi in fp32) was measured to add 5e-7..1.2e-6 rms per feature, i.e. as much
 // as the bf16 hi/lo rounding itself, and is not used.
 __global__ void features_bf16_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long P,
@@ -749,7 +749,8 @@ __global__ void features_bf16_kernel(const float* __restrict__ x, const float* _
     float kq = rintf(ph * 0.15915494309189535f);
     float r = fmaf(-kq, 6.2831855f, ph);          // 2pi_hi = fl(2 pi)
     r = fmaf(-kq, -1.7484555e-07f, r);            // 2pi_lo = 2 pi - 2pi_hi
-    sincospif(r * 0.3183098861837907f, &sn[k], &cs[k]);
+    sn[k] = __sinf(r);   // MUFU on the reduced argument: abs error <= 2^-20.9 (PTX sin.approx), 15x below the
+    cs[k] = __cosf(r);   // 2^-17 relative rounding of the hi/lo split that follows
   }
   uint32_t h0, l0, h1, l1;
   long o = p * 2L * M + j;
