@@ -1093,20 +1093,28 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             for (int s = 0; s < 4; ++s) u[s] = fmaf(z[s][i], w, u[s]);
           }
         }
-        // previous round's bulk stores must have drained the staging boxes
-        if (et == 0) tma_store_wait_read();
-        named_bar_sync(2, F_EPI_WARPS * 32);
+        // The last layer stages the value stream only: two box pairs alternate between rounds, so a round never
+        // waits for its predecessor's bulk store (one barrier per round); the other layers need all 8 boxes per
+        // round and first let the previous round's stores drain them.
+        const int sb = kLast ? 2 * (r & 1) : 0;
+        if (!kLast) {
+          if (et == 0) tma_store_wait_read();
+          named_bar_sync(2, F_EPI_WARPS * 32);
+        }
 #pragma unroll
         for (int s = 0; s < (kLast ? 1 : 4); ++s) {
           uint32_t h[4], lo[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) split_bf16x2(z[s][2 * i], z[s][2 * i + 1], h[i], lo[i]);
-          uint8_t* bh = sO + (2 * s) * F_BOX;
+          uint8_t* bh = sO + (sb + 2 * s) * F_BOX;
           uint8_t* bl = bh + F_BOX;
           *reinterpret_cast<uint4*>(bh + piece0) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(bl + piece0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         fence_proxy_async_smem();
+        // kLast: every store issued up to the previous round has read its boxes (so the pair the NEXT round writes,
+        // last used two rounds ago, is free once all threads have passed the barrier below)
+        if (kLast && et == 0) tma_store_wait_read();
         named_bar_sync(3, F_EPI_WARPS * 32);
         if (et == 0) {
           if (!kLast) {
@@ -1116,8 +1124,8 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
               tma_store_3d(&tmOl, sO + (2 * s + 1) * F_BOX, r * 32, mt * 128, l * 4 + s);
             }
           }
-          tma_store_3d(&tmSh, sO, r * 32, (int)args.p_off + mt * 128, l);
-          tma_store_3d(&tmSl, sO + F_BOX, r * 32, (int)args.p_off + mt * 128, l);
+          tma_store_3d(&tmSh, sO + sb * F_BOX, r * 32, (int)args.p_off + mt * 128, l);
+          tma_store_3d(&tmSl, sO + (sb + 1) * F_BOX, r * 32, (int)args.p_off + mt * 128, l);
           tma_store_commit();
         }
       }
