@@ -328,16 +328,16 @@ def run_ours(args):
         roof = None
         if l0_n:
             ach = flops_l0 / (l0_ms * 1e-3) / 1e12
-            # DRAM traffic of this kernel from the committed ncu capture (profiles/r1_ncu_full.csv: 2.069 GB read +
-            # 1.305 GB written by one launch over 32768 points), scaled to the points one launch covers here
+            # DRAM traffic of this kernel from the committed ncu capture (profiles/r1_ncu_full.csv: 1.656 GB read +
+            # 1.040 GB written by one launch over 32768 points), scaled to the points one launch covers here
             pts_per_launch = P * args.steps / l0_n
-            traffic = (2.068802e9 + 1.304666e9) / 32768 * pts_per_launch
+            traffic = (1.655711e9 + 1.040122e9) / 32768 * pts_per_launch
             roof = {"kernel": "big2_gemm_kernel<K-major, L0FwdEpi> (layer-0 4-stream forward GEMM, tcgen05 cta_group::2, bf16x3)",
                     "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                     "frac": ach / pk["tf_sust"], "traffic": traffic,
-                    "traffic_note": "bytes per launch = ncu dram read+write per point (102.95 KB, profiles/r1_ncu_full.csv) x "
-                                    "points per launch; algorithmic bytes are 8 KB (Phi) + 32.5 KB (activation streams "
-                                    "out) per point + 67 MB of folded weights per launch",
+                    "traffic_note": "bytes per launch = ncu dram read+write per point (82.27 KB, profiles/r1_ncu_full.csv) x "
+                                    "points per launch; algorithmic bytes are 8 KB (Phi) + 32 KB (3 derivative streams + the saved value "
+                                    "stream out) per point + 67 MB of folded weights per launch",
                     "peak_source": pk["src"] + " bf16 sustained",
                     "issued_frac": 3 * ach / pk["tf_sust"], "launches": l0_n, "avg_launch_ms": l0_ms / l0_n,
                     "note": "achieved = ALGORITHMIC fp32-equivalent FLOPs; every MAC is issued as 3 bf16 MMAs "
