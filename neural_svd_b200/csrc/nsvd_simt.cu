@@ -614,6 +614,125 @@ gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, c
   if (tid == 0) *counter = 0u;
 }
 
+// ------------------------------------------------------------------------------------------
+// K2 for 16 < L <= 64 on the warp-level tensor cores (mma.sync m16n8k8, 3xTF32): at L = 64 the Gram is 32 FLOP/B,
+// past the CUDA-core ridge.  A block of 4 warps walks its rows in chunks of 32: the chunk (a contiguous
+// run of 32 L floats) is loaded coalesced into shared memory (row stride LP + 8 floats: fragment reads hit 32
+// different banks), every warp owns one 16-row band of the LP x LP Gram (LP = 64) or half of one (LP = 32).
+// v = hi + lo with hi = tf32(v), lo = tf32(v - hi): lo*hi + hi*lo + hi*hi is exact to 2^-22.  A chunk is accumulated
+// from zero (12 MMAs) and then added to the running sums with ordinary fp32 additions, which keeps the tensor-core
+// accumulate (it truncates) out of the long sum.  sum_l v_l f Tf rides on the load loop.  Partials have the layout of
+// gram_stage1_kernel (cross = 0), so stage 2 is shared and the result is deterministic.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int LP>  // 32 or 64
+__global__ void __launch_bounds__(128)
+gram_mma_kernel(const float* __restrict__ F, const float* __restrict__ TF, const float* __restrict__ vmask, int L,
+                long row_begin, long row_end, int rows_per_block, float* __restrict__ partials, int partial_stride,
+                int block_off) {
+  constexpr int TM = LP / 16, TN = LP / 8;      // Gram tiles: 16 rows x 8 columns each
+  constexpr int WPM = 4 / TM;                   // warps sharing one 16-row band
+  constexpr int NT = TN / WPM;                  // column tiles per warp
+  constexpr int SS = LP + 8, CH = 32;
+  __shared__ float S[CH][SS];
+  __shared__ float s_ops[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int mt = warp % TM, n0 = (warp / TM) * NT;
+  const long r0 = row_begin + (long)blockIdx.x * rows_per_block;
+  const long r1 = r0 + rows_per_block < row_end ? r0 + rows_per_block : row_end;
+  float tot[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tot[i][j] = 0.f;
+  float ops = 0.f;
+  for (int i = tid; i < CH * SS; i += 128) (&S[0][0])[i] = 0.f;   // columns >= L stay zero
+  __syncthreads();
+  const int dq = 128 / L, dr = 128 % L;         // (row, col) advance of a thread between its elements
+  for (long c0 = r0; c0 < r1; c0 += CH) {
+    const int nrows = (int)((r1 - c0) < CH ? (r1 - c0) : CH);
+    const long base = c0 * L;
+    const int nel = nrows * L;
+    int row = tid / L, col = tid % L;
+    for (int e = tid; e < CH * L; e += 128) {
+      float f = 0.f;
+      if (e < nel) {
+        f = F[base + e];
+        ops = fmaf(vmask[col] * f, TF[base + e], ops);
+      }
+      S[row][col] = f;
+      row += dq;
+      col += dr;
+      if (col >= L) {
+        col -= L;
+        ++row;
+      }
+    }
+    __syncthreads();
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < CH / 8; ++ks) {
+      const float* s0 = &S[ks * 8 + t][0];
+      const float* s1 = &S[ks * 8 + t + 4][0];
+      // A = F^T (M = Gram row i, K = data row): a0 (g, t), a1 (g + 8, t), a2 (g, t + 4), a3 (g + 8, t + 4)
+      const float av[4] = {s0[16 * mt + g], s0[16 * mt + g + 8], s1[16 * mt + g], s1[16 * mt + g + 8]};
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ah[i] = to_tf32(av[i]);
+        al[i] = to_tf32(av[i] - __uint_as_float(ah[i]));
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        // B (K = data row, N = Gram column j): b0 (k = t, n = g), b1 (k = t + 4, n = g)
+        const float bv[2] = {s0[8 * (n0 + nt) + g], s1[8 * (n0 + nt) + g]};
+        uint32_t bh[2], bl[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          bh[i] = to_tf32(bv[i]);
+          bl[i] = to_tf32(bv[i] - __uint_as_float(bh[i]));
+        }
+        mma_tf32_16x8x8(acc[nt], al, bh);
+        mma_tf32_16x8x8(acc[nt], ah, bl);
+        mma_tf32_16x8x8(acc[nt], ah, bh);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tot[i][j] += acc[i][j];
+    __syncthreads();
+  }
+  // C fragment: c0 (g, 2t), c1 (g, 2t + 1), c2 (g + 8, 2t), c3 (g + 8, 2t + 1) inside tile (mt, n0 + nt)
+  float* out = partials + (long)(block_off + blockIdx.x) * partial_stride;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i_ = 16 * mt + g + (j >> 1) * 8, j_ = 8 * (n0 + nt) + 2 * t + (j & 1);
+      if (i_ < L && j_ < L) out[i_ * L + j_] = tot[nt][j];
+    }
+  }
+  ops = warp_sum(ops);
+  if (lane == 0) s_ops[warp] = ops;
+  __syncthreads();
+  if (tid == 0) out[L * L] = (s_ops[0] + s_ops[1]) + (s_ops[2] + s_ops[3]);   // slot read by stage 2 (cross = 0)
+}
+
 // stage 2: out[e] (+)= sum over blocks [b0, b1) of partials[b][src_off + e]
 __global__ void gram_stage2_kernel(const float* __restrict__ partials, int partial_stride, int b0,
                                    int b1, int src_off, int n, float* __restrict__ out,
@@ -661,6 +780,22 @@ static int gram_launch(const float* F, const float* TF, const float* vmask, cons
 static int gram_dispatch(const float* F, const float* TF, const float* vmask, const float* roww,
                          const float* xrow, int L, long rb, long re, int cross, float* partials, int stride,
                          int block_off, int* nblocks, cudaStream_t st) {
+  if (!cross && !roww && L > 16 && L <= 64) {   // tensor-core path of K2
+    long rows = re - rb;
+    if (rows <= 0) {
+      *nblocks = 0;
+      return 0;
+    }
+    int nb = gram_blocks_for(rows);
+    int rpb = (int)((rows + nb - 1) / nb);
+    rpb = (rpb + 31) / 32 * 32;                 // whole 32-row chunks per block
+    nb = (int)((rows + rpb - 1) / rpb);
+    if (L <= 32) gram_mma_kernel<32><<<nb, 128, 0, st>>>(F, TF, vmask, L, rb, re, rpb, partials, stride, block_off);
+    else gram_mma_kernel<64><<<nb, 128, 0, st>>>(F, TF, vmask, L, rb, re, rpb, partials, stride, block_off);
+    NSVD_LAUNCH_CHECK();
+    *nblocks = nb;
+    return 0;
+  }
   if (L <= 16) return gram_launch<16>(F, TF, vmask, roww, xrow, L, rb, re, cross, partials, stride, block_off, nblocks, st);
   if (L <= 32) return gram_launch<32>(F, TF, vmask, roww, xrow, L, rb, re, cross, partials, stride, block_off, nblocks, st);
   if (L <= 48) return gram_launch<48>(F, TF, vmask, roww, xrow, L, rb, re, cross, partials, stride, block_off, nblocks, st);
