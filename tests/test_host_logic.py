@@ -143,3 +143,27 @@ def test_potentials_match_reference_formulas():
     x = torch.tensor([[3.0, 4.0]])
     assert torch.allclose(N.hydrogen_potential(x, charge=2.0), torch.tensor([[-0.4]]))
     assert torch.allclose(N.harmonic_oscillator_potential(x, k=0.5), torch.tensor([[12.5]]))
+
+
+def test_sketchy_encoder_shapes_and_cpu_guards():
+    """the mirror of main_sketchy.py:107-115 has the script's shapes; device-only helpers refuse CPU."""
+    enc = N.get_sketchy_encoder()
+    shapes = {k: tuple(v.shape) for k, v in enc.state_dict().items()}
+    assert shapes == {"backbones.x.0.weight": (8192, 512), "backbones.x.0.bias": (8192,),
+                      "backbones.x.2.weight": (512, 8192), "backbones.x.2.bias": (512,),
+                      "backbones.y.0.weight": (8192, 512), "backbones.y.0.bias": (8192,),
+                      "backbones.y.2.weight": (512, 8192), "backbones.y.2.bias": (512,)}
+    assert enc.output_dims == {"x": 512, "y": 512} and enc.mu == 16.0
+    z = 10 * torch.randn(32, 512)
+    out = N.normalize(z, 4.0, "l2_ball")
+    assert float(out.norm(dim=1).max()) <= 4.0 + 1e-4            # rows outside the ball are projected onto it
+    small = 0.01 * torch.randn(4, 512)
+    assert torch.equal(N.normalize(small, 4.0, "l2_ball"), small)   # rows inside are untouched
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        N.sample_points(16, "uniform", 1.0, seed=0, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        N.sample_gaussian(16, 1.0, seed=0, device="cpu")
+    from torch.distributions import Laplace
+    lap = Laplace(torch.zeros(2), 2.5 * torch.ones(2))
+    closure = lambda x: lap.log_prob(x).sum(-1).exp().view(-1, 1)  # noqa: E731
+    assert operators.describe_importance(closure) == dict(importance=1, sigma=2.5)
