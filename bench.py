@@ -42,7 +42,17 @@ def parse():
     ap.add_argument("--engine", default="bf16x3", choices=["bf16x3", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-BASELINE-config block")
     return ap.parse_args()
+
+
+def workload_config(P, L, world):
+    """`config` of the JSON line; the reference arm prints the SAME dict (it times a bounded sample of this workload)."""
+    return {"workload": f"2D hydrogen (H=-Lap-1/r, scale 100), joint nesting, L={L}, M_ff=1024, "
+                        f"{P} Gaussian(sigma=16) collocation points per GPU per step, exact Laplacian "
+                        f"(laplacian_eps=0), loss+grad", "points_per_gpu": P, "neigs": L,
+            "parallelism": f"dp{world} over points", "laplacian": "exact",
+            "l2": "512 MB flush write between timed steps"}
 
 
 def peaks():
@@ -132,10 +142,12 @@ def cpu_reference_run(cfg, budget_s, steps=None, warmup=1):
                 if steps is None and (time.perf_counter() - t_all > budget_s / 2 and len(ts) >= 2):
                     break
             res[tag] = B / statistics.median(ts)
-        out.update(kind="reference", value=res["fd"], unit=UNIT, exact_value=res["exact"],
+        out.update(kind="reference", value=res["exact"], unit=UNIT, exact_value=res["exact"], fd_value=res["fd"],
+                   sample_points=B,
                    sample=f"unmodified reference (torch {torch.__version__} CPU, {cores} threads), hydrogen L={cfg.neigs}, "
-                          f"B={B} points/step, loss+grad; value = finite-difference Laplacian eps=0.01 (script default), "
-                          f"exact_value = autograd exact Laplacian (the parity oracle)")
+                          f"B={B} points/step, loss+grad; value = exact_value = autograd exact Laplacian (laplacian_eps=0: the "
+                          f"operator the GPU arm evaluates, and the parity oracle), fd_value = finite-difference Laplacian "
+                          f"eps=0.01 (the scripts' default, hydrogen.sh:20)")
         return out
     B = 2048
     params = O.init_params_like_reference(cfg, 0)
@@ -147,13 +159,16 @@ def cpu_reference_run(cfg, budget_s, steps=None, warmup=1):
         ts.append(time.perf_counter() - t0)
         if (steps is not None and len(ts) >= steps) or (steps is None and time.perf_counter() - t_all > budget_s and len(ts) >= 2):
             break
-    out.update(kind="port", value=B / statistics.median(ts), unit=UNIT,
+    out.update(kind="port", value=B / statistics.median(ts), unit=UNIT, sample_points=B,
                sample=f"numpy oracle port (fp32, forward-mode exact Laplacian, {cores} BLAS threads), hydrogen "
                       f"L={cfg.neigs}, B={B} points/step")
     return out
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the SAME workload (same operator: exact Laplacian, laplacian_eps=0),
+    each step a bounded sample (B=512 points) of it; the script-default finite-difference mode is reported next to it
+    (cpu_baseline.fd_value)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -163,13 +178,138 @@ def run_reference_arm(args):
     r = cpu_reference_run(cfg, budget_s=60.0, steps=max(args.steps, 2), warmup=max(args.warmup, 1))
     v = r["value"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * 512 / v if r.get("kind") == "reference" else 1e3 * 2048 / v,
+            "warmup": args.warmup, "ms_per_step": 1e3 * r["sample_points"] / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"2D hydrogen, joint nesting, L={args.neigs}, CPU sample (see cpu_baseline.sample)"},
+            "config": workload_config(args.points, args.neigs, args.gpus),
             "cpu_baseline": r, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line))
 
+
+# ------------------------------------------------------------------------------------------
+# problem builders (the product API only: no oracle, no test code) and per-config timing
+# ------------------------------------------------------------------------------------------
+def script_args(kind, neigs):
+    """Hyper-parameters of scripts/exps/pde/{hydrogen,oscillator}.sh with BASELINE's L."""
+    from types import SimpleNamespace
+    base = dict(problem="sch", ndim=2, neigs=neigs, charge=1.0, laplacian_eps=0.0, lim=50.0, use_fourier_feature=True,
+                fourier_deterministic=False, fourier_append_raw=False, mlp_hidden_dims="128,128,128",
+                nonlinearity="softplus", parallel=True, apply_boundary=False, boundary_mode="dir_box_sqrt",
+                hard_mul_const=1.0)
+    if kind == "hydrogen":          # hydrogen.sh:11-65
+        base.update(potential_type="hydrogen", operator_scale=100.0, operator_shift=0.0, fourier_mapping_size=1024,
+                    fourier_scale=0.1, apply_exp_mask=False, exp_mask_init_scale=100.0, sampling_scale=16.0)
+    else:                           # oscillator.sh:11-67
+        base.update(potential_type="harmonic_oscillator", operator_scale=1.0, operator_shift=16.0,
+                    fourier_mapping_size=256, fourier_scale=1.0, apply_exp_mask=True, exp_mask_init_scale=10.0,
+                    sampling_scale=4.0)
+    return SimpleNamespace(**base)
+
+
+def make_problem(N, kind, neigs, sequential, dev, seed=0):
+    import torch
+    cfg = script_args(kind, neigs)
+    torch.manual_seed(seed)
+    operator, _gt = N.get_problem(cfg)
+    model = N.get_wavefunctions(cfg)
+    method = N.NestedLoRA(model=model, neigs=neigs, step=1, sort=False, sequential=sequential).to(dev)
+    return cfg, method, operator, N.GaussianImportance(cfg.sampling_scale, cfg.ndim)
+
+
+def time_events(fn, steps, warmup, sync):
+    """ms per call of fn() over `steps` calls after `warmup`, CUDA events on the current stream."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    sync()
+    return e0.elapsed_time(e1) / steps
+
+
+def small_config(N, kind, B, neigs, sequential, dev, steps=50, warmup=10):
+    """eager and CUDA-graph step time of one of the reference's own small-batch configurations (1 GPU)."""
+    import torch
+    cfg, method, operator, importance = make_problem(N, kind, neigs, sequential, dev)
+    g = torch.Generator().manual_seed(7)
+    xs = [(cfg.sampling_scale * torch.randn((B, 1, 2), generator=g)).reshape(B, 2).to(dev) for _ in range(4)]
+    it = [0]
+
+    def eager():
+        method.zero_grad(set_to_none=True)
+        loss, _ = method.compute_loss_operator(operator, xs[it[0] % 4], importance=importance)
+        loss.backward()
+        it[0] += 1
+
+    sync = lambda: torch.cuda.synchronize(dev)
+    ms_eager = time_events(eager, steps, warmup, sync)
+    method.zero_grad(set_to_none=True)
+    gstep = N.GraphedOperatorStep(method, operator, importance, B)
+    ms_graph = time_events(lambda: gstep(xs[0]), steps, warmup, sync)
+    return {"points": B, "neigs": neigs, "nesting": "sequential" if sequential else "joint", "problem": kind,
+            "ms_per_step_eager": ms_eager, "ms_per_step_graphed": ms_graph,
+            "points_per_s_eager": B / (ms_eager * 1e-3), "points_per_s_graphed": B / (ms_graph * 1e-3)}
+
+
+def cdk_config(N, dev, B=4096, L=512, steps=20, warmup=5):
+    """BASELINE config 5: CDK NestedLoRA loss forward + backward on (B, L) embeddings (+1 constant mode), joint."""
+    import torch
+    g = torch.Generator().manual_seed(10)
+    f = torch.randn(B, L, generator=g).to(dev).requires_grad_()
+    gg = torch.randn(B, L, generator=g).to(dev).requires_grad_()
+    method = N.NestedLoRAForCDK(model=None, neigs=L, step=1, sequential=False, set_first_mode_const=True)
+    out = {}
+    for tag, diag in (("with_diagnostics", True), ("without_diagnostics", False)):
+        method.diagnostics = diag
+
+        def step():
+            f.grad = gg.grad = None
+            loss = method.compute_loss(f, gg)[0]
+            loss.backward()
+
+        ms = time_events(step, steps, warmup, lambda: torch.cuda.synchronize(dev))
+        out[tag] = {"ms_per_step": ms, "pairs_per_s": B / (ms * 1e-3)}
+    out.update(rows=B, feature_dim=L, what="NestedLoRAForCDK.compute_loss + backward (loss only, no encoder)")
+    return out
+
+
+def strong_scaling_config(N, dev, dp, world, rank, total_points=1 << 20, neigs=64, steps=3, warmup=2):
+    """BASELINE config 4: 2^20 hydrogen collocation points per step, L=64, joint, sharded over the ranks (STRONG
+    scaling: total work fixed), including both all-reduces."""
+    import torch
+    import torch.distributed as dist
+    P = total_points // world
+    cfg, method, operator, importance = make_problem(N, "hydrogen", neigs, False, dev)
+    method.data_parallel = dp
+    g = torch.Generator().manual_seed(300 + rank)
+    x = (cfg.sampling_scale * torch.randn((P, 1, 2), generator=g)).reshape(P, 2).to(dev)
+
+    def step():
+        method.zero_grad(set_to_none=True)
+        loss, _ = method.compute_loss_operator(operator, x, importance=importance)
+        loss.backward()
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    ms = time_events(step, steps, warmup, sync)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    L, K0 = neigs, 2 * cfg.fourier_mapping_size
+    flop_pt = L * (2 * 4 * (K0 * 128 + 2 * 128 * 128 + 128) + 2 * (K0 * 128 + 4 * 128 * 128 + 2 * 128))
+    return {"total_points": total_points, "points_per_gpu": P, "neigs": neigs, "n_gpus": world, "scaling": "strong",
+            "ms_per_step": ms, "points_per_s": total_points / (ms * 1e-3),
+            "tflops_algorithmic": flop_pt * total_points / (ms * 1e-3) / 1e12,
+            "grad_allreduce_mbytes": sum(p.numel() for p in method.parameters() if p.requires_grad) * 4 / 1e6}
 
 # ------------------------------------------------------------------------------------------
 # our arm
@@ -179,7 +319,6 @@ def run_ours(args):
     import torch.distributed as dist
     import neural_svd_b200 as N
     from neural_svd_b200 import _lib
-    from types import SimpleNamespace
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -195,19 +334,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
         dp = N.PointParallel()
 
-    # scripts/exps/pde/hydrogen.sh hyper-parameters with BASELINE's L (the product API only: no oracle, no test code)
-    cfg = SimpleNamespace(
-        problem="sch", potential_type="hydrogen", ndim=2, neigs=args.neigs, charge=1.0, laplacian_eps=0.0,
-        operator_scale=100.0, operator_shift=0.0, lim=50.0, use_fourier_feature=True, fourier_mapping_size=1024,
-        fourier_scale=0.1, fourier_deterministic=False, fourier_append_raw=False, mlp_hidden_dims="128,128,128",
-        nonlinearity="softplus", parallel=True, apply_boundary=False, boundary_mode="dir_box_sqrt",
-        apply_exp_mask=False, exp_mask_init_scale=100.0, hard_mul_const=1.0, sampling_scale=16.0)
     N.set_engine(args.engine)
-    torch.manual_seed(0)
-    operator, _gt = N.get_problem(cfg)
-    model = N.get_wavefunctions(cfg)
-    method = N.NestedLoRA(model=model, neigs=cfg.neigs, step=1, sort=False, sequential=False).to(dev)
-    importance = N.GaussianImportance(cfg.sampling_scale, cfg.ndim)
+    cfg, method, operator, importance = make_problem(N, "hydrogen", args.neigs, False, dev)
     method.data_parallel = dp
     P = args.points
     g = torch.Generator().manual_seed(100 + rank)
@@ -299,6 +427,7 @@ def run_ours(args):
 
     # ---- third column: the same step replayed as ONE CUDA graph (GraphedOperatorStep; single GPU only)
     graphed = None
+    gstep = None
     if world == 1:
         method.zero_grad(set_to_none=True)
         try:
@@ -319,6 +448,37 @@ def run_ours(args):
             gms = g0.elapsed_time(g1) / args.steps
             graphed = {"value": P / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms,
                        "what": "loss+grad step replayed as one CUDA graph (no L2 flush between steps)"}
+
+    # ---- the other BASELINE.json configurations (each at the same parity bar in tests/; here: their step times)
+    configs = {}
+    if not args.no_configs:
+        del gstep
+        xs_dev.clear()
+        method.zero_grad(set_to_none=True)
+        method.__dict__.pop("_nsvd_scratch", None)
+        del flush
+        torch.cuda.empty_cache()
+        if world == 1:
+            configs["config1_hydrogen_b128_seq_L16"] = small_config(N, "hydrogen", 128, 16, True, dev)
+            configs["config2_oscillator_b512_jnt_L16"] = small_config(N, "oscillator", 512, 16, False, dev)
+            configs["config3_hydrogen_b512_jnt_L16"] = small_config(N, "hydrogen", 512, 16, False, dev)
+            configs["config5_cdk_b4096_L512"] = cdk_config(N, dev)
+            # reference-grade CUDA-core engine on the headline workload, once (validation engine, not the product path)
+            N.set_engine("fp32")
+            c32, m32, o32, i32 = make_problem(N, "hydrogen", args.neigs, False, dev)
+            x32 = (c32.sampling_scale * torch.randn((P, 1, 2))).reshape(P, 2).to(dev)
+
+            def step32():
+                m32.zero_grad(set_to_none=True)
+                loss, _ = m32.compute_loss_operator(o32, x32, importance=i32)
+                loss.backward()
+
+            ms32 = time_events(step32, 2, 1, lambda: torch.cuda.synchronize(dev))
+            configs["fp32_engine_headline_workload"] = {"points": P, "ms_per_step": ms32, "points_per_s": P / (ms32 * 1e-3)}
+            del m32, x32
+            N.set_engine(args.engine)
+            torch.cuda.empty_cache()
+        configs["config4_hydrogen_2p20_L64_strong"] = strong_scaling_config(N, dev, dp, world, rank)
 
     if rank == 0:
         pk = peaks()
@@ -356,21 +516,25 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16x3 (fp32 operands split hi/lo, fp32 accumulate)" if args.engine == "bf16x3" else "f32",
                 "data": "synthetic",
-                "config": {"workload": f"2D hydrogen (H=-Lap-1/r, scale 100), joint nesting, L={L}, M_ff=1024, "
-                                       f"{P} Gaussian(sigma=16) collocation points per GPU per step, exact forward-mode "
-                                       f"Laplacian, loss+grad", "points_per_gpu": P, "neigs": L,
-                           "parallelism": f"dp{world} over points", "l2": "512 MB flush write between timed steps",
-                           "engine": args.engine, "algorithmic_mflop_per_point": flop_pt / 1e6},
+                "config": workload_config(P, L, world), "engine": args.engine,
+                "algorithmic_mflop_per_point": flop_pt / 1e6,
                 "clocks": sampler.result(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": P * 2 * 4 * world,
                         "d2h_bytes_per_step": 4 * world},
                 "with_optimizer": {"value": world * P / (full_ms * 1e-3), "unit": UNIT, "ms_per_step": full_ms,
                                    "what": "device sampler + loss+grad + fused RMSprop/EMA/cosine update (no L2 flush)"},
                 "graphed": graphed, "roofline": roof, "kernels": kernels,
-                "step_tflops_algorithmic": flop_pt * value / 1e12}
+                "step_tflops_algorithmic": flop_pt * value / 1e12, "configs": configs}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import nsvd_oracle as O        # cpu_baseline leg only
-            line["cpu_baseline"] = cpu_reference_run(O.PathConfig.hydrogen(neigs=args.neigs), args.cpu_seconds)
+            cb = line["cpu_baseline"] = cpu_reference_run(O.PathConfig.hydrogen(neigs=args.neigs), args.cpu_seconds)
+            c3 = configs.get("config3_hydrogen_b512_jnt_L16")
+            if c3 and cb.get("kind") == "reference":
+                # same problem, same batch (B=512), same operator (exact Laplacian): GPU step vs the reference on the host
+                c3["cpu_reference_exact_points_per_s"] = cb["exact_value"]
+                c3["cpu_reference_fd_points_per_s"] = cb["fd_value"]
+                c3["speedup_vs_cpu_exact_same_batch"] = c3["points_per_s_graphed"] / cb["exact_value"]
+                c3["speedup_vs_cpu_fd_same_batch"] = c3["points_per_s_graphed"] / cb["fd_value"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

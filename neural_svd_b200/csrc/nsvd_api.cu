@@ -28,6 +28,24 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+// Every entry point runs on the device that owns its buffers, whichever device is current in the calling thread
+// (a model on cuda:1 while cuda:0 is current must not launch on cuda:0); the previous device is restored on return.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const void* p) {
+    cudaPointerAttributes a;
+    if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) {
+      if (cudaGetDevice(&prev) == cudaSuccess && prev != a.device) switched = cudaSetDevice(a.device) == cudaSuccess;
+    } else {
+      cudaGetLastError();   // not a device pointer known to this process: leave the current device alone
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 static int check_problem(const nsvd_problem_t* pb) {
   NSVD_CHECK_ARG(pb != nullptr, "problem is NULL");
   NSVD_CHECK_ARG(pb->n_points >= 2, "n_points must be >= 2 (got %d)", pb->n_points);
@@ -116,6 +134,7 @@ int nsvd_scratch_bytes(const nsvd_problem_t* pb, int engine, size_t* saved_bytes
 int nsvd_fwd_streams(const nsvd_problem_t* pb, const nsvd_params_t* pr, int engine, const float* x,
                      float* F, float* TF, void* saved, size_t saved_bytes, void* work,
                      size_t work_bytes, void* stream) {
+  DeviceGuard dg_(x);
   int rc = check_problem(pb);
   if (rc) return rc;
   if ((rc = check_params(pb, pr))) return rc;
@@ -134,6 +153,7 @@ int nsvd_fwd_streams(const nsvd_problem_t* pb, const nsvd_params_t* pr, int engi
 int nsvd_mlp_bwd(const nsvd_problem_t* pb, const nsvd_params_t* pr, int engine, const float* x,
                  const float* dF, const void* saved, size_t saved_bytes, nsvd_grads_t* gr, void* work,
                  size_t work_bytes, void* stream) {
+  DeviceGuard dg_(dF);
   int rc = check_problem(pb);
   if (rc) return rc;
   if ((rc = check_params(pb, pr))) return rc;
@@ -156,6 +176,7 @@ size_t nsvd_gram_partials_bytes(int32_t n_points, int32_t n_copies) {
 
 int nsvd_gram_reduce(const float* F, const float* TF, const float* vector_mask, int32_t n_points,
                      int32_t n_copies, int32_t b1, float* terms, void* partials, void* stream) {
+  DeviceGuard dg_(F);
   NSVD_CHECK_ARG(F && TF && vector_mask && terms && partials, "NULL buffer");
   NSVD_CHECK_ARG(n_points >= 1 && n_copies >= 1 && n_copies <= 64, "bad shape B=%d L=%d", n_points, n_copies);
   NSVD_CHECK_ARG(b1 >= 0 && b1 <= n_points, "b1=%d out of range", b1);
@@ -165,6 +186,7 @@ int nsvd_gram_reduce(const float* F, const float* TF, const float* vector_mask, 
 
 int nsvd_cross_gram(const float* F, const float* TF, const float* roww, const float* x, int32_t n_points,
                     int32_t n_copies, float* cov, float* quad, void* partials, void* stream) {
+  DeviceGuard dg_(F);
   NSVD_CHECK_ARG(F && TF && cov && quad && partials, "NULL buffer");
   NSVD_CHECK_ARG(n_points >= 1 && n_copies >= 1 && n_copies <= 64, "bad shape B=%d L=%d", n_points, n_copies);
   return cross_gram(F, TF, roww, x, n_points, n_copies, cov, quad, partials, (cudaStream_t)stream);
@@ -172,6 +194,7 @@ int nsvd_cross_gram(const float* F, const float* TF, const float* roww, const fl
 
 int nsvd_loss_finalize(const float* terms, const float* matrix_mask, int32_t n_copies, int64_t Bg,
                        int64_t B1g, int64_t B2g, float* loss, float* coef, void* stream) {
+  DeviceGuard dg_(terms);
   NSVD_CHECK_ARG(terms && matrix_mask && loss && coef, "NULL buffer");
   NSVD_CHECK_ARG(Bg > 0 && B1g > 0 && B2g > 0 && B1g + B2g == Bg, "bad counts B=%ld B1=%ld B2=%ld", (long)Bg, (long)B1g, (long)B2g);
   return loss_finalize(terms, matrix_mask, n_copies, Bg, B1g, B2g, loss, coef, (cudaStream_t)stream);
@@ -180,6 +203,7 @@ int nsvd_loss_finalize(const float* terms, const float* matrix_mask, int32_t n_c
 int nsvd_loss_dF(const float* F, const float* TF, const float* vector_mask, const float* coef,
                  const float* grad_scale, int32_t n_points, int32_t n_copies, int32_t b1, int64_t Bg,
                  float* dF, void* stream) {
+  DeviceGuard dg_(F);
   NSVD_CHECK_ARG(F && vector_mask && dF && (TF || coef), "NULL buffer");
   NSVD_CHECK_ARG(b1 >= 0 && b1 <= n_points && Bg > 0, "bad b1/Bg");
   NSVD_CHECK_ARG(n_copies >= 1 && n_copies <= 64, "n_copies %d out of [1,64]", n_copies);
@@ -204,6 +228,7 @@ static int cdk_check(int engine, const void* work, size_t work_bytes, int n_rows
 int nsvd_cdk_fwd(const float* f, const float* g, const float* vector_mask, int32_t n_rows, int32_t n_feat,
                  int32_t first_const, int engine, float* terms, float* rs_joint, void* work, size_t work_bytes,
                  void* stream) {
+  DeviceGuard dg_(f);
   NSVD_CHECK_ARG(f && g && vector_mask && terms, "NULL buffer");
   int rc = cdk_check(engine, work, work_bytes, n_rows, n_feat, first_const);
   if (rc) return rc;
@@ -213,12 +238,14 @@ int nsvd_cdk_fwd(const float* f, const float* g, const float* vector_mask, int32
 }
 int nsvd_cdk_finalize(const float* terms, const float* matrix_mask, int32_t Lp, int64_t Bg, float* losses,
                       float* coef, void* stream) {
+  DeviceGuard dg_(terms);
   NSVD_CHECK_ARG(terms && matrix_mask && losses && coef && Lp >= 1 && Bg >= 1, "bad args");
   return cdk_finalize(terms, matrix_mask, Lp, Bg, losses, coef, (cudaStream_t)stream);
 }
 int nsvd_cdk_bwd(const float* f, const float* g, const float* vector_mask, const float* coef,
                  const float* grad_scale, int32_t n_rows, int32_t n_feat, int32_t first_const, int64_t Bg, int engine,
                  float* grad_f, float* grad_g, void* work, size_t work_bytes, void* stream) {
+  DeviceGuard dg_(f);
   NSVD_CHECK_ARG(f && g && vector_mask && coef && grad_f && grad_g, "NULL buffer");
   int rc = cdk_check(engine, work, work_bytes, n_rows, n_feat, first_const);
   if (rc) return rc;
@@ -230,6 +257,7 @@ int nsvd_cdk_bwd(const float* f, const float* g, const float* vector_mask, const
 }
 int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_feat, int32_t first_const, int engine,
                      float* rs_indep, void* work, size_t work_bytes, void* stream) {
+  DeviceGuard dg_(f);
   NSVD_CHECK_ARG(f && g && rs_indep, "NULL buffer");
   int rc = cdk_check(engine, work, work_bytes, n_rows, n_feat, first_const);
   if (rc) return rc;
@@ -241,6 +269,7 @@ int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_f
 int nsvd_rmsprop_ema_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* square_avg,
                           float* const* ema, const int64_t* sizes, float lr, float alpha, float eps,
                           float ema_one_minus_decay, void* stream) {
+  DeviceGuard dg_((n_tensors >= 1 && params) ? params[0] : nullptr);
   NSVD_CHECK_ARG(n_tensors >= 1 && n_tensors <= 16, "n_tensors must be in [1,16] (got %d)", n_tensors);
   NSVD_CHECK_ARG(params && grads && square_avg && sizes, "NULL table");
   OptTensors t{};
@@ -257,12 +286,14 @@ int nsvd_rmsprop_ema_step(int32_t n_tensors, float* const* params, const float* 
 }
 
 int nsvd_sample_gaussian(float* x, int64_t n_points, float sigma, uint64_t seed, uint64_t offset, void* stream) {
+  DeviceGuard dg_(x);
   NSVD_CHECK_ARG(x && n_points >= 0 && sigma > 0.f, "bad args");
   return sample_gaussian2(x, n_points, sigma, seed, offset, (cudaStream_t)stream);
 }
 
 int nsvd_sample_points(float* x, int64_t n_points, int32_t importance, float scale, uint64_t seed, uint64_t offset,
                        void* stream) {
+  DeviceGuard dg_(x);
   NSVD_CHECK_ARG(x && n_points >= 0 && scale > 0.f, "bad args");
   if (importance == NSVD_IMP_GAUSSIAN) return sample_gaussian2(x, n_points, scale, seed, offset, (cudaStream_t)stream);
   NSVD_CHECK_ARG(importance == NSVD_IMP_LAPLACE || importance == NSVD_IMP_UNIFORM, "no sampler for importance %d",
@@ -272,6 +303,7 @@ int nsvd_sample_points(float* x, int64_t n_points, int32_t importance, float sca
 
 int nsvd_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K,
                           int32_t a_kmajor, int32_t b_kmajor, void* work, size_t work_bytes, void* stream) {
+  DeviceGuard dg_(A);
   NSVD_CHECK_ARG(A && B && D && work, "NULL buffer");
   return tc_gemm_selftest(A, B, D, M, N, K, a_kmajor, b_kmajor, work, work_bytes, (cudaStream_t)stream);
 }

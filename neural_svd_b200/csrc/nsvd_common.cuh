@@ -40,6 +40,20 @@ void set_error(const char* fmt, ...);
 
 extern long g_launches;
 
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per DEVICE (the attribute is per device: a flag
+// per process would leave the second GPU of a process without the opt-in).
+constexpr int kMaxDevices = 64;
+#define NSVD_SMEM_OPTIN(kern, bytes)                                                                   \
+  do {                                                                                                 \
+    static bool done_[::nsvd::kMaxDevices] = {};                                                       \
+    int dev_ = 0;                                                                                      \
+    NSVD_CUDA(cudaGetDevice(&dev_));                                                                   \
+    if (dev_ < 0 || dev_ >= ::nsvd::kMaxDevices || !done_[dev_]) {                                     \
+      NSVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));     \
+      if (dev_ >= 0 && dev_ < ::nsvd::kMaxDevices) done_[dev_] = true;                                 \
+    }                                                                                                  \
+  } while (0)
+
 // kernel classes timed by the optional profiler (nsvd_profile_*): CUDA events on the launch stream
 enum KernelClass { KC_L0_FWD = 0, KC_HID_FWD, KC_HID_BWD, KC_L0_WGRAD, KC_GRAM, KC_DF, KC_PREP, KC_HEAD_BWD, KC_COUNT };
 struct ProfScope {

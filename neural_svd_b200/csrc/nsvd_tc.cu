@@ -513,12 +513,8 @@ __global__ void split_planes_kernel(const float* __restrict__ src, __nv_bfloat16
 template <bool kMN, class Epi, int FMT = 0>
 static int launch_big(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                       const BigShape& shape, const Epi& epi, cudaStream_t st) {
-  static bool configured = false;
   auto kern = big_gemm_kernel<kMN, Epi, FMT>;
-  if (!configured) {
-    NSVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, big::SMEM_BYTES));
-    configured = true;
-  }
+  NSVD_SMEM_OPTIN(kern, big::SMEM_BYTES);
   int tiles = shape.m_tiles * shape.n_tiles * shape.batches * shape.k_slices;
   if (tiles <= 0) return 0;
   int grid = tiles < 148 ? tiles : 148;
@@ -530,12 +526,8 @@ static int launch_big(const CUtensorMap& ah, const CUtensorMap& al, const CUtens
 template <bool kMN, class Epi, int FMT = 0>
 static int launch_big2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                        const BigShape& shape, int batches_valid, const Epi& epi, cudaStream_t st) {
-  static bool configured = false;
   auto kern = big2_gemm_kernel<kMN, Epi, FMT>;
-  if (!configured) {
-    NSVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, big2::SMEM_BYTES));
-    configured = true;
-  }
+  NSVD_SMEM_OPTIN(kern, big2::SMEM_BYTES);
   int tiles = shape.m_tiles * shape.n_tiles * shape.batches * shape.k_slices;
   if (tiles <= 0) return 0;
   int clusters = tiles < 74 ? tiles : 74;
@@ -1576,12 +1568,8 @@ static int launch_hidden_fwd(const CUtensorMap& ah, const CUtensorMap& al, const
                              const CUtensorMap& wl, const CUtensorMap& oh, const CUtensorMap& ol,
                              const CUtensorMap& sh, const CUtensorMap& sl, const CUtensorMap& vh, const CUtensorMap& vl,
                              const HidFwdArgs& a, cudaStream_t st) {
-  static bool configured = false;
   auto kern = hidden_fwd_kernel<kLast>;
-  if (!configured) {
-    NSVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hid::SMEM_FWD));
-    configured = true;
-  }
+  NSVD_SMEM_OPTIN(kern, hid::SMEM_FWD);
   int T = a.L * a.m_tiles;
   int grid = T < 148 ? T : 148;
   kern<<<grid, hid::F_THREADS, hid::SMEM_FWD, st>>>(ah, al, wh, wl, oh, ol, sh, sl, vh, vl, a);
@@ -1696,11 +1684,7 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
   uint8_t* sv = align1k(const_cast<void*>(saved_v));
   uint8_t* wk = align1k(work_v);
   int rc;
-  static bool configured = false;
-  if (!configured) {
-    NSVD_CUDA(cudaFuncSetAttribute(hidden_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hid::SMEM_BWD2));
-    configured = true;
-  }
+  NSVD_SMEM_OPTIN(hidden_bwd2_kernel, hid::SMEM_BWD2);
   // gradients are accumulated with reductions: start from zero
   NSVD_CUDA(cudaMemsetAsync(gr.dW[0], 0, sizeof(float) * L * H * K0, st));
   NSVD_CUDA(cudaMemsetAsync(gr.dW[1], 0, sizeof(float) * L * H * H, st));

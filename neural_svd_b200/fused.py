@@ -214,8 +214,7 @@ class _FusedOperatorStep(torch.autograd.Function):
         dev = F.device
         B, L = F.shape
         b1 = (B + 1) // 2                                     # torch.chunk(f, 2), nestedlora.py:263
-        v = method.vector_mask.to(device=dev, dtype=torch.float32).contiguous()
-        Mm = method.matrix_mask.to(device=dev, dtype=torch.float32).contiguous()
+        v, Mm = _nesting_masks(method, dev)
         terms = torch.empty(2 * L * L + 1, dtype=torch.float32, device=dev)
         _lib.check(lib.nsvd_gram_reduce(_lib.ptr(F), _lib.ptr(TF), _lib.ptr(v), B, L, b1, _lib.ptr(terms),
                                         _lib.ptr(sc.partials), _stream(dev)), "nsvd_gram_reduce")
@@ -265,11 +264,38 @@ class _FusedOperatorStep(torch.autograd.Function):
         return (None, None, None, None, None, None) + tuple(views)
 
 
+def _sort_permutation(method):
+    """sort_indices of register_eigvals() when it is active (NestedLoRA.forward, nestedlora.py:195-200), else None."""
+    si = getattr(method, "sort_indices", None)
+    if si is None or not getattr(method, "training", True):
+        return None
+    return si.to(torch.long)
+
+
+def _nesting_masks(method, dev):
+    """(vector_mask, matrix_mask) on the device.  With registered eigenvalues the reference permutes the model's OUTPUT
+    columns, f'[:, j] = f[:, s_j] (nestedlora.py:197-198), before the loss; the loss of f' under (v, M) equals the loss of
+    the unpermuted f under v'[s_j] = v[j], M'[s_j, s_k] = M[j, k], so the kernels run on the network's own column order
+    with permuted masks and dF comes out in that order too."""
+    v = method.vector_mask.to(device=dev, dtype=torch.float32)
+    Mm = method.matrix_mask.to(device=dev, dtype=torch.float32)
+    si = _sort_permutation(method)
+    if si is not None:
+        si = si.to(dev)
+        v2, M2 = torch.empty_like(v), torch.empty_like(Mm)
+        v2[si] = v
+        M2[si[:, None], si[None, :]] = Mm
+        v, Mm = v2, M2
+    return v.contiguous(), Mm.contiguous()
+
+
 def compute_loss_operator(method, operator, x, importance, dp=None):
     """Fused equivalent of NestedLoRA.compute_loss_operator (nestedlora.py:254-267)."""
     md = describe_model(method)
-    if getattr(method, "sort_indices", None) is not None:
-        raise NotImplementedError("register_eigvals()/sort_indices is not supported by the fused path")
     params = [md["Bff"]] + md["ws"] + md["bs"] + ([md["scales"]] if md["scales"] is not None else [])
     loss, F, TF = _FusedOperatorStep.apply(method, operator, importance, x, dp, *params)
+    si = _sort_permutation(method)
+    if si is not None:                       # the caller sees the permuted columns, as operator(self, x) returns them
+        si = si.to(F.device)
+        F, TF = F[:, si], TF[:, si]
     return loss, dict(f=F, Tf=TF, eigvals=None)

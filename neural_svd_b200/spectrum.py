@@ -74,8 +74,8 @@ def compute_spectrum_evd(model, dataloader, operator, importance_train=None, imp
             part = torch.empty(npart, dtype=torch.uint8, device=dev)
         roww = (sqrt_ws_train / sqrt_ws_val)
         roww = roww.reshape(-1).float().contiguous() if torch.is_tensor(roww) else None
-        if return_eigfuncs:
-            eigfuncs.append((sqrt_ws_train * phi).cpu() if torch.is_tensor(sqrt_ws_train) else phi.cpu())
+        if return_eigfuncs:       # kept on the device: ONE device-to-host copy after the loop, as spectrum.py:83
+            eigfuncs.append(sqrt_ws_train * phi if torch.is_tensor(sqrt_ws_train) else phi)
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(lib.nsvd_cross_gram(_lib.ptr(phi), _lib.ptr(Tphi), _lib.ptr(roww), _lib.ptr(x2), B, L,
                                        _lib.ptr(cov), _lib.ptr(quad), _lib.ptr(part), st), "nsvd_cross_gram")
@@ -91,7 +91,7 @@ def compute_spectrum_evd(model, dataloader, operator, importance_train=None, imp
     quad = (quad / n).cpu().numpy()
     print(f"Took {time.time() - start}s to compute spectrum with data of size {n}")
     outputs = dict()
-    outputs["eigfuncs"] = eigfuncs = torch.cat(eigfuncs, dim=0).numpy() if eigfuncs else None
+    outputs["eigfuncs"] = eigfuncs = torch.cat(eigfuncs, dim=0).cpu().numpy() if eigfuncs else None
     outputs["cov"], outputs["quad"] = cov, quad
     outputs["eigvals"] = eigvals = np.diag(quad) / np.diag(cov)
     outputs["norms"] = norms = np.diag(cov)

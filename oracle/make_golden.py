@@ -63,6 +63,9 @@ CASES = {
                                                         boundary_mode="dir_box_exp", apply_exp_mask=True,
                                                         exp_mask_init_scale=8.0, hydrogen_mol_ion_R=1.5,
                                                         hard_mul_const=2.0), B=101, seed=8),
+    # register_eigvals(): the model's output columns are permuted by sort_indices in training mode (nestedlora.py:195-206)
+    "hyd_small_sorted": dict(cfg=O.PathConfig.hydrogen(neigs=6, fourier_mapping_size=64, sequential=True), B=64, seed=13,
+                             eigvals=[3.0, 9.0, 1.0, 7.0, 8.0, 2.0]),
     "osc_no_importance": dict(cfg=O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64, sampling_mode="none"),
                               B=64, seed=9),
 }
@@ -75,13 +78,28 @@ CDK_CASES = {
 }
 
 
+# methods/spectrum.py:29-102 on a small validation grid (main_pde.py:119-129) that contains the origin; evaluated by
+# the reference's own compute_spectrum_evd with every output branch: plain, normalize, normalize+sort+post_align.
+SPECTRUM_CASES = {
+    "spec_hyd_small": dict(cfg=O.PathConfig.hydrogen(neigs=4, fourier_mapping_size=64, operator_shift=400.0),
+                           seed=11, lim=4.0, val_eps=0.25, chunk=300),
+    "spec_osc_small": dict(cfg=O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64, sequential=True,
+                                                       operator_shift=150.0), seed=12, lim=3.0, val_eps=0.25,
+                           chunk=128),
+}
+SPECTRUM_FLAGS = {"plain": dict(), "norm": dict(normalize=True),
+                  "all": dict(normalize=True, sort=True, post_align=True)}
+
+
 def checksum(a: np.ndarray):
     a = a.astype(np.float64)
     return np.array([a.sum(), (a * a).sum()])
 
 
-def run_reference(ref, cfg, seed, x32, dtype):
+def run_reference(ref, cfg, seed, x32, dtype, eigvals=None):
     method, operator, importance, gt = RB.build_reference_problem(ref, cfg, seed, 0.0, dtype)
+    if eigvals is not None:
+        method.register_eigvals(eigvals)
     x = torch.from_numpy(x32).to(dtype)
     loss, aux = method.compute_loss_operator(operator, x, importance=importance)
     loss.backward()
@@ -102,13 +120,15 @@ def make_case(ref, name, spec):
         x32 = (-cfg.sampling_scale * u.sign() * torch.log1p(-2 * u.abs())).float().reshape(B, -1).numpy()
     else:                                                           # main_pde.py:92-93
         x32 = (cfg.sampling_scale * torch.randn((B, 1, cfg.ndim), generator=g)).reshape(B, -1).numpy()
-    r64 = run_reference(ref, cfg, seed, x32, torch.float64)
-    r32 = run_reference(ref, cfg, seed, x32, torch.float32)
+    r64 = run_reference(ref, cfg, seed, x32, torch.float64, spec.get("eigvals"))
+    r32 = run_reference(ref, cfg, seed, x32, torch.float32, spec.get("eigvals"))
     mine = O.init_params_like_reference(cfg, seed)
     out = dict(x=x32, seed=np.int64(seed), config=json.dumps(dataclasses.asdict(cfg)),
                loss64=np.float64(r64["loss"]), loss32=np.float64(r32["loss"]),
                f64=r64["f"], Tf64=r64["Tf"], f32=r32["f"], Tf32=r32["Tf"],
                gt=np.asarray(r64["gt"], np.float64))
+    if spec.get("eigvals") is not None:
+        out["eigvals"] = np.asarray(spec["eigvals"], np.float64)
     rs = np.random.RandomState(seed)
     for n in O.param_names(cfg):
         p_ref = r32["params"][n]
@@ -169,6 +189,40 @@ def make_cdk_case(ref, name, spec):
     print(f"{name}: loss64={r['loss']:.9g} loss32={res['32']['loss']:.9g}")
 
 
+def spectrum_grid(lim, val_eps):
+    ax = np.arange(-lim, lim, val_eps)                              # main_pde.py:121-124
+    xxs = np.meshgrid(ax, ax)
+    return np.array(list(zip(*[xx.flatten() for xx in xxs]))).astype(np.float32)
+
+
+def make_spectrum_case(ref, name, spec):
+    cfg, seed, lim, chunk = spec["cfg"], spec["seed"], spec["lim"], spec["chunk"]
+    grid = spectrum_grid(lim, spec["val_eps"])
+    assert (np.abs(grid).sum(1) == 0).any(), "the grid must contain the origin (spectrum.py:73)"
+    out = dict(seed=np.int64(seed), config=json.dumps(dataclasses.asdict(cfg)), lim=np.float64(lim),
+               val_eps=np.float64(spec["val_eps"]), chunk=np.int64(chunk))
+    for tag, dt in (("64", torch.float64), ("32", torch.float32)):
+        method, operator, importance, _ = RB.build_reference_problem(ref, cfg, seed, 0.0, dt)
+        data = torch.from_numpy(grid).to(dt)
+
+        def loader():                                               # main_pde.py:125-127
+            for i in range(0, len(data), chunk):
+                yield data[i:i + chunk], 0.
+
+        def importance_val(x):                                      # main_pde.py:128-129
+            return (1 / (2 * lim) ** cfg.ndim * torch.ones(x.shape[0], 1)).to(dt).view(-1, 1)
+
+        for fl, kw in SPECTRUM_FLAGS.items():
+            o = ref.compute_spectrum_evd(method, loader(), operator, importance_train=importance,
+                                         importance_val=importance_val, device="cpu", **kw)
+            for k, v in o.items():
+                out[f"{fl}{tag}/{k}"] = np.asarray(v)
+            if tag == "64":
+                print(f"{name}[{fl}]: eigvals {np.round(o['eigvals'], 4)} norms {np.round(o['norms'], 5)}",
+                      ("aligned " + str(np.round(o['eigvals_aligned'], 4))) if 'eigvals_aligned' in o else "")
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+
+
 def main(argv):
     os.makedirs(GOLD, exist_ok=True)
     ref = RB.import_reference("/root/reference")
@@ -180,6 +234,9 @@ def main(argv):
     for name, spec in CDK_CASES.items():
         if want is None or name in want:
             make_cdk_case(ref, name, spec)
+    for name, spec in SPECTRUM_CASES.items():
+        if want is None or name in want:
+            make_spectrum_case(ref, name, spec)
 
 
 if __name__ == "__main__":

@@ -374,15 +374,24 @@ def mlp_backward(x, dF, params, cfg: PathConfig, u0, acts, sigs, aux) -> Dict[st
     return grads
 
 
-def train_step(x: np.ndarray, params: Dict[str, np.ndarray], cfg: PathConfig):
+def train_step(x: np.ndarray, params: Dict[str, np.ndarray], cfg: PathConfig, sort_indices=None):
     """One loss+grad evaluation == reference `compute_loss_operator` + `loss.backward()`
-    with `laplacian_eps<=0` (nestedlora.py:254-267, operator/__init__.py:62-68)."""
+    with `laplacian_eps<=0` (nestedlora.py:254-267, operator/__init__.py:62-68).
+    `sort_indices`: the permutation NestedLoRA.forward applies to the model output in training mode after
+    register_eigvals() (nestedlora.py:195-206); f, Tf, dF are returned in the permuted column order."""
     u, acts, sigs = forward_streams(x, params, cfg, keep=True)
     Tf, f, aux = operator_apply(x, u, params, cfg)
+    if sort_indices is not None:
+        si = np.asarray(sort_indices)
+        f, Tf = f[:, si], Tf[:, si]
     v, M = nesting_masks(cfg.neigs, cfg.sequential, cfg.step)
     loss, lam1, lam2 = loss_forward(f, Tf, v, M)
     dF = loss_dF(f, Tf, v, M, lam1, lam2)
-    grads = mlp_backward(x, dF, params, cfg, u[0], acts, sigs, aux)
+    dF_net = dF
+    if sort_indices is not None:
+        dF_net = np.empty_like(dF)
+        dF_net[:, si] = dF                                          # backward of the column gather
+    grads = mlp_backward(x, dF_net, params, cfg, u[0], acts, sigs, aux)
     return dict(loss=loss, f=f, Tf=Tf, dF=dF, grads=grads, lam1=lam1, lam2=lam2)
 
 
@@ -420,25 +429,55 @@ def cdk_forward_backward(f: np.ndarray, g: np.ndarray, neigs: int, sequential: b
 # --------------------------------------------------------------------------
 # spectrum evaluation  (methods/spectrum.py:29-102), uniform validation importance
 # --------------------------------------------------------------------------
-def spectrum_evd(xs: np.ndarray, params, cfg: PathConfig, lim: float, chunk: int = 4096):
+def spectrum_evd(xs: np.ndarray, params, cfg: PathConfig, lim: float, chunk: int = 4096, normalize: bool = False,
+                 sort: bool = False, post_align: bool = False):
+    """compute_spectrum_evd (methods/spectrum.py:29-102) with the training importance of `cfg` and the uniform
+    validation importance of main_pde.py:128-129 on [-lim, lim]^D.  Chunked like the reference's dataloader so the
+    accumulation order of cov / quad is the same."""
     dt = xs.dtype
     L = cfg.neigs
     cov = np.zeros((L, L), dt)
     quad = np.zeros((L, L), dt)
+    eigfuncs = []
     for i in range(0, len(xs), chunk):
         x = xs[i:i + chunk]
         u = forward_streams(x, params, cfg)
         Tf, f, _ = operator_apply(x, u, params, cfg)
-        sw_tr = np.sqrt(importance_gaussian(x, cfg.sampling_scale))[:, None]
-        sw_va = math.sqrt(1.0 / (2 * lim) ** cfg.ndim)
-        sw = sw_tr / sw_va
-        phi, Tphi = np.nan_to_num(sw * f), np.nan_to_num(sw * Tf)
-        Tphi[np.all(np.isclose(x, 0.0), axis=1)] = 0.0              # spectrum.py:73
+        w, _, _ = importance_terms(x, cfg)
+        sw_tr = np.sqrt(w)[:, None] if w is not None else np.ones((len(x), 1), dt)       # spectrum.py:16-27
+        # importance_val builds its constant in fp32 (main_pde.py:128-129); the square root is taken in x's dtype
+        sw_va = float(np.sqrt(np.float32(1.0 / (2 * lim) ** cfg.ndim).astype(dt)))
+        sw = sw_tr / sw_va                                          # spectrum.py:61
+        eigfuncs.append(sw_tr * f)                                  # spectrum.py:65
+        phi, Tphi = np.nan_to_num(sw * f), np.nan_to_num(sw * Tf)   # spectrum.py:66-72
+        Tphi[np.all(np.isclose(x, 0.0), axis=1)] *= 0.0             # spectrum.py:73
         cov += phi.T @ phi
         quad += phi.T @ Tphi
     cov /= len(xs)
     quad /= len(xs)
-    return dict(cov=cov, quad=quad, eigvals=np.diag(quad) / np.diag(cov), norms=np.diag(cov))
+    out = dict(eigfuncs=np.concatenate(eigfuncs, 0), cov=cov, quad=quad)
+    out["eigvals"] = eigvals = np.diag(quad) / np.diag(cov)         # spectrum.py:86
+    out["norms"] = norms = np.diag(cov)                             # spectrum.py:87
+    if normalize:                                                   # spectrum.py:88-90
+        out["cov"] = cov / (np.sqrt(norms[:, None]) @ np.sqrt(norms[:, None]).T)
+        out["eigfuncs"] = out["eigfuncs"] / np.sqrt(norms).reshape(1, -1)
+    if sort:                                                        # spectrum.py:91-97
+        si = np.argsort(eigvals)[::-1]
+        out["eigvals"] = out["eigvals"][si]
+        out["eigfuncs"] = out["eigfuncs"][:, si]
+        out["cov"] = out["cov"][:, si][si, :]
+        out["quad"] = out["quad"][:, si][si, :]
+        out["norms"] = out["norms"][si]
+    if post_align:                                                  # spectrum.py:98-101, 161-170
+        from scipy.linalg import eigh
+        ec, Vc = eigh(out["cov"])
+        whitening = Vc @ np.diag(1 / np.sqrt(ec)) @ Vc.T
+        ev, V = eigh(whitening @ out["quad"] @ whitening)
+        out["eigvals_aligned"] = np.sqrt(ev[::-1])
+        V = V[:, ::-1]
+        out["eigfuncs_aligned"] = out["eigfuncs"] @ (V.T @ whitening).T
+        out["cov_aligned"] = np.eye(L)
+    return out
 
 
 # --------------------------------------------------------------------------

@@ -49,7 +49,9 @@ def import_reference(root: str | None = None):
     from examples.operator.pde.problems import get_problem         # problems.py:23
     from methods.nestedlora import (NestedLoRA, NestedLoRAForCDK, NestedLoRALossFunctionEVD,
                                     NestedLoRALossFunctionForCDK)
+    from methods.spectrum import compute_spectrum_evd              # spectrum.py:29
     return SimpleNamespace(root=root, get_wavefunctions=get_wavefunctions, get_problem=get_problem,
+                           compute_spectrum_evd=compute_spectrum_evd,
                            NestedLoRA=NestedLoRA, NestedLoRAForCDK=NestedLoRAForCDK,
                            NestedLoRALossFunctionEVD=NestedLoRALossFunctionEVD,
                            NestedLoRALossFunctionForCDK=NestedLoRALossFunctionForCDK)

@@ -12,7 +12,7 @@ from oracle import nsvd_oracle as O
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 ENGINES = ["fp32", "bf16x3"]
-PDE_CASES = ["hyd_small_odd", "osc_small_seq", "hyd_b128_seq_L16", "osc_b512_jnt_L16", "hyd_b512_jnt_L16",
+PDE_CASES = ["hyd_small_odd", "osc_small_seq", "hyd_small_sorted", "hyd_b128_seq_L16", "osc_b512_jnt_L16", "hyd_b512_jnt_L16",
              "hyd_b64_jnt_L64",
              # infinite well / cosine / H2+ potentials, uniform / Laplace / no importance,
              # Dirichlet box masks (sqrt, exp; alone and under the exp mask), deterministic Fourier features
@@ -23,6 +23,8 @@ def _step(name, engine):
     d, cfg = load_golden(name)
     N.set_engine(engine)
     method, operator, importance, _ = build_problem(cfg, int(d["seed"]), "cuda")
+    if "eigvals" in d:                       # nestedlora.py:202-206: output columns sorted by the registered eigenvalues
+        method.register_eigvals(d["eigvals"])
     x = torch.from_numpy(d["x"]).cuda()
     loss, aux = method.compute_loss_operator(operator, x, importance=importance)
     loss.backward()
@@ -200,6 +202,33 @@ def test_spectrum_evd_matches_oracle():
     assert rel(out["cov"], ref["cov"]) < TOL and rel(out["quad"], ref["quad"]) < TOL
     assert rel(out["eigvals"], ref["eigvals"]) < TOL and rel(out["norms"], ref["norms"]) < TOL
     assert out["eigfuncs"].shape == (len(grid), 4)
+
+
+@pytest.mark.parametrize("engine", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("name", ["spec_hyd_small", "spec_osc_small"])
+def test_spectrum_evd_matches_reference_fixture(name, engine):
+    # methods/spectrum.py:29-102 as run by the UNMODIFIED reference (oracle/make_golden.py SPECTRUM_CASES): plain,
+    # normalize, and normalize + sort + post_align outputs on a validation grid that contains the origin
+    from test_oracle_golden import _spec_grid, spec_close
+    d, cfg = load_golden(name)
+    N.set_engine(engine)
+    method, operator, importance, _ = build_problem(cfg, int(d["seed"]), "cuda")
+    grid, lim, chunk = torch.from_numpy(_spec_grid(d)), float(d["lim"]), int(d["chunk"])
+
+    def loader():
+        for i in range(0, len(grid), chunk):
+            yield grid[i:i + chunk], 0.0
+
+    def importance_val(x):
+        return (1 / (2 * lim) ** 2 * torch.ones(x.shape[0], 1)).to(x.device).float()
+
+    for flags, kw in dict(plain={}, norm=dict(normalize=True),
+                          all=dict(normalize=True, sort=True, post_align=True)).items():
+        out = N.compute_spectrum_evd(method, loader(), operator, importance_train=importance,
+                                     importance_val=importance_val, device="cuda", **kw)
+        # the aligned outputs go through two eigendecompositions of 4x4 matrices with condition ~1e3
+        spec_close(out, d, flags + "64", TOL, aligned_tol=20 * TOL)
+    N.set_engine("bf16x3")
 
 
 def test_fused_rmsprop_ema_matches_torch():

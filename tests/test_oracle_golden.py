@@ -6,7 +6,7 @@ import pytest
 from conftest import golden_grad_errors, load_golden, rel
 from oracle import nsvd_oracle as O
 
-PDE_SMALL = ["hyd_small_odd", "osc_small_seq",
+PDE_SMALL = ["hyd_small_odd", "osc_small_seq", "hyd_small_sorted",
              # other potentials, samplers, Dirichlet box masks, deterministic features
              "well_uniform_boxsqrt", "cosine_uniform_detff", "molion_laplace_boxexp_mask", "osc_no_importance"]
 PDE_FULL = ["hyd_b128_seq_L16", "osc_b512_jnt_L16", "hyd_b512_jnt_L16"]
@@ -20,7 +20,10 @@ def _run(name, dtype):
         a = p[n].astype(np.float64)
         assert np.allclose([a.sum(), (a * a).sum()], ck, rtol=1e-12, atol=1e-12), n
     p = {k: v.astype(dtype) for k, v in p.items()}
-    r = O.train_step(d["x"].astype(dtype), p, cfg)
+    si = None
+    if "eigvals" in d:                                  # register_eigvals(): torch.sort(eigvals)[1].flip(0)
+        si = np.argsort(d["eigvals"], kind="stable")[::-1].copy()
+    r = O.train_step(d["x"].astype(dtype), p, cfg, sort_indices=si)
     return d, cfg, r
 
 
@@ -85,3 +88,39 @@ def test_analytic_spectra_known_answers():
     assert np.allclose(gt[9:16], 100 / 49)
     d, _ = load_golden("osc_b512_jnt_L16")
     assert np.allclose(d["gt"][:6], 16 - np.array([2, 4, 4, 6, 6, 6]))
+
+
+SPEC_KEYS = ["cov", "quad", "eigvals", "norms", "eigfuncs"]
+
+
+def _spec_grid(d):
+    ax = np.arange(-float(d["lim"]), float(d["lim"]), float(d["val_eps"]))
+    xxs = np.meshgrid(ax, ax)
+    return np.array(list(zip(*[xx.flatten() for xx in xxs]))).astype(np.float32)
+
+
+def spec_close(out, d, tag, tol, aligned_tol=None):
+    """compare a compute_spectrum_evd output dict with the fixture group `tag` (e.g. 'all64')."""
+    for k in SPEC_KEYS:
+        assert rel(out[k], d[f"{tag}/{k}"]) < tol, (tag, k, rel(out[k], d[f"{tag}/{k}"]))
+    if f"{tag}/eigvals_aligned" in d:
+        at = aligned_tol or tol
+        assert rel(out["eigvals_aligned"], d[f"{tag}/eigvals_aligned"]) < at
+        assert rel(out["cov_aligned"], d[f"{tag}/cov_aligned"]) < at
+        a, b = np.asarray(out["eigfuncs_aligned"], np.float64), d[f"{tag}/eigfuncs_aligned"].astype(np.float64)
+        sgn = np.sign((a * b).sum(0))                    # eigenvectors are defined up to sign
+        assert rel(a * sgn[None, :], b) < at
+
+
+@pytest.mark.parametrize("name", ["spec_hyd_small", "spec_osc_small"])
+@pytest.mark.parametrize("flags", ["plain", "norm", "all"])
+def test_oracle_spectrum_matches_reference(name, flags):
+    # methods/spectrum.py:29-102 run by the unmodified reference (oracle/make_golden.py: SPECTRUM_CASES), every output
+    # branch: nan_to_num + origin-row zeroing (the grid contains the origin), sqrt_ws re-weighting, normalize, sort,
+    # post_align
+    d, cfg = load_golden(name)
+    p = {k: v.astype(np.float64) for k, v in O.init_params_like_reference(cfg, int(d["seed"])).items()}
+    kw = dict(plain={}, norm=dict(normalize=True), all=dict(normalize=True, sort=True, post_align=True))[flags]
+    with np.errstate(all="ignore"):
+        out = O.spectrum_evd(_spec_grid(d).astype(np.float64), p, cfg, float(d["lim"]), chunk=int(d["chunk"]), **kw)
+    spec_close(out, d, flags + "64", 1e-10, aligned_tol=1e-8)
