@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--points", type=int, default=131072, help="collocation points per GPU per step")
     ap.add_argument("--neigs", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="bf16x3", choices=["bf16x3", "fp32"])
+    ap.add_argument("--engine", default="f16x3", choices=["f16x3", "bf16x3", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-BASELINE-config block")
@@ -492,7 +492,7 @@ def run_ours(args):
             # 1.040 GB written by one launch over 32768 points), scaled to the points one launch covers here
             pts_per_launch = P * args.steps / l0_n
             traffic = (1.655711e9 + 1.040122e9) / 32768 * pts_per_launch
-            roof = {"kernel": "big2_gemm_kernel<K-major, L0FwdEpi> (layer-0 4-stream forward GEMM, tcgen05 cta_group::2, bf16x3)",
+            roof = {"kernel": "big2s_gemm_kernel<K-major, L0FwdEpi> (layer-0 4-stream forward GEMM, tcgen05 cta_group::2, fp16 hi/lo planes x 3 products)",
                     "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                     "frac": ach / pk["tf_sust"], "traffic": traffic,
                     "traffic_note": "bytes per launch = ncu dram read+write per point (82.27 KB, profiles/r1_ncu_full.csv) x "
@@ -500,8 +500,8 @@ def run_ours(args):
                                     "stream out) per point + 67 MB of folded weights per launch",
                     "peak_source": pk["src"] + " bf16 sustained",
                     "issued_frac": 3 * ach / pk["tf_sust"], "launches": l0_n, "avg_launch_ms": l0_ms / l0_n,
-                    "note": "achieved = ALGORITHMIC fp32-equivalent FLOPs; every MAC is issued as 3 bf16 MMAs "
-                            "(hi*hi + hi*lo + lo*hi), so tensor-pipe issue rate = issued_frac of the bf16 peak"}
+                    "note": "achieved = ALGORITHMIC fp32-equivalent FLOPs; every MAC is issued as 3 fp16 MMAs "
+                            "(hi*hi + hi*lo + lo*hi), so tensor-pipe issue rate = issued_frac of the 16-bit dense peak"}
         gram_ms, gram_n = prof["gram_reduce"]
         df_ms, df_n = prof["loss_dF"]
         kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
@@ -514,7 +514,7 @@ def run_ours(args):
         flop_pt = L * (2 * 4 * (K0 * 128 + 2 * 128 * 128 + 128) + 2 * (K0 * 128 + 4 * 128 * 128 + 2 * 128))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16x3 (fp32 operands split hi/lo, fp32 accumulate)" if args.engine == "bf16x3" else "f32",
+                "vs_baseline": None, "dtype": "f16x3 (fp32 operands as fp16 hi/lo planes, 3 tensor-core products, fp32 accumulate)" if args.engine == "f16x3" else "f32",
                 "data": "synthetic",
                 "config": workload_config(P, L, world), "engine": args.engine,
                 "algorithmic_mflop_per_point": flop_pt / 1e6,

@@ -52,10 +52,13 @@ enum { NSVD_BOX_NONE = 0, NSVD_BOX_SQRT = 1, NSVD_BOX_EXP = 2 };
 
 /* arithmetic engines for the dense contractions.
  *   FP32_SIMT   : CUDA-core fp32 FMA. Reference-grade accuracy; validation and tiny batches.
- *   BF16X3_TC   : tcgen05 tensor cores, every fp32 operand split into bf16 hi+lo and the
- *                 product formed as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM
- *                 (~2^-16 relative operand error, measured 1e-5 on loss/grad: DESIGN.md §4). */
-enum { NSVD_ENGINE_FP32_SIMT = 0, NSVD_ENGINE_BF16X3_TC = 1 };
+ *   F16X3_TC    : tcgen05 tensor cores.  Operator path: every fp32 operand v is stored as two fp16 planes of s*v
+ *                 (s = power of two from a rigorous bound of |v|, 22 significant bits) and a product is formed as
+ *                 hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM in chains of <= 72 MMAs, each chain
+ *                 corrected for the accumulator's truncation bias (1e-6 on loss / gradients: DESIGN.md §3).
+ *                 CDK loss: bf16 hi/lo planes (inputs of unknown range), 1e-5.
+ *   NSVD_ENGINE_BF16X3_TC is the round-1 name of the same value. */
+enum { NSVD_ENGINE_FP32_SIMT = 0, NSVD_ENGINE_F16X3_TC = 1, NSVD_ENGINE_BF16X3_TC = 1 };
 
 /* One problem instance = what the reference spreads over get_problem (pde/problems.py:23-130),
  * get_wavefunctions (pde/__init__.py:19-55) and the Gaussian sampler (pde/main_pde.py:89-100). */

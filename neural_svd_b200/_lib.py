@@ -34,9 +34,11 @@ class Grads(C.Structure):
 POT_HYDROGEN, POT_HARMONIC, POT_HYDROGEN_MOL_ION, POT_INFINITE_WELL, POT_COSINE = 0, 1, 2, 3, 4
 IMP_GAUSSIAN, IMP_LAPLACE, IMP_UNIFORM, IMP_NONE = 0, 1, 2, 3
 BOX_NONE, BOX_SQRT, BOX_EXP = 0, 1, 2
-ENGINE_FP32_SIMT, ENGINE_BF16X3_TC = 0, 1
-ENGINES = {"fp32": ENGINE_FP32_SIMT, "fp32_simt": ENGINE_FP32_SIMT, "bf16x3": ENGINE_BF16X3_TC,
-           "tc": ENGINE_BF16X3_TC}
+ENGINE_FP32_SIMT, ENGINE_F16X3_TC = 0, 1
+# "f16x3": tcgen05 tensor cores, every fp32 operand as two fp16 planes (three bf16 products in the CDK loss);
+# "bf16x3" is the round-1 name of the same engine slot and stays accepted.
+ENGINES = {"fp32": ENGINE_FP32_SIMT, "fp32_simt": ENGINE_FP32_SIMT, "f16x3": ENGINE_F16X3_TC, "tc": ENGINE_F16X3_TC,
+           "bf16x3": ENGINE_F16X3_TC}
 
 _vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 _PB, _PR, _GR = C.POINTER(Problem), C.POINTER(Params), C.POINTER(Grads)

@@ -1,8 +1,9 @@
-// nsvd_tc.cu — tcgen05 / TMEM / TMA engine (bf16x3) of the NestedLoRA step.
+// nsvd_tc.cu — tcgen05 / TMEM / TMA engine (f16x3) of the NestedLoRA step.
 //
 // Every dense contraction D = A . B^T with fp32 operands is evaluated on the 5th-generation tensor
-// cores as  A_hi B_hi + A_lo B_hi + A_hi B_lo  (bf16 operands, fp32 accumulation in TMEM), where
-// v = v_hi + v_lo is the two-term bf16 split (16 significant bits).  Kernels are persistent and
+// cores as  A_hi B_hi + A_lo B_hi + A_hi B_lo  (16-bit operand planes, fp32 accumulation in TMEM), where
+// v = v_hi + v_lo is a two-plane split: fp16 planes of a power-of-two multiple of v on the operator path
+// (22 significant bits, see "Operand plan" below), bf16 planes (16 bits) in the CDK loss.  Kernels are persistent and
 // warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
 // allocator, warps 4.. = epilogue (TMEM -> registers -> fused math -> global / staged TMA stores):
 // 8 epilogue warps in the layer-0 GEMMs (MMA-bound), 16 in the hidden-layer kernels (epilogue-bound).
@@ -54,6 +55,24 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
   }
   return 0;
 }
+
+// The fp32 accumulation in TMEM truncates toward zero: every chained MMA shrinks the accumulator by 1.61e-8 relative,
+// coherently - measured 1.53e-8 .. 1.64e-8 per MMA for chains of 12 .. 384 MMAs on two operand distributions
+// (profiles/truncation_probe.py; K = 2048: 7.2e-6 -> 3.6e-6 after rescaling, what remains is the incoherent part).  Each
+// finished chain is therefore multiplied by 1 + kTruncPerMma * (number of MMAs in the chain) when it leaves TMEM.
+constexpr float kTruncPerMma = 1.61e-8f;
+
+// Optional phase timelines of block 0 (development builds: nvcc -DNSVD_TIMELINE; see profiles/timeline_probe.py)
+#ifdef NSVD_TIMELINE
+__device__ long long g_timeline_l0[64 * 8];
+#define NSVD_TL0(tile, slot, val) \
+  do { if (blockIdx.x == 0 && (tile) < 64) g_timeline_l0[(tile) * 8 + (slot)] = (val); } while (0)
+extern "C" int nsvd_debug_timeline_l0(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_timeline_l0, sizeof(long long) * 64 * 8);
+}
+#else
+#define NSVD_TL0(tile, slot, val) do {} while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------
 // S1: "big GEMM" skeleton.  Tile 128 x 256, K chunk 64, hi/lo planes, 2 smem stages (96 KB each),
@@ -467,6 +486,281 @@ big2_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// S1 on CTA pairs with SHORT ACCUMULATION CHAINS (the two layer-0 GEMMs).  The fp32 accumulator in TMEM truncates: the
+// error of a chain grows linearly with the number of chained MMAs (1.9e-8 each: K = 2048 -> 7e-6 whatever the operand
+// format, profiles/format_probe.py), which alone breaks the fixed-seed trajectory tolerance
+// (profiles/trajectory_emulation.py: hh:chain=2048 -> 2.9e-3, chain=256 -> 1.2e-4).  Here a tile's K range is cut into
+// sub-chains of `sub_chunks` K chunks; each sub-chain accumulates from zero in one of the two TMEM buffers and is added
+// to REGISTER accumulators by the epilogue warps (round-to-nearest fp32 adds) while the next sub-chain runs in the
+// other buffer.  16 epilogue warps: warp (q, sub) owns TMEM lanes [32 q, 32 q + 32) and 4 groups of 16 columns chosen
+// by the epilogue functor (64 fp32 accumulators per thread); the fused math then runs on the registers, with both TMEM
+// buffers already handed back to the MMA issuer.
+// ------------------------------------------------------------------------------------------
+namespace big2s {
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 3;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int BH_BYTES = (BN / 2) * BK * 2;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = (2 + EPI_WARPS) * 32;   // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer, 2..17: epilogue
+constexpr int EPI_STAGING = 32768;              // output staging of the epilogue (8 KB per TMEM lane quarter)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_STAGING;
+// End of the accumulation chain that starts at K chunk ks0 of a tile covering [kc0, kc1): the first two chains of a
+// tile take `sub_first` chunks, the others `sub_chunks`.  While the epilogue warps run the fused math and stores of
+// the previous tile (10k cycles) the MMA issuer can only fill the two TMEM buffers; two longer first chains give it
+// that much look-ahead (6 + 6 chunks = 18k cycles) without lengthening the other chains (timeline_l0_probe.py).
+__device__ __forceinline__ int chain_end(int ks0, int kc0, int kc1, int sub_chunks, int sub_first) {
+  const int e = ks0 + ((ks0 - kc0) < 2 * sub_first ? sub_first : sub_chunks);
+  return e < kc1 ? e : kc1;
+}
+}  // namespace big2s
+
+template <bool kMN, class Epi, int FMT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(big2s::THREADS, 1)
+big2s_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                  const BigShape shape, const int batches_valid, const int sub_chunks, const int sub_first,
+                  const Epi epi) {
+  using namespace big2s;
+  using namespace tc;
+  constexpr MmaDescs md = make_descs(2 * BM, BN, kMN ? 1 : 0, kMN ? 1 : 0, FMT & 3, (FMT >> 2) & 3, (FMT >> 4) & 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                   // [STAGES]  (the leader's are used)
+  uint64_t* empty = bars + STAGES;         // [STAGES]  (each CTA waits on its own)
+  uint64_t* tfull = bars + 2 * STAGES;     // [2]       (each CTA waits on its own)
+  uint64_t* tempty = tfull + 2;            // [2]       (the leader's are used, 2 x EPI_WARPS arrivals)
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int num_tiles = shape.m_tiles * shape.n_tiles * shape.batches * shape.k_slices;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAh);
+    tma_prefetch_desc(&tmAl);
+    tma_prefetch_desc(&tmBh);
+    tma_prefetch_desc(&tmBl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        TileCoord c = decode_tile(shape, t);
+        const int kc0 = c.ks * shape.k_chunks_per_slice;
+        int kc1 = kc0 + shape.k_chunks_per_slice;
+        if (kc1 > shape.k_chunks_total) kc1 = shape.k_chunks_total;
+        const int bpair = kMN ? 2 * c.b + (int)rank : c.b;
+        const int ab = shape.a_batched ? bpair : 0, bb = shape.b_batched ? c.b : 0;
+        for (int kc = kc0; kc < kc1; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1, 51);
+          uint8_t* sA = smem + stage * STAGE_BYTES;
+          uint8_t* sB = sA + 2 * A_BYTES;
+          const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+          if (!kMN) {
+            const int arow = (2 * c.mt + (int)rank) * BM, brow = c.nt * BN + (int)rank * (BN / 2);
+            tma_load_3d_pair(sA, &tmAh, lead_full, kc * BK, arow, ab);
+            tma_load_3d_pair(sA + A_BYTES, &tmAl, lead_full, kc * BK, arow, ab);
+            tma_load_3d_pair(sB, &tmBh, lead_full, kc * BK, brow, bb);
+            tma_load_3d_pair(sB + BH_BYTES, &tmBl, lead_full, kc * BK, brow, bb);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              tma_load_3d_pair(sA + i * 8192, &tmAh, lead_full, c.mt * BM + i * 64, kc * BK, ab);
+              tma_load_3d_pair(sA + A_BYTES + i * 8192, &tmAl, lead_full, c.mt * BM + i * 64, kc * BK, ab);
+              const int ncol = c.nt * BN + ((int)rank * 2 + i) * 64;
+              tma_load_3d_pair(sB + i * 8192, &tmBh, lead_full, ncol, kc * BK, bb);
+              tma_load_3d_pair(sB + BH_BYTES + i * 8192, &tmBl, lead_full, ncol, kc * BK, bb);
+            }
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (lane == 0 && rank == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+#ifdef NSVD_TIMELINE
+      int tl_i = 0;
+#endif
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        TileCoord c = decode_tile(shape, t);
+        const int kc0 = c.ks * shape.k_chunks_per_slice;
+        int kc1 = kc0 + shape.k_chunks_per_slice;
+        if (kc1 > shape.k_chunks_total) kc1 = shape.k_chunks_total;
+#ifdef NSVD_TIMELINE
+        long long tl_we = 0, tl_wf = 0, tl_t;
+        NSVD_TL0(tl_i, 0, clock64());
+#endif
+        for (int ks0 = kc0, ks1; ks0 < kc1; ks0 = ks1) {        // one sub-chain per TMEM buffer
+          ks1 = chain_end(ks0, kc0, kc1, sub_chunks, sub_first);
+#ifdef NSVD_TIMELINE
+          tl_t = clock64();
+#endif
+          mbar_wait(&tempty[acc], acc_phase ^ 1, 52);
+#ifdef NSVD_TIMELINE
+          tl_we += clock64() - tl_t;
+#endif
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kc = ks0; kc < ks1; ++kc) {
+#ifdef NSVD_TIMELINE
+            tl_t = clock64();
+#endif
+            mbar_wait(&full[stage], phase, 53);
+#ifdef NSVD_TIMELINE
+            tl_wf += clock64() - tl_t;
+#endif
+            tc_fence_after();
+            const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t sB = sA + 2 * A_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              uint64_t ah, al, bh, bl;
+              if (!kMN) {
+                ah = make_sdesc_sw128(sA + kk * 32, 16, 1024);
+                al = make_sdesc_sw128(sA + A_BYTES + kk * 32, 16, 1024);
+                bh = make_sdesc_sw128(sB + kk * 32, 16, 1024);
+                bl = make_sdesc_sw128(sB + BH_BYTES + kk * 32, 16, 1024);
+              } else {
+                ah = make_sdesc_sw128(sA + kk * 2048, 8192, 1024);
+                al = make_sdesc_sw128(sA + A_BYTES + kk * 2048, 8192, 1024);
+                bh = make_sdesc_sw128(sB + kk * 2048, 8192, 1024);
+                bl = make_sdesc_sw128(sB + BH_BYTES + kk * 2048, 8192, 1024);
+              }
+              umma_f16_pair(d_tmem, al, bh, md.lh, (kc > ks0 || kk > 0) ? 1u : 0u);
+              umma_f16_pair(d_tmem, ah, bl, md.hl, 1u);
+              umma_f16_pair(d_tmem, ah, bh, md.hh, 1u);
+            }
+            umma_commit_pair(&empty[stage]);   // frees the stage in both CTAs
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit_pair(&tfull[acc]);       // this sub-chain is complete in both CTAs
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+#ifdef NSVD_TIMELINE
+        NSVD_TL0(tl_i, 1, tl_we);
+        NSVD_TL0(tl_i, 2, tl_wf);
+        NSVD_TL0(tl_i, 3, clock64());
+        ++tl_i;
+#endif
+      }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue warps (both CTAs, own TMEM half): drain sub-chains, then the fused math ==========
+    // a warp reaches the TMEM lanes [32 (warp % 4), +32): q follows the hardware warp index
+    const int q = warp & 3, sub = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+#ifdef NSVD_TIMELINE
+    int tl_i = 0;
+    const bool tl_on = warp == 2 && lane == 0;
+#endif
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      TileCoord c = decode_tile(shape, t);
+      const int kc0 = c.ks * shape.k_chunks_per_slice;
+      int kc1 = kc0 + shape.k_chunks_per_slice;
+      if (kc1 > shape.k_chunks_total) kc1 = shape.k_chunks_total;
+#ifdef NSVD_TIMELINE
+      long long tl_dr = 0, tl_t = 0;
+#endif
+      bool valid = true;
+      if (kMN) {
+        c.b = 2 * c.b + (int)rank;
+        valid = c.b < batches_valid;
+      } else {
+        c.mt = 2 * c.mt + (int)rank;
+      }
+      float r[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) r[i] = 0.f;
+      for (int ks0 = kc0, ks1; ks0 < kc1; ks0 = ks1) {
+        ks1 = chain_end(ks0, kc0, kc1, sub_chunks, sub_first);
+        mbar_wait(&tfull[acc], acc_phase, 54);
+#ifdef NSVD_TIMELINE
+        tl_t = clock64();
+        if (tl_on && ks0 == kc0) NSVD_TL0(tl_i, 4, tl_t);
+#endif
+        tc_fence_after();
+        const uint32_t tl = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+        const int nk = (ks1 - ks0) * (BK / 16) * 3;   // MMAs in this chain
+        const float corr = 1.f + kTruncPerMma * (float)nk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v[16];
+          tmem_ld16(tl + Epi::col0(sub, j), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[j * 16 + i] = fmaf(v[i], corr, r[j * 16 + i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+#ifdef NSVD_TIMELINE
+        tl_dr += clock64() - tl_t;
+#endif
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+#ifdef NSVD_TIMELINE
+      if (tl_on) NSVD_TL0(tl_i, 5, clock64());
+#endif
+      if (valid) epi(r, c, q, sub, lane, smem + STAGES * STAGE_BYTES + 256);
+#ifdef NSVD_TIMELINE
+      if (tl_on) {
+        NSVD_TL0(tl_i, 6, clock64());
+        NSVD_TL0(tl_i, 7, tl_dr);
+      }
+      ++tl_i;
+#endif
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still arrive on our barriers / read our shared memory until here
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // plain epilogue: D[b][row][col] = acc   (self-test / generic GEMM)
 struct StoreEpi {
   float* D;
@@ -532,6 +826,25 @@ static int launch_big2(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   if (tiles <= 0) return 0;
   int clusters = tiles < 74 ? tiles : 74;
   kern<<<2 * clusters, big2::THREADS, big2::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, batches_valid, epi);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+constexpr int kFmtHH = tc::PF_HH | (tc::PF_HH << 2);   // fp16 hi/lo planes for both operands
+
+template <bool kMN, class Epi, int FMT>
+static int launch_big2s(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                        const BigShape& shape, int batches_valid, int sub_chunks, int sub_first, const Epi& epi,
+                        cudaStream_t st) {
+  auto kern = big2s_gemm_kernel<kMN, Epi, FMT>;
+  NSVD_SMEM_OPTIN(kern, big2s::SMEM_BYTES);
+  int tiles = shape.m_tiles * shape.n_tiles * shape.batches * shape.k_slices;
+  if (tiles <= 0) return 0;
+  int clusters = tiles < 74 ? tiles : 74;
+  if (sub_chunks <= 0 || sub_chunks > shape.k_chunks_per_slice) sub_chunks = shape.k_chunks_per_slice;
+  if (sub_first < sub_chunks) sub_first = sub_chunks;
+  kern<<<2 * clusters, big2s::THREADS, big2s::SMEM_BYTES, st>>>(ah, al, bh, bl, shape, batches_valid, sub_chunks, sub_first,
+                                                                epi);
   NSVD_LAUNCH_CHECK();
   return 0;
 }
@@ -630,7 +943,12 @@ __device__ __forceinline__ void act_streams(float z0, float z1, float z2, float 
                                             float& a2, float& a3) {
   float e = __expf(-fabsf(z0));
   float u = 1.f + e;
+#ifdef NSVD_RCP_RN
   float inv = __frcp_rn(u);
+#else
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(u));   // one MUFU op, 1 ulp (u in [1, 2])
+#endif
   float sg = z0 >= 0.f ? inv : e * inv;
   a0 = fmaxf(z0, 0.f) + __logf(u);
   a1 = sg * z1;
@@ -665,18 +983,241 @@ __device__ __forceinline__ void load_merge16(const __nv_bfloat16* hi, const __nv
     v[2 * i + 1] = a.y + b.y;
   }
 }
+// fp16 hi/lo (PF_HH) versions
+__device__ __forceinline__ void store_split16h(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tc::split2<tc::PF_HH>(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  uint4* ph = reinterpret_cast<uint4*>(hi);
+  uint4* pl = reinterpret_cast<uint4*>(lo);
+  ph[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  pl[0] = make_uint4(l[0], l[1], l[2], l[3]);
+  pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+__device__ __forceinline__ float merge1h(uint32_t hbits, uint32_t lbits) {   // one fp16 hi + fp16 lo pair -> fp32
+  return __half2float(__ushort_as_half((unsigned short)hbits)) + __half2float(__ushort_as_half((unsigned short)lbits));
+}
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
+// Operand plan.  Every MMA operand v is stored as two fp16 planes of s*v (PF_HH: hi = fp16(s v), lo = fp16(s v - hi)):
+// 22 significant bits for |s v| >= 2^-3 and an absolute error of 2^-25 below (fp16 subnormals are honoured by the tensor
+// cores).  s is a power of two per (tensor, copy, stream) taken from a RIGOROUS bound of |v|, so that |s v| <= 2^15 can
+// never overflow (fp16 max 65504); the bounds are propagated from the weights (forward) and from max|dF| (backward) by
+// the small kernels below - nothing is measured on the activations, nothing depends on an earlier step.  The formulas are
+// restated and checked on the CPU in profiles/scale_plan_emulation.py:
+//   features          |phi_s[j]| <= c_s[j],  c = (1, |B_0j|, |B_1j|, B_0j^2 + B_1j^2)
+//   layer 0           |z_s[h]| <= R0_s = max_h sum_j (|W0[h,j]| + |W0[h,M+j]|) c_s[j]   (+ max|b0| for s = 0)
+//   softplus streams  a_0 <= z_0 + ln 2,  |a_d| <= z_d,  |a_3| <= z_3 + (z_1^2 + z_2^2) / 4
+//   hidden layer i    |z_s| <= (max_h sum_k |W_i[h,k]|) A_s   (+ max|b_i| for s = 0)
+//   backward          |dZ2| <= |c| max|dF| max|W3|,  |dZ_{i-1}| <= (max_k sum_j |W_i[j,k]|) |dZ_i|
+// Why not bf16 planes (round 1): two bf16 planes carry 16 bits, and the 1e-5 per-step error they leave fails the 1e-3
+// fixed-seed trajectory tolerance (tests/test_gpu_training_run.py, profiles/trajectory_emulation.py); three bf16 planes
+// would double the MMA count; mixed fp16 x bf16 MMAs are illegal (profiles/format_probe.py).
+// ------------------------------------------------------------------------------------------
+enum PlanSlot : int {
+  PL_SW0 = 0,      // [4] scale of the folded layer-0 weights, per stream
+  PL_INV_W0 = 4,   // [4] 1 / PL_SW0 (Phi is stored unscaled)
+  PL_SA0 = 8,      // [4] scale of the a0 streams (layer-0 output)
+  PL_SW1 = 12,
+  PL_U1 = 13,      // [4] 1 / (SA0[s] SW1): layer-1 accumulator -> z
+  PL_SA1 = 17,     // [4]
+  PL_SW2 = 21,
+  PL_U2 = 22,      // [4] 1 / (SA1[s] SW2)
+  PL_SA2 = 26,     // value stream only (the derivative streams of a2 never leave the kernel)
+  PL_INV_SA0 = 27, PL_INV_SA1 = 28, PL_INV_SA2 = 29,   // 1 / SA_i[0]: the backward reads the saved value streams
+  PL_SDZ2 = 30, PL_SDZ1 = 31, PL_SDZ0 = 32,            // scales of the dZ_i planes
+  PL_UD2 = 33,     // 1 / (SW2 SDZ2): layer-2 dgrad accumulator -> dA1
+  PL_UD1 = 34,
+  PL_UW2 = 35,     // 1 / (SDZ2 SA1[0]): layer-2 wgrad accumulator -> dW2
+  PL_UW1 = 36,
+  PL_UW0 = 37,     // 1 / SDZ0
+  PL_STRIDE = 40
+};
+constexpr float kPlaneTarget = 32768.f;   // 2^15
+
+__device__ __forceinline__ float pow2_scale(float bound) {
+  if (!(bound > 0.f) || !isfinite(bound)) return 1.f;
+  int e = ilogbf(kPlaneTarget / (bound * 1.001f));   // floor(log2(.)); 1.001 covers the rounding of the bound's own sums
+  e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  return ldexpf(1.f, e);
+}
+
+// one block per row (l, h) of W0: rowstat[(l*128 + h)*5 + s] = sum_j (|W0[h,j]| + |W0[h,M+j]|) c_s[j], [4] = max|W0[h,:]|
+__global__ void __launch_bounds__(256) w0_stats_kernel(const float* __restrict__ W0, const float* __restrict__ Bff,
+                                                       float* __restrict__ rowstat, int M) {
+  const long row = blockIdx.x;
+  const float* w = W0 + row * 2L * M;
+  float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const float ws = fabsf(w[j]), wc = fabsf(w[M + j]), pr = ws + wc;
+    const float b0 = Bff[j], b1 = Bff[M + j];
+    a[0] += pr;
+    a[1] = fmaf(pr, fabsf(b0), a[1]);
+    a[2] = fmaf(pr, fabsf(b1), a[2]);
+    a[3] = fmaf(pr, fmaf(b0, b0, b1 * b1), a[3]);
+    a[4] = fmaxf(a[4], fmaxf(ws, wc));
+  }
+  __shared__ float red[8][5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    float v = a[i];
+    for (int o = 16; o > 0; o >>= 1) {
+      float t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = i == 4 ? fmaxf(v, t) : v + t;
+    }
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float v = red[0][threadIdx.x];
+    for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv)
+      v = threadIdx.x == 4 ? fmaxf(v, red[wv][threadIdx.x]) : v + red[wv][threadIdx.x];
+    rowstat[row * 5 + threadIdx.x] = v;
+  }
+}
+
+// grid (L, 2), 128 threads: hstat[(i*L + l)*3 + {0: max_h sum_k |W[h,k]|, 1: max|W|, 2: max_k sum_h |W[h,k]|}] for W = W_{i+1}[l]
+__global__ void __launch_bounds__(128) hid_stats_kernel(const float* __restrict__ W1, const float* __restrict__ W2,
+                                                        float* __restrict__ hstat, int L) {
+  const int l = blockIdx.x, i = blockIdx.y, t = threadIdx.x;
+  const float* W = (i == 0 ? W1 : W2) + (long)l * kHidden * kHidden;
+  float rs = 0.f, cs = 0.f, mx = 0.f;      // thread t: row t (strided reads, 64 KB in all) and column t (coalesced)
+  for (int k = 0; k < kHidden; ++k) {
+    const float r = fabsf(W[t * kHidden + k]);
+    rs += r;
+    cs += fabsf(W[k * kHidden + t]);
+    mx = fmaxf(mx, r);
+  }
+  __shared__ float red[3][4];
+  float v[3] = {rs, mx, cs};
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    float x = v[q];
+    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    if ((t & 31) == 0) red[q][t >> 5] = x;
+  }
+  __syncthreads();
+  if (t < 3) hstat[((long)i * L + l) * 3 + t] = fmaxf(fmaxf(red[t][0], red[t][1]), fmaxf(red[t][2], red[t][3]));
+}
+
+// one block, 128 threads: forward part of the plan (thread l < L owns copy l)
+__global__ void __launch_bounds__(128) fwd_plan_kernel(const float* __restrict__ rowstat, const float* __restrict__ hstat,
+                                                       const float* __restrict__ Bff, const float* __restrict__ b0,
+                                                       const float* __restrict__ b1, const float* __restrict__ b2,
+                                                       float* __restrict__ plan, int L, int M) {
+  __shared__ float mB[4][4];
+  const int t = threadIdx.x;
+  float c1 = 0.f, c2 = 0.f, c3 = 0.f;
+  for (int j = t; j < M; j += 128) {
+    const float x0 = Bff[j], x1 = Bff[M + j];
+    c1 = fmaxf(c1, fabsf(x0));
+    c2 = fmaxf(c2, fabsf(x1));
+    c3 = fmaxf(c3, fmaf(x0, x0, x1 * x1));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+    c2 = fmaxf(c2, __shfl_xor_sync(0xffffffffu, c2, o));
+    c3 = fmaxf(c3, __shfl_xor_sync(0xffffffffu, c3, o));
+  }
+  if ((t & 31) == 0) {
+    mB[t >> 5][1] = c1;
+    mB[t >> 5][2] = c2;
+    mB[t >> 5][3] = c3;
+  }
+  __syncthreads();
+  if (t >= L) return;
+  const int l = t;
+  float cmax[4] = {1.f, 0.f, 0.f, 0.f};
+  for (int s = 1; s < 4; ++s) cmax[s] = fmaxf(fmaxf(mB[0][s], mB[1][s]), fmaxf(mB[2][s], mB[3][s]));
+  float Z[4] = {0.f, 0.f, 0.f, 0.f}, mW0 = 0.f;
+  for (int h = 0; h < kHidden; ++h) {
+    const float* r = rowstat + ((long)l * kHidden + h) * 5;
+    for (int s = 0; s < 4; ++s) Z[s] = fmaxf(Z[s], r[s]);
+    mW0 = fmaxf(mW0, r[4]);
+  }
+  float* P = plan + (long)l * PL_STRIDE;
+  for (int s = 0; s < 4; ++s) {
+    const float sw = pow2_scale(mW0 * cmax[s]);
+    P[PL_SW0 + s] = sw;
+    P[PL_INV_W0 + s] = 1.f / sw;
+  }
+  const float* bias[3] = {b0, b1, b2};
+  float SA[3][4];
+  for (int i = 0; i < 3; ++i) {
+    float mb = 0.f;
+    for (int h = 0; h < kHidden; ++h) mb = fmaxf(mb, fabsf(bias[i][l * kHidden + h]));
+    Z[0] += mb;
+    float A[4] = {Z[0] + 0.6931472f, Z[1], Z[2], Z[3] + 0.25f * (Z[1] * Z[1] + Z[2] * Z[2])};
+    for (int s = 0; s < 4; ++s) SA[i][s] = pow2_scale(A[s]);
+    if (i < 2) {
+      const float R = hstat[((long)i * L + l) * 3 + 0];
+      for (int s = 0; s < 4; ++s) Z[s] = R * A[s];
+    }
+  }
+  const float sw1 = pow2_scale(hstat[((long)0 * L + l) * 3 + 1]), sw2 = pow2_scale(hstat[((long)1 * L + l) * 3 + 1]);
+  P[PL_SW1] = sw1;
+  P[PL_SW2] = sw2;
+  for (int s = 0; s < 4; ++s) {
+    P[PL_SA0 + s] = SA[0][s];
+    P[PL_SA1 + s] = SA[1][s];
+    P[PL_U1 + s] = 1.f / (SA[0][s] * sw1);
+    P[PL_U2 + s] = 1.f / (SA[1][s] * sw2);
+  }
+  P[PL_SA2] = SA[2][0];
+  P[PL_INV_SA0] = 1.f / SA[0][0];
+  P[PL_INV_SA1] = 1.f / SA[1][0];
+  P[PL_INV_SA2] = 1.f / SA[2][0];
+}
+
+// mdF[l] = max_b |dF[b, l]|  (mdF zero-initialised; non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256) col_absmax_kernel(const float* __restrict__ dF, long n, int L,
+                                                         float* __restrict__ mdF) {
+  // every thread keeps ONE column: the stride of the grid-stride loop is a multiple of L
+  const long stride = ((long)gridDim.x * blockDim.x / L) * L;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (stride == 0 || i >= stride) return;
+  float m = 0.f;
+  for (; i < n; i += stride) m = fmaxf(m, fabsf(dF[i]));
+  atomicMax(reinterpret_cast<unsigned int*>(mdF) + (((long)blockIdx.x * blockDim.x + threadIdx.x) % L), __float_as_uint(m));
+}
+
+// backward part of the plan (one block, thread l < L owns copy l)
+__global__ void __launch_bounds__(128) bwd_plan_kernel(float* __restrict__ plan, const float* __restrict__ hstat,
+                                                       const float* __restrict__ mdF, const float* __restrict__ W3,
+                                                       float hard_mul_const, int L) {
+  const int l = threadIdx.x;
+  if (l >= L) return;
+  float* P = plan + (long)l * PL_STRIDE;
+  float m3 = 0.f;
+  for (int h = 0; h < kHidden; ++h) m3 = fmaxf(m3, fabsf(W3[l * kHidden + h]));
+  const float dz2 = fabsf(hard_mul_const) * mdF[l] * m3;       // sigma <= 1, rho <= 1, masks <= 1
+  const float dz1 = hstat[((long)1 * L + l) * 3 + 2] * dz2;      // column L1 norm of W2
+  const float dz0 = hstat[((long)0 * L + l) * 3 + 2] * dz1;      // column L1 norm of W1
+  const float s2 = pow2_scale(dz2), s1 = pow2_scale(dz1), s0 = pow2_scale(dz0);
+  P[PL_SDZ2] = s2;
+  P[PL_SDZ1] = s1;
+  P[PL_SDZ0] = s0;
+  P[PL_UD2] = 1.f / (P[PL_SW2] * s2);
+  P[PL_UD1] = 1.f / (P[PL_SW1] * s1);
+  P[PL_UW2] = 1.f / (s2 * P[PL_SA1]);
+  P[PL_UW1] = 1.f / (s1 * P[PL_SA0]);
+  P[PL_UW0] = 1.f / s0;
+}
+
+// ------------------------------------------------------------------------------------------
 // weight / feature preparation (SIMT, HBM-bound, tiny next to the GEMMs)
 // ------------------------------------------------------------------------------------------
 // Folded layer-0 weights: all four streams are W'_s . [sin p ; cos p]   (probe10)
-//   rows n = l*512 + (h/64)*256 + s*64 + (h%64),  K-major, hi/lo planes.
+//   rows n = l*512 + (h/64)*256 + s*64 + (h%64),  K-major, fp16 hi/lo planes of PL_SW0[s] * W'_s.
 __global__ void fold_w0_kernel(const float* __restrict__ W0, const float* __restrict__ Bff,
-                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int L, int M) {
+                               const float* __restrict__ plan, __nv_bfloat16* __restrict__ hi,
+                               __nv_bfloat16* __restrict__ lo, int L, int M) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long n = (long)L * kHidden * M;
   if (i >= n) return;
@@ -689,42 +1230,44 @@ __global__ void fold_w0_kernel(const float* __restrict__ W0, const float* __rest
   float vs[4] = {ws, -wc * b0, -wc * b1, nb2 * ws};  // coefficient of sin p_j
   float vc[4] = {wc, ws * b0, ws * b1, nb2 * wc};    // coefficient of cos p_j
   long rbase = (long)l * 512 + (h / 64) * 256 + (h % 64);
+  uint16_t* hi16 = reinterpret_cast<uint16_t*>(hi);
+  uint16_t* lo16 = reinterpret_cast<uint16_t*>(lo);
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
+    const float sc = plan[(long)l * PL_STRIDE + PL_SW0 + s];
     long o = (rbase + s * 64) * K0;
-    __nv_bfloat16 a, b;
-    tc::split_bf16(vs[s], a, b);
-    hi[o + j] = a;
-    lo[o + j] = b;
-    tc::split_bf16(vc[s], a, b);
-    hi[o + M + j] = a;
-    lo[o + M + j] = b;
+    uint16_t a, b;
+    tc::split1<tc::PF_HH>(vs[s] * sc, a, b);
+    hi16[o + j] = a;
+    lo16[o + j] = b;
+    tc::split1<tc::PF_HH>(vc[s] * sc, a, b);
+    hi16[o + M + j] = a;
+    lo16[o + M + j] = b;
   }
 }
 
-// out[l][c][r] = in[l][r][c] when transpose (128x128 blocks), hi/lo planes
-__global__ void split_w_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ hi,
-                               __nv_bfloat16* __restrict__ lo, int L, int transpose) {
+// out[l][c][r] = in[l][r][c] when transpose (128x128 blocks), fp16 hi/lo planes of plan[slot] * W
+__global__ void split_w_kernel(const float* __restrict__ W, const float* __restrict__ plan, int slot,
+                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int L, int transpose) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long n = (long)L * kHidden * kHidden;
   if (i >= n) return;
   int c = (int)(i % kHidden), r = (int)((i / kHidden) % kHidden), l = (int)(i / (kHidden * kHidden));
   float v = transpose ? W[((long)l * kHidden + c) * kHidden + r] : W[i];
-  __nv_bfloat16 a, b;
-  tc::split_bf16(v, a, b);
-  hi[i] = a;
-  lo[i] = b;
+  uint16_t a, b;
+  tc::split1<tc::PF_HH>(v * plan[(long)l * PL_STRIDE + slot], a, b);
+  reinterpret_cast<uint16_t*>(hi)[i] = a;
+  reinterpret_cast<uint16_t*>(lo)[i] = b;
 }
 
-// Phi = [sin(x B), cos(x B)] as bf16 hi/lo planes (B, 2M)   (examples/utils.py:139-140)
+// Phi = [sin(x B), cos(x B)] as fp16 hi/lo planes (B, 2M), unscaled (|Phi| <= 1)   (examples/utils.py:139-140)
 // One thread = 4 consecutive features of one point (8-byte stores).  The phase p = x.B is formed in fp32 exactly
 // like the reference; a two-constant Cody-Waite step (k = rint(p / 2pi), r = p - k 2pi_hi - k 2pi_lo with FMAs,
-// 3.5e-8 rms error) brings it to [-pi, pi], where the MUFU sine / cosine are accurate to 5e-7 absolute (the accurate
-// sincospif path cost 0.14 ms/step more for an error that the hi/lo rounding hides).  Reducing in turns (p / 2pi in fp32) was measured to add 5e-7..1.2e-6 rms per feature, i.e. as much
-// as the bf16 hi/lo rounding itself, and is not used.
-__global__ void features_bf16_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
-                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long P,
-                                     int M) {
+// 3.5e-8 rms error) brings it to [-pi, pi].  kAccurate: sinf / cosf of the reduced argument (1 ulp) - the fp16 hi/lo
+// planes carry 2^-22, so the 5e-7 of the MUFU approximations would be the largest error of the whole layer.
+__global__ void features_f16_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long P,
+                                    int M) {
   const int M4 = M >> 2;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * M4) return;
@@ -741,17 +1284,16 @@ __global__ void features_bf16_kernel(const float* __restrict__ x, const float* _
     float kq = rintf(ph * 0.15915494309189535f);
     float r = fmaf(-kq, 6.2831855f, ph);          // 2pi_hi = fl(2 pi)
     r = fmaf(-kq, -1.7484555e-07f, r);            // 2pi_lo = 2 pi - 2pi_hi
-    sn[k] = __sinf(r);   // MUFU on the reduced argument: abs error <= 2^-20.9 (PTX sin.approx), 15x below the
-    cs[k] = __cosf(r);   // 2^-17 relative rounding of the hi/lo split that follows
+    sincosf(r, &sn[k], &cs[k]);                   // |r| <= pi: the fast path of sincosf (no Payne-Hanek)
   }
   uint32_t h0, l0, h1, l1;
   long o = p * 2L * M + j;
-  tc::split_bf16x2(sn[0], sn[1], h0, l0);
-  tc::split_bf16x2(sn[2], sn[3], h1, l1);
+  tc::split2<tc::PF_HH>(sn[0], sn[1], h0, l0);
+  tc::split2<tc::PF_HH>(sn[2], sn[3], h1, l1);
   *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
   *reinterpret_cast<uint2*>(lo + o) = make_uint2(l0, l1);
-  tc::split_bf16x2(cs[0], cs[1], h0, l0);
-  tc::split_bf16x2(cs[2], cs[3], h1, l1);
+  tc::split2<tc::PF_HH>(cs[0], cs[1], h0, l0);
+  tc::split2<tc::PF_HH>(cs[2], cs[3], h1, l1);
   *reinterpret_cast<uint2*>(hi + o + M) = make_uint2(h0, h1);
   *reinterpret_cast<uint2*>(lo + o + M) = make_uint2(l0, l1);
 }
@@ -763,66 +1305,113 @@ __global__ void features_bf16_kernel(const float* __restrict__ x, const float* _
 // ------------------------------------------------------------------------------------------
 struct L0FwdEpi {
   const float* bias;            // b0 (L,128)
+  const float* plan;            // operand plan (PL_* slots per copy)
   __nv_bfloat16 *str_hi, *str_lo;  // [L][4][P][128]
   __nv_bfloat16 *sav_hi, *sav_lo;  // [L][Btot][128]
   int P;
   long Btot, p_off;
-  __device__ __forceinline__ void operator()(uint32_t tmem_acc, const TileCoord& c, int ewarp, int lane) const {
-    const int q = ewarp & 3, half = ewarp >> 2;
-    const int pt = c.mt * big::BM + q * 32 + lane;
-    const int l = c.b, hc = c.nt;
-    const uint32_t tl = tmem_acc + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-    for (int ch = 0; ch < 2; ++ch) {
-      const int hh = half * 32 + ch * 16;
-      float z[4][16];
+  // accumulator group j of epilogue warp `sub` = stream j, hidden units [16 sub, 16 sub + 16) of the tile's 64
+  __device__ static __forceinline__ uint32_t col0(int sub, int j) { return (uint32_t)(j * 64 + sub * 16); }
+  __device__ __forceinline__ void operator()(float (&r)[64], const TileCoord& c, int q, int sub, int lane,
+                                             uint8_t* staging) const {
+    const int l = c.b, h0 = c.nt * 64 + sub * 16;
+    const float* pl = plan + (long)l * PL_STRIDE;
+    const float i0 = __ldg(pl + PL_INV_W0), i1 = __ldg(pl + PL_INV_W0 + 1), i2 = __ldg(pl + PL_INV_W0 + 2),
+                i3 = __ldg(pl + PL_INV_W0 + 3);
+    const float s0 = __ldg(pl + PL_SA0), s1 = __ldg(pl + PL_SA0 + 1), s2 = __ldg(pl + PL_SA0 + 2),
+                s3 = __ldg(pl + PL_SA0 + 3);
+    float bs[16];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) tc::tmem_ld16(tl + s * 64 + hh, z[s]);
-      tc::tmem_ld_wait();
-      const int h0 = hc * 64 + hh;
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + l * kHidden + h0) + i);
+      bs[4 * i] = b4.x;
+      bs[4 * i + 1] = b4.y;
+      bs[4 * i + 2] = b4.z;
+      bs[4 * i + 3] = b4.w;
+    }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float zb = z[0][i] + __ldg(bias + l * kHidden + h0 + i);
-        act_streams(zb, z[1][i], z[2][i], z[3][i], z[0][i], z[1][i], z[2][i], z[3][i]);
-      }
-      if (pt < P) {
-        // the value stream lives only in `saved` (the next layer and the backward both read it there);
-        // the derivative streams go to the micro-batch stream buffer
+    for (int i = 0; i < 16; ++i) {
+      const float zb = fmaf(r[i], i0, bs[i]);
+      float a0, a1, a2, a3;
+#ifdef NSVD_PROBE_NOMATH
+      a0 = zb; a1 = r[16 + i] * i1; a2 = r[32 + i] * i2; a3 = r[48 + i] * i3;
+#else
+      act_streams(zb, r[16 + i] * i1, r[32 + i] * i2, r[48 + i] * i3, a0, a1, a2, a3);
+#endif
+      r[i] = a0 * s0;
+      r[16 + i] = a1 * s1;
+      r[32 + i] = a2 * s2;
+      r[48 + i] = a3 * s3;
+    }
+    // Stores.  A thread holds 16 units (32 bytes per plane) of ONE point row; written directly, every store
+    // instruction would touch 32 different 128-byte lines (measured: 12k of the epilogue's 14k cycles,
+    // profiles/timeline_l0_probe.py).  The four warps of a TMEM lane quarter (sub = 0..3: units [16 sub, +16) of the same
+    // 32 rows) therefore stage one (stream, plane) at a time in shared memory as [32 rows][128 B] (16-byte pieces
+    // XOR-swizzled with the row: conflict-free both ways) and write it back with every instruction covering four
+    // full lines.  Two 4 KB buffers per quarter alternate, so one named barrier per round suffices.
+    uint8_t* stq = staging + q * 8192;
+    const int gt = sub * 32 + lane;                     // thread index inside the quarter group (128 threads)
+    const int row_base = c.mt * big::BM + q * 32;       // first point row of the quarter inside the micro-batch
+    const uint32_t wr0 = (uint32_t)lane * 128 + ((uint32_t)((sub * 2) ^ (lane & 7)) << 4);
+    const uint32_t wr1 = (uint32_t)lane * 128 + ((uint32_t)((sub * 2 + 1) ^ (lane & 7)) << 4);
 #pragma unroll
-        for (int s = 1; s < 4; ++s) {
-          long o = (((long)l * 4 + s) * P + pt) * kHidden + h0;
-          store_split16(z[s], str_hi + o, str_lo + o);
+    for (int st = 0; st < 4; ++st) {
+      uint32_t h[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tc::split2<tc::PF_HH>(r[st * 16 + 2 * i], r[st * 16 + 2 * i + 1], h[i], lo[i]);
+#pragma unroll
+      for (int plane = 0; plane < 2; ++plane) {
+        uint8_t* buf = stq + ((st * 2 + plane) & 1) * 4096;
+        const uint32_t* w = plane ? lo : h;
+        *reinterpret_cast<uint4*>(buf + wr0) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(buf + wr1) = make_uint4(w[4], w[5], w[6], w[7]);
+        tc::named_bar_sync(1 + q, 128);
+        // destination of this (stream, plane): the value stream lives only in `saved` (the next layer and the backward
+        // both read it there); the derivative streams go to the micro-batch stream buffer
+        __nv_bfloat16* dst = st == 0 ? (plane ? sav_lo : sav_hi) + ((long)l * Btot + p_off) * kHidden
+                                     : (plane ? str_lo : str_hi) + ((long)l * 4 + st) * (long)P * kHidden;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int piece = gt + 128 * k, rr = piece >> 3, cc = piece & 7;
+          const int pt = row_base + rr;
+#ifdef NSVD_PROBE_NOSTORE
+          if (pt < P && r[0] == 12345.678f)
+#else
+          if (pt < P)
+#endif
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst + (long)pt * kHidden + c.nt * 64) + cc * 16) =
+                *reinterpret_cast<const uint4*>(buf + rr * 128 + ((cc ^ (rr & 7)) << 4));
         }
-        long o = ((long)l * Btot + p_off + pt) * kHidden + h0;
-        store_split16(z[0], sav_hi + o, sav_lo + o);
       }
     }
+    tc::named_bar_sync(1 + q, 128);   // the last round's reads are done before the next tile's first write
   }
 };
 
 // layer-0 weight-gradient epilogue (S1, MN-major): tile = (copy l, 256 features, k-slice of points)
-//   dW0[l][j][n] += acc   (fp32 vector reductions in L2)
+//   dW0[l][j][n] += acc / SDZ0[l]   (fp32 vector reductions in L2)
 struct L0WgradEpi {
   float* dW0;
+  const float* plan;
   int K0;
-  __device__ __forceinline__ void operator()(uint32_t tmem_acc, const TileCoord& c, int ewarp, int lane) const {
-    const int q = ewarp & 3, half = ewarp >> 2;
+  __device__ static __forceinline__ uint32_t col0(int sub, int j) { return (uint32_t)(sub * 64 + j * 16); }
+  __device__ __forceinline__ void operator()(float (&r)[64], const TileCoord& c, int q, int sub, int lane,
+                                             uint8_t*) const {
     const int j = q * 32 + lane;
     float* drow = dW0 + ((long)c.b * kHidden + j) * K0;
-    const uint32_t tl = tmem_acc + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-    for (int ch = 0; ch < 8; ++ch) {
-      const int col0 = half * 128 + ch * 16;
-      float v[16];
-      tc::tmem_ld16(tl + col0, v);
-      tc::tmem_ld_wait();
-      const int n0 = c.nt * big::BN + col0;
+    const float un = __ldg(plan + (long)c.b * PL_STRIDE + PL_UW0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int n0 = c.nt * big::BN + sub * 64 + g * 16;
       if (n0 + 16 <= K0) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) red_add_v4(drow + n0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 16; i += 4)
+          red_add_v4(drow + n0 + i, r[g * 16 + i] * un, r[g * 16 + i + 1] * un, r[g * 16 + i + 2] * un,
+                     r[g * 16 + i + 3] * un);
       } else {
+#pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (n0 + i < K0) atomicAdd(drow + n0 + i, v[i]);
+          if (n0 + i < K0) atomicAdd(drow + n0 + i, r[g * 16 + i] * un);
       }
     }
   }
@@ -871,6 +1460,8 @@ struct HidFwdArgs {
   int L, P, m_tiles;
   long Btot, p_off;
   const float* bias;                 // b_i (L,128)
+  const float* plan;                 // operand plan
+  int u_slot, sa_slot;               // PL_U1 / PL_U2 (accumulator -> z, per stream), PL_SA1 / PL_SA2 (output scales)
   // kLast only
   const float* W3;                   // (L,128)
   const float* b3;                   // (L)
@@ -988,7 +1579,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, 0, false, false);   // fp16 x fp16 planes
       int stage = 0, cur_l = -1;
       uint32_t phase = 0, wphase = 0, tphase = 0;
       const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + PLANE;
@@ -1043,6 +1634,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     const uint32_t piece0 = (uint32_t)row * 64 + (((uint32_t)sub ^ sw) << 4);
     uint32_t tphase = 0;
     int cur_l = -1;
+    float un[4] = {1.f, 1.f, 1.f, 1.f}, so[4] = {1.f, 1.f, 1.f, 1.f};   // accumulator -> z ; activation -> stored plane
     for (int t = t_begin; t < t_end; ++t) {
       const int l = t / args.m_tiles, mt = t % args.m_tiles;
       const int pt = mt * 128 + row;
@@ -1050,6 +1642,12 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         if (et < 128) {
           bias_s[et] = args.bias[l * kHidden + et];
           if (kLast) w3_s[et] = args.W3[l * kHidden + et];
+        }
+        const float* pl = args.plan + (long)l * PL_STRIDE;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          un[s] = __ldg(pl + args.u_slot + s) * (1.f + kTruncPerMma * 24.f);   // K = 128: chains of 24 MMAs
+          so[s] = __ldg(pl + args.sa_slot + (kLast ? 0 : s));
         }
         cur_l = l;
         named_bar_sync(1, F_EPI_WARPS * 32);
@@ -1074,8 +1672,8 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float zb = z[0][i] + bias_s[h0 + i];
-          act_streams(zb, z[1][i], z[2][i], z[3][i], z[0][i], z[1][i], z[2][i], z[3][i]);
+          float zb = fmaf(z[0][i], un[0], bias_s[h0 + i]);
+          act_streams(zb, z[1][i] * un[1], z[2][i] * un[2], z[3][i] * un[3], z[0][i], z[1][i], z[2][i], z[3][i]);
         }
         if (kLast) {
 #pragma unroll
@@ -1097,7 +1695,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         for (int s = 0; s < (kLast ? 1 : 4); ++s) {
           uint32_t h[4], lo[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) split_bf16x2(z[s][2 * i], z[s][2 * i + 1], h[i], lo[i]);
+          for (int i = 0; i < 4; ++i) split2<PF_HH>(z[s][2 * i] * so[s], z[s][2 * i + 1] * so[s], h[i], lo[i]);
           uint8_t* bh = sO + (sb + 2 * s) * F_BOX;
           uint8_t* bl = bh + F_BOX;
           *reinterpret_cast<uint4*>(bh + piece0) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -1161,7 +1759,11 @@ struct HidBwdArgs {
   long Btot, p_off;
   float* dW;                                 // (L,128,128) accumulated with reductions
   float* db_prev;                            // (L,128) accumulated with atomics
+  const float* plan;                         // operand plan
+  int ud_slot, inv_sa_slot, sdz_slot, uw_slot;   // dgrad accumulator -> dA ; saved a_{i-1} plane -> a ; scale of the
+                                                 // dZ_{i-1} planes written ; wgrad accumulator -> dW_i
 };
+constexpr int kWgradFlush = 4;   // half tiles (64 points) per TMEM accumulation chain of the hidden-layer weight gradient
 
 // ------------------------------------------------------------------------------------------
 // S2-bwd: backward of hidden layer i for one copy.  One pass over dZ_i produces BOTH the input gradient
@@ -1226,11 +1828,16 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
     mbar_init(wfull, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;       // columns [0,64) and [64,128): dgrad buffers; [128,256): wgrad
+  // columns [0,64) and [64,128): dgrad buffers; [128,256) and [256,384): wgrad buffers.  The wgrad chain is restarted
+  // every kWgradFlush half tiles in the other buffer (TMEM accumulation truncates: 48 chained MMAs = 9e-7) and the
+  // finished chain is added to register accumulators by the epilogue threads.  Re-using a wgrad buffer two chains later
+  // needs no barrier of its own: the MMAs of half tile j wait for full[j & 1], which is loaded only after the epilogue
+  // of half tile j - 2 (including its drain) has released the stage.
+  const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d2 = tmem_base + 128;
 
   if (warp == 0) {
@@ -1267,12 +1874,11 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_d = make_idesc_bf16(128, HROWS, 0, 0);  // dgrad: K-major, M = units, N = points
-      constexpr uint32_t idesc_w = make_idesc_bf16(128, 128, 1, 1);    // wgrad: MN-major operands
+      constexpr uint32_t idesc_d = make_idesc_f16(128, HROWS, 0, 0, false, false);  // dgrad: K-major, M = units, N = points
+      constexpr uint32_t idesc_w = make_idesc_f16(128, 128, 1, 1, false, false);    // wgrad: MN-major operands
       const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + PLANE;
-      int cur_l = -1;
+      int cur_l = -1, hrun = 0, cidx = -1;
       uint32_t wphase = 0;
-      bool first_of_run = true;
       for (int t = t_begin; t < t_end; ++t) {
         const int j = t - t_begin, s = j & 1, u = j >> 1;
         const int l = t / h_tiles;
@@ -1280,8 +1886,12 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
           mbar_wait(wfull, wphase, 42);
           wphase ^= 1;
           cur_l = l;
-          first_of_run = true;
+          hrun = 0;
         }
+        const bool first_of_chain = (hrun % kWgradFlush) == 0;
+        if (first_of_chain) ++cidx;
+        const uint32_t tmem_w = tmem_d2 + (uint32_t)(cidx & 1) * 128;
+        ++hrun;
         mbar_wait(&full[s], (uint32_t)(u & 1), 43);   // implies stage s and TMEM buffer s were released
         tc_fence_after();
         const uint32_t z_hi = smem_u32(sS + s * B2_STAGE), z_lo = z_hi + HPLANE;
@@ -1301,12 +1911,11 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
           const uint32_t off = kk * 2048;
           uint64_t ah = make_sdesc_sw128(z_hi + off, HCHUNK, 1024), al = make_sdesc_sw128(z_lo + off, HCHUNK, 1024);
           uint64_t bh = make_sdesc_sw128(a_hi + off, HCHUNK, 1024), bl = make_sdesc_sw128(a_lo + off, HCHUNK, 1024);
-          umma_f16(tmem_d2, al, bh, idesc_w, (first_of_run && kk == 0) ? 0u : 1u);
-          umma_f16(tmem_d2, ah, bl, idesc_w, 1u);
-          umma_f16(tmem_d2, ah, bh, idesc_w, 1u);
+          umma_f16(tmem_w, al, bh, idesc_w, (first_of_chain && kk == 0) ? 0u : 1u);
+          umma_f16(tmem_w, ah, bl, idesc_w, 1u);
+          umma_f16(tmem_w, ah, bh, idesc_w, 1u);
         }
         umma_commit(&mma_done[s]);
-        first_of_run = false;
       }
     }
   } else if (warp == 3) {
@@ -1336,9 +1945,25 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
     const uint32_t koff = (uint32_t)((k >> 6) * HCHUNK + (k & 7) * 2);
     const int piece = (k & 63) >> 3;
     float dbacc = 0.f;
+    float wacc[32];                 // dW_i[row k][cg*32 .. cg*32+31] of the current copy, summed over finished chains
+#pragma unroll
+    for (int i = 0; i < 32; ++i) wacc[i] = 0.f;
+    int cur_l = -1, hrun = 0, cidx = -1;
+    float ud = 1.f, inv_sa = 1.f, sdz = 1.f, uw = 1.f;
     for (int t = t_begin; t < t_end; ++t) {
       const int j = t - t_begin, s = j & 1, u = j >> 1;
       const int l = t / h_tiles;
+      if (l != cur_l) {
+        const float* pl = args.plan + (long)l * PL_STRIDE;
+        ud = __ldg(pl + args.ud_slot) * (1.f + kTruncPerMma * 24.f);   // dgrad: K = 128, chains of 24 MMAs
+        inv_sa = __ldg(pl + args.inv_sa_slot);
+        sdz = __ldg(pl + args.sdz_slot);
+        uw = __ldg(pl + args.uw_slot);
+        cur_l = l;
+        hrun = 0;
+      }
+      if ((hrun % kWgradFlush) == 0) ++cidx;
+      ++hrun;
       mbar_wait(&mma_done[s], (uint32_t)(u & 1), 45);
       tc_fence_after();
       float v[16];
@@ -1352,25 +1977,34 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
         const uint32_t off = koff + (uint32_t)(pt * 128 + ((piece ^ (pt & 7)) << 4));
         const uint32_t ahb = *reinterpret_cast<const uint16_t*>(st + 2 * HPLANE + off);
         const uint32_t alb = *reinterpret_cast<const uint16_t*>(st + 3 * HPLANE + off);
-        const float a = __uint_as_float(ahb << 16) + __uint_as_float(alb << 16);
-        const float val = v[i] * sig_fast(a);
+        const float a = merge1h(ahb, alb) * inv_sa;
+        const float val = v[i] * ud * sig_fast(a);
         dbacc += val;
-        const __nv_bfloat16 h = __float2bfloat16_rn(val);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(h));
-        *reinterpret_cast<__nv_bfloat16*>(st + off) = h;
-        *reinterpret_cast<__nv_bfloat16*>(st + HPLANE + off) = lo;
+        uint16_t h16, l16;
+        split1<PF_HH>(val * sdz, h16, l16);
+        *reinterpret_cast<uint16_t*>(st + off) = h16;
+        *reinterpret_cast<uint16_t*>(st + HPLANE + off) = l16;
       }
       const bool last_of_run = (t + 1 == t_end) || ((t + 1) / h_tiles != l);
-      if (last_of_run) {
-        float* drow = args.dW + ((long)l * kHidden + k) * kHidden;   // wgrad accumulator: lane = row j of dW
-#pragma unroll 1
+      if (last_of_run || (hrun % kWgradFlush) == 0) {       // the wgrad chain in buffer cidx & 1 is complete
+        const uint32_t tw = tl + 128 + (uint32_t)(cidx & 1) * 128 + (uint32_t)(cg * 32);
+        const int nh = ((hrun - 1) % kWgradFlush) + 1;                  // half tiles in this chain, 12 MMAs each
+        const float corr = 1.f + kTruncPerMma * (float)(12 * nh);
+#pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-          const int k0 = cg * 32 + ch * 16;
           float w[16];
-          tmem_ld16(tl + 128 + k0, w);
+          tmem_ld16(tw + ch * 16, w);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) red_add_v4(drow + k0 + 4 * i, w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          for (int i = 0; i < 16; ++i) wacc[ch * 16 + i] = fmaf(w[i], corr, wacc[ch * 16 + i]);
+        }
+      }
+      if (last_of_run) {
+        float* drow = args.dW + ((long)l * kHidden + k) * kHidden + cg * 32;   // lane = row j of dW
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          red_add_v4(drow + i, wacc[i] * uw, wacc[i + 1] * uw, wacc[i + 2] * uw, wacc[i + 3] * uw);
+          wacc[i] = wacc[i + 1] = wacc[i + 2] = wacc[i + 3] = 0.f;
         }
         atomicAdd(args.db_prev + l * kHidden + k, dbacc);
         dbacc = 0.f;
@@ -1384,7 +2018,7 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1397,6 +2031,7 @@ __global__ void __launch_bounds__(128)
 head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
                      const __nv_bfloat16* __restrict__ a2_hi, const __nv_bfloat16* __restrict__ a2_lo,
                      const float* __restrict__ W3, const float* __restrict__ x, const float* __restrict__ mscales,
+                     const float* __restrict__ plan,
                      nsvd_problem_t pb, __nv_bfloat16* __restrict__ dz_hi, __nv_bfloat16* __restrict__ dz_lo,
                      float* __restrict__ dW3, float* __restrict__ db3, float* __restrict__ db2,
                      float* __restrict__ dscales, int P, long Btot, long p_off) {
@@ -1409,6 +2044,7 @@ head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
 #pragma unroll
   for (int i = 0; i < 4; ++i) w3[i] = W3[l * kHidden + lane * 4 + i];
   float sc = pb.has_exp_mask ? mscales[l] : 1.f;
+  const float inv_sa2 = plan[(long)l * PL_STRIDE + PL_INV_SA2], sdz2 = plan[(long)l * PL_STRIDE + PL_SDZ2];
   // each warp owns 32 consecutive points: lane i evaluates the per-point factor du of point i once, then the
   // warp walks the 32 points with 4 rows of a2 in flight (lane = 4 hidden units)
   {
@@ -1438,13 +2074,10 @@ head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
         const int p = pw + j0 + u;
         const float du = __shfl_sync(0xffffffffu, du_l, j0 + u);
         if (p >= p_end) continue;
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&h[u]);
-        const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&lo2[u]);
         float a[4];
         {
-          float2 t0 = __bfloat1622float2(hh[0]), t1 = __bfloat1622float2(hh[1]);
-          float2 u0 = __bfloat1622float2(ll[0]), u1 = __bfloat1622float2(ll[1]);
-          a[0] = t0.x + u0.x; a[1] = t0.y + u0.y; a[2] = t1.x + u1.x; a[3] = t1.y + u1.y;
+          float2 t0 = tc::merge2<tc::PF_HH>(h[u].x, lo2[u].x), t1 = tc::merge2<tc::PF_HH>(h[u].y, lo2[u].y);
+          a[0] = t0.x * inv_sa2; a[1] = t0.y * inv_sa2; a[2] = t1.x * inv_sa2; a[3] = t1.y * inv_sa2;
         }
         float dz[4];
 #pragma unroll
@@ -1454,8 +2087,8 @@ head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
           accB[i] += dz[i];
         }
         uint32_t h01, l01, h23, l23;
-        tc::split_bf16x2(dz[0], dz[1], h01, l01);
-        tc::split_bf16x2(dz[2], dz[3], h23, l23);
+        tc::split2<tc::PF_HH>(dz[0] * sdz2, dz[1] * sdz2, h01, l01);
+        tc::split2<tc::PF_HH>(dz[2] * sdz2, dz[3] * sdz2, h23, l23);
         const long oz = ((long)l * P + p) * kHidden + lane * 4;
         *reinterpret_cast<uint2*>(dz_hi + oz) = make_uint2(h01, h23);
         *reinterpret_cast<uint2*>(dz_lo + oz) = make_uint2(l01, l23);
@@ -1505,7 +2138,7 @@ static int tc_micro_batch() {
 
 struct TcLayout {
   // saved (whole batch)
-  size_t phi_hi, phi_lo, av_hi[3], av_lo[3], u0, saved_total;
+  size_t phi_hi, phi_lo, av_hi[3], av_lo[3], u0, plan, rowstat, hstat, mdf, saved_total;
   // work
   size_t w0_hi, w0_lo, w_hi[2], w_lo[2], str_hi[2], str_lo[2], dz_hi[2], dz_lo[2], work_total;
   long P;
@@ -1529,6 +2162,10 @@ static TcLayout tc_layout(const nsvd_problem_t& pb) {
     t.av_lo[i] = take(L * B * H * 2);
   }
   t.u0 = take(B * L * 4);
+  t.plan = take(L * PL_STRIDE * 4);        // operand plan: written by the forward, completed and read by the backward
+  t.rowstat = take(L * H * 5 * 4);
+  t.hstat = take(2 * L * 3 * 4);
+  t.mdf = take(L * 4);
   t.saved_total = o + 1024;
   o = 0;
   t.w0_hi = take(L * 512 * K0 * 2);
@@ -1585,22 +2222,31 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
   uint8_t* sv = align1k(saved_v);
   uint8_t* wk = align1k(work_v);
   int rc;
-  // ---- per-call preparation: features of all points, folded / split weights
+  // ---- per-call preparation: operand plan, features of all points, folded / split weights
+  float* plan = reinterpret_cast<float*>(sv + t.plan);
+  float* rowstat = reinterpret_cast<float*>(sv + t.rowstat);
+  float* hstat = reinterpret_cast<float*>(sv + t.hstat);
   {
   ProfScope prep(KC_PREP, st);
-  features_bf16_kernel<<<cdiv(B * (M / 4), 256), 256, 0, st>>>(x, pr.Bff, BF(sv + t.phi_hi), BF(sv + t.phi_lo), B, (int)M);
+  w0_stats_kernel<<<(unsigned)(L * H), 256, 0, st>>>(pr.W[0], pr.Bff, rowstat, (int)M);
   NSVD_LAUNCH_CHECK();
-  fold_w0_kernel<<<cdiv(L * H * M, 256), 256, 0, st>>>(pr.W[0], pr.Bff, BF(wk + t.w0_hi), BF(wk + t.w0_lo), (int)L,
+  hid_stats_kernel<<<dim3((unsigned)L, 2), 128, 0, st>>>(pr.W[1], pr.W[2], hstat, (int)L);
+  NSVD_LAUNCH_CHECK();
+  fwd_plan_kernel<<<1, 128, 0, st>>>(rowstat, hstat, pr.Bff, pr.b[0], pr.b[1], pr.b[2], plan, (int)L, (int)M);
+  NSVD_LAUNCH_CHECK();
+  features_f16_kernel<<<cdiv(B * (M / 4), 256), 256, 0, st>>>(x, pr.Bff, BF(sv + t.phi_hi), BF(sv + t.phi_lo), B, (int)M);
+  NSVD_LAUNCH_CHECK();
+  fold_w0_kernel<<<cdiv(L * H * M, 256), 256, 0, st>>>(pr.W[0], pr.Bff, plan, BF(wk + t.w0_hi), BF(wk + t.w0_lo), (int)L,
                                                        (int)M);
   NSVD_LAUNCH_CHECK();
   for (int i = 0; i < 2; ++i) {
-    split_w_kernel<<<cdiv(L * H * H, 256), 256, 0, st>>>(pr.W[i + 1], BF(wk + t.w_hi[i]), BF(wk + t.w_lo[i]), (int)L, 0);
+    split_w_kernel<<<cdiv(L * H * H, 256), 256, 0, st>>>(pr.W[i + 1], plan, i == 0 ? PL_SW1 : PL_SW2, BF(wk + t.w_hi[i]),
+                                                         BF(wk + t.w_lo[i]), (int)L, 0);
     NSVD_LAUNCH_CHECK();
   }
   }
   CUtensorMap mW0h, mW0l, mWh[2], mWl[2];
-  const bool pair = tc_use_pair();
-  const uint32_t w0_box = pair ? big::BN / 2 : big::BN;   // a CTA of a pair loads half of the 256 W' rows
+  const uint32_t w0_box = big::BN / 2;   // a CTA of a pair loads half of the 256 W' rows
   if ((rc = make_tmap_bf16_3d(&mW0h, wk + t.w0_hi, K0, 512, L, K0 * 2, 512 * K0 * 2, 64, w0_box))) return rc;
   if ((rc = make_tmap_bf16_3d(&mW0l, wk + t.w0_lo, K0, 512, L, K0 * 2, 512 * K0 * 2, 64, w0_box))) return rc;
   for (int i = 0; i < 2; ++i) {
@@ -1624,16 +2270,16 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
     s.a_batched = 0;
     s.b_batched = 1;
     static const int mgroup = env_int("NSVD_L0_MGROUP", 16);
-    s.m_group = pair ? mgroup : 2 * mgroup;   // 4096 points x 8 KB of Phi per group
-    L0FwdEpi e0{pr.b[0], BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), BF(sv + t.av_hi[0]), BF(sv + t.av_lo[0]), P, B, p0};
+    s.m_group = mgroup;   // 4096 points x 8 KB of Phi per group
+    L0FwdEpi e0{pr.b[0], plan, BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), BF(sv + t.av_hi[0]), BF(sv + t.av_lo[0]), P, B, p0};
     {
       ProfScope ps(KC_L0_FWD, st);
-      if (pair) {
-        s.m_tiles = cdiv(P, 2 * big::BM);
-        if ((rc = launch_big2<false>(mPh, mPl, mW0h, mW0l, s, (int)L, e0, st))) return rc;
-      } else {
-        if ((rc = launch_big<false>(mPh, mPl, mW0h, mW0l, s, e0, st))) return rc;
-      }
+      // K0 in sub-chains of 4 chunks (K = 256, 48 chained MMAs per TMEM accumulation), the first two of a tile 6 chunks.
+      // Chains of 8 chunks miss the fixed-seed trajectory tolerance (profiles/trajectory_probe.py: 1.6e-3 vs 4.7e-4).
+      static const int sub = env_int("NSVD_L0_SUBCHUNKS", 4);
+      s.m_tiles = cdiv(P, 2 * big::BM);
+      static const int sub_first = env_int("NSVD_L0_SUBFIRST", 6);
+      if ((rc = launch_big2s<false, L0FwdEpi, kFmtHH>(mPh, mPl, mW0h, mW0l, s, (int)L, sub, sub_first, e0, st))) return rc;
     }
     // ---- hidden layers 1, 2
     for (int i = 0; i < 2; ++i) {
@@ -1657,6 +2303,9 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
       a.Btot = B;
       a.p_off = p0;
       a.bias = pr.b[i + 1];
+      a.plan = plan;
+      a.u_slot = i == 0 ? PL_U1 : PL_U2;
+      a.sa_slot = i == 0 ? PL_SA1 : PL_SA2;
       ProfScope ps(KC_HID_FWD, st);
       if (i == 0) {
         if ((rc = launch_hidden_fwd<false>(mAh, mAl, mWh[0], mWl[0], mOh, mOl, mSh, mSl, mVh, mVl, a, st))) return rc;
@@ -1693,10 +2342,20 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
   for (int i = 0; i < 3; ++i) NSVD_CUDA(cudaMemsetAsync(gr.db[i], 0, sizeof(float) * L * H, st));
   NSVD_CUDA(cudaMemsetAsync(gr.db[3], 0, sizeof(float) * L, st));
   if (pb.has_exp_mask && gr.dmask_scales) NSVD_CUDA(cudaMemsetAsync(gr.dmask_scales, 0, sizeof(float) * L, st));
+  // backward half of the operand plan: scales of the dZ planes from max|dF| per copy
+  float* plan = reinterpret_cast<float*>(sv + t.plan);
+  float* mdf = reinterpret_cast<float*>(sv + t.mdf);
+  NSVD_CUDA(cudaMemsetAsync(mdf, 0, sizeof(float) * L, st));
+  col_absmax_kernel<<<148 * 2, 256, 0, st>>>(dF, B * L, (int)L, mdf);
+  NSVD_LAUNCH_CHECK();
+  bwd_plan_kernel<<<1, 128, 0, st>>>(plan, reinterpret_cast<const float*>(sv + t.hstat), mdf, pr.W[3], pb.hard_mul_const,
+                                     (int)L);
+  NSVD_LAUNCH_CHECK();
   // transposed hidden weights (dgrad B operand, K-major): WT_i[l][k][j] = W_i[l][j][k]
   CUtensorMap mWh[2], mWl[2];
   for (int i = 0; i < 2; ++i) {
-    split_w_kernel<<<cdiv(L * H * H, 256), 256, 0, st>>>(pr.W[i + 1], BF(wk + t.w_hi[i]), BF(wk + t.w_lo[i]), (int)L, 1);
+    split_w_kernel<<<cdiv(L * H * H, 256), 256, 0, st>>>(pr.W[i + 1], plan, i == 0 ? PL_SW1 : PL_SW2, BF(wk + t.w_hi[i]),
+                                                         BF(wk + t.w_lo[i]), (int)L, 1);
     NSVD_LAUNCH_CHECK();
     if ((rc = make_tmap_bf16_3d(&mWh[i], wk + t.w_hi[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
     if ((rc = make_tmap_bf16_3d(&mWl[i], wk + t.w_lo[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
@@ -1709,7 +2368,7 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
     {
       ProfScope ps(KC_HEAD_BWD, st);
       head_bwd_bf16_kernel<<<hg, 128, 0, st>>>(dF, reinterpret_cast<const float*>(sv + t.u0), BF(sv + t.av_hi[2]),
-                                               BF(sv + t.av_lo[2]), pr.W[3], x, pr.mask_scales, pb, BF(wk + t.dz_hi[0]),
+                                               BF(sv + t.av_lo[2]), pr.W[3], x, pr.mask_scales, plan, pb, BF(wk + t.dz_hi[0]),
                                                BF(wk + t.dz_lo[0]), gr.dW[3], gr.db[3], gr.db[2], gr.dmask_scales, P, B, p0);
       NSVD_LAUNCH_CHECK();
     }
@@ -1733,6 +2392,11 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
       a.p_off = p0;
       a.dW = gr.dW[i];
       a.db_prev = gr.db[i - 1];
+      a.plan = plan;
+      a.ud_slot = i == 2 ? PL_UD2 : PL_UD1;
+      a.inv_sa_slot = i == 2 ? PL_INV_SA1 : PL_INV_SA0;
+      a.sdz_slot = i == 2 ? PL_SDZ1 : PL_SDZ0;
+      a.uw_slot = i == 2 ? PL_UW2 : PL_UW1;
       int T = (int)L * a.m_tiles;
       int grid = T < 148 ? T : 148;
       {
@@ -1759,15 +2423,12 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
     s.a_batched = 1;
     s.b_batched = 0;
     s.k_group = kgroup;   // 4096 points per group: dZ0 (all copies) + Phi of a group stay in L2
-    L0WgradEpi ew{gr.dW[0], (int)K0};
+    L0WgradEpi ew{gr.dW[0], plan, (int)K0};
     {
       ProfScope ps(KC_L0_WGRAD, st);
-      if (tc_use_pair()) {
-        s.batches = cdiv(L, 2);   // a CTA pair stacks two copies along M
-        if ((rc = launch_big2<true>(mZh, mZl, mPh, mPl, s, (int)L, ew, st))) return rc;
-      } else {
-        if ((rc = launch_big<true>(mZh, mZl, mPh, mPl, s, ew, st))) return rc;
-      }
+      static const int sub = env_int("NSVD_WGRAD_SUBCHUNKS", 8);   // 512 points per TMEM accumulation chain
+      s.batches = cdiv(L, 2);   // a CTA pair stacks two copies along M
+      if ((rc = launch_big2s<true, L0WgradEpi, kFmtHH>(mZh, mZl, mPh, mPl, s, (int)L, sub, sub, ew, st))) return rc;
     }
   }
   return 0;

@@ -17,11 +17,12 @@ import torch
 from . import _lib
 from .operators import describe_importance, describe_operator
 
-_ENGINE = os.environ.get("NSVD_ENGINE", "bf16x3")
+_ENGINE = os.environ.get("NSVD_ENGINE", "f16x3")
 
 
 def set_engine(name: str):
-    """'bf16x3' (tcgen05 tensor cores, default) or 'fp32' (CUDA-core validation engine)."""
+    """'f16x3' (tcgen05 tensor cores, fp32 operands as fp16 hi/lo planes; default) or 'fp32' (CUDA-core validation
+    engine).  'bf16x3' / 'tc' are accepted aliases of 'f16x3'."""
     global _ENGINE
     if name not in _lib.ENGINES:
         raise ValueError(f"unknown engine {name!r}; choose from {sorted(_lib.ENGINES)}")

@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 for pts in (128, 512, 4096):
-    for eng in ("bf16x3", "fp32"):
+    for eng in ("f16x3", "fp32"):
         r = subprocess.run([sys.executable, "bench.py", "--steps", "50", "--warmup", "10", "--points", str(pts),
                             "--engine", eng, "--no-cpu-baseline"], capture_output=True, text=True)
         try:
@@ -24,7 +24,7 @@ from conftest import build_problem
 from oracle import nsvd_oracle as O
 for pts in (128, 512, 4096):
     cfg = O.PathConfig.hydrogen()
-    N.set_engine("bf16x3")
+    N.set_engine("f16x3")
     method, operator, importance, _ = build_problem(cfg, 0, "cuda")
     step = N.GraphedOperatorStep(method, operator, importance, pts)
     x = (cfg.sampling_scale * torch.randn(pts, 2)).pin_memory()

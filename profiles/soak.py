@@ -13,7 +13,7 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 which = sys.argv[3] if len(sys.argv) > 3 else 'hydrogen'
 cfg = O.PathConfig.hydrogen(sequential=True) if which == 'hydrogen' else O.PathConfig.oscillator(sequential=(which == 'osc_seq'))
-N.set_engine("bf16x3")
+N.set_engine("f16x3")
 method, operator, importance, gt = build_problem(cfg, 0, "cuda")
 opt = N.FusedRMSpropEMA(method.parameters(), lr=1e-4, alpha=0.999, eps=1e-10, ema_decay=0.995, num_iters=steps)
 losses = []

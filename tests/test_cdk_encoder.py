@@ -44,7 +44,7 @@ def test_encoder_mirror_equals_reference_modules(mode):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("engine", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("engine", ["fp32", "f16x3"])
 def test_cdk_step_with_encoder_matches_reference(engine):
     torch.manual_seed(1)
     ref_net, _ = _reference_encoder([64, 256, 48], 16.0, "l2_ball")

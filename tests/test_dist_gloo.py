@@ -83,7 +83,7 @@ def _gpu_worker(rank, world, port, xg, seed, q):
     import neural_svd_b200 as N
     _init(rank, world, port)
     cfg = O.PathConfig.hydrogen(neigs=4, fourier_mapping_size=64)
-    N.set_engine("bf16x3")
+    N.set_engine("f16x3")
     method, operator, importance, _ = build_problem(cfg, seed, "cuda:0")
     method.data_parallel = N.PointParallel()
     x = N.shard_points(torch.from_numpy(xg), rank, world).cuda()
@@ -108,7 +108,7 @@ def test_two_rank_fused_step_equals_single_rank_gpu():
     [p.start() for p in procs]
     loss2, grads2 = q.get(timeout=300)
     [p.join(60) for p in procs]
-    N.set_engine("bf16x3")
+    N.set_engine("f16x3")
     method, operator, importance, _ = build_problem(cfg, seed, "cuda:0")
     loss1, _ = method.compute_loss_operator(operator, torch.from_numpy(xg).cuda(), importance=importance)
     loss1.backward()

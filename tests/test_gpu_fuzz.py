@@ -47,7 +47,7 @@ def test_engines_agree_on_random_shapes(seed):
         else:
             x = cfg.sampling_scale * torch.randn(B, 2, generator=g)
         out = {}
-        for engine in ("fp32", "bf16x3"):
+        for engine in ("fp32", "f16x3"):
             N.set_engine(engine)
             method, operator, importance, _ = build_problem(cfg, 50 + seed, "cuda")
             with torch.no_grad():                              # exercise the biases (zero at initialisation)
@@ -58,7 +58,7 @@ def test_engines_agree_on_random_shapes(seed):
             loss.backward()
             out[engine] = (float(loss.detach()), aux["f"].cpu().numpy(), aux["Tf"].cpu().numpy(),
                            {n: p.grad.cpu().numpy() for n, p in method.named_parameters() if p.grad is not None})
-        a, b = out["fp32"], out["bf16x3"]
+        a, b = out["fp32"], out["f16x3"]
         assert np.isfinite(a[0]) and abs(a[0] - b[0]) <= 1e-4 * abs(a[0]), (cfg, B)
         assert rel(b[1], a[1]) < 1e-4 and rel(b[2], a[2]) < 1e-4, (cfg, B)
         assert sorted(a[3]) == sorted(b[3])

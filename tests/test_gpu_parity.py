@@ -11,7 +11,7 @@ from oracle import nsvd_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-ENGINES = ["fp32", "bf16x3"]
+ENGINES = ["fp32", "f16x3"]
 PDE_CASES = ["hyd_small_odd", "osc_small_seq", "hyd_small_sorted", "hyd_b128_seq_L16", "osc_b512_jnt_L16", "hyd_b512_jnt_L16",
              "hyd_b64_jnt_L64",
              # infinite well / cosine / H2+ potentials, uniform / Laplace / no importance,
@@ -204,7 +204,7 @@ def test_spectrum_evd_matches_oracle():
     assert out["eigfuncs"].shape == (len(grid), 4)
 
 
-@pytest.mark.parametrize("engine", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("engine", ["fp32", "f16x3"])
 @pytest.mark.parametrize("name", ["spec_hyd_small", "spec_osc_small"])
 def test_spectrum_evd_matches_reference_fixture(name, engine):
     # methods/spectrum.py:29-102 as run by the UNMODIFIED reference (oracle/make_golden.py SPECTRUM_CASES): plain,
@@ -228,7 +228,7 @@ def test_spectrum_evd_matches_reference_fixture(name, engine):
                                      importance_val=importance_val, device="cuda", **kw)
         # the aligned outputs go through two eigendecompositions of 4x4 matrices with condition ~1e3
         spec_close(out, d, flags + "64", TOL, aligned_tol=20 * TOL)
-    N.set_engine("bf16x3")
+    N.set_engine("f16x3")
 
 
 def test_fused_rmsprop_ema_matches_torch():
@@ -325,7 +325,7 @@ def test_micro_batch_boundaries():
         for B, mb in ((1000, 256), (65536 + 300, 65536)):
             x = (cfg.sampling_scale * torch.randn(B, 2, generator=g)).cuda()
             res = {}
-            for engine in ("fp32", "bf16x3"):
+            for engine in ("fp32", "f16x3"):
                 N.set_engine(engine)
                 N.set_microbatch(mb)
                 method, operator, importance, _ = build_problem(cfg, 21, "cuda")
@@ -333,10 +333,10 @@ def test_micro_batch_boundaries():
                 loss.backward()
                 res[engine] = (float(loss.detach()), aux["Tf"].cpu().numpy(),
                                {n: p.grad.cpu().numpy() for n, p in method.named_parameters() if p.grad is not None})
-            assert abs(res["bf16x3"][0] - res["fp32"][0]) < TOL * abs(res["fp32"][0])
-            assert rel(res["bf16x3"][1], res["fp32"][1]) < TOL
+            assert abs(res["f16x3"][0] - res["fp32"][0]) < TOL * abs(res["fp32"][0])
+            assert rel(res["f16x3"][1], res["fp32"][1]) < TOL
             for n in res["fp32"][2]:
-                assert rel(res["bf16x3"][2][n], res["fp32"][2][n]) < TOL, (B, n)
+                assert rel(res["f16x3"][2][n], res["fp32"][2][n]) < TOL, (B, n)
     finally:
         N.set_microbatch(65536)
 
@@ -348,7 +348,7 @@ def test_config4_shape_L64_engines_agree():
     g = torch.Generator().manual_seed(64)
     x = (cfg.sampling_scale * torch.randn(3000, 2, generator=g)).cuda()
     res = {}
-    for engine in ("fp32", "bf16x3"):
+    for engine in ("fp32", "f16x3"):
         N.set_engine(engine)
         method, operator, importance, _ = build_problem(cfg, 8, "cuda")
         loss, aux = method.compute_loss_operator(operator, x, importance=importance)
@@ -357,15 +357,50 @@ def test_config4_shape_L64_engines_agree():
                        {n: p.grad.cpu().numpy() for n, p in method.named_parameters() if p.grad is not None})
         del method
         torch.cuda.empty_cache()
-    assert abs(res["bf16x3"][0] - res["fp32"][0]) < TOL * abs(res["fp32"][0])
-    assert rel(res["bf16x3"][1], res["fp32"][1]) < TOL and rel(res["bf16x3"][2], res["fp32"][2]) < TOL
+    assert abs(res["f16x3"][0] - res["fp32"][0]) < TOL * abs(res["fp32"][0])
+    assert rel(res["f16x3"][1], res["fp32"][1]) < TOL and rel(res["f16x3"][2], res["fp32"][2]) < TOL
     for n in res["fp32"][3]:
-        assert rel(res["bf16x3"][3][n], res["fp32"][3][n]) < TOL, n
+        assert rel(res["f16x3"][3][n], res["fp32"][3][n]) < TOL, n
+
+
+def test_config4_full_size_L64_gradient_parity():
+    # BASELINE configs[3] at a full micro-batch: hydrogen, L=64, B=65536 (one tensor-core micro-batch: 1024 half tiles
+    # per copy in the hidden-layer weight gradient, 64 k-slices in the layer-0 one).  Tensor-core engine against the
+    # CUDA-core fp32 engine (pinned to the reference at B <= 512 above) on loss, f, Tf and EVERY gradient tensor, and
+    # against the numpy oracle on a sample of rows of f / Tf.
+    cfg = O.PathConfig.hydrogen(neigs=64)
+    B = 65536
+    g = torch.Generator().manual_seed(65)
+    x = (cfg.sampling_scale * torch.randn(B, 2, generator=g)).cuda()
+    res = {}
+    for engine in ("fp32", "f16x3"):
+        N.set_engine(engine)
+        method, operator, importance, _ = build_problem(cfg, 9, "cuda")
+        loss, aux = method.compute_loss_operator(operator, x, importance=importance)
+        loss.backward()
+        res[engine] = (float(loss.detach()), aux["f"].cpu().numpy(), aux["Tf"].cpu().numpy(),
+                       {n: p.grad.cpu().numpy() for n, p in method.named_parameters() if p.grad is not None})
+        params = {n: p.detach().cpu().numpy().astype(np.float64) for n, p in method.named_parameters()}
+        method.__dict__.pop("_nsvd_scratch", None)
+        del method, loss, aux
+        torch.cuda.empty_cache()
+    tc, ref = res["f16x3"], res["fp32"]
+    assert abs(tc[0] - ref[0]) < TOL * abs(ref[0])
+    assert rel(tc[1], ref[1]) < TOL and rel(tc[2], ref[2]) < TOL
+    errs = {n: rel(tc[3][n], ref[3][n]) for n in ref[3]}
+    print("L=64 B=65536 grads tc-vs-fp32:", " ".join(f"{n.split('.')[-2]}{n.split('.')[-1]}={v:.1e}" for n, v in errs.items()))
+    assert max(errs.values()) < TOL, errs
+    rows = np.random.RandomState(0).choice(B, 1024, replace=False)
+    xs = x[torch.from_numpy(rows).cuda()].cpu().numpy().astype(np.float64)
+    u = O.forward_streams(xs, params, cfg)
+    Tf, f, _ = O.operator_apply(xs, u, params, cfg)
+    for eng in (tc, ref):
+        assert rel(eng[1][rows], f) < TOL and rel(eng[2][rows], Tf) < TOL
 
 
 def test_no_grad_and_double_backward_calls():
     d, cfg = load_golden("hyd_small_odd")
-    N.set_engine("bf16x3")
+    N.set_engine("f16x3")
     method, operator, importance, _ = build_problem(cfg, int(d["seed"]), "cuda")
     x = torch.from_numpy(d["x"]).cuda()
     with torch.no_grad():

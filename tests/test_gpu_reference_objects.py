@@ -39,7 +39,7 @@ def test_reference_objects_run_on_the_fused_kernels(which):
     # the SAME reference classes, parameters moved to the GPU, stepped by our kernels
     m_gpu, op_gpu, imp_gpu, _ = RB.build_reference_problem(ref, cfg, 31, 0.0)
     m_gpu = m_gpu.to("cuda")
-    N.set_engine("bf16x3")
+    N.set_engine("f16x3")
     loss, aux = N.compute_loss_operator(m_gpu, op_gpu, x.cuda(), imp_gpu)
     loss.backward()
     assert abs(float(loss.detach()) - float(loss_ref.detach())) < 1e-4 * abs(float(loss_ref.detach()))

@@ -1,5 +1,5 @@
 """North-star acceptance check: learned eigenvalue estimates after a fixed-seed, fixed-step training
-run agree with the reference within 1e-3 relative.
+run agree with the reference within 1e-3 relative - asserted with the same thresholds for both engines.
 
 Fixture `run_hyd_b128_seq_L16.npz` (oracle/make_golden_run.py): the unmodified reference on CPU, exact
 Laplacian, hydrogen B=128 sequential L=16, 200 steps of RMSprop(1e-4, alpha .999, eps 1e-10) + cosine LR,
@@ -18,7 +18,7 @@ from oracle import nsvd_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("engine", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("engine", ["f16x3", "fp32"])
 def test_fixed_seed_training_run_matches_reference(engine):
     d, _ = load_golden("run_hyd_b128_seq_L16")
     S, B, seed = int(d["steps"]), int(d["B"]), int(d["seed"])
@@ -56,16 +56,10 @@ def test_fixed_seed_training_run_matches_reference(engine):
     print(f"[{engine}] norms per mode   :", " ".join(f"{v:.1e}" for v in e_norm))
     print(f"[{engine}] rayleigh per mode:", " ".join(f"{v:.1e}" for v in e_ray))
     assert abs(losses[0] / d["loss64"][0] - 1) < 1e-4
-    if engine == "fp32":
-        # reference-grade arithmetic: every mode within 1e-3 (in fact at the reference's own fp32 self-noise)
-        assert e_norm.max() < 1e-3, e_norm
-        assert np.all(e_ray < 1e-3 + 2 * self_ray), (e_ray, self_ray)
-    else:
-        # bf16x3 carries 1e-5 per step instead of fp32's 1e-7, and the trajectory inherits that factor of ~100:
-        # the reference's own fp32 run ends 7e-6 away from its fp64 run in the loss and 2e-4 in the estimators;
-        # bf16x3 ends ~1e-3 away in the loss, ~1e-3 (median) in the estimators, with the worst (smallest-norm)
-        # modes at 2e-3 .. 7e-3.  Which modes are worst changes with any re-ordering of the arithmetic.  The bar
-        # below is a regression guard, not the north-star 1e-3 (which the fp32 engine meets): DESIGN.md §3.
-        assert abs(losses[-1] / d["loss64"][-1] - 1) < 5e-3
-        assert np.median(e_norm) < 3e-3 and e_norm.max() < 3e-2, e_norm
-        assert np.median(e_ray) < 3e-3 and e_ray.max() < 3e-2, e_ray
+    # north star: learned eigenvalues after the fixed-seed fixed-step run within 1e-3 relative, on EVERY mode, for both
+    # engines.  The reference's own fp32 run sits at 2.1e-4 (norms) / 1.3e-4 (Rayleigh) from its fp64 run; the
+    # tensor-core engine (fp16 hi/lo operand planes = 22 bits, TMEM accumulation chains of <= 96 MMAs) measures
+    # 9e-5 / 5e-4, the CUDA-core fp32 engine 2.1e-4 / 1.7e-4.
+    assert abs(losses[-1] / d["loss64"][-1] - 1) < 1e-4
+    assert e_norm.max() < 1e-3, e_norm
+    assert e_ray.max() < 1e-3, e_ray
