@@ -1754,6 +1754,360 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// S2-fwd fused: hidden layers 1 AND 2 (+ head + operator) in one persistent kernel.  The three derivative streams of
+// a1 never reach DRAM: a CTA writes them (TMA bulk stores) into a private scratch of two tile slots (2 x 192 KB per CTA,
+// 57 MB for the grid - resident in the 126 MB L2, rewritten every group before it could be evicted) and reads them
+// straight back as the A operand of layer 2.  Only the value streams (needed by the backward) and F / TF leave the chip:
+// 48 KB per point and 16 copies instead of 107 KB with one kernel per layer.  (Keeping a1 in shared memory is not
+// possible: 4 streams x 128 units x 4 B = 2 KB per point next to 128 KB of W1 + W2 planes.)
+//   work items of a CTA, in groups of two tiles of its range:  A(t0) A(t1) B(t0) B(t1)   (A = layer 1, B = layer 2)
+//   smem : W planes of the layer in use (64 KB, reloaded when (layer, copy) changes) | ring 3 x 32 KB | 64 KB staging
+//   TMEM : 4 x 128 columns (one block per stream), one item at a time
+//   adone[slot] : the bulk stores of A(slot) have completed (cp.async.bulk.wait_group 0 by the issuing thread) - the
+//                 producer waits for it before loading B(slot)'s operands.
+// ------------------------------------------------------------------------------------------
+struct HidFwd12Maps {
+  CUtensorMap a0h, a0l;   // a0 derivative streams   [H][P][4 L]            load box {64, 128}
+  CUtensorMap v0h, v0l;   // saved a0 value stream   [H][B][L]              load box {64, 128}
+  CUtensorMap w1h, w1l, w2h, w2l;
+  CUtensorMap s1h, s1l;   // saved a1 value stream   [H][B][L]              store box {32, 128}, 64-byte swizzle
+  CUtensorMap v1h, v1l;   // the same buffer                                 load box {64, 128}
+  CUtensorMap s2h, s2l;   // saved a2 value stream                           store box {32, 128}
+  CUtensorMap xsh, xsl;   // scratch  [H][128][grid x 2 slots x 3 streams]   store box {32, 128}
+  CUtensorMap xlh, xll;   // the same buffer                                 load box {64, 128}
+};
+struct HidFwd12Args {
+  int L, P, m_tiles;
+  long Btot, p_off;
+  const float *bias1, *bias2;        // b1, b2 (L,128)
+  const float* plan;                 // operand plan
+  const float* W3;                   // (L,128)
+  const float* b3;                   // (L)
+  const float* x;                    // (Btot,2)
+  const float* mscales;              // (L) or null
+  float *F, *TF, *U0;                // (Btot, L)
+  nsvd_problem_t pb;
+};
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__global__ void __launch_bounds__(hid::F_THREADS, 1)
+hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args args) {
+  using namespace hid;
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;                       // [hi c0 | hi c1 | lo c0 | lo c1]
+  uint8_t* sA = smem + 2 * PLANE;           // ring
+  uint8_t* sO = sA + F_STAGES * F_STAGE_BYTES;  // staging boxes
+  uint64_t* bars = (uint64_t*)(sO + F_STAGING);
+  uint64_t* full = bars;                    // [3]
+  uint64_t* empty = bars + 3;               // [3]
+  uint64_t* wfull = bars + 6;
+  uint64_t* wfree = bars + 7;
+  uint64_t* tfull = bars + 8;
+  uint64_t* tempty = bars + 9;
+  uint64_t* adone = bars + 10;              // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+  float* bias_s = (float*)(bars + 16);      // [128]
+  float* w3_s = bias_s + 128;               // [128]
+  float* ubuf = (float*)(sO + 6 * F_BOX);   // [128][3][4] head partial sums (layer 2: boxes 2..7 are unused)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = args.L * args.m_tiles;
+  const int tpc = (T + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * tpc;
+  const int t_end = (t_begin + tpc < T) ? t_begin + tpc : T;
+  const int n_items = t_end > t_begin ? 4 * ((t_end - t_begin + 1) / 2) : 0;
+  // item i: group g = i / 4, layer = (i / 2) & 1 (0: layer 1, 1: layer 2), slot = i & 1, tile = t_begin + 2 g + slot
+
+  if (warp == 0 && lane == 0) {
+    const CUtensorMap* m = &tm.a0h;
+    for (int i = 0; i < 18; ++i) tma_prefetch_desc(m + i);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < F_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(wfull, 1);
+    mbar_init(wfree, 1);
+    mbar_init(tfull, 1);
+    mbar_init(tempty, F_EPI_WARPS);
+    mbar_init(&adone[0], 1);
+    mbar_init(&adone[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0, cur_key = -1, done = 0;   // done = items already issued (valid ones)
+      uint32_t phase = 0;
+      for (int i = 0; i < n_items; ++i) {
+        const int g = i >> 2, layer = (i >> 1) & 1, slot = i & 1, t = t_begin + 2 * g + slot;
+        if (t >= t_end) continue;
+        const int l = t / args.m_tiles, mt = t % args.m_tiles;
+        const int key = l * 2 + layer;
+        if (key != cur_key) {
+          if (done > 0) mbar_wait(wfree, (uint32_t)((done - 1) & 1), 60);   // MMAs of the previous item retired
+          mbar_arrive_expect_tx(wfull, 2 * PLANE);
+          const CUtensorMap* wh = layer ? &tm.w2h : &tm.w1h;
+          const CUtensorMap* wl = layer ? &tm.w2l : &tm.w1l;
+          tma_load_3d(sW, wh, wfull, 0, 0, l);
+          tma_load_3d(sW + CHUNK, wh, wfull, 64, 0, l);
+          tma_load_3d(sW + PLANE, wl, wfull, 0, 0, l);
+          tma_load_3d(sW + PLANE + CHUNK, wl, wfull, 64, 0, l);
+          cur_key = key;
+        }
+        if (layer) {   // layer-2 operands of this slot were written by this CTA: wait until those stores have completed
+          mbar_wait(&adone[slot], (uint32_t)(g & 1), 61);
+          fence_proxy_async_all();
+        }
+        const int xs = ((int)blockIdx.x * 2 + slot) * 3;
+        {
+          // L2 prefetch of the layer-1 operands (256 KB from DRAM) of the tile that starts one or two items later:
+          // A(t0) announces t1, B(t0) / B(t1) announce the next group's t0 / t1
+          const int tn = layer ? t + 2 : (slot == 0 ? t + 1 : -1);
+          if (tn >= 0 && tn < t_end) {
+            const int ln = tn / args.m_tiles, mn = tn % args.m_tiles;
+            for (int sc = 0; sc < 8; ++sc) {
+              const int s = sc >> 1, c = sc & 1;
+              if (s == 0) {
+                tma_prefetch_3d(&tm.v0h, 64 * c, (int)args.p_off + mn * 128, ln);
+                tma_prefetch_3d(&tm.v0l, 64 * c, (int)args.p_off + mn * 128, ln);
+              } else {
+                tma_prefetch_3d(&tm.a0h, 64 * c, mn * 128, ln * 4 + s);
+                tma_prefetch_3d(&tm.a0l, 64 * c, mn * 128, ln * 4 + s);
+              }
+            }
+          }
+        }
+        for (int sc = 0; sc < 8; ++sc) {  // (stream, K-chunk)
+          const int s = sc >> 1, c = sc & 1;
+          mbar_wait(&empty[stage], phase ^ 1, 62);
+          uint8_t* d = sA + stage * F_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], F_STAGE_BYTES);
+          if (s == 0) {   // value stream: from `saved` (whole-batch rows)
+            tma_load_3d(d, layer ? &tm.v1h : &tm.v0h, &full[stage], 64 * c, (int)args.p_off + mt * 128, l);
+            tma_load_3d(d + CHUNK, layer ? &tm.v1l : &tm.v0l, &full[stage], 64 * c, (int)args.p_off + mt * 128, l);
+          } else if (!layer) {
+            tma_load_3d(d, &tm.a0h, &full[stage], 64 * c, mt * 128, l * 4 + s);
+            tma_load_3d(d + CHUNK, &tm.a0l, &full[stage], 64 * c, mt * 128, l * 4 + s);
+          } else {
+            tma_load_3d(d, &tm.xlh, &full[stage], 64 * c, 0, xs + s - 1);
+            tma_load_3d(d + CHUNK, &tm.xll, &full[stage], 64 * c, 0, xs + s - 1);
+          }
+          if (++stage == F_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ++done;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, 0, false, false);   // fp16 x fp16 planes
+      int stage = 0, cur_key = -1;
+      uint32_t phase = 0, wphase = 0, tphase = 0;
+      const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + PLANE;
+      for (int i = 0; i < n_items; ++i) {
+        const int g = i >> 2, layer = (i >> 1) & 1, slot = i & 1, t = t_begin + 2 * g + slot;
+        if (t >= t_end) continue;
+        const int key = (t / args.m_tiles) * 2 + layer;
+        if (key != cur_key) {
+          mbar_wait(wfull, wphase, 63);
+          wphase ^= 1;
+          cur_key = key;
+        }
+        mbar_wait(tempty, tphase ^ 1, 64);
+        tc_fence_after();
+        for (int sc = 0; sc < 8; ++sc) {
+          const int s = sc >> 1, c = sc & 1;
+          mbar_wait(&full[stage], phase, 65);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(sA + stage * F_STAGE_BYTES), a_lo = a_hi + CHUNK;
+          const uint32_t d_tmem = tmem_base + s * 128;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t off = kk * 32;
+            uint64_t ah = make_sdesc_sw128(a_hi + off, 16, 1024), al = make_sdesc_sw128(a_lo + off, 16, 1024);
+            uint64_t bh = make_sdesc_sw128(w_hi + c * CHUNK + off, 16, 1024);
+            uint64_t bl = make_sdesc_sw128(w_lo + c * CHUNK + off, 16, 1024);
+            umma_f16(d_tmem, al, bh, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+            umma_f16(d_tmem, ah, bl, idesc, 1u);
+            umma_f16(d_tmem, ah, bh, idesc, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == F_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull);
+        umma_commit(wfree);
+        tphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== 16 epilogue warps (as hidden_fwd_kernel) =====================
+    const int ewarp = warp - 4, q = ewarp & 3, sub = ewarp >> 2;
+    const int et = threadIdx.x - 128;        // 0..511 among the epilogue threads
+    const int row = q * 32 + lane;           // point row inside the tile == TMEM lane
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t sw = (uint32_t)((row >> 1) & 3);
+    const uint32_t piece0 = (uint32_t)row * 64 + (((uint32_t)sub ^ sw) << 4);
+    uint32_t tphase = 0;
+    int cur_key = -1;
+    float un[4] = {1.f, 1.f, 1.f, 1.f}, so[4] = {1.f, 1.f, 1.f, 1.f};
+    for (int i = 0; i < n_items; ++i) {
+      const int g = i >> 2, layer = (i >> 1) & 1, slot = i & 1, t = t_begin + 2 * g + slot;
+      if (t >= t_end) continue;
+      (void)g;
+      const bool last = layer != 0;
+      const int l = t / args.m_tiles, mt = t % args.m_tiles;
+      const int pt = mt * 128 + row;
+      const int key = l * 2 + layer;
+      // is this the last layer-1 item of its group (the next valid item is a layer-2 one)?
+      const bool closes_a = !last && (slot == 1 || t + 1 >= t_end);
+      if (key != cur_key) {  // all epilogue threads are past the previous item's last staging barrier
+        if (et < 128) {
+          bias_s[et] = (last ? args.bias2 : args.bias1)[l * kHidden + et];
+          w3_s[et] = args.W3[l * kHidden + et];
+        }
+        const float* pl = args.plan + (long)l * PL_STRIDE;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          un[s] = __ldg(pl + (last ? PL_U2 : PL_U1) + s) * (1.f + kTruncPerMma * 24.f);   // K = 128: chains of 24 MMAs
+          so[s] = last ? __ldg(pl + PL_SA2) : __ldg(pl + PL_SA1 + s);
+        }
+        cur_key = key;
+        named_bar_sync(1, F_EPI_WARPS * 32);
+      }
+      mbar_wait(tfull, tphase, 66);
+      tphase ^= 1;
+      tc_fence_after();
+      float u[4] = {0.f, 0.f, 0.f, 0.f};
+      const int xs = ((int)blockIdx.x * 2 + slot) * 3;
+#pragma unroll 1
+      for (int r = 0; r < 4; ++r) {          // h-quarters of 32 hidden units; this warp takes 8 of them
+        const int h0 = r * 32 + sub * 8;
+        float z[4][8];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tmem_ld8(tl + s * 128 + h0, z[s]);
+        tmem_ld_wait();
+        if (r == 3) {                        // last TMEM read of this item: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float zb = fmaf(z[0][k], un[0], bias_s[h0 + k]);
+          act_streams(zb, z[1][k] * un[1], z[2][k] * un[2], z[3][k] * un[3], z[0][k], z[1][k], z[2][k], z[3][k]);
+        }
+        if (last) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float w = w3_s[h0 + k];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) u[s] = fmaf(z[s][k], w, u[s]);
+          }
+        }
+        // layer 2 stages the value stream only: two box pairs alternate between rounds, so a round never waits for its
+        // predecessor's bulk store (one barrier per round); layer 1 needs all 8 boxes per round and first lets the
+        // previous round's stores drain them.
+        const int sb = last ? 2 * (r & 1) : 0;
+        if (!last) {
+          if (et == 0) {
+            if (r == 0 && slot == 1) {       // A(t0)'s stores were issued a whole MMA phase ago: they are complete
+              tma_store_wait_all();
+              mbar_arrive(&adone[0]);
+            } else {
+              tma_store_wait_read();
+            }
+          }
+          named_bar_sync(2, F_EPI_WARPS * 32);
+        } else if (r == 0) {                 // the previous item may have been a layer-1 one that used all 8 boxes
+          if (et == 0) tma_store_wait_read();
+          named_bar_sync(2, F_EPI_WARPS * 32);
+        }
+        const int ns = last ? 1 : 4;
+        for (int s = 0; s < ns; ++s) {
+          uint32_t h[4], lo[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) split2<PF_HH>(z[s][2 * k] * so[s], z[s][2 * k + 1] * so[s], h[k], lo[k]);
+          uint8_t* bh = sO + (sb + 2 * s) * F_BOX;
+          uint8_t* bl = bh + F_BOX;
+          *reinterpret_cast<uint4*>(bh + piece0) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(bl + piece0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async_smem();
+        if (last && et == 0) tma_store_wait_read();
+        named_bar_sync(3, F_EPI_WARPS * 32);
+        if (et == 0) {
+          if (!last) {
+#pragma unroll
+            for (int s = 1; s < 4; ++s) {
+              tma_store_3d(&tm.xsh, sO + (2 * s) * F_BOX, r * 32, 0, xs + s - 1);
+              tma_store_3d(&tm.xsl, sO + (2 * s + 1) * F_BOX, r * 32, 0, xs + s - 1);
+            }
+            tma_store_3d(&tm.s1h, sO, r * 32, (int)args.p_off + mt * 128, l);
+            tma_store_3d(&tm.s1l, sO + F_BOX, r * 32, (int)args.p_off + mt * 128, l);
+          } else {
+            tma_store_3d(&tm.s2h, sO + sb * F_BOX, r * 32, (int)args.p_off + mt * 128, l);
+            tma_store_3d(&tm.s2l, sO + (sb + 1) * F_BOX, r * 32, (int)args.p_off + mt * 128, l);
+          }
+          tma_store_commit();
+        }
+      }
+      if (closes_a && et == 0) {             // every store of this group's layer-1 items has completed
+        tma_store_wait_all();
+        if (slot == 0) mbar_arrive(&adone[0]);
+        else mbar_arrive(&adone[1]);
+      }
+      if (last) {
+        if (sub != 0) {
+#pragma unroll
+          for (int s = 0; s < 4; ++s) ubuf[(row * 3 + sub - 1) * 4 + s] = u[s];
+        }
+        named_bar_sync(1, F_EPI_WARPS * 32);
+        if (sub == 0 && pt < args.P) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) u[s] += ubuf[(row * 3 + j) * 4 + s];
+          u[0] += __ldg(args.b3 + l);
+          const long pg = args.p_off + pt;
+          PointGeom gm = point_geom(args.x[2 * pg], args.x[2 * pg + 1], args.pb);
+          float f, tf;
+          operator_epilogue(gm, args.pb, args.pb.has_exp_mask != 0, args.pb.has_exp_mask ? args.mscales[l] : 1.f,
+                            u[0], u[1], u[2], u[3], f, tf);
+          args.F[pg * args.L + l] = f;
+          args.TF[pg * args.L + l] = tf;
+          args.U0[pg * args.L + l] = u[0];
+        }
+        named_bar_sync(1, F_EPI_WARPS * 32);  // ubuf (staging boxes 6-7) is free again
+      }
+    }
+    if (et == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 struct HidBwdArgs {
   int L, P, m_tiles;
   long Btot, p_off;
@@ -2136,11 +2490,13 @@ static int tc_micro_batch() {
   return g_tc_micro_batch;
 }
 
+constexpr int kHidGrid = 148;   // CTAs of the hidden-layer kernels (one per SM)
+
 struct TcLayout {
   // saved (whole batch)
   size_t phi_hi, phi_lo, av_hi[3], av_lo[3], u0, plan, rowstat, hstat, mdf, saved_total;
   // work
-  size_t w0_hi, w0_lo, w_hi[2], w_lo[2], str_hi[2], str_lo[2], dz_hi[2], dz_lo[2], work_total;
+  size_t w0_hi, w0_lo, w_hi[2], w_lo[2], str_hi[2], str_lo[2], dz_hi[2], dz_lo[2], scr_hi, scr_lo, work_total;
   long P;
 };
 static TcLayout tc_layout(const nsvd_problem_t& pb) {
@@ -2178,6 +2534,9 @@ static TcLayout tc_layout(const nsvd_problem_t& pb) {
     t.str_hi[i] = take(L * 4 * P * H * 2);
     t.str_lo[i] = take(L * 4 * P * H * 2);
   }
+  // L2-resident scratch of the fused hidden forward: 148 CTAs x 2 tile slots x 3 derivative streams x (128 x 128) planes
+  t.scr_hi = take((size_t)kHidGrid * 6 * hid::PLANE);
+  t.scr_lo = take((size_t)kHidGrid * 6 * hid::PLANE);
   // backward reuses the stream area for the dZ planes (two ping-pong pairs)
   for (int i = 0; i < 2; ++i) {
     t.dz_hi[i] = t.str_hi[i];
@@ -2281,7 +2640,55 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
       static const int sub_first = env_int("NSVD_L0_SUBFIRST", 6);
       if ((rc = launch_big2s<false, L0FwdEpi, kFmtHH>(mPh, mPl, mW0h, mW0l, s, (int)L, sub, sub_first, e0, st))) return rc;
     }
-    // ---- hidden layers 1, 2
+    // ---- hidden layers 1, 2 (+ head + operator)
+    static const int fused = env_int("NSVD_HIDDEN_FUSED", 1);
+    if (fused) {
+      HidFwd12Maps hm;
+      const uint64_t PH = (uint64_t)P * H * 2, BH = (uint64_t)B * H * 2;
+      const int T = (int)L * m_tiles, grid = T < kHidGrid ? T : kHidGrid;
+      if ((rc = make_tmap_bf16_3d(&hm.a0h, wk + t.str_hi[0], H, P, 4 * L, H * 2, PH, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.a0l, wk + t.str_lo[0], H, P, 4 * L, H * 2, PH, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.v0h, sv + t.av_hi[0], H, B, L, H * 2, BH, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.v0l, sv + t.av_lo[0], H, B, L, H * 2, BH, 64, 128))) return rc;
+      hm.w1h = mWh[0];
+      hm.w1l = mWl[0];
+      hm.w2h = mWh[1];
+      hm.w2l = mWl[1];
+      if ((rc = make_tmap_bf16_3d(&hm.s1h, sv + t.av_hi[1], H, B, L, H * 2, BH, 32, 128, 64))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.s1l, sv + t.av_lo[1], H, B, L, H * 2, BH, 32, 128, 64))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.v1h, sv + t.av_hi[1], H, B, L, H * 2, BH, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.v1l, sv + t.av_lo[1], H, B, L, H * 2, BH, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.s2h, sv + t.av_hi[2], H, B, L, H * 2, BH, 32, 128, 64))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.s2l, sv + t.av_lo[2], H, B, L, H * 2, BH, 32, 128, 64))) return rc;
+      const uint64_t nslot = (uint64_t)kHidGrid * 6;
+      if ((rc = make_tmap_bf16_3d(&hm.xsh, wk + t.scr_hi, H, 128, nslot, H * 2, hid::PLANE, 32, 128, 64))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.xsl, wk + t.scr_lo, H, 128, nslot, H * 2, hid::PLANE, 32, 128, 64))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.xlh, wk + t.scr_hi, H, 128, nslot, H * 2, hid::PLANE, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16_3d(&hm.xll, wk + t.scr_lo, H, 128, nslot, H * 2, hid::PLANE, 64, 128))) return rc;
+      HidFwd12Args a{};
+      a.L = (int)L;
+      a.P = P;
+      a.m_tiles = m_tiles;
+      a.Btot = B;
+      a.p_off = p0;
+      a.bias1 = pr.b[1];
+      a.bias2 = pr.b[2];
+      a.plan = plan;
+      a.W3 = pr.W[3];
+      a.b3 = pr.b[3];
+      a.x = x;
+      a.mscales = pr.mask_scales;
+      a.F = F;
+      a.TF = TF;
+      a.U0 = reinterpret_cast<float*>(sv + t.u0);
+      a.pb = pb;
+      NSVD_SMEM_OPTIN(hidden_fwd12_kernel, hid::SMEM_FWD);
+      ProfScope ps(KC_HID_FWD, st);
+      hidden_fwd12_kernel<<<grid, hid::F_THREADS, hid::SMEM_FWD, st>>>(hm, a);
+      NSVD_LAUNCH_CHECK();
+      continue;
+    }
+    // one kernel per layer (NSVD_HIDDEN_FUSED=0): the derivative streams of a1 go through the second stream buffer
     for (int i = 0; i < 2; ++i) {
       CUtensorMap mAh, mAl, mOh, mOl, mSh, mSl;
       if ((rc = make_tmap_bf16_3d(&mAh, wk + t.str_hi[i], H, P, 4 * L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;
