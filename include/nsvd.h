@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NSVD_ABI_VERSION 2
+#define NSVD_ABI_VERSION 3
 
 enum {
   NSVD_E_BADARG = 10001,   /* shape / enum / alignment violation */
@@ -79,6 +79,9 @@ typedef struct nsvd_problem {
   int32_t box_mask;        /* NSVD_BOX_*: Dirichlet box mask multiplying every eigenfunction    */
   float pot_coef2;         /* second potential coefficient                                      */
   float box_lim;           /* half-width `lim` of the Dirichlet box                             */
+  float fd_eps;            /* laplacian_eps (ABI 3): <= 0 exact Laplacian (forward-mode streams); > 0 the
+                            * finite-difference Laplacian of the shipped scripts, pde/diff_ops.py:25-52      */
+  int32_t reserved_;       /* keeps the struct a multiple of 8 bytes                                      */
 } nsvd_problem_t;
 
 /* Parameters in the reference's own layout (ParallelMLP, mlp.py:181-199):

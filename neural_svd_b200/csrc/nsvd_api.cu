@@ -57,6 +57,7 @@ static int check_problem(const nsvd_problem_t* pb) {
   NSVD_CHECK_ARG(pb->importance == NSVD_IMP_NONE || pb->sampling_sigma > 0.f, "sampling_sigma must be > 0");
   NSVD_CHECK_ARG(pb->box_mask >= NSVD_BOX_NONE && pb->box_mask <= NSVD_BOX_EXP, "unknown box mask mode %d", pb->box_mask);
   NSVD_CHECK_ARG(pb->box_mask == NSVD_BOX_NONE || pb->box_lim > 0.f, "box_lim must be > 0");
+  NSVD_CHECK_ARG(pb->fd_eps == pb->fd_eps && pb->fd_eps < 1e30f, "fd_eps must be finite (got %f)", (double)pb->fd_eps);
   return 0;
 }
 static int check_params(const nsvd_problem_t* pb, const nsvd_params_t* pr) {

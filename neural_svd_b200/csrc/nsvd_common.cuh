@@ -196,6 +196,58 @@ __device__ __forceinline__ void operator_epilogue(const PointGeom& g, const nsvd
   tf = pb.op_scale * negH + pb.op_shift * f;       // examples/__init__.py:9
 }
 
+// ---- finite-difference Laplacian (laplacian_eps > 0: VectorizedLaplacian.approx_laplacian, pde/diff_ops.py:25-52) ----
+// un-clamped sqrt(w(y)) of the sampler's density; 1 without importance (diff_ops.py:10-13)
+__device__ __forceinline__ float sqrt_w(float y0, float y1, const nsvd_problem_t& pb) {
+  const float sg = pb.sampling_sigma;
+  if (pb.importance == NSVD_IMP_GAUSSIAN) {
+    const float s2 = sg * sg;
+    return sqrtf(expf(-(y0 * y0 + y1 * y1) / (2.f * s2) - logf(6.283185307179586f * s2)));
+  }
+  if (pb.importance == NSVD_IMP_LAPLACE) return sqrtf(expf(-(fabsf(y0) + fabsf(y1)) / sg - 2.f * logf(2.f * sg)));
+  if (pb.importance == NSVD_IMP_UNIFORM) return sqrtf(1.f / (4.f * sg * sg));
+  return 1.f;
+}
+// g(y) = sqrt(w(y)) * hard_mul_const * exp-mask_l(y) * box-mask(y) * u : the function whose second differences are taken
+__device__ __forceinline__ float weighted_value(float y0, float y1, const nsvd_problem_t& pb, bool has_mask,
+                                                float mscale, float u) {
+  float m = 1.f;
+  if (has_mask) m = expf(-sqrtf(y0 * y0 + y1 * y1) / mscale);
+  if (pb.box_mask != NSVD_BOX_NONE) {
+    float m0, m1, a, c;
+    box_factor(y0, pb.box_lim, pb.box_mask, m0, a, c);
+    box_factor(y1, pb.box_lim, pb.box_mask, m1, a, c);
+    m *= m0 * m1;
+  }
+  return sqrt_w(y0, y1, pb) * (pb.hard_mul_const * m * u);
+}
+// TF of one (point, copy) from the raw network values at x (uc) and at x + eps e_0, x - eps e_0, x + eps e_1,
+// x - eps e_1 (us[0..3]); the accumulation order is the reference's (diff_ops.py:40-48)
+__device__ __forceinline__ float fd_operator(float x0, float x1, const nsvd_problem_t& pb, bool has_mask, float mscale,
+                                             float uc, const float* us) {
+  const float eps = pb.fd_eps;
+  const float gc = weighted_value(x0, x1, pb, has_mask, mscale, uc);
+  float lap = -4.f * gc;
+  lap += weighted_value(x0 + eps, x1, pb, has_mask, mscale, us[0]) + weighted_value(x0 - eps, x1, pb, has_mask, mscale, us[1]);
+  lap += weighted_value(x0, x1 + eps, pb, has_mask, mscale, us[2]) + weighted_value(x0, x1 - eps, pb, has_mask, mscale, us[3]);
+  lap = lap / (float)((double)eps * (double)eps);
+  float fs = gc;
+  if (pb.importance != NSVD_IMP_NONE) {
+    const float sw = fmaxf(sqrt_w(x0, x1, pb), 1e-5f);          // diff_ops.py:15
+    lap = lap / sw;
+    fs = gc / sw;
+  }
+  PointGeom g = point_geom(x0, x1, pb);
+  const float negH = pb.scale_kinetic * lap - g.V * fs;          // schrodinger/__init__.py:19-22
+  return pb.op_scale * negH + pb.op_shift * fs;                  // examples/__init__.py:9
+}
+// coordinates of shifted point set s (0: +e_0, 1: -e_0, 2: +e_1, 3: -e_1)
+__device__ __forceinline__ void fd_shift(int s, float eps, float& y0, float& y1) {
+  const float d = (s & 1) ? -eps : eps;
+  if (s < 2) y0 += d;
+  else y1 += d;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

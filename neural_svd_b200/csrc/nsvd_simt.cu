@@ -201,6 +201,64 @@ __global__ void head_operator_kernel(const float* __restrict__ A2, const float* 
   }
 }
 
+// ---- finite-difference mode (pb.fd_eps > 0): the four stream slots carry the four SHIFTED point sets
+// x + eps e_0, x - eps e_0, x + eps e_1, x - eps e_1 through the same contractions, value stream only.
+__global__ void features_shift_f32_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
+                                          float* __restrict__ phis, int P, int M, float eps) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)P * M) return;
+  int p = (int)(i / M), j = (int)(i % M);
+  const float b0 = Bff[j], b1 = Bff[M + j];
+  const long K0 = 2L * M, SP = (long)P * K0;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    float y0 = x[2 * p], y1 = x[2 * p + 1];
+    fd_shift(s, eps, y0, y1);
+    float sn, cs;
+    sincosf(fmaf(y1, b1, y0 * b0), &sn, &cs);
+    phis[s * SP + (long)p * K0 + j] = sn;
+    phis[s * SP + (long)p * K0 + M + j] = cs;
+  }
+}
+// plain softplus on all four slots of Z[l][s][p][h] (in place)
+__global__ void softplus_values_kernel(float* __restrict__ Z, const float* __restrict__ bias, int L, int P) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n = (long)L * 4 * P * kHidden;
+  if (i >= n) return;
+  int h = (int)(i % kHidden);
+  int l = (int)(i / ((long)kHidden * P * 4));
+  float a, sg;
+  softplus_sig(Z[i] + bias[l * kHidden + h], a, sg);
+  Z[i] = a;
+}
+// last layer on the four shifted slots + finite-difference operator; the central value comes from U0 (exact pass)
+__global__ void head_fd_kernel(const float* __restrict__ A2, const float* __restrict__ W3,
+                               const float* __restrict__ b3, const float* __restrict__ x,
+                               const float* __restrict__ mscales, nsvd_problem_t pb,
+                               const float* __restrict__ U0, float* __restrict__ TF, int P, long p_off) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int L = pb.n_copies;
+  if (w >= P * L) return;
+  int p = w / L, l = w % L;
+  long SP = (long)P * kHidden;
+  const float* a = A2 + (long)l * 4 * SP + (long)p * kHidden;
+  float u[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int h = lane + 32 * q;
+    float wv = W3[l * kHidden + h];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) u[s] = fmaf(a[s * SP + h], wv, u[s]);
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) u[s] = warp_sum(u[s]) + b3[l];
+  if (lane == 0) {
+    long pg = p_off + p;
+    TF[pg * L + l] = fd_operator(x[2 * pg], x[2 * pg + 1], pb, pb.has_exp_mask != 0,
+                                 pb.has_exp_mask ? mscales[l] : 1.f, U0[pg * L + l], u);
+  }
+}
+
 // backward of the head: du = dF * c * m * rho ; dZ2 = du W3 (.) sigma(a2) ; T3 = du * a2 (for dW3)
 __global__ void head_bwd_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
                                 const float* __restrict__ a2, const float* __restrict__ W3,
@@ -323,6 +381,31 @@ int simt_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float*
     head_operator_kernel<<<cdiv(nw * 32, 256), 256, 0, st>>>(cur, pr.W[3], pr.b[3], x, pr.mask_scales,
                                                              pb, F, TF, sv.u0, P, p0);
     NSVD_LAUNCH_CHECK();
+    if (pb.fd_eps > 0.f) {
+      // finite-difference Laplacian: second pass, the four slots = the four shifted point sets, values only;
+      // TF is overwritten, F / U0 / the saved activations of the central pass stay (the backward uses them)
+      features_shift_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(x + 2 * p0, pr.Bff, phis, P, (int)M, pb.fd_eps);
+      NSVD_LAUNCH_CHECK();
+      if ((rc = sgemm_strided(g, (int)L, st))) return rc;
+      long n4 = 4 * ne;
+      softplus_values_kernel<<<cdiv(n4, 256), 256, 0, st>>>(bufA, pr.b[0], (int)L, P);
+      NSVD_LAUNCH_CHECK();
+      cur = bufA;
+      nxt = bufB;
+      for (int i = 1; i <= 2; ++i) {
+        SGemm h{};
+        h.A = cur; h.a_rs = kHidden; h.a_cs = 1; h.a_bs = 4L * P * kHidden;
+        h.B = pr.W[i]; h.b_rs = 1; h.b_cs = kHidden; h.b_bs = (long)kHidden * kHidden;
+        h.C = nxt; h.c_rs = kHidden; h.c_bs = 4L * P * kHidden;
+        h.M = 4 * P; h.N = kHidden; h.K = kHidden; h.alpha = 1.f; h.accumulate = 0;
+        if ((rc = sgemm_strided(h, (int)L, st))) return rc;
+        softplus_values_kernel<<<cdiv(n4, 256), 256, 0, st>>>(nxt, pr.b[i], (int)L, P);
+        NSVD_LAUNCH_CHECK();
+        float* t = cur; cur = nxt; nxt = t;
+      }
+      head_fd_kernel<<<cdiv(nw * 32, 256), 256, 0, st>>>(cur, pr.W[3], pr.b[3], x, pr.mask_scales, pb, sv.u0, TF, P, p0);
+      NSVD_LAUNCH_CHECK();
+    }
   }
   return 0;
 }

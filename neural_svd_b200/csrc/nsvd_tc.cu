@@ -1298,6 +1298,58 @@ __global__ void features_f16_kernel(const float* __restrict__ x, const float* __
   *reinterpret_cast<uint2*>(lo + o + M) = make_uint2(l0, l1);
 }
 
+// ---- finite-difference mode (pb.fd_eps > 0, pde/diff_ops.py:25-52): a second forward pass in which the four stream
+// slots carry the four SHIFTED point sets x + eps e_0, x - eps e_0, x + eps e_1, x - eps e_1, value stream only.
+// Phi of the shifted sets, rows s * P + p of a (4 P, 2 M) matrix, fp16 hi/lo planes
+__global__ void features_shift_f16_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
+                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long P, int M,
+                                          float eps) {
+  const int M4 = M >> 2;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * P * M4) return;
+  const long row = i / M4;
+  const int j = (int)(i % M4) * 4, s = (int)(row / P);
+  const long p = row % P;
+  float y0 = x[2 * p], y1 = x[2 * p + 1];
+  fd_shift(s, eps, y0, y1);
+  const float4 b0 = *reinterpret_cast<const float4*>(Bff + j);
+  const float4 b1 = *reinterpret_cast<const float4*>(Bff + M + j);
+  const float bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+  float sn[4], cs[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float ph = fmaf(y1, bb1[k], y0 * bb0[k]);
+    float kq = rintf(ph * 0.15915494309189535f);
+    float r = fmaf(-kq, 6.2831855f, ph);
+    r = fmaf(-kq, -1.7484555e-07f, r);
+    sincosf(r, &sn[k], &cs[k]);
+  }
+  uint32_t h0, l0, h1, l1;
+  long o = row * 2L * M + j;
+  tc::split2<tc::PF_HH>(sn[0], sn[1], h0, l0);
+  tc::split2<tc::PF_HH>(sn[2], sn[3], h1, l1);
+  *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(lo + o) = make_uint2(l0, l1);
+  tc::split2<tc::PF_HH>(cs[0], cs[1], h0, l0);
+  tc::split2<tc::PF_HH>(cs[2], cs[3], h1, l1);
+  *reinterpret_cast<uint2*>(hi + o + M) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(lo + o + M) = make_uint2(l0, l1);
+}
+// W0 itself (not folded with the stream scalings), rows l * 128 + h, fp16 hi/lo planes of PL_SW0[0] * W0
+__global__ void split_w0_kernel(const float* __restrict__ W0, const float* __restrict__ plan,
+                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int L, long K0) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  long n = (long)L * kHidden * K0;
+  if (i >= n) return;
+  const int l = (int)(i / (kHidden * K0));
+  uint16_t a, b;
+  tc::split1<tc::PF_HH>(W0[i] * plan[(long)l * PL_STRIDE + PL_SW0], a, b);
+  reinterpret_cast<uint16_t*>(hi)[i] = a;
+  reinterpret_cast<uint16_t*>(lo)[i] = b;
+}
+// softplus alone at epilogue rate (value-only passes)
+__device__ __forceinline__ float softplus_fast(float z) { return fmaxf(z, 0.f) + __logf(1.f + __expf(-fabsf(z))); }
+
 // ------------------------------------------------------------------------------------------
 // layer-0 forward epilogue (S1, K-major): tile = (copy l, hidden half hc, 128 points)
 //   TMEM columns [s*64 + hh]; writes the 4 activation streams as hi/lo planes for layer 1 and
@@ -1385,6 +1437,30 @@ struct L0FwdEpi {
       }
     }
     tc::named_bar_sync(1 + q, 128);   // the last round's reads are done before the next tile's first write
+  }
+};
+
+// layer-0 VALUE-ONLY epilogue (finite-difference pass): tile = (256 stacked rows of the 4 P shifted points, 2 copies x 128
+// units); a0 = softplus(W0 phi + b0) goes to slot s = row / P of the stream buffer [L][4][P][128]
+struct L0ValEpi {
+  const float* bias;            // b0 (L,128)
+  const float* plan;
+  __nv_bfloat16 *str_hi, *str_lo;
+  int P, L;
+  __device__ static __forceinline__ uint32_t col0(int sub, int j) { return (uint32_t)(sub * 64 + j * 16); }
+  __device__ __forceinline__ void operator()(float (&r)[64], const TileCoord& c, int q, int sub, int lane,
+                                             uint8_t*) const {
+    const long R = (long)c.mt * big::BM + q * 32 + lane;
+    const int l = 2 * c.nt + (sub >> 1), u0 = (sub & 1) * 64;
+    if (R >= 4L * P || l >= L) return;
+    const int s = (int)(R / P);
+    const long p = R % P;
+    const float inv = __ldg(plan + (long)l * PL_STRIDE + PL_INV_W0), sa = __ldg(plan + (long)l * PL_STRIDE + PL_SA0);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) r[i] = softplus_fast(fmaf(r[i], inv, __ldg(bias + l * kHidden + u0 + i))) * sa;
+    const long o = (((long)l * 4 + s) * P + p) * kHidden + u0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) store_split16h(&r[j * 16], str_hi + o + j * 16, str_lo + o + j * 16);
   }
 };
 
@@ -1774,7 +1850,7 @@ struct HidFwd12Maps {
   CUtensorMap s1h, s1l;   // saved a1 value stream   [H][B][L]              store box {32, 128}, 64-byte swizzle
   CUtensorMap v1h, v1l;   // the same buffer                                 load box {64, 128}
   CUtensorMap s2h, s2l;   // saved a2 value stream                           store box {32, 128}
-  CUtensorMap xsh, xsl;   // scratch  [H][128][grid x 2 slots x 3 streams]   store box {32, 128}
+  CUtensorMap xsh, xsl;   // scratch  [H][128][grid x 2 slots x 4 streams]   store box {32, 128}
   CUtensorMap xlh, xll;   // the same buffer                                 load box {64, 128}
 };
 struct HidFwd12Args {
@@ -1788,6 +1864,8 @@ struct HidFwd12Args {
   const float* mscales;              // (L) or null
   float *F, *TF, *U0;                // (Btot, L)
   nsvd_problem_t pb;
+  int vmode;                         // finite-difference pass: the 4 stream slots are 4 shifted point sets, values only;
+                                     // reads U0 (central pass), writes TF, stores nothing else
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -1870,7 +1948,8 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           mbar_wait(&adone[slot], (uint32_t)(g & 1), 61);
           fence_proxy_async_all();
         }
-        const int xs = ((int)blockIdx.x * 2 + slot) * 3;
+        const int xs = ((int)blockIdx.x * 2 + slot) * 4;
+        const bool vm = args.vmode != 0;
         {
           // L2 prefetch of the layer-1 operands (256 KB from DRAM) of the tile that starts one or two items later:
           // A(t0) announces t1, B(t0) / B(t1) announce the next group's t0 / t1
@@ -1879,7 +1958,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
             const int ln = tn / args.m_tiles, mn = tn % args.m_tiles;
             for (int sc = 0; sc < 8; ++sc) {
               const int s = sc >> 1, c = sc & 1;
-              if (s == 0) {
+              if (s == 0 && !vm) {
                 tma_prefetch_3d(&tm.v0h, 64 * c, (int)args.p_off + mn * 128, ln);
                 tma_prefetch_3d(&tm.v0l, 64 * c, (int)args.p_off + mn * 128, ln);
               } else {
@@ -1894,15 +1973,15 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           mbar_wait(&empty[stage], phase ^ 1, 62);
           uint8_t* d = sA + stage * F_STAGE_BYTES;
           mbar_arrive_expect_tx(&full[stage], F_STAGE_BYTES);
-          if (s == 0) {   // value stream: from `saved` (whole-batch rows)
+          if (s == 0 && !vm) {   // value stream: from `saved` (whole-batch rows)
             tma_load_3d(d, layer ? &tm.v1h : &tm.v0h, &full[stage], 64 * c, (int)args.p_off + mt * 128, l);
             tma_load_3d(d + CHUNK, layer ? &tm.v1l : &tm.v0l, &full[stage], 64 * c, (int)args.p_off + mt * 128, l);
           } else if (!layer) {
             tma_load_3d(d, &tm.a0h, &full[stage], 64 * c, mt * 128, l * 4 + s);
             tma_load_3d(d + CHUNK, &tm.a0l, &full[stage], 64 * c, mt * 128, l * 4 + s);
           } else {
-            tma_load_3d(d, &tm.xlh, &full[stage], 64 * c, 0, xs + s - 1);
-            tma_load_3d(d + CHUNK, &tm.xll, &full[stage], 64 * c, 0, xs + s - 1);
+            tma_load_3d(d, &tm.xlh, &full[stage], 64 * c, 0, xs + s);
+            tma_load_3d(d + CHUNK, &tm.xll, &full[stage], 64 * c, 0, xs + s);
           }
           if (++stage == F_STAGES) {
             stage = 0;
@@ -1968,6 +2047,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
     uint32_t tphase = 0;
     int cur_key = -1;
     float un[4] = {1.f, 1.f, 1.f, 1.f}, so[4] = {1.f, 1.f, 1.f, 1.f};
+    const bool vm = args.vmode != 0;
     for (int i = 0; i < n_items; ++i) {
       const int g = i >> 2, layer = (i >> 1) & 1, slot = i & 1, t = t_begin + 2 * g + slot;
       if (t >= t_end) continue;
@@ -1986,8 +2066,9 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
         const float* pl = args.plan + (long)l * PL_STRIDE;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          un[s] = __ldg(pl + (last ? PL_U2 : PL_U1) + s) * (1.f + kTruncPerMma * 24.f);   // K = 128: chains of 24 MMAs
-          so[s] = last ? __ldg(pl + PL_SA2) : __ldg(pl + PL_SA1 + s);
+          const int ss = vm ? 0 : s;             // value-only pass: every slot carries a value stream
+          un[s] = __ldg(pl + (last ? PL_U2 : PL_U1) + ss) * (1.f + kTruncPerMma * 24.f);   // K = 128: chains of 24 MMAs
+          so[s] = last ? __ldg(pl + PL_SA2) : __ldg(pl + PL_SA1 + ss);
         }
         cur_key = key;
         named_bar_sync(1, F_EPI_WARPS * 32);
@@ -1996,7 +2077,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
       tphase ^= 1;
       tc_fence_after();
       float u[4] = {0.f, 0.f, 0.f, 0.f};
-      const int xs = ((int)blockIdx.x * 2 + slot) * 3;
+      const int xs = ((int)blockIdx.x * 2 + slot) * 4;
 #pragma unroll 1
       for (int r = 0; r < 4; ++r) {          // h-quarters of 32 hidden units; this warp takes 8 of them
         const int h0 = r * 32 + sub * 8;
@@ -2009,10 +2090,17 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty);
         }
+        if (!vm) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float zb = fmaf(z[0][k], un[0], bias_s[h0 + k]);
-          act_streams(zb, z[1][k] * un[1], z[2][k] * un[2], z[3][k] * un[3], z[0][k], z[1][k], z[2][k], z[3][k]);
+          for (int k = 0; k < 8; ++k) {
+            float zb = fmaf(z[0][k], un[0], bias_s[h0 + k]);
+            act_streams(zb, z[1][k] * un[1], z[2][k] * un[2], z[3][k] * un[3], z[0][k], z[1][k], z[2][k], z[3][k]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) z[s][k] = softplus_fast(fmaf(z[s][k], un[s], bias_s[h0 + k]));
         }
         if (last) {
 #pragma unroll
@@ -2040,7 +2128,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           if (et == 0) tma_store_wait_read();
           named_bar_sync(2, F_EPI_WARPS * 32);
         }
-        const int ns = last ? 1 : 4;
+        const int ns = last ? (vm ? 0 : 1) : 4;
         for (int s = 0; s < ns; ++s) {
           uint32_t h[4], lo[4];
 #pragma unroll
@@ -2057,12 +2145,17 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           if (!last) {
 #pragma unroll
             for (int s = 1; s < 4; ++s) {
-              tma_store_3d(&tm.xsh, sO + (2 * s) * F_BOX, r * 32, 0, xs + s - 1);
-              tma_store_3d(&tm.xsl, sO + (2 * s + 1) * F_BOX, r * 32, 0, xs + s - 1);
+              tma_store_3d(&tm.xsh, sO + (2 * s) * F_BOX, r * 32, 0, xs + s);
+              tma_store_3d(&tm.xsl, sO + (2 * s + 1) * F_BOX, r * 32, 0, xs + s);
             }
-            tma_store_3d(&tm.s1h, sO, r * 32, (int)args.p_off + mt * 128, l);
-            tma_store_3d(&tm.s1l, sO + F_BOX, r * 32, (int)args.p_off + mt * 128, l);
-          } else {
+            if (vm) {      // slot 0 is a shifted point set too: scratch, not `saved`
+              tma_store_3d(&tm.xsh, sO, r * 32, 0, xs);
+              tma_store_3d(&tm.xsl, sO + F_BOX, r * 32, 0, xs);
+            } else {
+              tma_store_3d(&tm.s1h, sO, r * 32, (int)args.p_off + mt * 128, l);
+              tma_store_3d(&tm.s1l, sO + F_BOX, r * 32, (int)args.p_off + mt * 128, l);
+            }
+          } else if (!vm) {
             tma_store_3d(&tm.s2h, sO + sb * F_BOX, r * 32, (int)args.p_off + mt * 128, l);
             tma_store_3d(&tm.s2l, sO + (sb + 1) * F_BOX, r * 32, (int)args.p_off + mt * 128, l);
           }
@@ -2085,15 +2178,23 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           for (int j = 0; j < 3; ++j)
 #pragma unroll
             for (int s = 0; s < 4; ++s) u[s] += ubuf[(row * 3 + j) * 4 + s];
-          u[0] += __ldg(args.b3 + l);
           const long pg = args.p_off + pt;
-          PointGeom gm = point_geom(args.x[2 * pg], args.x[2 * pg + 1], args.pb);
-          float f, tf;
-          operator_epilogue(gm, args.pb, args.pb.has_exp_mask != 0, args.pb.has_exp_mask ? args.mscales[l] : 1.f,
-                            u[0], u[1], u[2], u[3], f, tf);
-          args.F[pg * args.L + l] = f;
-          args.TF[pg * args.L + l] = tf;
-          args.U0[pg * args.L + l] = u[0];
+          const float msc = args.pb.has_exp_mask ? args.mscales[l] : 1.f;
+          if (vm) {        // finite differences of the four shifted values around the central one (first pass)
+            const float b3v = __ldg(args.b3 + l);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) u[s] += b3v;
+            args.TF[pg * args.L + l] = fd_operator(args.x[2 * pg], args.x[2 * pg + 1], args.pb,
+                                                   args.pb.has_exp_mask != 0, msc, args.U0[pg * args.L + l], u);
+          } else {
+            u[0] += __ldg(args.b3 + l);
+            PointGeom gm = point_geom(args.x[2 * pg], args.x[2 * pg + 1], args.pb);
+            float f, tf;
+            operator_epilogue(gm, args.pb, args.pb.has_exp_mask != 0, msc, u[0], u[1], u[2], u[3], f, tf);
+            args.F[pg * args.L + l] = f;
+            args.TF[pg * args.L + l] = tf;
+            args.U0[pg * args.L + l] = u[0];
+          }
         }
         named_bar_sync(1, F_EPI_WARPS * 32);  // ubuf (staging boxes 6-7) is free again
       }
@@ -2496,7 +2597,8 @@ struct TcLayout {
   // saved (whole batch)
   size_t phi_hi, phi_lo, av_hi[3], av_lo[3], u0, plan, rowstat, hstat, mdf, saved_total;
   // work
-  size_t w0_hi, w0_lo, w_hi[2], w_lo[2], str_hi[2], str_lo[2], dz_hi[2], dz_lo[2], scr_hi, scr_lo, work_total;
+  size_t w0_hi, w0_lo, w_hi[2], w_lo[2], str_hi[2], str_lo[2], dz_hi[2], dz_lo[2], scr_hi, scr_lo, phis_hi, phis_lo,
+      w0v_hi, w0v_lo, work_total;
   long P;
 };
 static TcLayout tc_layout(const nsvd_problem_t& pb) {
@@ -2535,8 +2637,14 @@ static TcLayout tc_layout(const nsvd_problem_t& pb) {
     t.str_lo[i] = take(L * 4 * P * H * 2);
   }
   // L2-resident scratch of the fused hidden forward: 148 CTAs x 2 tile slots x 3 derivative streams x (128 x 128) planes
-  t.scr_hi = take((size_t)kHidGrid * 6 * hid::PLANE);
-  t.scr_lo = take((size_t)kHidGrid * 6 * hid::PLANE);
+  t.scr_hi = take((size_t)kHidGrid * 8 * hid::PLANE);
+  t.scr_lo = take((size_t)kHidGrid * 8 * hid::PLANE);
+  if (pb.fd_eps > 0.f) {   // finite-difference pass: features of the 4 shifted point sets, W0 planes (not folded)
+    t.phis_hi = take(4 * P * K0 * 2);
+    t.phis_lo = take(4 * P * K0 * 2);
+    t.w0v_hi = take(L * H * K0 * 2);
+    t.w0v_lo = take(L * H * K0 * 2);
+  }
   // backward reuses the stream area for the dZ planes (two ping-pong pairs)
   for (int i = 0; i < 2; ++i) {
     t.dz_hi[i] = t.str_hi[i];
@@ -2603,6 +2711,10 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
                                                          BF(wk + t.w_lo[i]), (int)L, 0);
     NSVD_LAUNCH_CHECK();
   }
+  if (pb.fd_eps > 0.f) {
+    split_w0_kernel<<<cdiv(L * H * K0, 256), 256, 0, st>>>(pr.W[0], plan, BF(wk + t.w0v_hi), BF(wk + t.w0v_lo), (int)L, K0);
+    NSVD_LAUNCH_CHECK();
+  }
   }
   CUtensorMap mW0h, mW0l, mWh[2], mWl[2];
   const uint32_t w0_box = big::BN / 2;   // a CTA of a pair loads half of the 256 W' rows
@@ -2660,7 +2772,7 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
       if ((rc = make_tmap_bf16_3d(&hm.v1l, sv + t.av_lo[1], H, B, L, H * 2, BH, 64, 128))) return rc;
       if ((rc = make_tmap_bf16_3d(&hm.s2h, sv + t.av_hi[2], H, B, L, H * 2, BH, 32, 128, 64))) return rc;
       if ((rc = make_tmap_bf16_3d(&hm.s2l, sv + t.av_lo[2], H, B, L, H * 2, BH, 32, 128, 64))) return rc;
-      const uint64_t nslot = (uint64_t)kHidGrid * 6;
+      const uint64_t nslot = (uint64_t)kHidGrid * 8;
       if ((rc = make_tmap_bf16_3d(&hm.xsh, wk + t.scr_hi, H, 128, nslot, H * 2, hid::PLANE, 32, 128, 64))) return rc;
       if ((rc = make_tmap_bf16_3d(&hm.xsl, wk + t.scr_lo, H, 128, nslot, H * 2, hid::PLANE, 32, 128, 64))) return rc;
       if ((rc = make_tmap_bf16_3d(&hm.xlh, wk + t.scr_hi, H, 128, nslot, H * 2, hid::PLANE, 64, 128))) return rc;
@@ -2683,12 +2795,47 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
       a.U0 = reinterpret_cast<float*>(sv + t.u0);
       a.pb = pb;
       NSVD_SMEM_OPTIN(hidden_fwd12_kernel, hid::SMEM_FWD);
-      ProfScope ps(KC_HID_FWD, st);
-      hidden_fwd12_kernel<<<grid, hid::F_THREADS, hid::SMEM_FWD, st>>>(hm, a);
-      NSVD_LAUNCH_CHECK();
+      {
+        ProfScope ps(KC_HID_FWD, st);
+        hidden_fwd12_kernel<<<grid, hid::F_THREADS, hid::SMEM_FWD, st>>>(hm, a);
+        NSVD_LAUNCH_CHECK();
+      }
+      if (pb.fd_eps > 0.f) {
+        // ---- finite-difference Laplacian (pde/diff_ops.py:25-52): second pass over this micro-batch.  The four
+        // stream slots carry the four shifted point sets, value stream only; F, U0 and the saved activations of the
+        // central pass stay (the backward needs exactly those), TF is overwritten.
+        const float* xm = x + 2 * p0;
+        features_shift_f16_kernel<<<cdiv(4L * P * (M / 4), 256), 256, 0, st>>>(xm, pr.Bff, BF(wk + t.phis_hi),
+                                                                              BF(wk + t.phis_lo), P, (int)M, pb.fd_eps);
+        NSVD_LAUNCH_CHECK();
+        CUtensorMap mXh, mXl, mVh, mVl;
+        if ((rc = make_tmap_bf16_3d(&mXh, wk + t.phis_hi, K0, 4 * (uint64_t)P, 1, K0 * 2, 4 * (uint64_t)P * K0 * 2, 64, big::BM))) return rc;
+        if ((rc = make_tmap_bf16_3d(&mXl, wk + t.phis_lo, K0, 4 * (uint64_t)P, 1, K0 * 2, 4 * (uint64_t)P * K0 * 2, 64, big::BM))) return rc;
+        if ((rc = make_tmap_bf16_3d(&mVh, wk + t.w0v_hi, K0, L * H, 1, K0 * 2, L * H * K0 * 2, 64, big::BN / 2))) return rc;
+        if ((rc = make_tmap_bf16_3d(&mVl, wk + t.w0v_lo, K0, L * H, 1, K0 * 2, L * H * K0 * 2, 64, big::BN / 2))) return rc;
+        BigShape sv2{};
+        sv2.m_tiles = cdiv(4L * P, 2 * big::BM);
+        sv2.n_tiles = cdiv(L * H, big::BN);
+        sv2.batches = 1;
+        sv2.k_slices = 1;
+        sv2.k_chunks_total = cdiv(K0, big::BK);
+        sv2.k_chunks_per_slice = sv2.k_chunks_total;
+        sv2.m_group = 16;
+        L0ValEpi ev{pr.b[0], plan, BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), P, (int)L};
+        {
+          ProfScope ps(KC_L0_FWD, st);
+          static const int sub = env_int("NSVD_L0_SUBCHUNKS", 4), sub_first = env_int("NSVD_L0_SUBFIRST", 6);
+          if ((rc = launch_big2s<false, L0ValEpi, kFmtHH>(mXh, mXl, mVh, mVl, sv2, 1, sub, sub_first, ev, st))) return rc;
+        }
+        a.vmode = 1;
+        ProfScope ps(KC_HID_FWD, st);
+        hidden_fwd12_kernel<<<grid, hid::F_THREADS, hid::SMEM_FWD, st>>>(hm, a);
+        NSVD_LAUNCH_CHECK();
+      }
       continue;
     }
     // one kernel per layer (NSVD_HIDDEN_FUSED=0): the derivative streams of a1 go through the second stream buffer
+    NSVD_CHECK_ARG(!(pb.fd_eps > 0.f), "the finite-difference pass exists in the fused hidden kernel only (NSVD_HIDDEN_FUSED=1)");
     for (int i = 0; i < 2; ++i) {
       CUtensorMap mAh, mAl, mOh, mOl, mSh, mSl;
       if ((rc = make_tmap_bf16_3d(&mAh, wk + t.str_hi[i], H, P, 4 * L, H * 2, (uint64_t)P * H * 2, 64, 128))) return rc;

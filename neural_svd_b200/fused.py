@@ -107,7 +107,7 @@ def _problem(md, od, imp, B) -> _lib.Problem:
                         pot_coef=od["pot_coef"], scale_kinetic=od["scale_kinetic"], op_scale=od["op_scale"],
                         op_shift=od["op_shift"], sampling_sigma=imp["sigma"], hard_mul_const=md["hard_mul_const"],
                         importance=imp["importance"], box_mask=md["box_mode"], pot_coef2=od.get("pot_coef2", 0.0),
-                        box_lim=md["box_lim"])
+                        box_lim=md["box_lim"], fd_eps=od.get("fd_eps", 0.0), reserved_=0)
 
 
 def _params_struct(md) -> _lib.Params:

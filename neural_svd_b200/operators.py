@@ -120,13 +120,9 @@ class OperatorWrapper:
         return fused.apply_operator(model, self, x, importance)
 
 
-_FD_WARNED = False
-
-
 def describe_operator(operator):
     """Recognise OperatorWrapper(NegativeHamiltonian(hydrogen|oscillator)) — by duck typing, so the
     reference's own objects are accepted too.  Anything else raises (no fallback)."""
-    global _FD_WARNED
     inner = getattr(operator, "operator", None)
     if inner is None or not hasattr(operator, "scale") or not hasattr(operator, "shift"):
         raise NotImplementedError("fused path needs an OperatorWrapper(NegativeHamiltonian(...))")
@@ -156,13 +152,14 @@ def describe_operator(operator):
         kind, coef, coef2 = 4, float(cs[0]), float(cs[1])
     else:
         raise NotImplementedError(f"unsupported potential {name!r}")
-    eps = getattr(inner, "laplacian_eps", 0.0)
-    if eps is not None and eps > 0 and not _FD_WARNED:
-        _FD_WARNED = True
-        warnings.warn(f"laplacian_eps={eps}: the fused kernel evaluates the EXACT Laplacian in forward mode "
-                      "(the limit the reference's finite difference approximates; see DESIGN.md)")
+    # laplacian_eps > 0: the finite-difference Laplacian of diff_ops.py:25-52 (what the shipped scripts run);
+    # <= 0 / None: the exact one (diff_ops.py:7, 54-61), evaluated in forward mode
+    eps = getattr(inner, "laplacian_eps", None)
+    if eps is None:
+        eps = getattr(getattr(inner, "laplacian", None), "eps", 0.0)
+    eps = float(eps) if eps is not None and eps > 0 else 0.0
     return dict(potential=kind, pot_coef=coef, pot_coef2=coef2, scale_kinetic=float(inner.scale_kinetic),
-                op_scale=float(operator.scale), op_shift=float(operator.shift))
+                op_scale=float(operator.scale), op_shift=float(operator.shift), fd_eps=eps)
 
 
 _IMP_CODES = {"gaussian": 0, "laplacian": 1, "uniform": 2}

@@ -66,6 +66,12 @@ CASES = {
     # register_eigvals(): the model's output columns are permuted by sort_indices in training mode (nestedlora.py:195-206)
     "hyd_small_sorted": dict(cfg=O.PathConfig.hydrogen(neigs=6, fourier_mapping_size=64, sequential=True), B=64, seed=13,
                              eigvals=[3.0, 9.0, 1.0, 7.0, 8.0, 2.0]),
+    # finite-difference Laplacian (the scripts' mode, diff_ops.py:25-52): eps = 0.1 is main_pde's default, 0.01 the
+    # value of scripts/exps/pde/*.sh; the fixture stores the reference's fp64 AND fp32 results (FD in fp32 is noisy)
+    "hyd_small_fd0p1": dict(cfg=O.PathConfig.hydrogen(neigs=4, fourier_mapping_size=64), B=96, seed=14, eps=0.1),
+    "osc_small_fd0p01": dict(cfg=O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64, sequential=True), B=64,
+                             seed=15, eps=0.01),
+    "hyd_b512_jnt_L16_fd0p01": dict(cfg=O.PathConfig.hydrogen(), B=512, seed=16, eps=0.01),
     "osc_no_importance": dict(cfg=O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64, sampling_mode="none"),
                               B=64, seed=9),
 }
@@ -96,8 +102,8 @@ def checksum(a: np.ndarray):
     return np.array([a.sum(), (a * a).sum()])
 
 
-def run_reference(ref, cfg, seed, x32, dtype, eigvals=None):
-    method, operator, importance, gt = RB.build_reference_problem(ref, cfg, seed, 0.0, dtype)
+def run_reference(ref, cfg, seed, x32, dtype, eigvals=None, eps=0.0):
+    method, operator, importance, gt = RB.build_reference_problem(ref, cfg, seed, eps, dtype)
     if eigvals is not None:
         method.register_eigvals(eigvals)
     x = torch.from_numpy(x32).to(dtype)
@@ -120,8 +126,8 @@ def make_case(ref, name, spec):
         x32 = (-cfg.sampling_scale * u.sign() * torch.log1p(-2 * u.abs())).float().reshape(B, -1).numpy()
     else:                                                           # main_pde.py:92-93
         x32 = (cfg.sampling_scale * torch.randn((B, 1, cfg.ndim), generator=g)).reshape(B, -1).numpy()
-    r64 = run_reference(ref, cfg, seed, x32, torch.float64, spec.get("eigvals"))
-    r32 = run_reference(ref, cfg, seed, x32, torch.float32, spec.get("eigvals"))
+    r64 = run_reference(ref, cfg, seed, x32, torch.float64, spec.get("eigvals"), spec.get("eps", 0.0))
+    r32 = run_reference(ref, cfg, seed, x32, torch.float32, spec.get("eigvals"), spec.get("eps", 0.0))
     mine = O.init_params_like_reference(cfg, seed)
     out = dict(x=x32, seed=np.int64(seed), config=json.dumps(dataclasses.asdict(cfg)),
                loss64=np.float64(r64["loss"]), loss32=np.float64(r32["loss"]),
@@ -129,6 +135,11 @@ def make_case(ref, name, spec):
                gt=np.asarray(r64["gt"], np.float64))
     if spec.get("eigvals") is not None:
         out["eigvals"] = np.asarray(spec["eigvals"], np.float64)
+    if spec.get("eps"):
+        out["laplacian_eps"] = np.float64(spec["eps"])
+        # the reference's own fp32-vs-fp64 noise in finite-difference mode
+        out["tf_self"] = np.float64(np.linalg.norm(r32["Tf"].astype(np.float64) - r64["Tf"]) / np.linalg.norm(r64["Tf"]))
+        out["loss_self"] = np.float64(abs(r32["loss"] / r64["loss"] - 1))
     rs = np.random.RandomState(seed)
     for n in O.param_names(cfg):
         p_ref = r32["params"][n]

@@ -374,13 +374,60 @@ def mlp_backward(x, dF, params, cfg: PathConfig, u0, acts, sigs, aux) -> Dict[st
     return grads
 
 
-def train_step(x: np.ndarray, params: Dict[str, np.ndarray], cfg: PathConfig, sort_indices=None):
+def weighted_values(y: np.ndarray, params: Dict[str, np.ndarray], cfg: PathConfig) -> np.ndarray:
+    """g(y) = sqrt(w(y)) * WaveFunctions(y)  (B, L): the function the finite-difference Laplacian differentiates
+    (diff_ops.py:13; without importance g = f, diff_ops.py:10-11)."""
+    dt = y.dtype
+    u0 = forward_streams(y, params, cfg)[0]                          # (B, L) raw network values
+    r = np.sqrt((y ** 2).sum(1))[:, None]
+    m = np.ones_like(u0)
+    if cfg.apply_exp_mask:
+        m = np.exp(-r / params["model.boundary_mask.scales"].astype(dt)[None, :])      # boundary.py:48-49
+    mb, _, _ = box_mask_terms(y, cfg)
+    w, _, _ = importance_terms(y, cfg)
+    sw = np.sqrt(w)[:, None] if w is not None else 1.0
+    return (sw * (cfg.hard_mul_const * m * mb[:, None] * u0)).astype(dt)
+
+
+def operator_apply_fd(x: np.ndarray, params: Dict[str, np.ndarray], cfg: PathConfig, eps: float):
+    """(Tf, f) with the FINITE-DIFFERENCE Laplacian the shipped scripts use (`laplacian_eps > 0`):
+    VectorizedLaplacian.approx_laplacian (pde/diff_ops.py:25-52) of g = sqrt(w) f, divided by clamp(sqrt w, 1e-5)
+    (:15-18), then NegativeHamiltonian / OperatorWrapper as in operator_apply.  The shift vector is built in fp32
+    (`torch.zeros((1, D))`, diff_ops.py:43-44) whatever x's dtype is, the division is by the python float eps**2."""
+    dt = x.dtype
+    D = cfg.ndim
+    g0 = weighted_values(x, params, cfg)
+    lap = -2.0 * D * g0                                             # diff_ops.py:40
+    sh = np.float32(eps).astype(dt)
+    for i in range(D):
+        e = np.zeros((1, D), dt)
+        e[0, i] = sh
+        lap = lap + (weighted_values(x + e, params, cfg) + weighted_values(x - e, params, cfg))
+    lap = lap / dt.type(eps ** 2)                                   # diff_ops.py:48
+    w, _, _ = importance_terms(x, cfg)
+    if w is not None:
+        sw = np.maximum(np.sqrt(w)[:, None], 1e-5)                  # diff_ops.py:15
+        lap, f = lap / sw, g0 / sw
+    else:
+        f = g0
+    V = potential(x, cfg)[:, None]
+    negH = cfg.scale_kinetic * lap - V * f
+    Tf = cfg.operator_scale * negH + cfg.operator_shift * f
+    return Tf.astype(dt), f.astype(dt)
+
+
+def train_step(x: np.ndarray, params: Dict[str, np.ndarray], cfg: PathConfig, sort_indices=None,
+               laplacian_eps: float = 0.0):
     """One loss+grad evaluation == reference `compute_loss_operator` + `loss.backward()`
-    with `laplacian_eps<=0` (nestedlora.py:254-267, operator/__init__.py:62-68).
+    (nestedlora.py:254-267, operator/__init__.py:62-68) with the exact Laplacian (`laplacian_eps <= 0`) or the
+    finite-difference one.  Either way the gradient flows through the CENTRAL evaluation's value stream only
+    (the custom backward returns None for Tf, nestedlora.py:98-111).
     `sort_indices`: the permutation NestedLoRA.forward applies to the model output in training mode after
     register_eigvals() (nestedlora.py:195-206); f, Tf, dF are returned in the permuted column order."""
     u, acts, sigs = forward_streams(x, params, cfg, keep=True)
     Tf, f, aux = operator_apply(x, u, params, cfg)
+    if laplacian_eps > 0:
+        Tf, f = operator_apply_fd(x, params, cfg, laplacian_eps)
     if sort_indices is not None:
         si = np.asarray(sort_indices)
         f, Tf = f[:, si], Tf[:, si]

@@ -35,12 +35,12 @@ def load_golden(name):
     return d, cfg
 
 
-def ref_args(cfg):
+def ref_args(cfg, laplacian_eps=0.0):
     """argparse-like namespace for get_problem / get_wavefunctions from an oracle PathConfig."""
     from types import SimpleNamespace
     return SimpleNamespace(
         problem="sch", potential_type=cfg.potential, ndim=cfg.ndim, neigs=cfg.neigs, charge=cfg.charge,
-        laplacian_eps=0.0, operator_scale=cfg.operator_scale, operator_shift=cfg.operator_shift, lim=cfg.lim,
+        laplacian_eps=laplacian_eps, operator_scale=cfg.operator_scale, operator_shift=cfg.operator_shift, lim=cfg.lim,
         use_fourier_feature=True, fourier_mapping_size=cfg.fourier_mapping_size, fourier_scale=cfg.fourier_scale,
         fourier_deterministic=cfg.fourier_deterministic, fourier_append_raw=False,
         mlp_hidden_dims=",".join(str(h) for h in cfg.hidden), nonlinearity="softplus", parallel=True,
@@ -50,11 +50,11 @@ def ref_args(cfg):
         sampling_scale=cfg.sampling_scale)
 
 
-def build_problem(cfg, seed, device="cpu"):
+def build_problem(cfg, seed, device="cpu", laplacian_eps=0.0):
     """(method, operator, importance) from the product's own mirror classes, reference RNG order."""
     import torch
     import neural_svd_b200 as N
-    args = ref_args(cfg)
+    args = ref_args(cfg, laplacian_eps)
     torch.manual_seed(seed)
     operator, gt = N.get_problem(args)
     model = N.get_wavefunctions(args)

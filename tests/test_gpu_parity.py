@@ -47,6 +47,43 @@ def test_step_matches_reference_golden(name, engine):
     assert max(errs.values()) < TOL, errs
 
 
+PDE_FD = ["hyd_small_fd0p1", "osc_small_fd0p01", "hyd_b512_jnt_L16_fd0p01"]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", PDE_FD)
+def test_finite_difference_step_matches_reference(name, engine):
+    # laplacian_eps > 0 (every shipped script: hydrogen.sh:20): VectorizedLaplacian.approx_laplacian, diff_ops.py:25-52.
+    # Parity is against the reference's FD path in fp64.  Second differences divide round-off by eps^2, so in fp32 the
+    # REFERENCE itself is this far from its own fp64 result (stored in the fixture): Tf 3e-4 (small cases), 4e-2
+    # (hydrogen L=16, eps = 0.01).  The bar: within 3x that self-noise for the fp32 engine, 10x for the tensor-core
+    # engine (22-bit operands), and never worse than 1e-4 where the reference's noise is below it.
+    d, cfg = load_golden(name)
+    eps = float(d["laplacian_eps"])
+    N.set_engine(engine)
+    method, operator, importance, _ = build_problem(cfg, int(d["seed"]), "cuda", laplacian_eps=eps)
+    x = torch.from_numpy(d["x"]).cuda()
+    loss, aux = method.compute_loss_operator(operator, x, importance=importance)
+    loss.backward()
+    grads = {n: p.grad.detach().cpu().numpy() for n, p in method.named_parameters() if p.grad is not None}
+    k = 3.0 if engine == "fp32" else 10.0
+    e_loss = abs(float(loss.detach()) / float(d["loss64"]) - 1)
+    e_f, e_tf = rel(aux["f"].cpu().numpy(), d["f64"]), rel(aux["Tf"].cpu().numpy(), d["Tf64"])
+    errs = golden_grad_errors(d, list(grads), grads)
+    print(f"[{engine}] {name}: loss {e_loss:.1e} (ref self {float(d['loss_self']):.1e}) f {e_f:.1e} Tf {e_tf:.1e} "
+          f"(ref self {float(d['tf_self']):.1e}) grads max {max(errs.values()):.1e}")
+    assert e_f < TOL                                      # f is the central evaluation: no cancellation
+    assert e_tf < max(TOL, k * float(d["tf_self"]))
+    # the loss is ONE number: the reference's own deviation is a single noise draw, so its bar is 10x for both engines
+    assert e_loss < max(TOL, 10.0 * float(d["loss_self"]))
+    for n, e in errs.items():
+        assert e < max(TOL, k * float(d[f"gself/{n}"])), (n, e, float(d[f"gself/{n}"]))
+    # the same model with laplacian_eps = 0 gives the exact-Laplacian result: the two modes really differ
+    method0, operator0, _, _ = build_problem(cfg, int(d["seed"]), "cuda")
+    _, aux0 = method0.compute_loss_operator(operator0, x, importance=importance)
+    assert rel(aux0["Tf"].cpu().numpy(), aux["Tf"].cpu().numpy()) > 1e-7
+
+
 @pytest.mark.parametrize("neigs", [6, 5])
 @pytest.mark.parametrize("engine", ENGINES)
 def test_step_matches_oracle_on_fresh_inputs(engine, neigs):

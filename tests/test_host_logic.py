@@ -45,7 +45,16 @@ def test_describe_operator_and_importance():
     d, cfg = load_golden("osc_small_seq")
     method, operator, importance, _ = build_problem(cfg, 0)
     od = operators.describe_operator(operator)
-    assert od == dict(potential=1, pot_coef=1.0, pot_coef2=0.0, scale_kinetic=1.0, op_scale=1.0, op_shift=16.0)
+    assert od == dict(potential=1, pot_coef=1.0, pot_coef2=0.0, scale_kinetic=1.0, op_scale=1.0, op_shift=16.0,
+                      fd_eps=0.0)
+    # laplacian_eps > 0 selects the finite-difference Laplacian (diff_ops.py:7), on the mirror and on a duck-typed
+    # reference-style object that only keeps it inside its VectorizedLaplacian
+    _, op_fd, _, _ = build_problem(cfg, 0, laplacian_eps=0.01)
+    assert operators.describe_operator(op_fd)["fd_eps"] == pytest.approx(0.01)
+    import types
+    ref_like = types.SimpleNamespace(local_potential_ftn=op_fd.operator.local_potential_ftn, scale_kinetic=1.0,
+                                     n_particles=1, laplacian=types.SimpleNamespace(eps=0.1))
+    assert operators.describe_operator(operators.OperatorWrapper(ref_like, 1.0, 0.0))["fd_eps"] == pytest.approx(0.1)
     assert operators.describe_importance(importance) == dict(importance=0, sigma=4.0)
     md = fused.describe_model(method)
     assert md["L"] == 4 and md["Mff"] == 64 and md["scales"] is not None and md["hard_mul_const"] == 0.5

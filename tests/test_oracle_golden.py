@@ -10,6 +10,8 @@ PDE_SMALL = ["hyd_small_odd", "osc_small_seq", "hyd_small_sorted",
              # other potentials, samplers, Dirichlet box masks, deterministic features
              "well_uniform_boxsqrt", "cosine_uniform_detff", "molion_laplace_boxexp_mask", "osc_no_importance"]
 PDE_FULL = ["hyd_b128_seq_L16", "osc_b512_jnt_L16", "hyd_b512_jnt_L16"]
+# finite-difference Laplacian (laplacian_eps > 0, the scripts' mode): fp64 parity only - FD in fp32 is noise-limited
+PDE_FD = ["hyd_small_fd0p1", "osc_small_fd0p01", "hyd_b512_jnt_L16_fd0p01"]
 
 
 def _run(name, dtype):
@@ -23,19 +25,21 @@ def _run(name, dtype):
     si = None
     if "eigvals" in d:                                  # register_eigvals(): torch.sort(eigvals)[1].flip(0)
         si = np.argsort(d["eigvals"], kind="stable")[::-1].copy()
-    r = O.train_step(d["x"].astype(dtype), p, cfg, sort_indices=si)
+    eps = float(d["laplacian_eps"]) if "laplacian_eps" in d else 0.0
+    r = O.train_step(d["x"].astype(dtype), p, cfg, sort_indices=si, laplacian_eps=eps)
     return d, cfg, r
 
 
-@pytest.mark.parametrize("name", PDE_SMALL + PDE_FULL)
+@pytest.mark.parametrize("name", PDE_SMALL + PDE_FULL + PDE_FD)
 def test_oracle_fp64_matches_reference(name):
     d, cfg, r = _run(name, np.float64)
-    assert abs(r["loss"] - float(d["loss64"])) <= 1e-11 * abs(float(d["loss64"]))
+    fd = name in PDE_FD              # second differences divide fp64 round-off by eps^2
+    assert abs(r["loss"] - float(d["loss64"])) <= (1e-8 if fd else 1e-11) * abs(float(d["loss64"]))
     assert rel(r["f"], d["f64"]) < 1e-12
-    assert rel(r["Tf"], d["Tf64"]) < 1e-12
+    assert rel(r["Tf"], d["Tf64"]) < (1e-8 if fd else 1e-12)
     errs = golden_grad_errors(d, [n for n in O.param_names(cfg) if n in r["grads"]], r["grads"])
     assert len(errs) >= 8
-    assert max(errs.values()) < 1e-11, errs
+    assert max(errs.values()) < (1e-8 if fd else 1e-11), errs
 
 
 @pytest.mark.parametrize("name", PDE_SMALL)
