@@ -189,10 +189,10 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # problem builders (the product API only: no oracle, no test code) and per-config timing
 # ------------------------------------------------------------------------------------------
-def script_args(kind, neigs):
+def script_args(kind, neigs, laplacian_eps=0.0):
     """Hyper-parameters of scripts/exps/pde/{hydrogen,oscillator}.sh with BASELINE's L."""
     from types import SimpleNamespace
-    base = dict(problem="sch", ndim=2, neigs=neigs, charge=1.0, laplacian_eps=0.0, lim=50.0, use_fourier_feature=True,
+    base = dict(problem="sch", ndim=2, neigs=neigs, charge=1.0, laplacian_eps=laplacian_eps, lim=50.0, use_fourier_feature=True,
                 fourier_deterministic=False, fourier_append_raw=False, mlp_hidden_dims="128,128,128",
                 nonlinearity="softplus", parallel=True, apply_boundary=False, boundary_mode="dir_box_sqrt",
                 hard_mul_const=1.0)
@@ -206,9 +206,9 @@ def script_args(kind, neigs):
     return SimpleNamespace(**base)
 
 
-def make_problem(N, kind, neigs, sequential, dev, seed=0):
+def make_problem(N, kind, neigs, sequential, dev, seed=0, laplacian_eps=0.0):
     import torch
-    cfg = script_args(kind, neigs)
+    cfg = script_args(kind, neigs, laplacian_eps)
     torch.manual_seed(seed)
     operator, _gt = N.get_problem(cfg)
     model = N.get_wavefunctions(cfg)
@@ -231,10 +231,10 @@ def time_events(fn, steps, warmup, sync):
     return e0.elapsed_time(e1) / steps
 
 
-def small_config(N, kind, B, neigs, sequential, dev, steps=50, warmup=10):
+def small_config(N, kind, B, neigs, sequential, dev, steps=50, warmup=10, laplacian_eps=0.0):
     """eager and CUDA-graph step time of one of the reference's own small-batch configurations (1 GPU)."""
     import torch
-    cfg, method, operator, importance = make_problem(N, kind, neigs, sequential, dev)
+    cfg, method, operator, importance = make_problem(N, kind, neigs, sequential, dev, laplacian_eps=laplacian_eps)
     g = torch.Generator().manual_seed(7)
     xs = [(cfg.sampling_scale * torch.randn((B, 1, 2), generator=g)).reshape(B, 2).to(dev) for _ in range(4)]
     it = [0]
@@ -251,6 +251,7 @@ def small_config(N, kind, B, neigs, sequential, dev, steps=50, warmup=10):
     gstep = N.GraphedOperatorStep(method, operator, importance, B)
     ms_graph = time_events(lambda: gstep(xs[0]), steps, warmup, sync)
     return {"points": B, "neigs": neigs, "nesting": "sequential" if sequential else "joint", "problem": kind,
+            "laplacian": f"finite differences, eps={laplacian_eps}" if laplacian_eps > 0 else "exact",
             "ms_per_step_eager": ms_eager, "ms_per_step_graphed": ms_graph,
             "points_per_s_eager": B / (ms_eager * 1e-3), "points_per_s_graphed": B / (ms_graph * 1e-3)}
 
@@ -463,6 +464,22 @@ def run_ours(args):
             configs["config2_oscillator_b512_jnt_L16"] = small_config(N, "oscillator", 512, 16, False, dev)
             configs["config3_hydrogen_b512_jnt_L16"] = small_config(N, "hydrogen", 512, 16, False, dev)
             configs["config5_cdk_b4096_L512"] = cdk_config(N, dev)
+            # the scripts' own Laplacian mode (laplacian_eps = 0.01, hydrogen.sh:20): second, value-only pass over the four
+            # shifted point sets; same batch as config 3 and the headline workload
+            configs["config3_fd_eps0p01"] = small_config(N, "hydrogen", 512, 16, False, dev, laplacian_eps=0.01)
+            cfd, mfd, ofd, ifd = make_problem(N, "hydrogen", args.neigs, False, dev, laplacian_eps=0.01)
+            xfd = (cfd.sampling_scale * torch.randn((P, 1, 2))).reshape(P, 2).to(dev)
+
+            def stepfd():
+                mfd.zero_grad(set_to_none=True)
+                loss, _ = mfd.compute_loss_operator(ofd, xfd, importance=ifd)
+                loss.backward()
+
+            msfd = time_events(stepfd, 5, 2, lambda: torch.cuda.synchronize(dev))
+            configs["headline_workload_fd_eps0p01"] = {"points": P, "ms_per_step": msfd, "points_per_s": P / (msfd * 1e-3)}
+            mfd.__dict__.pop("_nsvd_scratch", None)
+            del mfd, xfd
+            torch.cuda.empty_cache()
             # reference-grade CUDA-core engine on the headline workload, once (validation engine, not the product path)
             N.set_engine("fp32")
             c32, m32, o32, i32 = make_problem(N, "hydrogen", args.neigs, False, dev)
@@ -534,7 +551,10 @@ def run_ours(args):
                 c3["cpu_reference_exact_points_per_s"] = cb["exact_value"]
                 c3["cpu_reference_fd_points_per_s"] = cb["fd_value"]
                 c3["speedup_vs_cpu_exact_same_batch"] = c3["points_per_s_graphed"] / cb["exact_value"]
-                c3["speedup_vs_cpu_fd_same_batch"] = c3["points_per_s_graphed"] / cb["fd_value"]
+                cfd3 = configs.get("config3_fd_eps0p01")
+                if cfd3:    # finite differences on both sides, same batch
+                    cfd3["cpu_reference_fd_points_per_s"] = cb["fd_value"]
+                    cfd3["speedup_vs_cpu_fd_same_batch"] = cfd3["points_per_s_graphed"] / cb["fd_value"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

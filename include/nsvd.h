@@ -101,6 +101,9 @@ typedef struct nsvd_grads {
 } nsvd_grads_t;
 
 int nsvd_abi_version(void);
+/* sha256 over the sources, this header and the compiler flags the library was built from (neural_svd_b200/build.py): a
+ * host layer that cannot rebuild refuses a library whose hash differs from its source tree.                     */
+const char* nsvd_build_hash(void);
 /* sizeof(nsvd_problem_t) / sizeof(nsvd_params_t) / sizeof(nsvd_grads_t) as compiled (which = 0, 1, 2): lets a
  * binding written in another language check its struct layout at load time.                            */
 size_t nsvd_struct_size(int32_t which);
@@ -154,7 +157,10 @@ int nsvd_cross_gram(const float* F, const float* TF, const float* roww, const fl
 /* Loss value from (all-reduced) terms: NestedLoRALossFunctionEVD.forward, nestedlora.py:70-94.
  * Bg, B1g, B2g are the GLOBAL row counts.  Writes loss[0] and coef (2*L*L):
  *   coef[0:L*L]   = (2/B1g) * M * Lambda2   (applied to rows of F1)
- *   coef[L*L:]    = (2/B2g) * M * Lambda1   (applied to rows of F2)                             */
+ *   coef[L*L:]    = (2/B2g) * M * Lambda1   (applied to rows of F2)
+ * Data-parallel form without a host copy of the counts: pass Bg <= 0 and let the counts travel in the all-reduced
+ * buffer itself, terms[2 L^2 + 1 .. +4] = sum over ranks of [n mod 2^16, n / 2^16, b1 mod 2^16, b1 / 2^16]; `coef`
+ * must then hold 2 L^2 + 1 floats (coef[2 L^2] = 4 / B_global, read by nsvd_loss_dF called with Bg <= 0).          */
 int nsvd_loss_finalize(const float* terms, const float* matrix_mask, int32_t n_copies, int64_t Bg,
                        int64_t B1g, int64_t B2g, float* loss, float* coef, void* stream);
 

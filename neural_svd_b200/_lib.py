@@ -46,6 +46,7 @@ _PB, _PR, _GR = C.POINTER(Problem), C.POINTER(Params), C.POINTER(Grads)
 # name -> (restype, argtypes); every symbol declared in include/nsvd.h
 SIGNATURES = {
     "nsvd_abi_version": (C.c_int, []),
+    "nsvd_build_hash": (C.c_char_p, []),
     "nsvd_struct_size": (C.c_size_t, [C.c_int32]),
     "nsvd_last_error": (C.c_char_p, []),
     "nsvd_launch_count": (C.c_long, []),

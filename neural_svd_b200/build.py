@@ -35,6 +35,17 @@ def _stale() -> bool:
     return open(HASHFILE).read().strip() != _source_hash()
 
 
+def embedded_hash(path: str = LIB):
+    """source hash compiled into a library (nsvd_build_hash), or None if it cannot be read"""
+    import ctypes
+    try:
+        lib = ctypes.CDLL(path)
+        lib.nsvd_build_hash.restype = ctypes.c_char_p
+        return lib.nsvd_build_hash().decode()
+    except (OSError, AttributeError):
+        return None
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Build the library if it is missing or older than its sources. Returns the .so path."""
     if not force and not _stale():
@@ -42,7 +53,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.isfile(nvcc):
         if os.path.isfile(LIB):
-            return LIB          # prebuilt library travelled with the tree (GPU box without nvcc)
+            # prebuilt library travelled with the tree (GPU box without nvcc): it must be the build of THESE sources -
+            # the hash file does not travel through git, so the hash compiled into the library is what is compared
+            have, want = embedded_hash(), _source_hash()
+            if have != want:
+                msg = (f"libnsvd.so was built from other sources (embedded hash {have}, tree {want}) and nvcc is not "
+                       "available to rebuild it")
+                if os.environ.get("NSVD_ALLOW_STALE") != "1":
+                    raise RuntimeError(msg + "; set NSVD_ALLOW_STALE=1 to load it anyway")
+                import warnings
+                warnings.warn(msg)
+            return LIB
         raise RuntimeError("nvcc not found and no prebuilt libnsvd.so in the tree")
     import fcntl
     with open(LIB + ".lock", "w") as lock:       # one builder at a time (torchrun starts N ranks at once)
@@ -50,7 +71,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not force and not _stale():
             return LIB
         tmp = f"{LIB}.tmp.{os.getpid()}"
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+        cmd = ([nvcc] + NVCC_FLAGS + [f'-DNSVD_SRC_HASH="{_source_hash()}"'] + (["-Xptxas", "-v"] if verbose else [])
+               + ["-o", tmp] + SOURCES)
         r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
         if verbose:
             sys.stderr.write(r.stderr)

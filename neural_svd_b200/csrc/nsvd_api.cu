@@ -73,6 +73,10 @@ using namespace nsvd;
 extern "C" {
 
 int nsvd_abi_version(void) { return NSVD_ABI_VERSION; }
+#ifndef NSVD_SRC_HASH
+#define NSVD_SRC_HASH "unknown"
+#endif
+const char* nsvd_build_hash(void) { return NSVD_SRC_HASH; }
 size_t nsvd_struct_size(int32_t which) {
   return which == 0 ? sizeof(nsvd_problem_t) : which == 1 ? sizeof(nsvd_params_t) : which == 2 ? sizeof(nsvd_grads_t) : 0;
 }
@@ -197,7 +201,7 @@ int nsvd_loss_finalize(const float* terms, const float* matrix_mask, int32_t n_c
                        int64_t B1g, int64_t B2g, float* loss, float* coef, void* stream) {
   DeviceGuard dg_(terms);
   NSVD_CHECK_ARG(terms && matrix_mask && loss && coef, "NULL buffer");
-  NSVD_CHECK_ARG(Bg > 0 && B1g > 0 && B2g > 0 && B1g + B2g == Bg, "bad counts B=%ld B1=%ld B2=%ld", (long)Bg, (long)B1g, (long)B2g);
+  NSVD_CHECK_ARG(Bg <= 0 || (B1g > 0 && B2g > 0 && B1g + B2g == Bg), "bad counts B=%ld B1=%ld B2=%ld", (long)Bg, (long)B1g, (long)B2g);
   return loss_finalize(terms, matrix_mask, n_copies, Bg, B1g, B2g, loss, coef, (cudaStream_t)stream);
 }
 
@@ -206,7 +210,7 @@ int nsvd_loss_dF(const float* F, const float* TF, const float* vector_mask, cons
                  float* dF, void* stream) {
   DeviceGuard dg_(F);
   NSVD_CHECK_ARG(F && vector_mask && dF && (TF || coef), "NULL buffer");
-  NSVD_CHECK_ARG(b1 >= 0 && b1 <= n_points && Bg > 0, "bad b1/Bg");
+  NSVD_CHECK_ARG(b1 >= 0 && b1 <= n_points, "bad b1");
   NSVD_CHECK_ARG(n_copies >= 1 && n_copies <= 64, "n_copies %d out of [1,64]", n_copies);
   ProfScope ps(KC_DF, (cudaStream_t)stream);
   return loss_dF(F, TF, vector_mask, coef, grad_scale, n_points, n_copies, b1, Bg, dF, (cudaStream_t)stream);

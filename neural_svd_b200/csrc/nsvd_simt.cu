@@ -938,6 +938,15 @@ __global__ void loss_finalize_kernel(const float* __restrict__ terms, const floa
                                      float* __restrict__ loss, float* __restrict__ coef) {
   __shared__ double sred[32];
   int LL = L * L;
+  if (Bg <= 0.0) {
+    // global row counts travel WITH the all-reduced buffer (no second collective, no host copy): four floats after the
+    // operator sum, [n mod 2^16, n / 2^16, b1 mod 2^16, b1 / 2^16] summed over the ranks (each sum exact in fp32)
+    const float* c = terms + 2 * LL + 1;
+    Bg = (double)c[0] + 65536.0 * (double)c[1];
+    B1g = (double)c[2] + 65536.0 * (double)c[3];
+    B2g = Bg - B1g;
+    if (threadIdx.x == 0) coef[2 * LL] = (float)(4.0 / Bg);      // read by loss_dF (Bg <= 0 there too)
+  }
   double s = 0.0;
   for (int e = threadIdx.x; e < LL; e += blockDim.x) {
     double lam1 = (double)terms[e] / B1g, lam2 = (double)terms[LL + e] / B2g;
@@ -969,6 +978,7 @@ __global__ void __launch_bounds__(256)
 loss_dF_kernel(const float* __restrict__ F, const float* __restrict__ TF,
                const float* __restrict__ vmask, const float* __restrict__ coef,
                const float* __restrict__ gscale, int B, int L, int b1, float c4, float* __restrict__ dF) {
+  if (c4 <= 0.f) c4 = coef[2 * L * L];          // 4 / B_global left by loss_finalize (device-side counts)
   extern __shared__ float sm[];
   float* sC = sm;                 // [2][L][LT]
   float* sV = sm + 2 * L * LT;    // [LT]
@@ -1013,6 +1023,7 @@ __global__ void __launch_bounds__(256)
 loss_dF16_kernel(const float* __restrict__ F, const float* __restrict__ TF, const float* __restrict__ vmask,
                  const float* __restrict__ coef, const float* __restrict__ gscale, int B, int b1, float c4,
                  float* __restrict__ dF) {
+  if (c4 <= 0.f) c4 = coef[512];                // 4 / B_global left by loss_finalize (device-side counts)
   __shared__ float4 sC[2][16][4];
   __shared__ float sV[16];
   __shared__ float sF[256][17];
@@ -1069,7 +1080,11 @@ loss_dF16_kernel(const float* __restrict__ F, const float* __restrict__ TF, cons
 
 int loss_dF(const float* F, const float* TF, const float* vmask, const float* coef,
             const float* gscale, int B, int L, int b1, long Bg, float* dF, cudaStream_t st) {
-  float c4 = (float)(4.0 / (double)Bg);
+  float c4 = Bg > 0 ? (float)(4.0 / (double)Bg) : 0.f;   // Bg <= 0: the kernels read 4 / B_global from coef[2 L^2]
+  if (Bg <= 0 && (!coef || !TF)) {
+    set_error("loss_dF: device-side counts (Bg <= 0) need both TF and coef");
+    return NSVD_E_BADARG;
+  }
   if (L == 16) {
     int nb16 = cdiv(B, 256);
     if (nb16 > 148 * 6) nb16 = 148 * 6;

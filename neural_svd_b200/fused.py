@@ -216,14 +216,15 @@ class _FusedOperatorStep(torch.autograd.Function):
         B, L = F.shape
         b1 = (B + 1) // 2                                     # torch.chunk(f, 2), nestedlora.py:263
         v, Mm = _nesting_masks(method, dev)
-        terms = torch.empty(2 * L * L + 1, dtype=torch.float32, device=dev)
+        terms = torch.empty(2 * L * L + 5, dtype=torch.float32, device=dev)   # + 4 count floats (data parallel)
         _lib.check(lib.nsvd_gram_reduce(_lib.ptr(F), _lib.ptr(TF), _lib.ptr(v), B, L, b1, _lib.ptr(terms),
                                         _lib.ptr(sc.partials), _stream(dev)), "nsvd_gram_reduce")
         Bg, B1g, B2g = B, b1, B - b1
         if dp is not None:
-            Bg, B1g, B2g = dp.allreduce_terms(terms, B, b1)   # all-reduce #1
+            dp.allreduce_terms(terms, B, b1)                  # all-reduce #1; the global counts travel inside it
+            Bg = B1g = B2g = 0                                # -> the kernels take them from the device buffer
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        coef = torch.empty(2 * L * L, dtype=torch.float32, device=dev)
+        coef = torch.empty(2 * L * L + 1, dtype=torch.float32, device=dev)
         _lib.check(lib.nsvd_loss_finalize(_lib.ptr(terms), _lib.ptr(Mm), L, Bg, B1g, B2g, _lib.ptr(loss),
                                           _lib.ptr(coef), _stream(dev)), "nsvd_loss_finalize")
         ctx.state = dict(md=md, pb=pb, sc=sc, version=sc.version, x=x, F=F, TF=TF, v=v, coef=coef, b1=b1,
@@ -293,6 +294,8 @@ def _nesting_masks(method, dev):
 def compute_loss_operator(method, operator, x, importance, dp=None):
     """Fused equivalent of NestedLoRA.compute_loss_operator (nestedlora.py:254-267)."""
     md = describe_model(method)
+    if dp is not None:
+        dp.sync_parameters(method)                            # once per module: replicas start from rank 0's weights
     params = [md["Bff"]] + md["ws"] + md["bs"] + ([md["scales"]] if md["scales"] is not None else [])
     loss, F, TF = _FusedOperatorStep.apply(method, operator, importance, x, dp, *params)
     si = _sort_permutation(method)

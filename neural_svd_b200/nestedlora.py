@@ -182,8 +182,9 @@ class NestedLoRALossFunctionForCDK(torch.autograd.Function):
         _lib.check(lib.nsvd_cdk_fwd(_lib.ptr(fd), _lib.ptr(gd), _lib.ptr(v), B, L, fc, engine, _lib.ptr(terms),
                                     _lib.ptr(rs_joint), _lib.ptr(work), nwork, st), "nsvd_cdk_fwd")
         Bg = B
-        if dp is not None:
-            Bg = dp.allreduce_terms(terms, B, B)[0]
+        if dp is not None:                      # rows are sharded: sum the Gram terms, and the row counts (python int)
+            dp.allreduce_grads(terms)
+            Bg = dp.global_counts(B, B, dev)[0]
         losses = torch.empty(3, dtype=torch.float32, device=dev)
         coef = torch.empty(2 * Lp * Lp, dtype=torch.float32, device=dev)
         _lib.check(lib.nsvd_cdk_finalize(_lib.ptr(terms), _lib.ptr(Mm), Lp, Bg, _lib.ptr(losses), _lib.ptr(coef), st),

@@ -43,12 +43,16 @@ def _cpu_worker(rank, world, port, xg, seed, q):
     Tf, f, aux = O.operator_apply(x, u, params, cfg)
     v, M = O.nesting_masks(cfg.neigs, cfg.sequential, cfg.step)
     G1, G2, ops = O.gram_terms(f, Tf, v.astype(np.float64), b1)
-    terms = torch.from_numpy(np.concatenate([G1.ravel(), G2.ravel(), [ops]]))
-    Bg, B1g, B2g = dp.allreduce_terms(terms, n, b1)                     # all-reduce #1
+    terms = torch.from_numpy(np.concatenate([G1.ravel(), G2.ravel(), [ops], np.zeros(4)]))
+    dp.allreduce_terms(terms, n, b1)                                    # all-reduce #1, counts travel inside it
     t = terms.numpy()
     L = cfg.neigs
-    loss, lam1, lam2 = O.loss_from_terms(t[:L * L].reshape(L, L), t[L * L:2 * L * L].reshape(L, L), t[-1], Bg, B1g, B2g,
-                                         M.astype(np.float64))
+    # what loss_finalize_kernel does with the four count floats (nsvd_simt.cu)
+    Bg, B1g = int(t[-4] + 65536 * t[-3]), int(t[-2] + 65536 * t[-1])
+    B2g = Bg - B1g
+    assert (Bg, B1g, B2g) == dp.global_counts(n, b1, "cpu")            # the host-side variant agrees
+    loss, lam1, lam2 = O.loss_from_terms(t[:L * L].reshape(L, L), t[L * L:2 * L * L].reshape(L, L), t[2 * L * L], Bg,
+                                         B1g, B2g, M.astype(np.float64))
     dF = O.loss_dF(f, Tf, v, M, lam1, lam2, B=Bg, B1=B1g, B2=B2g, b1_local=b1)
     grads = O.mlp_backward(x, dF, params, cfg, u[0], acts, sigs, aux)
     names = sorted(grads)
