@@ -1402,6 +1402,9 @@ struct L0FwdEpi {
     // XOR-swizzled with the row: conflict-free both ways) and write it back with every instruction covering four
     // full lines.  Two 4 KB buffers per quarter alternate, so one named barrier per round suffices.
     uint8_t* stq = staging + q * 8192;
+    // the 32 KB per point written here are read by the next kernel only after gigabytes of other traffic: evict first,
+    // so that they do not push the Phi group (re-used by every copy) out of the L2
+    const uint64_t pol_once = tc::l2_policy_evict_first();
     const int gt = sub * 32 + lane;                     // thread index inside the quarter group (128 threads)
     const int row_base = c.mt * big::BM + q * 32;       // first point row of the quarter inside the micro-batch
     const uint32_t wr0 = (uint32_t)lane * 128 + ((uint32_t)((sub * 2) ^ (lane & 7)) << 4);
@@ -1431,8 +1434,8 @@ struct L0FwdEpi {
 #else
           if (pt < P)
 #endif
-            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst + (long)pt * kHidden + c.nt * 64) + cc * 16) =
-                *reinterpret_cast<const uint4*>(buf + rr * 128 + ((cc ^ (rr & 7)) << 4));
+            tc::st_global_v4_hint(reinterpret_cast<uint8_t*>(dst + (long)pt * kHidden + c.nt * 64) + cc * 16,
+                                  *reinterpret_cast<const uint4*>(buf + rr * 128 + ((cc ^ (rr & 7)) << 4)), pol_once);
         }
       }
     }
@@ -1837,7 +1840,7 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 // straight back as the A operand of layer 2.  Only the value streams (needed by the backward) and F / TF leave the chip:
 // 48 KB per point and 16 copies instead of 107 KB with one kernel per layer.  (Keeping a1 in shared memory is not
 // possible: 4 streams x 128 units x 4 B = 2 KB per point next to 128 KB of W1 + W2 planes.)
-//   work items of a CTA, in groups of two tiles of its range:  A(t0) A(t1) B(t0) B(t1)   (A = layer 1, B = layer 2)
+//   work items of a CTA, in groups of kHidGroup tiles of its range:  A(t0) [A(t1)] B(t0) [B(t1)]   (A = layer 1, B = layer 2)
 //   smem : W planes of the layer in use (64 KB, reloaded when (layer, copy) changes) | ring 3 x 32 KB | 64 KB staging
 //   TMEM : 4 x 128 columns (one block per stream), one item at a time
 //   adone[slot] : the bulk stores of A(slot) have completed (cp.async.bulk.wait_group 0 by the issuing thread) - the
@@ -1868,6 +1871,11 @@ struct HidFwd12Args {
                                      // reads U0 (central pass), writes TF, stores nothing else
 };
 
+#ifndef NSVD_HID_GROUP
+#define NSVD_HID_GROUP 1
+#endif
+constexpr int kHidGroup = NSVD_HID_GROUP;   // tiles per group (1 or 2): the scratch holds kHidGroup tile slots per CTA
+
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __global__ void __launch_bounds__(hid::F_THREADS, 1)
@@ -1897,8 +1905,9 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
   const int tpc = (T + gridDim.x - 1) / gridDim.x;
   const int t_begin = blockIdx.x * tpc;
   const int t_end = (t_begin + tpc < T) ? t_begin + tpc : T;
-  const int n_items = t_end > t_begin ? 4 * ((t_end - t_begin + 1) / 2) : 0;
-  // item i: group g = i / 4, layer = (i / 2) & 1 (0: layer 1, 1: layer 2), slot = i & 1, tile = t_begin + 2 g + slot
+  constexpr int G = kHidGroup;
+  const int n_items = t_end > t_begin ? 2 * G * ((t_end - t_begin + G - 1) / G) : 0;
+  // item i: group g = i / (2 G), layer = (i / G) & 1 (0: layer 1, 1: layer 2), slot = i % G, tile = t_begin + G g + slot
 
   if (warp == 0 && lane == 0) {
     const CUtensorMap* m = &tm.a0h;
@@ -1928,8 +1937,9 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
     if (lane == 0) {
       int stage = 0, cur_key = -1, done = 0;   // done = items already issued (valid ones)
       uint32_t phase = 0;
+      const uint64_t pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
       for (int i = 0; i < n_items; ++i) {
-        const int g = i >> 2, layer = (i >> 1) & 1, slot = i & 1, t = t_begin + 2 * g + slot;
+        const int g = i / (2 * G), layer = (i / G) & 1, slot = i % G, t = t_begin + G * g + slot;
         if (t >= t_end) continue;
         const int l = t / args.m_tiles, mt = t % args.m_tiles;
         const int key = l * 2 + layer;
@@ -1948,12 +1958,12 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           mbar_wait(&adone[slot], (uint32_t)(g & 1), 61);
           fence_proxy_async_all();
         }
-        const int xs = ((int)blockIdx.x * 2 + slot) * 4;
+        const int xs = ((int)blockIdx.x * G + slot) * 4;
         const bool vm = args.vmode != 0;
         {
           // L2 prefetch of the layer-1 operands (256 KB from DRAM) of the tile that starts one or two items later:
-          // A(t0) announces t1, B(t0) / B(t1) announce the next group's t0 / t1
-          const int tn = layer ? t + 2 : (slot == 0 ? t + 1 : -1);
+          // a layer-2 item announces the same slot of the next group, A(t0) of a two-tile group announces t1
+          const int tn = layer ? t + G : ((G == 2 && slot == 0) ? t + 1 : -1);
           if (tn >= 0 && tn < t_end) {
             const int ln = tn / args.m_tiles, mn = tn % args.m_tiles;
             for (int sc = 0; sc < 8; ++sc) {
@@ -1973,15 +1983,17 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           mbar_wait(&empty[stage], phase ^ 1, 62);
           uint8_t* d = sA + stage * F_STAGE_BYTES;
           mbar_arrive_expect_tx(&full[stage], F_STAGE_BYTES);
+          // operands read once (a0 from DRAM; a1 / the scratch for the last time) leave the L2 first
           if (s == 0 && !vm) {   // value stream: from `saved` (whole-batch rows)
-            tma_load_3d(d, layer ? &tm.v1h : &tm.v0h, &full[stage], 64 * c, (int)args.p_off + mt * 128, l);
-            tma_load_3d(d + CHUNK, layer ? &tm.v1l : &tm.v0l, &full[stage], 64 * c, (int)args.p_off + mt * 128, l);
+            tma_load_3d_hint(d, layer ? &tm.v1h : &tm.v0h, &full[stage], 64 * c, (int)args.p_off + mt * 128, l, pol_once);
+            tma_load_3d_hint(d + CHUNK, layer ? &tm.v1l : &tm.v0l, &full[stage], 64 * c, (int)args.p_off + mt * 128, l,
+                             pol_once);
           } else if (!layer) {
-            tma_load_3d(d, &tm.a0h, &full[stage], 64 * c, mt * 128, l * 4 + s);
-            tma_load_3d(d + CHUNK, &tm.a0l, &full[stage], 64 * c, mt * 128, l * 4 + s);
+            tma_load_3d_hint(d, &tm.a0h, &full[stage], 64 * c, mt * 128, l * 4 + s, pol_once);
+            tma_load_3d_hint(d + CHUNK, &tm.a0l, &full[stage], 64 * c, mt * 128, l * 4 + s, pol_once);
           } else {
-            tma_load_3d(d, &tm.xlh, &full[stage], 64 * c, 0, xs + s);
-            tma_load_3d(d + CHUNK, &tm.xll, &full[stage], 64 * c, 0, xs + s);
+            tma_load_3d_hint(d, &tm.xlh, &full[stage], 64 * c, 0, xs + s, pol_keep);
+            tma_load_3d_hint(d + CHUNK, &tm.xll, &full[stage], 64 * c, 0, xs + s, pol_keep);
           }
           if (++stage == F_STAGES) {
             stage = 0;
@@ -1994,12 +2006,15 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
+      // (Issuing the unit dimension in two halves of 64 columns, so that the epilogue of one half overlaps the MMAs of the
+      // other, was measured: the A tiles then pass through the ring twice and the kernel, which is bound by the ~42 B/clk
+      // per SM of L2 -> SM fill bandwidth, gets slower - 4.5 ms instead of 3.5 ms per 131072 points.)
       constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, 0, false, false);   // fp16 x fp16 planes
       int stage = 0, cur_key = -1;
       uint32_t phase = 0, wphase = 0, tphase = 0;
       const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + PLANE;
       for (int i = 0; i < n_items; ++i) {
-        const int g = i >> 2, layer = (i >> 1) & 1, slot = i & 1, t = t_begin + 2 * g + slot;
+        const int g = i / (2 * G), layer = (i / G) & 1, slot = i % G, t = t_begin + G * g + slot;
         if (t >= t_end) continue;
         const int key = (t / args.m_tiles) * 2 + layer;
         if (key != cur_key) {
@@ -2048,8 +2063,9 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
     int cur_key = -1;
     float un[4] = {1.f, 1.f, 1.f, 1.f}, so[4] = {1.f, 1.f, 1.f, 1.f};
     const bool vm = args.vmode != 0;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
     for (int i = 0; i < n_items; ++i) {
-      const int g = i >> 2, layer = (i >> 1) & 1, slot = i & 1, t = t_begin + 2 * g + slot;
+      const int g = i / (2 * G), layer = (i / G) & 1, slot = i % G, t = t_begin + G * g + slot;
       if (t >= t_end) continue;
       (void)g;
       const bool last = layer != 0;
@@ -2057,7 +2073,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
       const int pt = mt * 128 + row;
       const int key = l * 2 + layer;
       // is this the last layer-1 item of its group (the next valid item is a layer-2 one)?
-      const bool closes_a = !last && (slot == 1 || t + 1 >= t_end);
+      const bool closes_a = !last && (slot == G - 1 || t + 1 >= t_end);
       if (key != cur_key) {  // all epilogue threads are past the previous item's last staging barrier
         if (et < 128) {
           bias_s[et] = (last ? args.bias2 : args.bias1)[l * kHidden + et];
@@ -2077,7 +2093,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
       tphase ^= 1;
       tc_fence_after();
       float u[4] = {0.f, 0.f, 0.f, 0.f};
-      const int xs = ((int)blockIdx.x * 2 + slot) * 4;
+      const int xs = ((int)blockIdx.x * G + slot) * 4;
 #pragma unroll 1
       for (int r = 0; r < 4; ++r) {          // h-quarters of 32 hidden units; this warp takes 8 of them
         const int h0 = r * 32 + sub * 8;
@@ -2145,19 +2161,19 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           if (!last) {
 #pragma unroll
             for (int s = 1; s < 4; ++s) {
-              tma_store_3d(&tm.xsh, sO + (2 * s) * F_BOX, r * 32, 0, xs + s);
-              tma_store_3d(&tm.xsl, sO + (2 * s + 1) * F_BOX, r * 32, 0, xs + s);
+              tma_store_3d_hint(&tm.xsh, sO + (2 * s) * F_BOX, r * 32, 0, xs + s, pol_keep);
+              tma_store_3d_hint(&tm.xsl, sO + (2 * s + 1) * F_BOX, r * 32, 0, xs + s, pol_keep);
             }
             if (vm) {      // slot 0 is a shifted point set too: scratch, not `saved`
-              tma_store_3d(&tm.xsh, sO, r * 32, 0, xs);
-              tma_store_3d(&tm.xsl, sO + F_BOX, r * 32, 0, xs);
-            } else {
-              tma_store_3d(&tm.s1h, sO, r * 32, (int)args.p_off + mt * 128, l);
-              tma_store_3d(&tm.s1l, sO + F_BOX, r * 32, (int)args.p_off + mt * 128, l);
+              tma_store_3d_hint(&tm.xsh, sO, r * 32, 0, xs, pol_keep);
+              tma_store_3d_hint(&tm.xsl, sO + F_BOX, r * 32, 0, xs, pol_keep);
+            } else {       // a1 value stream: read back by layer 2 of this tile, then by the backward
+              tma_store_3d_hint(&tm.s1h, sO, r * 32, (int)args.p_off + mt * 128, l, pol_keep);
+              tma_store_3d_hint(&tm.s1l, sO + F_BOX, r * 32, (int)args.p_off + mt * 128, l, pol_keep);
             }
           } else if (!vm) {
-            tma_store_3d(&tm.s2h, sO + sb * F_BOX, r * 32, (int)args.p_off + mt * 128, l);
-            tma_store_3d(&tm.s2l, sO + (sb + 1) * F_BOX, r * 32, (int)args.p_off + mt * 128, l);
+            tma_store_3d_hint(&tm.s2h, sO + sb * F_BOX, r * 32, (int)args.p_off + mt * 128, l, pol_once);
+            tma_store_3d_hint(&tm.s2l, sO + (sb + 1) * F_BOX, r * 32, (int)args.p_off + mt * 128, l, pol_once);
           }
           tma_store_commit();
         }
