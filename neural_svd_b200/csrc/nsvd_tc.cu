@@ -1246,18 +1246,23 @@ __global__ void fold_w0_kernel(const float* __restrict__ W0, const float* __rest
   }
 }
 
-// out[l][c][r] = in[l][r][c] when transpose (128x128 blocks), fp16 hi/lo planes of plan[slot] * W
-__global__ void split_w_kernel(const float* __restrict__ W, const float* __restrict__ plan, int slot,
-                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int L, int transpose) {
+// both hidden weight tensors in one launch: out_i[l][c][r] = W_i[l][r][c] when transpose (128x128 blocks), fp16 hi/lo
+// planes of PL_SW_i * W_i
+__global__ void split_w_kernel(const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ plan,
+                               __nv_bfloat16* __restrict__ hi1, __nv_bfloat16* __restrict__ lo1,
+                               __nv_bfloat16* __restrict__ hi2, __nv_bfloat16* __restrict__ lo2, int L, int transpose) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  long n = (long)L * kHidden * kHidden;
-  if (i >= n) return;
+  const long n = (long)L * kHidden * kHidden;
+  if (i >= 2 * n) return;
+  const int which = i >= n;
+  if (which) i -= n;
+  const float* W = which ? W2 : W1;
   int c = (int)(i % kHidden), r = (int)((i / kHidden) % kHidden), l = (int)(i / (kHidden * kHidden));
   float v = transpose ? W[((long)l * kHidden + c) * kHidden + r] : W[i];
   uint16_t a, b;
-  tc::split1<tc::PF_HH>(v * plan[(long)l * PL_STRIDE + slot], a, b);
-  reinterpret_cast<uint16_t*>(hi)[i] = a;
-  reinterpret_cast<uint16_t*>(lo)[i] = b;
+  tc::split1<tc::PF_HH>(v * plan[(long)l * PL_STRIDE + (which ? PL_SW2 : PL_SW1)], a, b);
+  reinterpret_cast<uint16_t*>(which ? hi2 : hi1)[i] = a;
+  reinterpret_cast<uint16_t*>(which ? lo2 : lo1)[i] = b;
 }
 
 // Phi = [sin(x B), cos(x B)] as fp16 hi/lo planes (B, 2M), unscaled (|Phi| <= 1)   (examples/utils.py:139-140)
@@ -2722,11 +2727,9 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
   fold_w0_kernel<<<cdiv(L * H * M, 256), 256, 0, st>>>(pr.W[0], pr.Bff, plan, BF(wk + t.w0_hi), BF(wk + t.w0_lo), (int)L,
                                                        (int)M);
   NSVD_LAUNCH_CHECK();
-  for (int i = 0; i < 2; ++i) {
-    split_w_kernel<<<cdiv(L * H * H, 256), 256, 0, st>>>(pr.W[i + 1], plan, i == 0 ? PL_SW1 : PL_SW2, BF(wk + t.w_hi[i]),
-                                                         BF(wk + t.w_lo[i]), (int)L, 0);
-    NSVD_LAUNCH_CHECK();
-  }
+  split_w_kernel<<<cdiv(2 * L * H * H, 256), 256, 0, st>>>(pr.W[1], pr.W[2], plan, BF(wk + t.w_hi[0]), BF(wk + t.w_lo[0]),
+                                                           BF(wk + t.w_hi[1]), BF(wk + t.w_lo[1]), (int)L, 0);
+  NSVD_LAUNCH_CHECK();
   if (pb.fd_eps > 0.f) {
     split_w0_kernel<<<cdiv(L * H * K0, 256), 256, 0, st>>>(pr.W[0], plan, BF(wk + t.w0v_hi), BF(wk + t.w0v_lo), (int)L, K0);
     NSVD_LAUNCH_CHECK();
@@ -2895,6 +2898,27 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
   return 0;
 }
 
+// zero up to 10 fp32 buffers in one launch (gradients are accumulated with reductions: they start from zero)
+struct ZeroList {
+  float* p[10];
+  long n[10];
+  int count;
+};
+__global__ void __launch_bounds__(256) zero_list_kernel(ZeroList z) {
+  const long stride = (long)gridDim.x * blockDim.x, t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int b = 0; b < z.count; ++b) {
+    float* p = z.p[b];
+    const long n = z.n[b];
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      float4* p4 = reinterpret_cast<float4*>(p);
+      for (long i = t0; i < n / 4; i += stride) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long i = (n / 4) * 4 + t0; i < n; i += stride) p[i] = 0.f;
+    } else {
+      for (long i = t0; i < n; i += stride) p[i] = 0.f;
+    }
+  }
+}
+
 int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x, const float* dF,
                 const void* saved_v, nsvd_grads_t& gr, void* work_v, size_t work_bytes, cudaStream_t st) {
   (void)work_bytes;
@@ -2905,17 +2929,27 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
   int rc;
   NSVD_SMEM_OPTIN(hidden_bwd2_kernel, hid::SMEM_BWD2);
   // gradients are accumulated with reductions: start from zero
-  NSVD_CUDA(cudaMemsetAsync(gr.dW[0], 0, sizeof(float) * L * H * K0, st));
-  NSVD_CUDA(cudaMemsetAsync(gr.dW[1], 0, sizeof(float) * L * H * H, st));
-  NSVD_CUDA(cudaMemsetAsync(gr.dW[2], 0, sizeof(float) * L * H * H, st));
-  NSVD_CUDA(cudaMemsetAsync(gr.dW[3], 0, sizeof(float) * L * H, st));
-  for (int i = 0; i < 3; ++i) NSVD_CUDA(cudaMemsetAsync(gr.db[i], 0, sizeof(float) * L * H, st));
-  NSVD_CUDA(cudaMemsetAsync(gr.db[3], 0, sizeof(float) * L, st));
-  if (pb.has_exp_mask && gr.dmask_scales) NSVD_CUDA(cudaMemsetAsync(gr.dmask_scales, 0, sizeof(float) * L, st));
+  // (one launch instead of ten memsets: the small-batch configurations are launch-bound)
+  float* mdf = reinterpret_cast<float*>(sv + t.mdf);
+  {
+    ZeroList z{};
+    z.p[0] = gr.dW[0]; z.n[0] = L * H * K0;
+    z.p[1] = gr.dW[1]; z.n[1] = L * H * H;
+    z.p[2] = gr.dW[2]; z.n[2] = L * H * H;
+    z.p[3] = gr.dW[3]; z.n[3] = L * H;
+    for (int i = 0; i < 3; ++i) { z.p[4 + i] = gr.db[i]; z.n[4 + i] = L * H; }
+    z.p[7] = gr.db[3]; z.n[7] = L;
+    z.p[8] = mdf; z.n[8] = L;
+    z.count = 9;
+    if (pb.has_exp_mask && gr.dmask_scales) { z.p[9] = gr.dmask_scales; z.n[9] = L; z.count = 10; }
+    long total = 0;
+    for (int i = 0; i < z.count; ++i) total += z.n[i];
+    int nb = cdiv(total / 4 + 1, 256);
+    zero_list_kernel<<<nb < 148 * 8 ? nb : 148 * 8, 256, 0, st>>>(z);
+    NSVD_LAUNCH_CHECK();
+  }
   // backward half of the operand plan: scales of the dZ planes from max|dF| per copy
   float* plan = reinterpret_cast<float*>(sv + t.plan);
-  float* mdf = reinterpret_cast<float*>(sv + t.mdf);
-  NSVD_CUDA(cudaMemsetAsync(mdf, 0, sizeof(float) * L, st));
   col_absmax_kernel<<<148 * 2, 256, 0, st>>>(dF, B * L, (int)L, mdf);
   NSVD_LAUNCH_CHECK();
   bwd_plan_kernel<<<1, 128, 0, st>>>(plan, reinterpret_cast<const float*>(sv + t.hstat), mdf, pr.W[3], pb.hard_mul_const,
@@ -2923,10 +2957,10 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
   NSVD_LAUNCH_CHECK();
   // transposed hidden weights (dgrad B operand, K-major): WT_i[l][k][j] = W_i[l][j][k]
   CUtensorMap mWh[2], mWl[2];
+  split_w_kernel<<<cdiv(2 * L * H * H, 256), 256, 0, st>>>(pr.W[1], pr.W[2], plan, BF(wk + t.w_hi[0]), BF(wk + t.w_lo[0]),
+                                                           BF(wk + t.w_hi[1]), BF(wk + t.w_lo[1]), (int)L, 1);
+  NSVD_LAUNCH_CHECK();
   for (int i = 0; i < 2; ++i) {
-    split_w_kernel<<<cdiv(L * H * H, 256), 256, 0, st>>>(pr.W[i + 1], plan, i == 0 ? PL_SW1 : PL_SW2, BF(wk + t.w_hi[i]),
-                                                         BF(wk + t.w_lo[i]), (int)L, 1);
-    NSVD_LAUNCH_CHECK();
     if ((rc = make_tmap_bf16_3d(&mWh[i], wk + t.w_hi[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
     if ((rc = make_tmap_bf16_3d(&mWl[i], wk + t.w_lo[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
   }
