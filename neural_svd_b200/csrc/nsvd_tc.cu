@@ -1042,28 +1042,111 @@ constexpr float kPlaneTarget = 32768.f;   // 2^15
 
 __device__ __forceinline__ float pow2_scale(float bound) {
   if (!(bound > 0.f) || !isfinite(bound)) return 1.f;
-  int e = ilogbf(kPlaneTarget / (bound * 1.001f));   // floor(log2(.)); 1.001 covers the rounding of the bound's own sums
+  // 2^floor(log2(target / bound')) from the exponent field; 1.001 covers the rounding of the bound's own sums
+  const float q = kPlaneTarget / (bound * 1.001f);
+  int e = (int)((__float_as_uint(q) >> 23) & 0xffu) - 127;   // subnormal q -> -127, infinite q -> 128: both clamped
   e = e > 100 ? 100 : (e < -100 ? -100 : e);
-  return ldexpf(1.f, e);
+  return __uint_as_float((unsigned)(e + 127) << 23);
 }
 
-// one block per row (l, h) of W0: rowstat[(l*128 + h)*5 + s] = sum_j (|W0[h,j]| + |W0[h,M+j]|) c_s[j], [4] = max|W0[h,:]|
-__global__ void __launch_bounds__(256) w0_stats_kernel(const float* __restrict__ W0, const float* __restrict__ Bff,
-                                                       float* __restrict__ rowstat, int M) {
+// blocks [0, L*128): one per row (l, h) of W0: rowstat[(l*128 + h)*5 + s] = sum_j (|W0[h,j]| + |W0[h,M+j]|) c_s[j],
+// [4] = max|W0[h,:]|.  blocks [L*128, L*128 + 2L): one per hidden matrix W = W_{i+1}[l]:
+// hstat[(i*L + l)*3 + {0: max_h sum_k |W[h,k]|, 1: max|W|, 2: max_k sum_h |W[h,k]|}]; one more block: feature bounds
+__global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restrict__ W0, const float* __restrict__ Bff,
+                                                           const float* __restrict__ W1, const float* __restrict__ W2,
+                                                           float* __restrict__ rowstat, float* __restrict__ hstat,
+                                                           int L, int M) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((int)blockIdx.x == L * kHidden + 2 * L) {
+    // last block: bounds of the feature streams, hstat[6 L + {1, 2, 3}] = max_j {|B_0j|, |B_1j|, B_0j^2 + B_1j^2}
+    float c[3] = {0.f, 0.f, 0.f};
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+      const float x0 = Bff[j], x1 = Bff[M + j];
+      c[0] = fmaxf(c[0], fabsf(x0));
+      c[1] = fmaxf(c[1], fabsf(x1));
+      c[2] = fmaxf(c[2], fmaf(x0, x0, x1 * x1));
+    }
+    __shared__ float cred[8][3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      for (int o = 16; o > 0; o >>= 1) c[q] = fmaxf(c[q], __shfl_xor_sync(0xffffffffu, c[q], o));
+      if (lane == 0) cred[warp][q] = c[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float v = cred[0][threadIdx.x];
+      for (int w = 1; w < 8; ++w) v = fmaxf(v, cred[w][threadIdx.x]);
+      hstat[6L * L + 1 + threadIdx.x] = v;
+    }
+    return;
+  }
+  if ((int)blockIdx.x >= L * kHidden) {
+    // hidden matrix: coalesced float4 sweep; a warp reads one row per step (row sum by shuffles), a thread always
+    // meets the same four columns (column sums in registers)
+    const int q = blockIdx.x - L * kHidden, i = q / L, l = q % L;
+    const float4* W = reinterpret_cast<const float4*>((i == 0 ? W1 : W2) + (long)l * kHidden * kHidden);
+    float cs[4] = {0.f, 0.f, 0.f, 0.f}, rmax = 0.f, mx = 0.f;
+#pragma unroll 4
+    for (int it = 0; it < kHidden / 8; ++it) {          // 8 rows per step (8 warps)
+      const float4 v = W[(it * 8 + warp) * (kHidden / 4) + lane];
+      const float a0 = fabsf(v.x), a1 = fabsf(v.y), a2 = fabsf(v.z), a3 = fabsf(v.w);
+      cs[0] += a0; cs[1] += a1; cs[2] += a2; cs[3] += a3;
+      mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+      float rs = (a0 + a1) + (a2 + a3);
+      for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+      rmax = fmaxf(rmax, rs);
+    }
+    __shared__ float csum[8][kHidden], wred[8][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) csum[warp][lane * 4 + c] = cs[c];
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+      wred[warp][0] = rmax;
+      wred[warp][1] = mx;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float cmax = 0.f;
+      for (int c = lane; c < kHidden; c += 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += csum[w][c];
+        cmax = fmaxf(cmax, t);
+      }
+      float r = lane < 8 ? wred[lane][0] : 0.f, m = lane < 8 ? wred[lane][1] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) {
+        cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      }
+      if (lane == 0) {
+        float* o = hstat + ((long)i * L + l) * 3;
+        o[0] = r;
+        o[1] = m;
+        o[2] = cmax;
+      }
+    }
+    return;
+  }
   const long row = blockIdx.x;
   const float* w = W0 + row * 2L * M;
   float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int j = threadIdx.x; j < M; j += blockDim.x) {
-    const float ws = fabsf(w[j]), wc = fabsf(w[M + j]), pr = ws + wc;
-    const float b0 = Bff[j], b1 = Bff[M + j];
-    a[0] += pr;
-    a[1] = fmaf(pr, fabsf(b0), a[1]);
-    a[2] = fmaf(pr, fabsf(b1), a[2]);
-    a[3] = fmaf(pr, fmaf(b0, b0, b1 * b1), a[3]);
-    a[4] = fmaxf(a[4], fmaxf(ws, wc));
+  for (int j = threadIdx.x * 4; j < M; j += blockDim.x * 4) {
+    const float4 s4 = *reinterpret_cast<const float4*>(w + j), c4 = *reinterpret_cast<const float4*>(w + M + j);
+    const float4 x4 = *reinterpret_cast<const float4*>(Bff + j), y4 = *reinterpret_cast<const float4*>(Bff + M + j);
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+    const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float ws = fabsf(sv[k]), wc = fabsf(cv[k]), pr = ws + wc;
+      a[0] += pr;
+      a[1] = fmaf(pr, fabsf(xv[k]), a[1]);
+      a[2] = fmaf(pr, fabsf(yv[k]), a[2]);
+      a[3] = fmaf(pr, fmaf(xv[k], xv[k], yv[k] * yv[k]), a[3]);
+      a[4] = fmaxf(a[4], fmaxf(ws, wc));
+    }
   }
   __shared__ float red[8][5];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
     float v = a[i];
@@ -1082,77 +1165,39 @@ __global__ void __launch_bounds__(256) w0_stats_kernel(const float* __restrict__
   }
 }
 
-// grid (L, 2), 128 threads: hstat[(i*L + l)*3 + {0: max_h sum_k |W[h,k]|, 1: max|W|, 2: max_k sum_h |W[h,k]|}] for W = W_{i+1}[l]
-__global__ void __launch_bounds__(128) hid_stats_kernel(const float* __restrict__ W1, const float* __restrict__ W2,
-                                                        float* __restrict__ hstat, int L) {
-  const int l = blockIdx.x, i = blockIdx.y, t = threadIdx.x;
-  const float* W = (i == 0 ? W1 : W2) + (long)l * kHidden * kHidden;
-  float rs = 0.f, cs = 0.f, mx = 0.f;      // thread t: row t (strided reads, 64 KB in all) and column t (coalesced)
-  for (int k = 0; k < kHidden; ++k) {
-    const float r = fabsf(W[t * kHidden + k]);
-    rs += r;
-    cs += fabsf(W[k * kHidden + t]);
-    mx = fmaxf(mx, r);
-  }
-  __shared__ float red[3][4];
-  float v[3] = {rs, mx, cs};
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    float x = v[q];
-    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
-    if ((t & 31) == 0) red[q][t >> 5] = x;
-  }
-  __syncthreads();
-  if (t < 3) hstat[((long)i * L + l) * 3 + t] = fmaxf(fmaxf(red[t][0], red[t][1]), fmaxf(red[t][2], red[t][3]));
-}
-
-// one block, 128 threads: forward part of the plan (thread l < L owns copy l)
+// forward part of the plan: one warp per copy (grid = ceil(L / 4) blocks of 4 warps), lanes parallel over hidden units
 __global__ void __launch_bounds__(128) fwd_plan_kernel(const float* __restrict__ rowstat, const float* __restrict__ hstat,
                                                        const float* __restrict__ Bff, const float* __restrict__ b0,
                                                        const float* __restrict__ b1, const float* __restrict__ b2,
                                                        float* __restrict__ plan, int L, int M) {
-  __shared__ float mB[4][4];
-  const int t = threadIdx.x;
-  float c1 = 0.f, c2 = 0.f, c3 = 0.f;
-  for (int j = t; j < M; j += 128) {
-    const float x0 = Bff[j], x1 = Bff[M + j];
-    c1 = fmaxf(c1, fabsf(x0));
-    c2 = fmaxf(c2, fabsf(x1));
-    c3 = fmaxf(c3, fmaf(x0, x0, x1 * x1));
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, o));
-    c2 = fmaxf(c2, __shfl_xor_sync(0xffffffffu, c2, o));
-    c3 = fmaxf(c3, __shfl_xor_sync(0xffffffffu, c3, o));
-  }
-  if ((t & 31) == 0) {
-    mB[t >> 5][1] = c1;
-    mB[t >> 5][2] = c2;
-    mB[t >> 5][3] = c3;
-  }
-  __syncthreads();
-  if (t >= L) return;
-  const int l = t;
-  float cmax[4] = {1.f, 0.f, 0.f, 0.f};
-  for (int s = 1; s < 4; ++s) cmax[s] = fmaxf(fmaxf(mB[0][s], mB[1][s]), fmaxf(mB[2][s], mB[3][s]));
-  float Z[4] = {0.f, 0.f, 0.f, 0.f}, mW0 = 0.f;
-  for (int h = 0; h < kHidden; ++h) {
+  const int lane = threadIdx.x & 31, l = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (l >= L) return;
+  auto wmax = [](float v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  };
+  const float cmax[4] = {1.f, hstat[6L * L + 1], hstat[6L * L + 2], hstat[6L * L + 3]};
+  float Z[4] = {0.f, 0.f, 0.f, 0.f}, mW0 = 0.f, mb[3] = {0.f, 0.f, 0.f};
+  const float* bias[3] = {b0, b1, b2};
+  for (int h = lane; h < kHidden; h += 32) {
     const float* r = rowstat + ((long)l * kHidden + h) * 5;
     for (int s = 0; s < 4; ++s) Z[s] = fmaxf(Z[s], r[s]);
     mW0 = fmaxf(mW0, r[4]);
+    for (int i = 0; i < 3; ++i) mb[i] = fmaxf(mb[i], fabsf(bias[i][l * kHidden + h]));
   }
+  for (int s = 0; s < 4; ++s) Z[s] = wmax(Z[s]);
+  mW0 = wmax(mW0);
+  for (int i = 0; i < 3; ++i) mb[i] = wmax(mb[i]);
+  if (lane != 0) return;
   float* P = plan + (long)l * PL_STRIDE;
   for (int s = 0; s < 4; ++s) {
     const float sw = pow2_scale(mW0 * cmax[s]);
     P[PL_SW0 + s] = sw;
     P[PL_INV_W0 + s] = 1.f / sw;
   }
-  const float* bias[3] = {b0, b1, b2};
   float SA[3][4];
   for (int i = 0; i < 3; ++i) {
-    float mb = 0.f;
-    for (int h = 0; h < kHidden; ++h) mb = fmaxf(mb, fabsf(bias[i][l * kHidden + h]));
-    Z[0] += mb;
+    Z[0] += mb[i];
     float A[4] = {Z[0] + 0.6931472f, Z[1], Z[2], Z[3] + 0.25f * (Z[1] * Z[1] + Z[2] * Z[2])};
     for (int s = 0; s < 4; ++s) SA[i][s] = pow2_scale(A[s]);
     if (i < 2) {
@@ -1187,27 +1232,27 @@ __global__ void __launch_bounds__(256) col_absmax_kernel(const float* __restrict
   atomicMax(reinterpret_cast<unsigned int*>(mdF) + (((long)blockIdx.x * blockDim.x + threadIdx.x) % L), __float_as_uint(m));
 }
 
-// backward part of the plan (one block, thread l < L owns copy l)
-__global__ void __launch_bounds__(128) bwd_plan_kernel(float* __restrict__ plan, const float* __restrict__ hstat,
-                                                       const float* __restrict__ mdF, const float* __restrict__ W3,
-                                                       float hard_mul_const, int L) {
-  const int l = threadIdx.x;
-  if (l >= L) return;
-  float* P = plan + (long)l * PL_STRIDE;
-  float m3 = 0.f;
-  for (int h = 0; h < kHidden; ++h) m3 = fmaxf(m3, fabsf(W3[l * kHidden + h]));
-  const float dz2 = fabsf(hard_mul_const) * mdF[l] * m3;       // sigma <= 1, rho <= 1, masks <= 1
+// backward part of the plan for copy l, from max|dF[:, l]| and max|W3[l, :]|; evaluated redundantly by every block of
+// the head backward kernel (its first block per copy publishes the slots the later kernels read)
+struct BwdScales {
+  float s2, s1, s0;
+};
+__device__ __forceinline__ BwdScales bwd_scales(const float* __restrict__ hstat, float mdf, float m3, float hard_mul_const,
+                                                int l, int L) {
+  const float dz2 = fabsf(hard_mul_const) * mdf * m3;            // sigma <= 1, rho <= 1, masks <= 1
   const float dz1 = hstat[((long)1 * L + l) * 3 + 2] * dz2;      // column L1 norm of W2
   const float dz0 = hstat[((long)0 * L + l) * 3 + 2] * dz1;      // column L1 norm of W1
-  const float s2 = pow2_scale(dz2), s1 = pow2_scale(dz1), s0 = pow2_scale(dz0);
-  P[PL_SDZ2] = s2;
-  P[PL_SDZ1] = s1;
-  P[PL_SDZ0] = s0;
-  P[PL_UD2] = 1.f / (P[PL_SW2] * s2);
-  P[PL_UD1] = 1.f / (P[PL_SW1] * s1);
-  P[PL_UW2] = 1.f / (s2 * P[PL_SA1]);
-  P[PL_UW1] = 1.f / (s1 * P[PL_SA0]);
-  P[PL_UW0] = 1.f / s0;
+  return BwdScales{pow2_scale(dz2), pow2_scale(dz1), pow2_scale(dz0)};
+}
+__device__ __forceinline__ void publish_bwd_plan(float* __restrict__ P, const BwdScales& b) {
+  P[PL_SDZ2] = b.s2;
+  P[PL_SDZ1] = b.s1;
+  P[PL_SDZ0] = b.s0;
+  P[PL_UD2] = 1.f / (P[PL_SW2] * b.s2);
+  P[PL_UD1] = 1.f / (P[PL_SW1] * b.s1);
+  P[PL_UW2] = 1.f / (b.s2 * P[PL_SA1]);
+  P[PL_UW1] = 1.f / (b.s1 * P[PL_SA0]);
+  P[PL_UW0] = 1.f / b.s0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1215,54 +1260,87 @@ __global__ void __launch_bounds__(128) bwd_plan_kernel(float* __restrict__ plan,
 // ------------------------------------------------------------------------------------------
 // Folded layer-0 weights: all four streams are W'_s . [sin p ; cos p]   (probe10)
 //   rows n = l*512 + (h/64)*256 + s*64 + (h%64),  K-major, fp16 hi/lo planes of PL_SW0[s] * W'_s.
-__global__ void fold_w0_kernel(const float* __restrict__ W0, const float* __restrict__ Bff,
-                               const float* __restrict__ plan, __nv_bfloat16* __restrict__ hi,
-                               __nv_bfloat16* __restrict__ lo, int L, int M) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  long n = (long)L * kHidden * M;
-  if (i >= n) return;
-  int j = (int)(i % M);
-  int h = (int)((i / M) % kHidden);
-  int l = (int)(i / ((long)M * kHidden));
+// One thread = 8 consecutive features j of one row (l, h): 16-byte loads and stores.
+__device__ __forceinline__ void fold_w0_body(long i, const float* __restrict__ W0, const float* __restrict__ Bff,
+                                             const float* __restrict__ plan, __nv_bfloat16* __restrict__ hi,
+                                             __nv_bfloat16* __restrict__ lo, int L, int M) {
+  const int M8 = M >> 3;
+  if (i >= (long)L * kHidden * M8) return;
+  const int j = (int)(i % M8) * 8;
+  const int h = (int)((i / M8) % kHidden);
+  const int l = (int)(i / ((long)M8 * kHidden));
   const long K0 = 2L * M;
-  float ws = W0[((long)l * kHidden + h) * K0 + j], wc = W0[((long)l * kHidden + h) * K0 + M + j];
-  float b0 = Bff[j], b1 = Bff[M + j], nb2 = -(b0 * b0 + b1 * b1);
-  float vs[4] = {ws, -wc * b0, -wc * b1, nb2 * ws};  // coefficient of sin p_j
-  float vc[4] = {wc, ws * b0, ws * b1, nb2 * wc};    // coefficient of cos p_j
-  long rbase = (long)l * 512 + (h / 64) * 256 + (h % 64);
-  uint16_t* hi16 = reinterpret_cast<uint16_t*>(hi);
-  uint16_t* lo16 = reinterpret_cast<uint16_t*>(lo);
+  const float* wrow = W0 + ((long)l * kHidden + h) * K0;
+  float ws[8], wc[8], b0[8], b1[8];
+  *reinterpret_cast<float4*>(ws) = *reinterpret_cast<const float4*>(wrow + j);
+  *reinterpret_cast<float4*>(ws + 4) = *reinterpret_cast<const float4*>(wrow + j + 4);
+  *reinterpret_cast<float4*>(wc) = *reinterpret_cast<const float4*>(wrow + M + j);
+  *reinterpret_cast<float4*>(wc + 4) = *reinterpret_cast<const float4*>(wrow + M + j + 4);
+  *reinterpret_cast<float4*>(b0) = *reinterpret_cast<const float4*>(Bff + j);
+  *reinterpret_cast<float4*>(b0 + 4) = *reinterpret_cast<const float4*>(Bff + j + 4);
+  *reinterpret_cast<float4*>(b1) = *reinterpret_cast<const float4*>(Bff + M + j);
+  *reinterpret_cast<float4*>(b1 + 4) = *reinterpret_cast<const float4*>(Bff + M + j + 4);
+  const long rbase = (long)l * 512 + (h / 64) * 256 + (h % 64);
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     const float sc = plan[(long)l * PL_STRIDE + PL_SW0 + s];
-    long o = (rbase + s * 64) * K0;
-    uint16_t a, b;
-    tc::split1<tc::PF_HH>(vs[s] * sc, a, b);
-    hi16[o + j] = a;
-    lo16[o + j] = b;
-    tc::split1<tc::PF_HH>(vc[s] * sc, a, b);
-    hi16[o + M + j] = a;
-    lo16[o + M + j] = b;
+    float vs[8], vc[8];   // coefficients of sin p_j and cos p_j in stream s
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float nb2 = -(b0[k] * b0[k] + b1[k] * b1[k]);
+      const float bd = s == 1 ? b0[k] : b1[k];
+      vs[k] = (s == 0 ? ws[k] : s == 3 ? nb2 * ws[k] : -wc[k] * bd) * sc;
+      vc[k] = (s == 0 ? wc[k] : s == 3 ? nb2 * wc[k] : ws[k] * bd) * sc;
+    }
+    uint32_t hs[4], ls[4], hc[4], lc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      tc::split2<tc::PF_HH>(vs[2 * k], vs[2 * k + 1], hs[k], ls[k]);
+      tc::split2<tc::PF_HH>(vc[2 * k], vc[2 * k + 1], hc[k], lc[k]);
+    }
+    const long o = (rbase + s * 64) * K0 + j;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(hs[0], hs[1], hs[2], hs[3]);
+    *reinterpret_cast<uint4*>(lo + o) = make_uint4(ls[0], ls[1], ls[2], ls[3]);
+    *reinterpret_cast<uint4*>(hi + o + M) = make_uint4(hc[0], hc[1], hc[2], hc[3]);
+    *reinterpret_cast<uint4*>(lo + o + M) = make_uint4(lc[0], lc[1], lc[2], lc[3]);
   }
 }
 
-// both hidden weight tensors in one launch: out_i[l][c][r] = W_i[l][r][c] when transpose (128x128 blocks), fp16 hi/lo
-// planes of PL_SW_i * W_i
-__global__ void split_w_kernel(const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ plan,
-                               __nv_bfloat16* __restrict__ hi1, __nv_bfloat16* __restrict__ lo1,
-                               __nv_bfloat16* __restrict__ hi2, __nv_bfloat16* __restrict__ lo2, int L, int transpose) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long n = (long)L * kHidden * kHidden;
-  if (i >= 2 * n) return;
-  const int which = i >= n;
-  if (which) i -= n;
-  const float* W = which ? W2 : W1;
-  int c = (int)(i % kHidden), r = (int)((i / kHidden) % kHidden), l = (int)(i / (kHidden * kHidden));
-  float v = transpose ? W[((long)l * kHidden + c) * kHidden + r] : W[i];
-  uint16_t a, b;
-  tc::split1<tc::PF_HH>(v * plan[(long)l * PL_STRIDE + (which ? PL_SW2 : PL_SW1)], a, b);
-  reinterpret_cast<uint16_t*>(which ? hi2 : hi1)[i] = a;
-  reinterpret_cast<uint16_t*>(which ? lo2 : lo1)[i] = b;
+// both hidden weight tensors: fp16 hi/lo planes of PL_SW_i * W_i, as stored (forward B operand, K-major) and
+// transposed, WT_i[l][c][r] = W_i[l][r][c] (dgrad B operand, K-major)
+struct HiddenPlanes {
+  __nv_bfloat16 *hi[2], *lo[2], *hiT[2], *loT[2];
+};
+// one block = one 32 x 32 tile of one matrix (blk = (which * L + l) * 16 + tile); the transposed planes go through a
+// shared-memory tile so that both writes are coalesced
+__device__ __forceinline__ void split_w_body(unsigned blk, const float* __restrict__ W1, const float* __restrict__ W2,
+                                             const float* __restrict__ plan, const HiddenPlanes& o, int L) {
+  __shared__ uint32_t tile[32][33];
+  const int tl = blk & 15, l = (blk >> 4) % L, which = (blk >> 4) / L;
+  const int r0 = (tl >> 2) * 32, c0 = (tl & 3) * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* W = (which ? W2 : W1) + (long)l * kHidden * kHidden;
+  const float sc = plan[(long)l * PL_STRIDE + (which ? PL_SW2 : PL_SW1)];
+  uint16_t* hi = reinterpret_cast<uint16_t*>(o.hi[which]) + (long)l * kHidden * kHidden;
+  uint16_t* lo = reinterpret_cast<uint16_t*>(o.lo[which]) + (long)l * kHidden * kHidden;
+  uint16_t* hiT = reinterpret_cast<uint16_t*>(o.hiT[which]) + (long)l * kHidden * kHidden;
+  uint16_t* loT = reinterpret_cast<uint16_t*>(o.loT[which]) + (long)l * kHidden * kHidden;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    uint16_t a, b;
+    tc::split1<tc::PF_HH>(W[r * kHidden + c] * sc, a, b);
+    hi[r * kHidden + c] = a;
+    lo[r * kHidden + c] = b;
+    tile[ty + 8 * k][tx] = (uint32_t)a | ((uint32_t)b << 16);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t v = tile[tx][ty + 8 * k];
+    const int it = (c0 + ty + 8 * k) * kHidden + r0 + tx;      // WT[c][r] = W[r][c]
+    hiT[it] = (uint16_t)(v & 0xffffu);
+    loT[it] = (uint16_t)(v >> 16);
+  }
 }
 
 // Phi = [sin(x B), cos(x B)] as fp16 hi/lo planes (B, 2M), unscaled (|Phi| <= 1)   (examples/utils.py:139-140)
@@ -1270,11 +1348,10 @@ __global__ void split_w_kernel(const float* __restrict__ W1, const float* __rest
 // like the reference; a two-constant Cody-Waite step (k = rint(p / 2pi), r = p - k 2pi_hi - k 2pi_lo with FMAs,
 // 3.5e-8 rms error) brings it to [-pi, pi].  kAccurate: sinf / cosf of the reduced argument (1 ulp) - the fp16 hi/lo
 // planes carry 2^-22, so the 5e-7 of the MUFU approximations would be the largest error of the whole layer.
-__global__ void features_f16_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
-                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long P,
-                                    int M) {
+__device__ __forceinline__ void features_f16_body(long i, const float* __restrict__ x, const float* __restrict__ Bff,
+                                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long P,
+                                                  int M) {
   const int M4 = M >> 2;
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * M4) return;
   long p = i / M4;
   int j = (int)(i % M4) * 4;
@@ -1341,9 +1418,8 @@ __global__ void features_shift_f16_kernel(const float* __restrict__ x, const flo
   *reinterpret_cast<uint2*>(lo + o + M) = make_uint2(l0, l1);
 }
 // W0 itself (not folded with the stream scalings), rows l * 128 + h, fp16 hi/lo planes of PL_SW0[0] * W0
-__global__ void split_w0_kernel(const float* __restrict__ W0, const float* __restrict__ plan,
-                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int L, long K0) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void split_w0_body(long i, const float* __restrict__ W0, const float* __restrict__ plan,
+                                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int L, long K0) {
   long n = (long)L * kHidden * K0;
   if (i >= n) return;
   const int l = (int)(i / (kHidden * K0));
@@ -1352,6 +1428,28 @@ __global__ void split_w0_kernel(const float* __restrict__ W0, const float* __res
   reinterpret_cast<uint16_t*>(hi)[i] = a;
   reinterpret_cast<uint16_t*>(lo)[i] = b;
 }
+// All per-call operand preparation in ONE launch (the small-batch configurations are bound by the number and the
+// latency of these kernels): block ranges = features of all points | folded layer-0 weights | hidden weight planes
+// (plain + transposed) | unfolded W0 planes (finite-difference pass only).
+struct PrepArgs {
+  const float *x, *Bff, *W0, *W1, *W2, *plan;
+  __nv_bfloat16 *phi_hi, *phi_lo, *w0_hi, *w0_lo, *w0v_hi, *w0v_lo;
+  HiddenPlanes hp;
+  long B;
+  int L, M;
+  unsigned n_feat, n_fold, n_split;   // blocks of the first three ranges
+};
+__global__ void __launch_bounds__(256) prep_operands_kernel(PrepArgs a) {
+  unsigned b = blockIdx.x;
+  if (b < a.n_feat) return features_f16_body((long)b * 256 + threadIdx.x, a.x, a.Bff, a.phi_hi, a.phi_lo, a.B, a.M);
+  b -= a.n_feat;
+  if (b < a.n_fold) return fold_w0_body((long)b * 256 + threadIdx.x, a.W0, a.Bff, a.plan, a.w0_hi, a.w0_lo, a.L, a.M);
+  b -= a.n_fold;
+  if (b < a.n_split) return split_w_body(b, a.W1, a.W2, a.plan, a.hp, a.L);
+  b -= a.n_split;
+  split_w0_body((long)b * 256 + threadIdx.x, a.W0, a.plan, a.w0v_hi, a.w0v_lo, a.L, 2L * a.M);
+}
+
 // softplus alone at epilogue rate (value-only passes)
 __device__ __forceinline__ float softplus_fast(float z) { return fmaxf(z, 0.f) + __logf(1.f + __expf(-fabsf(z))); }
 
@@ -2502,32 +2600,37 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
 // head backward (SIMT, HBM-bound): du = dF c m rho ; dZ2 = du W3 (.) sigma(a2) -> hi/lo planes ;
 // dW3, db3, db2, dscales accumulated (block partials + atomics).  grid = (point chunks, L)
 // ------------------------------------------------------------------------------------------
-constexpr int kHeadChunk = 128;  // points per block
+constexpr int kHeadChunk = 128;  // points per block (32 per warp); small batches use 32 (8 per warp) for more blocks
 __global__ void __launch_bounds__(128)
 head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
                      const __nv_bfloat16* __restrict__ a2_hi, const __nv_bfloat16* __restrict__ a2_lo,
                      const float* __restrict__ W3, const float* __restrict__ x, const float* __restrict__ mscales,
-                     const float* __restrict__ plan,
+                     float* __restrict__ plan, const float* __restrict__ hstat, const float* __restrict__ mdf,
                      nsvd_problem_t pb, __nv_bfloat16* __restrict__ dz_hi, __nv_bfloat16* __restrict__ dz_lo,
                      float* __restrict__ dW3, float* __restrict__ db3, float* __restrict__ db2,
-                     float* __restrict__ dscales, int P, long Btot, long p_off) {
+                     float* __restrict__ dscales, int P, long Btot, long p_off, int chunk) {
   __shared__ float red[4][2 * kHidden + 2];
   const int l = blockIdx.y, L = pb.n_copies;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p_begin = blockIdx.x * kHeadChunk;
-  const int p_end = p_begin + kHeadChunk < P ? p_begin + kHeadChunk : P;
+  const int p_begin = blockIdx.x * chunk, wpts = chunk >> 2;   // points per warp
+  const int p_end = p_begin + chunk < P ? p_begin + chunk : P;
   float w3[4], accW[4] = {0, 0, 0, 0}, accB[4] = {0, 0, 0, 0}, acc_b3 = 0.f, acc_s = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) w3[i] = W3[l * kHidden + lane * 4 + i];
   float sc = pb.has_exp_mask ? mscales[l] : 1.f;
-  const float inv_sa2 = plan[(long)l * PL_STRIDE + PL_INV_SA2], sdz2 = plan[(long)l * PL_STRIDE + PL_SDZ2];
-  // each warp owns 32 consecutive points: lane i evaluates the per-point factor du of point i once, then the
-  // warp walks the 32 points with 4 rows of a2 in flight (lane = 4 hidden units)
+  const float inv_sa2 = plan[(long)l * PL_STRIDE + PL_INV_SA2];
+  float m3 = fmaxf(fmaxf(fabsf(w3[0]), fabsf(w3[1])), fmaxf(fabsf(w3[2]), fabsf(w3[3])));
+  for (int o = 16; o > 0; o >>= 1) m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, o));
+  const BwdScales bsc = bwd_scales(hstat, mdf[l], m3, pb.hard_mul_const, l, L);
+  if (blockIdx.x == 0 && threadIdx.x == 0) publish_bwd_plan(plan + (long)l * PL_STRIDE, bsc);
+  const float sdz2 = bsc.s2;
+  // each warp owns chunk / 4 consecutive points: lane i evaluates the per-point factor du of point i once, then the
+  // warp walks its points with 4 rows of a2 in flight (lane = 4 hidden units)
   {
-    const int pw = p_begin + warp * 32;
+    const int pw = p_begin + warp * wpts;
     const int pmine = pw + lane;
     float du_l = 0.f;
-    if (pmine < p_end) {
+    if (lane < wpts && pmine < p_end) {
       const long pg = p_off + pmine;
       PointGeom g = point_geom(x[2 * pg], x[2 * pg + 1], pb);
       float m = pb.has_exp_mask ? expf(-g.r / sc) : 1.f;
@@ -2536,7 +2639,7 @@ head_bwd_bf16_kernel(const float* __restrict__ dF, const float* __restrict__ U0,
       acc_b3 = du_l;
       if (pb.has_exp_mask) acc_s = du_l * U0[pg * L + l] * g.r / (sc * sc);
     }
-    for (int j0 = 0; j0 < 32 && pw + j0 < p_end; j0 += 4) {
+    for (int j0 = 0; j0 < wpts && pw + j0 < p_end; j0 += 4) {
       uint2 h[4], lo2[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -2618,7 +2721,7 @@ struct TcLayout {
   // saved (whole batch)
   size_t phi_hi, phi_lo, av_hi[3], av_lo[3], u0, plan, rowstat, hstat, mdf, saved_total;
   // work
-  size_t w0_hi, w0_lo, w_hi[2], w_lo[2], str_hi[2], str_lo[2], dz_hi[2], dz_lo[2], scr_hi, scr_lo, phis_hi, phis_lo,
+  size_t w0_hi, w0_lo, w_hi[2], w_lo[2], wT_hi[2], wT_lo[2], str_hi[2], str_lo[2], dz_hi[2], dz_lo[2], scr_hi, scr_lo, phis_hi, phis_lo,
       w0v_hi, w0v_lo, work_total;
   long P;
 };
@@ -2643,7 +2746,7 @@ static TcLayout tc_layout(const nsvd_problem_t& pb) {
   t.u0 = take(B * L * 4);
   t.plan = take(L * PL_STRIDE * 4);        // operand plan: written by the forward, completed and read by the backward
   t.rowstat = take(L * H * 5 * 4);
-  t.hstat = take(2 * L * 3 * 4);
+  t.hstat = take((2 * L * 3 + 4) * 4);   // + the three feature-stream bounds
   t.mdf = take(L * 4);
   t.saved_total = o + 1024;
   o = 0;
@@ -2652,6 +2755,8 @@ static TcLayout tc_layout(const nsvd_problem_t& pb) {
   for (int i = 0; i < 2; ++i) {
     t.w_hi[i] = take(L * H * H * 2);
     t.w_lo[i] = take(L * H * H * 2);
+    t.wT_hi[i] = take(L * H * H * 2);
+    t.wT_lo[i] = take(L * H * H * 2);
   }
   for (int i = 0; i < 2; ++i) {
     t.str_hi[i] = take(L * 4 * P * H * 2);
@@ -2716,24 +2821,30 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
   float* hstat = reinterpret_cast<float*>(sv + t.hstat);
   {
   ProfScope prep(KC_PREP, st);
-  w0_stats_kernel<<<(unsigned)(L * H), 256, 0, st>>>(pr.W[0], pr.Bff, rowstat, (int)M);
+  weight_stats_kernel<<<(unsigned)(L * H + 2 * L + 1), 256, 0, st>>>(pr.W[0], pr.Bff, pr.W[1], pr.W[2], rowstat, hstat, (int)L,
+                                                                 (int)M);
   NSVD_LAUNCH_CHECK();
-  hid_stats_kernel<<<dim3((unsigned)L, 2), 128, 0, st>>>(pr.W[1], pr.W[2], hstat, (int)L);
+  fwd_plan_kernel<<<cdiv(L, 4), 128, 0, st>>>(rowstat, hstat, pr.Bff, pr.b[0], pr.b[1], pr.b[2], plan, (int)L, (int)M);
   NSVD_LAUNCH_CHECK();
-  fwd_plan_kernel<<<1, 128, 0, st>>>(rowstat, hstat, pr.Bff, pr.b[0], pr.b[1], pr.b[2], plan, (int)L, (int)M);
-  NSVD_LAUNCH_CHECK();
-  features_f16_kernel<<<cdiv(B * (M / 4), 256), 256, 0, st>>>(x, pr.Bff, BF(sv + t.phi_hi), BF(sv + t.phi_lo), B, (int)M);
-  NSVD_LAUNCH_CHECK();
-  fold_w0_kernel<<<cdiv(L * H * M, 256), 256, 0, st>>>(pr.W[0], pr.Bff, plan, BF(wk + t.w0_hi), BF(wk + t.w0_lo), (int)L,
-                                                       (int)M);
-  NSVD_LAUNCH_CHECK();
-  split_w_kernel<<<cdiv(2 * L * H * H, 256), 256, 0, st>>>(pr.W[1], pr.W[2], plan, BF(wk + t.w_hi[0]), BF(wk + t.w_lo[0]),
-                                                           BF(wk + t.w_hi[1]), BF(wk + t.w_lo[1]), (int)L, 0);
-  NSVD_LAUNCH_CHECK();
-  if (pb.fd_eps > 0.f) {
-    split_w0_kernel<<<cdiv(L * H * K0, 256), 256, 0, st>>>(pr.W[0], plan, BF(wk + t.w0v_hi), BF(wk + t.w0v_lo), (int)L, K0);
-    NSVD_LAUNCH_CHECK();
+  PrepArgs pa{};
+  pa.x = x; pa.Bff = pr.Bff; pa.W0 = pr.W[0]; pa.W1 = pr.W[1]; pa.W2 = pr.W[2]; pa.plan = plan;
+  pa.phi_hi = BF(sv + t.phi_hi); pa.phi_lo = BF(sv + t.phi_lo);
+  pa.w0_hi = BF(wk + t.w0_hi); pa.w0_lo = BF(wk + t.w0_lo);
+  for (int i = 0; i < 2; ++i) {
+    pa.hp.hi[i] = BF(wk + t.w_hi[i]); pa.hp.lo[i] = BF(wk + t.w_lo[i]);
+    pa.hp.hiT[i] = BF(wk + t.wT_hi[i]); pa.hp.loT[i] = BF(wk + t.wT_lo[i]);
   }
+  pa.B = B; pa.L = (int)L; pa.M = (int)M;
+  pa.n_feat = (unsigned)cdiv(B * (M / 4), 256);
+  pa.n_fold = (unsigned)cdiv(L * H * (M / 8), 256);
+  pa.n_split = (unsigned)(2 * L * 16);   // 32 x 32 tiles of the 128 x 128 hidden matrices
+  unsigned n_w0v = 0;
+  if (pb.fd_eps > 0.f) {
+    pa.w0v_hi = BF(wk + t.w0v_hi); pa.w0v_lo = BF(wk + t.w0v_lo);
+    n_w0v = (unsigned)cdiv(L * H * K0, 256);
+  }
+  prep_operands_kernel<<<pa.n_feat + pa.n_fold + pa.n_split + n_w0v, 256, 0, st>>>(pa);
+  NSVD_LAUNCH_CHECK();
   }
   CUtensorMap mW0h, mW0l, mWh[2], mWl[2];
   const uint32_t w0_box = big::BN / 2;   // a CTA of a pair loads half of the 256 W' rows
@@ -2950,30 +3061,30 @@ int tc_backward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* 
   }
   // backward half of the operand plan: scales of the dZ planes from max|dF| per copy
   float* plan = reinterpret_cast<float*>(sv + t.plan);
-  col_absmax_kernel<<<148 * 2, 256, 0, st>>>(dF, B * L, (int)L, mdf);
+  {
+    const long want = cdiv(B * L, 256 * 8);   // >= 8 elements per thread; small batches get a small grid
+    col_absmax_kernel<<<(unsigned)(want < 148 * 2 ? (want > 1 ? want : 1) : 148 * 2), 256, 0, st>>>(dF, B * L, (int)L, mdf);
+  }
   NSVD_LAUNCH_CHECK();
-  bwd_plan_kernel<<<1, 128, 0, st>>>(plan, reinterpret_cast<const float*>(sv + t.hstat), mdf, pr.W[3], pb.hard_mul_const,
-                                     (int)L);
-  NSVD_LAUNCH_CHECK();
-  // transposed hidden weights (dgrad B operand, K-major): WT_i[l][k][j] = W_i[l][j][k]
+  // transposed hidden weights (dgrad B operand, K-major): WT_i[l][k][j] = W_i[l][j][k], written by the forward's
+  // operand preparation (the version check of the Python layer guarantees the forward of THIS step wrote them)
   CUtensorMap mWh[2], mWl[2];
-  split_w_kernel<<<cdiv(2 * L * H * H, 256), 256, 0, st>>>(pr.W[1], pr.W[2], plan, BF(wk + t.w_hi[0]), BF(wk + t.w_lo[0]),
-                                                           BF(wk + t.w_hi[1]), BF(wk + t.w_lo[1]), (int)L, 1);
-  NSVD_LAUNCH_CHECK();
   for (int i = 0; i < 2; ++i) {
-    if ((rc = make_tmap_bf16_3d(&mWh[i], wk + t.w_hi[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
-    if ((rc = make_tmap_bf16_3d(&mWl[i], wk + t.w_lo[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mWh[i], wk + t.wT_hi[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mWl[i], wk + t.wT_lo[i], H, H, L, H * 2, H * H * 2, 64, 128))) return rc;
   }
   for (long p0 = 0; p0 < B; p0 += t.P) {
     const int P = (int)((B - p0) < t.P ? (B - p0) : t.P);
     const int m_tiles = cdiv(P, 128);
     // ---- head: dZ2 planes (pair 0), dW3, db3, db2, dscales
-    dim3 hg(cdiv(P, kHeadChunk), (unsigned)L);
+    const int hchunk = P <= 8192 ? 32 : kHeadChunk;
+    dim3 hg(cdiv(P, hchunk), (unsigned)L);
     {
       ProfScope ps(KC_HEAD_BWD, st);
       head_bwd_bf16_kernel<<<hg, 128, 0, st>>>(dF, reinterpret_cast<const float*>(sv + t.u0), BF(sv + t.av_hi[2]),
-                                               BF(sv + t.av_lo[2]), pr.W[3], x, pr.mask_scales, plan, pb, BF(wk + t.dz_hi[0]),
-                                               BF(wk + t.dz_lo[0]), gr.dW[3], gr.db[3], gr.db[2], gr.dmask_scales, P, B, p0);
+                                               BF(sv + t.av_lo[2]), pr.W[3], x, pr.mask_scales, plan,
+                                               reinterpret_cast<const float*>(sv + t.hstat), mdf, pb, BF(wk + t.dz_hi[0]),
+                                               BF(wk + t.dz_lo[0]), gr.dW[3], gr.db[3], gr.db[2], gr.dmask_scales, P, B, p0, hchunk);
       NSVD_LAUNCH_CHECK();
     }
     // ---- hidden layers 2, 1: dgrad + wgrad in one pass
