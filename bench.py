@@ -275,6 +275,38 @@ def cdk_config(N, dev, B=4096, L=512, steps=20, warmup=5):
         ms = time_events(step, steps, warmup, lambda: torch.cuda.synchronize(dev))
         out[tag] = {"ms_per_step": ms, "pairs_per_s": B / (ms * 1e-3)}
     out.update(rows=B, feature_dim=L, what="NestedLoRAForCDK.compute_loss + backward (loss only, no encoder)")
+    # the whole CDK step of main_sketchy.py:176-186: two 512 -> 8192 -> 512 towers (dense layers on the library's own
+    # tcgen05 GEMM kernels) -> l2_ball -> fused CDK loss -> backward into the tower weights; next to it the same
+    # towers on torch / cuBLAS fp32 (TF32 off: same arithmetic contract) feeding the same loss kernels
+    net = N.get_sketchy_encoder().to(dev)
+    x, y = torch.randn(B, 512, generator=g).to(dev), torch.randn(B, 512, generator=g).to(dev)
+    m2 = N.NestedLoRAForCDK(model=net, neigs=L, step=1, sequential=False, set_first_mode_const=True).to(dev)
+    m2.diagnostics = False
+
+    def enc_step():
+        m2.zero_grad(set_to_none=True)
+        _, fx, _, fy = m2(x, y)
+        m2.compute_loss(fx, fy)[0].backward()
+
+    ms = time_events(enc_step, steps, warmup, lambda: torch.cuda.synchronize(dev))
+    flop = 2 * 3 * 2 * B * (512 * 8192 + 8192 * 512)          # 2 towers x (fwd + dgrad + wgrad) x 2 B K N per layer
+    out["with_encoder"] = {"ms_per_step": ms, "pairs_per_s": B / (ms * 1e-3), "encoder_gflop": flop / 1e9,
+                           "encoder_tflops_algorithmic": flop / (ms * 1e-3) / 1e12,
+                           "what": "HeteroNetwork towers (TCLinear: nsvd_linear_fwd/bwd) + CDK loss + backward"}
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    towers = [torch.nn.Sequential(torch.nn.Linear(512, 8192), torch.nn.LeakyReLU(0.2), torch.nn.Linear(8192, 512)).to(dev)
+              for _ in range(2)]
+
+    def cublas_step():
+        for t in towers:
+            t.zero_grad(set_to_none=True)
+        fx, fy = N.normalize(towers[0](x), 4.0, "l2_ball"), N.normalize(towers[1](y), 4.0, "l2_ball")
+        m2.compute_loss(fx, fy)[0].backward()
+
+    ms_c = time_events(cublas_step, steps, warmup, lambda: torch.cuda.synchronize(dev))
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    out["with_encoder"]["cublas_fp32_ms_per_step"] = ms_c
     return out
 
 

@@ -220,6 +220,20 @@ int nsvd_sample_gaussian(float* x, int64_t n_points, float sigma, uint64_t seed,
 int nsvd_sample_points(float* x, int64_t n_points, int32_t importance, float scale, uint64_t seed, uint64_t offset,
                        void* stream);
 
+/* Dense layers of the CDK encoder on the tcgen05 GEMM block: replaces `nn.Linear` (+ LeakyReLU / ReLU)
+ * inside `get_mlp` (/root/reference/examples/models/mlp.py:129-164) as `HeteroNetwork` uses it
+ * (/root/reference/examples/models/siam.py:132-165; main_sketchy.py:107-115: two 512 -> 8192 -> 512 towers).
+ *   forward : y (rows, out) = act(x (rows, in) . W (out, in)^T + bias),  act = 0 none | 1 leaky ReLU(slope), slope 0 = ReLU
+ *   backward: dz = dy * act'(y);  dx = dz . W;  dW = dz^T . x;  db = column sums of dz   (dx / dW / db may be NULL)
+ * fp32 tensors, row-major; operands go through bf16 hi/lo planes (3 products, fp32 accumulation in bounded chains).
+ * in / out features must be multiples of 8.  `work` >= nsvd_linear_work_bytes(rows, in, out) bytes.              */
+size_t nsvd_linear_work_bytes(int32_t rows, int32_t in_features, int32_t out_features);
+int nsvd_linear_fwd(const float* x, const float* W, const float* bias, float* y, int32_t rows, int32_t in_features,
+                    int32_t out_features, int32_t act, float slope, void* work, size_t work_bytes, void* stream);
+int nsvd_linear_bwd(const float* x, const float* W, const float* y, const float* dy, int32_t rows, int32_t in_features,
+                    int32_t out_features, int32_t act, float slope, float* dx, float* dW, float* db, void* work,
+                    size_t work_bytes, void* stream);
+
 /* Self-test hooks for the tcgen05 building block (tests/test_gpu_tc_gemm.py):
  *   D (M,N) fp32 = A . B^T with bf16x3 splitting; A (M,K), B (N,K) fp32 when *_kmajor = 1,
  *   A (K,M) / B (K,N) when 0 (MN-major operands, as the weight-gradient GEMMs use them).       */

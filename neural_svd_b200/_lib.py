@@ -71,6 +71,9 @@ SIGNATURES = {
                                         C.POINTER(_i64), C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
     "nsvd_sample_gaussian": (C.c_int, [_vp, _i64, C.c_float, C.c_uint64, C.c_uint64, _vp]),
     "nsvd_sample_points": (C.c_int, [_vp, _i64, _i32, C.c_float, C.c_uint64, C.c_uint64, _vp]),
+    "nsvd_linear_work_bytes": (_sz, [_i32, _i32, _i32]),
+    "nsvd_linear_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, C.c_float, _vp, _sz, _vp]),
+    "nsvd_linear_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, C.c_float, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nsvd_tc_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
 }
 

@@ -306,6 +306,26 @@ int nsvd_sample_points(float* x, int64_t n_points, int32_t importance, float sca
   return sample_other2(x, n_points, importance == NSVD_IMP_LAPLACE, scale, seed, offset, (cudaStream_t)stream);
 }
 
+size_t nsvd_linear_work_bytes(int32_t rows, int32_t in_features, int32_t out_features) {
+  return tc_linear_work_bytes(rows, in_features, out_features);
+}
+int nsvd_linear_fwd(const float* x, const float* W, const float* bias, float* y, int32_t rows, int32_t in_features,
+                    int32_t out_features, int32_t act, float slope, void* work, size_t work_bytes, void* stream) {
+  DeviceGuard dg_(x);
+  NSVD_CHECK_ARG(x && W && y, "NULL buffer");
+  NSVD_CHECK_ARG(act == 0 || act == 1, "unknown activation %d", act);
+  return tc_linear_fwd(x, W, bias, y, rows, in_features, out_features, act, slope, work, work_bytes, (cudaStream_t)stream);
+}
+int nsvd_linear_bwd(const float* x, const float* W, const float* y, const float* dy, int32_t rows, int32_t in_features,
+                    int32_t out_features, int32_t act, float slope, float* dx, float* dW, float* db, void* work,
+                    size_t work_bytes, void* stream) {
+  DeviceGuard dg_(dy);
+  NSVD_CHECK_ARG(x && W && dy, "NULL buffer");
+  NSVD_CHECK_ARG(act == 0 || act == 1, "unknown activation %d", act);
+  return tc_linear_bwd(x, W, y, dy, rows, in_features, out_features, act, slope, dx, dW, db, work, work_bytes,
+                       (cudaStream_t)stream);
+}
+
 int nsvd_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K,
                           int32_t a_kmajor, int32_t b_kmajor, void* work, size_t work_bytes, void* stream) {
   DeviceGuard dg_(A);

@@ -70,6 +70,11 @@ int tc_cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int
 int tc_cdk_bwd(const float* f, const float* g, const float* v, const float* coef, const float* gscale, int B, int L,
                int fc, long Bg, float* grad_f, float* grad_g, void* work, cudaStream_t st);
 int tc_cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* out, void* work, cudaStream_t st);
+size_t tc_linear_work_bytes(int rows, int in_f, int out_f);
+int tc_linear_fwd(const float* x, const float* W, const float* bias, float* y, int rows, int in_f, int out_f, int act,
+                  float slope, void* work, size_t work_bytes, cudaStream_t st);
+int tc_linear_bwd(const float* x, const float* W, const float* y, const float* dy, int rows, int in_f, int out_f, int act,
+                  float slope, float* dx, float* dW, float* db, void* work, size_t work_bytes, cudaStream_t st);
 int tc_gemm_selftest(const float* A, const float* B, float* D, int M, int N, int K, int a_kmajor,
                      int b_kmajor, void* work, size_t work_bytes, cudaStream_t st);
 

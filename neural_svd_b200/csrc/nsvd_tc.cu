@@ -97,6 +97,8 @@ struct BigShape {
                                             // while every (batch, n-tile) of B sweeps over them
   int k_group;                              // k-slices per group (0 = off): same idea for the weight-gradient GEMM,
                                             // whose long dimension is K (points)
+  int a_xbatch;                             // big2s, MN-major: batches of A are column blocks of ONE matrix, batch b starts
+                                            // at column b * a_xbatch (0 = batches are the third TMA coordinate)
 };
 struct TileCoord {
   int b, nt, ks, mt;
@@ -590,8 +592,9 @@ big2s_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
           } else {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              tma_load_3d_pair(sA + i * 8192, &tmAh, lead_full, c.mt * BM + i * 64, kc * BK, ab);
-              tma_load_3d_pair(sA + A_BYTES + i * 8192, &tmAl, lead_full, c.mt * BM + i * 64, kc * BK, ab);
+              const int acol = c.mt * BM + i * 64 + ab * shape.a_xbatch, az = shape.a_xbatch ? 0 : ab;
+              tma_load_3d_pair(sA + i * 8192, &tmAh, lead_full, acol, kc * BK, az);
+              tma_load_3d_pair(sA + A_BYTES + i * 8192, &tmAl, lead_full, acol, kc * BK, az);
               const int ncol = c.nt * BN + ((int)rank * 2 + i) * 64;
               tma_load_3d_pair(sB + i * 8192, &tmBh, lead_full, ncol, kc * BK, bb);
               tma_load_3d_pair(sB + BH_BYTES + i * 8192, &tmBl, lead_full, ncol, kc * BK, bb);
@@ -3380,6 +3383,270 @@ int tc_cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* 
   }
   s.m_tiles = cdiv(B, big::BM);
   return launch_big<false>(mah, mal, mbh, mbl, s, epi, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Dense layers of the CDK encoder (examples/models/mlp.py:129-164 `get_mlp`, siam.py:132-165
+// `HeteroNetwork`; main_sketchy.py:107-115 builds two 512 -> 8192 -> 512 towers) on the CTA-pair GEMM block with
+// bounded accumulation chains (big2s), 3 products of fp16 hi/lo planes:
+//   forward   y  = act(x W^T + b)          K-major,  K = in features
+//   backward  dz = dy * act'(y);  dx = dz W (K-major, K = out features, transposed W planes);
+//             dW = dz^T x (MN-major, K = rows, the out features in column blocks of 128 stacked by the CTA pair);
+//             db = column sums of dz.
+// Every tensor is stored as planes of s v with s = 2^k from its measured max |v| (one reduction pass per tensor), so
+// that |s v| <= 2^15: 22 significant bits.  (bf16 planes, 16 bits, need no scale but leave 1e-5 in y - enough for y itself,
+// not for the gradients behind the activation kink: with 33 M hidden activations per tower, ~60 of them change sign
+// against the fp32 reference and dW of the first layer moves by 1.4e-3, measured.)
+// ------------------------------------------------------------------------------------------
+struct AbsmaxList {
+  const float* p[3];
+  long n[3];
+  int count;
+};
+// out[t] = max |p[t][i]|  (out zero-initialised; non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256) absmax_list_kernel(AbsmaxList a, float* __restrict__ out) {
+  __shared__ float red[8];
+  for (int t = 0; t < a.count; ++t) {
+    const float* p = a.p[t];
+    float m = 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n[t]; i += (long)gridDim.x * blockDim.x)
+      m = fmaxf(m, fabsf(p[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+      if (m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out) + t, __float_as_uint(m));
+    }
+    __syncthreads();
+  }
+}
+
+struct LinearEpi {
+  float* D;
+  const float* bias;        // per output column, or null
+  const float *amax_a, *amax_b;   // max |.| of the two operands (their planes carry pow2_scale(max) * v)
+  int M, N;                 // valid rows / columns of D
+  long ldd;
+  int rows_per_batch;       // MN-major: batch b covers the rows [b * rows_per_batch, +128)
+  int act;                  // 0 none, 1 leaky ReLU with `slope` (0 = ReLU)
+  float slope;
+  __device__ static __forceinline__ uint32_t col0(int sub, int j) { return (uint32_t)(sub * 64 + j * 16); }
+  __device__ __forceinline__ void operator()(float (&r)[64], const TileCoord& c, int q, int sub, int lane,
+                                             uint8_t*) const {
+    const long row = (long)c.b * rows_per_batch + (long)c.mt * big::BM + q * 32 + lane;
+    if (row >= M) return;
+    const float un = 1.f / (pow2_scale(__ldg(amax_a)) * pow2_scale(__ldg(amax_b)));
+    float* drow = D + row * ldd;
+    const bool vec = (ldd & 3) == 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int n0 = c.nt * big::BN + sub * 64 + g * 16;
+      if (n0 < N) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float v = r[g * 16 + i] * un;
+          if (bias && n0 + i < N) v += __ldg(bias + n0 + i);
+          if (act == 1) v = v > 0.f ? v : v * slope;
+          r[g * 16 + i] = v;
+        }
+        if (vec && n0 + 16 <= N) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(drow + n0 + i) = make_float4(r[g * 16 + i], r[g * 16 + i + 1], r[g * 16 + i + 2],
+                                                                    r[g * 16 + i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + i < N) drow[n0 + i] = r[g * 16 + i];
+        }
+      }
+    }
+  }
+};
+
+// fp16 hi/lo planes of pow2_scale(*amax) * src
+__global__ void __launch_bounds__(256) split_scaled_kernel(const float* __restrict__ src, const float* __restrict__ amax,
+                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                           long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint16_t a, b;
+  tc::split1<tc::PF_HH>(src[i] * pow2_scale(__ldg(amax)), a, b);
+  reinterpret_cast<uint16_t*>(hi)[i] = a;
+  reinterpret_cast<uint16_t*>(lo)[i] = b;
+}
+
+// src (R, C) fp32 -> planes of the TRANSPOSE (C, R); 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) split_scaled_transposed_kernel(const float* __restrict__ src,
+                                                                      const float* __restrict__ amax,
+                                                                      __nv_bfloat16* __restrict__ hi,
+                                                                      __nv_bfloat16* __restrict__ lo, int R, int C) {
+  __shared__ uint32_t tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float sc = pow2_scale(__ldg(amax));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    uint16_t a = 0, b = 0;
+    if (r < R && c < C) tc::split1<tc::PF_HH>(src[(long)r * C + c] * sc, a, b);
+    tile[ty + 8 * k][tx] = (uint32_t)a | ((uint32_t)b << 16);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, r = r0 + tx;
+    if (c < C && r < R) {
+      const uint32_t v = tile[tx][ty + 8 * k];
+      reinterpret_cast<uint16_t*>(hi)[(long)c * R + r] = (uint16_t)(v & 0xffffu);
+      reinterpret_cast<uint16_t*>(lo)[(long)c * R + r] = (uint16_t)(v >> 16);
+    }
+  }
+}
+
+// dz = dy * act'(y) -> planes scaled by pow2_scale(max |dy|) (|act'| <= 1); db[col] += sum over this block's 64 rows.
+// grid (cols / 256, rows / 64)
+__global__ void __launch_bounds__(256) linear_dz_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act,
+                                                        float slope, const float* __restrict__ amax,
+                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                        float* __restrict__ db, int M, int N) {
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= N) return;
+  const int r0 = blockIdx.y * 64, r1 = r0 + 64 < M ? r0 + 64 : M;
+  const float sc = pow2_scale(__ldg(amax));
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const long o = (long)r * N + col;
+    float g = dy[o];
+    if (act == 1 && !(y[o] > 0.f)) g *= slope;
+    acc += g;
+    uint16_t a, b;
+    tc::split1<tc::PF_HH>(g * sc, a, b);
+    reinterpret_cast<uint16_t*>(hi)[o] = a;
+    reinterpret_cast<uint16_t*>(lo)[o] = b;
+  }
+  if (db) atomicAdd(db + col, acc);
+}
+
+static size_t linear_planes(long rows, long cols) { return align_up((size_t)rows * cols * 2, 1024); }
+size_t tc_linear_work_bytes(int rows, int in_f, int out_f) {
+  // 1 KB of scales, then (backward needs the most) dz planes, transposed W planes, x planes (hi + lo each)
+  return 1024 + 2 * (linear_planes(rows, out_f) + linear_planes(out_f, in_f) + linear_planes(rows, in_f)) + 2048;
+}
+
+static int linear_check(int rows, int in_f, int out_f, float slope, const void* work, size_t work_bytes) {
+  NSVD_CHECK_ARG(rows >= 1 && in_f >= 8 && out_f >= 8 && in_f % 8 == 0 && out_f % 8 == 0,
+                 "dense layer: rows >= 1, in/out features positive multiples of 8 (got %d x %d -> %d)", rows, in_f, out_f);
+  NSVD_CHECK_ARG(slope >= -1.f && slope <= 1.f, "dense layer: |slope| must be <= 1 (got %g)", (double)slope);
+  NSVD_CHECK_ARG(work != nullptr, "work is NULL");
+  if (work_bytes < tc_linear_work_bytes(rows, in_f, out_f)) {
+    set_error("dense layer work too small: %zu < %zu", work_bytes, tc_linear_work_bytes(rows, in_f, out_f));
+    return NSVD_E_WORKSPACE;
+  }
+  return 0;
+}
+
+constexpr int kLinearSub = 8;   // K chunks (512 terms x 3 products) per TMEM accumulation chain
+
+static int linear_absmax(const float* a, long na, const float* b, long nb, const float* c, long nc, float* out,
+                         cudaStream_t st) {
+  NSVD_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(float), st));
+  AbsmaxList l{};
+  l.p[0] = a; l.n[0] = na;
+  l.p[1] = b; l.n[1] = nb;
+  l.p[2] = c; l.n[2] = nc;
+  l.count = c ? 3 : 2;
+  long most = na > nb ? na : nb;
+  if (nc > most) most = nc;
+  const long want = cdiv(most, 256 * 16);
+  absmax_list_kernel<<<(unsigned)(want < 148 * 4 ? (want > 1 ? want : 1) : 148 * 4), 256, 0, st>>>(l, out);
+  NSVD_LAUNCH_CHECK();
+  return 0;
+}
+
+// D (M, N) = A (M, K) . B (N, K)^T from K-major fp16 hi/lo planes
+static int linear_gemm_kmajor(const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* b_hi, const uint8_t* b_lo, int M,
+                              int N, int K, const LinearEpi& epi, cudaStream_t st) {
+  CUtensorMap mah, mal, mbh, mbl;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&mah, a_hi, K, M, 1, (uint64_t)K * 2, (uint64_t)M * K * 2, 64, big::BM))) return rc;
+  if ((rc = make_tmap_bf16_3d(&mal, a_lo, K, M, 1, (uint64_t)K * 2, (uint64_t)M * K * 2, 64, big::BM))) return rc;
+  if ((rc = make_tmap_bf16_3d(&mbh, b_hi, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN / 2))) return rc;
+  if ((rc = make_tmap_bf16_3d(&mbl, b_lo, K, N, 1, (uint64_t)K * 2, (uint64_t)N * K * 2, 64, big::BN / 2))) return rc;
+  BigShape s{};
+  s.m_tiles = cdiv(M, 2 * big::BM);
+  s.n_tiles = cdiv(N, big::BN);
+  s.batches = 1;
+  s.k_slices = 1;
+  s.k_chunks_total = cdiv(K, big::BK);
+  s.k_chunks_per_slice = s.k_chunks_total;
+  s.m_group = 8;   // 2048 rows of A stay in the L2 while the column tiles of B sweep over them
+  return launch_big2s<false, LinearEpi, kFmtHH>(mah, mal, mbh, mbl, s, 1, kLinearSub, kLinearSub, epi, st);
+}
+
+int tc_linear_fwd(const float* x, const float* W, const float* bias, float* y, int rows, int in_f, int out_f, int act,
+                  float slope, void* work, size_t work_bytes, cudaStream_t st) {
+  int rc;
+  if ((rc = linear_check(rows, in_f, out_f, slope, work, work_bytes))) return rc;
+  uint8_t* wk = align1k(work);
+  float* amax = reinterpret_cast<float*>(wk);      // [0] x, [1] W
+  wk += 1024;
+  const size_t nx = linear_planes(rows, in_f), nw = linear_planes(out_f, in_f);
+  uint8_t *x_hi = wk, *x_lo = wk + nx, *w_hi = wk + 2 * nx, *w_lo = wk + 2 * nx + nw;
+  if ((rc = linear_absmax(x, (long)rows * in_f, W, (long)out_f * in_f, nullptr, 0, amax, st))) return rc;
+  split_scaled_kernel<<<cdiv((long)rows * in_f, 256), 256, 0, st>>>(x, amax, BF(x_hi), BF(x_lo), (long)rows * in_f);
+  NSVD_LAUNCH_CHECK();
+  split_scaled_kernel<<<cdiv((long)out_f * in_f, 256), 256, 0, st>>>(W, amax + 1, BF(w_hi), BF(w_lo), (long)out_f * in_f);
+  NSVD_LAUNCH_CHECK();
+  LinearEpi epi{y, bias, amax, amax + 1, rows, out_f, (long)out_f, 0, act, slope};
+  return linear_gemm_kmajor(x_hi, x_lo, w_hi, w_lo, rows, out_f, in_f, epi, st);
+}
+
+int tc_linear_bwd(const float* x, const float* W, const float* y, const float* dy, int rows, int in_f, int out_f, int act,
+                  float slope, float* dx, float* dW, float* db, void* work, size_t work_bytes, cudaStream_t st) {
+  int rc;
+  if ((rc = linear_check(rows, in_f, out_f, slope, work, work_bytes))) return rc;
+  NSVD_CHECK_ARG(act == 0 || y != nullptr, "dense layer backward: the activation needs the layer output y");
+  uint8_t* wk = align1k(work);
+  float* amax = reinterpret_cast<float*>(wk);      // [0] dy (bounds dz), [1] W, [2] x
+  wk += 1024;
+  const size_t nz = linear_planes(rows, out_f), nw = linear_planes(out_f, in_f), nx = linear_planes(rows, in_f);
+  uint8_t *z_hi = wk, *z_lo = wk + nz, *wT_hi = wk + 2 * nz, *wT_lo = wT_hi + nw, *x_hi = wT_lo + nw, *x_lo = x_hi + nx;
+  if ((rc = linear_absmax(dy, (long)rows * out_f, W, (long)out_f * in_f, x, (long)rows * in_f, amax, st))) return rc;
+  if (db) NSVD_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * out_f, st));
+  linear_dz_kernel<<<dim3(cdiv(out_f, 256), cdiv(rows, 64)), 256, 0, st>>>(dy, y, act, slope, amax, BF(z_hi), BF(z_lo), db,
+                                                                         rows, out_f);
+  NSVD_LAUNCH_CHECK();
+  if (dx) {   // dx (rows, in) = dz (rows, out) . W (out, in): B operand = W^T planes (in, out), K-major over out
+    split_scaled_transposed_kernel<<<dim3(cdiv(in_f, 32), cdiv(out_f, 32)), 256, 0, st>>>(W, amax + 1, BF(wT_hi), BF(wT_lo),
+                                                                                        out_f, in_f);
+    NSVD_LAUNCH_CHECK();
+    LinearEpi epi{dx, nullptr, amax, amax + 1, rows, in_f, (long)in_f, 0, 0, 0.f};
+    if ((rc = linear_gemm_kmajor(z_hi, z_lo, wT_hi, wT_lo, rows, in_f, out_f, epi, st))) return rc;
+  }
+  if (dW) {   // dW (out, in) = dz^T . x: both operands MN-major (K = rows), out features in column blocks of 128
+    split_scaled_kernel<<<cdiv((long)rows * in_f, 256), 256, 0, st>>>(x, amax + 2, BF(x_hi), BF(x_lo), (long)rows * in_f);
+    NSVD_LAUNCH_CHECK();
+    CUtensorMap mah, mal, mbh, mbl;
+    if ((rc = make_tmap_bf16_3d(&mah, z_hi, out_f, rows, 1, (uint64_t)out_f * 2, (uint64_t)rows * out_f * 2, 64, 64))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mal, z_lo, out_f, rows, 1, (uint64_t)out_f * 2, (uint64_t)rows * out_f * 2, 64, 64))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mbh, x_hi, in_f, rows, 1, (uint64_t)in_f * 2, (uint64_t)rows * in_f * 2, 64, 64))) return rc;
+    if ((rc = make_tmap_bf16_3d(&mbl, x_lo, in_f, rows, 1, (uint64_t)in_f * 2, (uint64_t)rows * in_f * 2, 64, 64))) return rc;
+    const int nb = cdiv(out_f, big::BM);
+    BigShape s{};
+    s.m_tiles = 1;
+    s.n_tiles = cdiv(in_f, big::BN);
+    s.batches = cdiv(nb, 2);
+    s.k_slices = 1;
+    s.k_chunks_total = cdiv(rows, big::BK);
+    s.k_chunks_per_slice = s.k_chunks_total;
+    s.a_batched = 1;
+    s.b_batched = 0;
+    s.a_xbatch = big::BM;
+    LinearEpi epi{dW, nullptr, amax, amax + 2, out_f, in_f, (long)in_f, big::BM, 0, 0.f};
+    if ((rc = launch_big2s<true, LinearEpi, kFmtHH>(mah, mal, mbh, mbl, s, nb, kLinearSub, kLinearSub, epi, st))) return rc;
+  }
+  return 0;
 }
 
 }  // namespace nsvd

@@ -5,10 +5,11 @@
   HeteroNetwork      examples/models/siam.py:132-165  (two towers x / y; main_sketchy.py:109-115 builds
                                                        512 -> 8192 -> 512 towers, mu = 16, l2_ball)
 
-The towers are plain dense layers: their GEMMs go to cuBLAS through torch (under the caller's autocast, as in
-main_sketchy.py:182), which is what SURVEY §8f ranks as adequate; the part of the CDK step that this package
-replaces with its own kernels is the loss (`NestedLoRAForCDK.compute_loss`, nsvd_cdk_*), fed by these modules.
-Parameter names match the reference (`backbones.x.0.weight`, ...), so its checkpoints load unchanged.
+The dense layers are `TCLinear` modules (neural_svd_b200/linear.py): forward and backward run on the library's own
+tcgen05 GEMM kernels (`nsvd_linear_fwd` / `nsvd_linear_bwd`), with LeakyReLU / ReLU fused into the GEMM epilogue; the
+activation module of the reference's Sequential stays as a parameter-free placeholder so that the state-dict keys
+(`backbones.x.0.weight`, `backbones.x.2.weight`, ...) match and the reference's checkpoints load unchanged.  The
+embeddings feed the fused CDK loss kernels (`NestedLoRAForCDK.compute_loss`, nsvd_cdk_*).
 """
 from __future__ import annotations
 
@@ -18,6 +19,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from .linear import FusedActivation, TCLinear
 
 
 def _activation(nonlinearity: str):
@@ -34,6 +37,15 @@ def _activation(nonlinearity: str):
     raise NotImplementedError(f"activation {nonlinearity!r}")
 
 
+def _fusable_slope(nonlinearity: str):
+    """negative slope when the activation is LeakyReLU / ReLU (fusable into the dense layer's epilogue), else None"""
+    if nonlinearity == "relu":
+        return 0.0
+    if nonlinearity.startswith("lrelu"):
+        return float(nonlinearity[len("lrelu"):])
+    return None
+
+
 def get_mlp(sizes, bias=True, nonlinearity="relu", use_bn=True, weight_normalization=False, last_layer_bn=True,
             feature_map=None):
     """Sequential of Linear (+ BatchNorm1d) (+ activation, none after the last layer); `.output_dim` attached."""
@@ -45,13 +57,16 @@ def get_mlp(sizes, bias=True, nonlinearity="relu", use_bn=True, weight_normaliza
         model = nn.BatchNorm1d(sizes[0]) if (use_bn and last_layer_bn) else nn.Identity()
     else:
         layers, n = [], len(sizes) - 1
+        fusable = _fusable_slope(nonlinearity)            # ReLU / LeakyReLU run in the GEMM epilogue
         for i in range(n):
-            layers.append(nn.Linear(sizes[i], sizes[i + 1], bias=bias))
             last = i == n - 1
-            if use_bn and (not last or last_layer_bn):
+            bn_here = use_bn and (not last or last_layer_bn)
+            fuse = fusable is not None and not last and not bn_here
+            layers.append(TCLinear(sizes[i], sizes[i + 1], bias=bias, fused_act=("leaky", fusable) if fuse else None))
+            if bn_here:
                 layers.append(nn.BatchNorm1d(sizes[i + 1]))
             if not last:
-                layers.append(act())
+                layers.append(FusedActivation(nonlinearity) if fuse else act())
         model = nn.Sequential(*layers)
     model.output_dim = sizes[-1]
     return model

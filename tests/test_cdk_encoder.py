@@ -24,7 +24,11 @@ def _reference_encoder(dims, mu, mode, act="lrelu0.2", use_bn=False):
 
 
 @pytest.mark.parametrize("mode", ["l2_ball", "l2_sphere", "clip", "tanh"])
-def test_encoder_mirror_equals_reference_modules(mode):
+def test_encoder_mirror_equals_reference_modules(mode, monkeypatch):
+    # module structure / state-dict / normalize on the CPU: the dense layers run their host mirror here (the product
+    # path refuses CPU tensors, see test_dense_layer_has_no_cpu_path)
+    from neural_svd_b200 import linear
+    monkeypatch.setattr(linear, "HOST_MIRROR", True)
     torch.manual_seed(0)
     ref, ref_normalize = _reference_encoder([48, 96, 32], 4.0, mode)
     mine = N.get_sketchy_encoder(network_dims="96,32", mu=4.0, regularize_mode=mode, input_dim=48)
@@ -68,3 +72,84 @@ def test_cdk_step_with_encoder_matches_reference(engine):
     assert rs_joint.shape == (B,) and rs_indep.shape == (B * B - B,)
     for (n, p), (_, q) in zip(ref_net.named_parameters(), net.named_parameters()):
         assert rel(q.grad.cpu().numpy(), p.grad.numpy()) < 1e-4, n
+
+
+def test_dense_layer_has_no_cpu_path():
+    from neural_svd_b200.linear import TCLinear
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        TCLinear(16, 8)(torch.randn(4, 16))
+
+
+def test_get_mlp_structure_matches_reference_indices():
+    """fused activations keep their slot in the Sequential, so `backbones.x.<i>.weight` indices do not move"""
+    from neural_svd_b200.linear import FusedActivation, TCLinear
+    m = N.get_mlp([8, 16, 24, 8], nonlinearity="lrelu0.2", use_bn=False)
+    assert [type(l) for l in m] == [TCLinear, FusedActivation, TCLinear, FusedActivation, TCLinear]
+    assert m[0].fused_act == ("leaky", 0.2) and m[4].fused_act is None
+    m = N.get_mlp([8, 16, 8], nonlinearity="relu", use_bn=True)      # BatchNorm sits between Linear and ReLU: not fused
+    assert [type(l).__name__ for l in m] == ["TCLinear", "BatchNorm1d", "ReLU", "TCLinear", "BatchNorm1d"]
+    m = N.get_mlp([8, 16, 8], nonlinearity="tanh", use_bn=False)
+    assert [type(l).__name__ for l in m] == ["TCLinear", "Tanh", "TCLinear"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,in_f,out_f,act", [(300, 72, 200, ("leaky", 0.2)), (256, 64, 48, None), (1, 8, 8, ("leaky", 0.0)),
+                                                 (1000, 520, 136, ("leaky", 0.2))])
+def test_dense_layer_kernels_match_fp64(rows, in_f, out_f, act):
+    """nsvd_linear_fwd / nsvd_linear_bwd (ragged shapes: partial tiles in every dimension) against fp64 torch"""
+    from neural_svd_b200.linear import TCLinear
+    torch.manual_seed(rows + in_f)
+    lin = TCLinear(in_f, out_f, fused_act=act).cuda()
+    x = (2 * torch.randn(rows, in_f)).cuda().requires_grad_()
+    gy = torch.randn(rows, out_f).cuda()
+    y = lin(x)
+    y.backward(gy)
+    xd = x.detach().double().requires_grad_()
+    wd, bd = lin.weight.detach().double().requires_grad_(), lin.bias.detach().double().requires_grad_()
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    if act is not None:
+        yd = torch.where(y.detach() > 0, yd, act[1] * yd)
+    yd.backward(gy.double())
+    # the activation mask of the fp64 reference is taken from OUR y: the kink is not what this test is about
+    assert rel(y.detach().cpu().numpy(), yd.detach().cpu().numpy()) < 2e-6
+    assert rel(x.grad.cpu().numpy(), xd.grad.cpu().numpy()) < 2e-6
+    assert rel(lin.weight.grad.cpu().numpy(), wd.grad.cpu().numpy()) < 2e-6
+    assert rel(lin.bias.grad.cpu().numpy(), bd.grad.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.gpu
+def test_sketchy_towers_full_size_against_cublas_fp32():
+    """config-5 encoder shape (4096 x 512 -> 8192 -> 512, lrelu0.2, l2_ball): hand-written kernels vs torch/cuBLAS fp32
+    (TF32 off) with the same weights; sampled fp64 check of the first layer.  Behind the LeakyReLU kink a hidden
+    activation within rounding distance of zero may take the other slope in either implementation (33 M activations per
+    tower: a handful do, also between cuBLAS and the CPU); the rows of the first layer's weight gradient that belong to
+    such hidden units are compared separately, everything else at 5e-5."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(3)
+    net = N.get_sketchy_encoder().cuda()
+    x, y = torch.randn(4096, 512, device="cuda"), torch.randn(4096, 512, device="cuda")
+    _, ex, _, ey = net(x, y)
+    (ex.square().sum() + (ex * ey).sum()).backward()
+    ref = torch.nn.Sequential(torch.nn.Linear(512, 8192), torch.nn.LeakyReLU(0.2), torch.nn.Linear(8192, 512)).cuda()
+    ref.load_state_dict(net.backbones["x"].state_dict())
+    rx = N.normalize(ref(x), 4.0, "l2_ball")
+    assert rel(ex.detach().cpu().numpy(), rx.detach().cpu().numpy()) < 2e-5
+    (rx.square().sum() + (rx * ey.detach()).sum()).backward()
+    with torch.no_grad():
+        h_mine, h_ref = net.backbones["x"][0](x), ref[1](ref[0](x))
+        flipped = (h_mine > 0) != (h_ref > 0)
+    n_flips = int(flipped.sum())
+    clean = (~flipped.any(dim=0)).cpu().numpy()          # hidden units without a flipped activation
+    print("kink flips:", n_flips, "of", flipped.numel(), "| hidden units touched:", int((~clean).sum()))
+    assert n_flips <= 32
+    g = {n: (p.grad.cpu().numpy(), q.grad.cpu().numpy())
+         for (n, p), (_, q) in zip(net.backbones["x"].named_parameters(), ref.named_parameters())}
+    assert rel(g["0.weight"][0][clean], g["0.weight"][1][clean]) < 5e-5
+    assert rel(g["0.bias"][0][clean], g["0.bias"][1][clean]) < 5e-5
+    assert rel(g["0.weight"][0], g["0.weight"][1]) < 2e-3     # with the flipped units: one row each, O(1/64) relative
+    assert rel(g["2.weight"][0], g["2.weight"][1]) < 5e-5
+    assert rel(g["2.bias"][0], g["2.bias"][1]) < 5e-5
+    idx = torch.randint(0, 4096, (64,), device="cuda")
+    h64 = torch.nn.functional.leaky_relu(x[idx].double() @ net.backbones["x"][0].weight.double().T
+                                         + net.backbones["x"][0].bias.double(), 0.2)
+    assert rel(h_mine[idx].cpu().numpy(), h64.detach().cpu().numpy()) < 2e-6
