@@ -2331,406 +2331,6 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// S2-fwd, transposed and double-buffered: hidden layers 1 and 2 (+ head + operator) of one copy, tile = (l, 128 points)
-// processed as four ITEMS of 64 points: (layer 1, half 0), (layer 1, half 1), (layer 2, half 0), (layer 2, half 1).
-// The contraction is issued transposed, as in hidden_bwd2_kernel: A = W_i[l] (M = 128 units, K-major, resident),
-// B = one stream of the item (N = 64 points, K-major), so an item's four stream accumulators take 4 x 64 = 256 TMEM
-// columns and TWO items fit: the MMAs of item i + 1 run while the 16 epilogue warps work on item i (the previous
-// version filled TMEM with one 128-point item and ran the two phases back to back).
-//   smem : W1 and W2 hi/lo resident (128 KB, reloaded when the copy changes) | ring of 5 x 16 KB operand stages
-//          (one K chunk of one stream of one item: hi | lo, [64 points][128 B] each, 128-byte swizzle)
-//   TMEM : buffer (item & 1) x 256 + stream x 64 + point; lane = hidden unit
-//   epilogue thread = (unit u = 32 q + lane, 16 points): bias is a register, outputs are written straight to global
-//          memory as 2-byte elements (a warp instruction covers 64 contiguous bytes): derivative streams of a1 into the
-//          per-CTA L2-resident scratch, value streams of a1 / a2 into `saved`; after a layer-1 item a proxy fence +
-//          barrier + adone[half] tell the producer that the item's TMA loads may start.  The 128 -> 1 head of a
-//          layer-2 item is a transpose-reduce over the 32 lanes (31 shuffles for 32 values) + a 4-way sum through
-//          shared memory.
-// ------------------------------------------------------------------------------------------
-struct HidFwd12TMaps {
-  CUtensorMap a0h, a0l;   // a0 derivative streams   [H][P][4 L]            load box {64, 64}
-  CUtensorMap v0h, v0l;   // saved a0 value stream   [H][B][L]
-  CUtensorMap v1h, v1l;   // saved a1 value stream   [H][B][L]
-  CUtensorMap xh, xl;     // scratch  [H][64][grid x 2 halves x 4 streams]
-  CUtensorMap w1h, w1l, w2h, w2l;   // [H][H][L], box {64, 128}
-};
-struct HidFwd12TPtrs {
-  __nv_bfloat16 *scr_hi, *scr_lo;     // scratch planes
-  __nv_bfloat16 *s1_hi, *s1_lo;       // saved a1 value stream (L, Btot, 128)
-  __nv_bfloat16 *s2_hi, *s2_lo;       // saved a2 value stream
-};
-namespace hid {
-constexpr int T_STAGES = 5;
-constexpr int T_STAGE_BYTES = 2 * HCHUNK;                    // 16 KB: one K chunk (64) of one stream, hi | lo
-constexpr int SMEM_FWDT = 4 * PLANE + T_STAGES * T_STAGE_BYTES + 1024 + 1024 + 8192;   // W1, W2 | ring | align | bars | ubuf
-}  // namespace hid
-
-__device__ __forceinline__ void st_global_u16_hint(void* addr, uint16_t v, uint64_t policy) {
-  asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(addr), "h"(v), "l"(policy) : "memory");
-}
-// sum over the 32 lanes of 32 per-lane values: lane j returns the total of v[j]  (31 shuffles)
-__device__ __forceinline__ float lane_transpose_sum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
-    const bool up = (lane & off) != 0;
-    const int half = n >> 1;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if (i < half) {
-        const float send = up ? v[i] : v[i + half];
-        const float keep = up ? v[i + half] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-      }
-    }
-  }
-  return v[0];
-}
-
-__global__ void __launch_bounds__(hid::F_THREADS, 1)
-hidden_fwd12t_kernel(const __grid_constant__ HidFwd12TMaps tm, const HidFwd12TPtrs out, const HidFwd12Args args) {
-  using namespace hid;
-  using namespace tc;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sW = smem;                       // layer i at + i * 2 PLANE: [hi c0 | hi c1 | lo c0 | lo c1]
-  uint8_t* sA = smem + 4 * PLANE;           // ring
-  uint64_t* bars = (uint64_t*)(sA + T_STAGES * T_STAGE_BYTES);
-  uint64_t* full = bars;                    // [5]
-  uint64_t* empty = bars + 5;               // [5]
-  uint64_t* wfull = bars + 10;
-  uint64_t* wfree = bars + 11;
-  uint64_t* tfull = bars + 12;              // [2]
-  uint64_t* tempty = bars + 14;             // [2]
-  uint64_t* adone = bars + 16;              // [2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 18);
-  float* ubuf = (float*)(bars + 128);       // [2 halves][4 cg][4 q][2 hh][32] head partial sums (8 KB)
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = args.L * args.m_tiles;
-  const int tpc = (T + gridDim.x - 1) / gridDim.x;
-  const int t_begin = blockIdx.x * tpc;
-  const int t_end = (t_begin + tpc < T) ? t_begin + tpc : T;
-  const int n_items = t_end > t_begin ? 4 * (t_end - t_begin) : 0;
-  // item i: tile t_begin + i / 4, layer (i >> 1) & 1, half i & 1 (= TMEM buffer)
-  const bool vm = args.vmode != 0;
-
-  if (warp == 0 && lane == 0) {
-    const CUtensorMap* m = &tm.a0h;
-    for (int i = 0; i < 12; ++i) tma_prefetch_desc(m + i);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < T_STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    mbar_init(wfull, 1);
-    mbar_init(wfree, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], F_EPI_WARPS);
-      mbar_init(&adone[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0, cur_l = -1;
-      uint32_t phase = 0;
-      const uint64_t pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
-      for (int i = 0; i < n_items; ++i) {
-        const int g = i >> 2, layer = (i >> 1) & 1, half = i & 1, t = t_begin + g;
-        const int l = t / args.m_tiles, mt = t % args.m_tiles;
-        if (l != cur_l) {
-          if (i > 0) mbar_wait(wfree, (uint32_t)((i - 1) & 1), 60);   // every MMA that reads the resident weights retired
-          mbar_arrive_expect_tx(wfull, 4 * PLANE);
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            const CUtensorMap* wh = w ? &tm.w2h : &tm.w1h;
-            const CUtensorMap* wl = w ? &tm.w2l : &tm.w1l;
-            uint8_t* d = sW + w * 2 * PLANE;
-            tma_load_3d(d, wh, wfull, 0, 0, l);
-            tma_load_3d(d + CHUNK, wh, wfull, 64, 0, l);
-            tma_load_3d(d + PLANE, wl, wfull, 0, 0, l);
-            tma_load_3d(d + PLANE + CHUNK, wl, wfull, 64, 0, l);
-          }
-          cur_l = l;
-        }
-        if (layer) {   // operands written by this CTA's epilogue threads (generic proxy): wait, then order the proxies
-          mbar_wait(&adone[half], (uint32_t)(g & 1), 61);
-          fence_proxy_async_all();
-        }
-        NSVD_TL(i, 5);
-        const int prow = mt * 128 + half * 64;              // first point of the item inside the micro-batch
-        const int xs = ((int)blockIdx.x * 2 + half) * 4;
-        for (int sc = 0; sc < 8; ++sc) {   // (stream, K chunk)
-          const int s = sc >> 1, c = sc & 1;
-          mbar_wait(&empty[stage], phase ^ 1, 62);
-          uint8_t* d = sA + stage * T_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], T_STAGE_BYTES);
-          const CUtensorMap *mh, *ml;
-          int r, z;
-          uint64_t pol = pol_once;
-          if (s == 0 && !vm) {          // value stream: from `saved` (whole-batch rows)
-            mh = layer ? &tm.v1h : &tm.v0h;
-            ml = layer ? &tm.v1l : &tm.v0l;
-            r = (int)args.p_off + prow;
-            z = l;
-          } else if (!layer) {
-            mh = &tm.a0h;
-            ml = &tm.a0l;
-            r = prow;
-            z = l * 4 + s;
-          } else {
-            mh = &tm.xh;
-            ml = &tm.xl;
-            r = 0;
-            z = xs + s;
-            pol = pol_keep;
-          }
-          tma_load_3d_hint(d, mh, &full[stage], 64 * c, r, z, pol);
-          tma_load_3d_hint(d + HCHUNK, ml, &full[stage], 64 * c, r, z, pol);
-          if (++stage == T_STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        NSVD_TL(i, 6);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-#ifdef NSVD_T_N128
-      constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, 0, false, false);
-#else
-      constexpr uint32_t idesc = make_idesc_f16(128, HROWS, 0, 0, false, false);   // M = units, N = points, fp16 planes
-#endif
-      int stage = 0, cur_l = -1;
-      uint32_t phase = 0, wphase = 0;
-      for (int i = 0; i < n_items; ++i) {
-        const int g = i >> 2, layer = (i >> 1) & 1, buf = i & 1, t = t_begin + g;
-        const int l = t / args.m_tiles;
-        if (l != cur_l) {
-          mbar_wait(wfull, wphase, 63);
-          wphase ^= 1;
-          cur_l = l;
-        }
-        const uint32_t w_hi = smem_u32(sW + layer * 2 * PLANE), w_lo = w_hi + PLANE;
-        mbar_wait(&tempty[buf], (uint32_t)(((i >> 1) & 1) ^ 1), 64);
-        tc_fence_after();
-        NSVD_TL(i, 0);
-        for (int sc = 0; sc < 8; ++sc) {
-          const int s = sc >> 1, c = sc & 1;
-          mbar_wait(&full[stage], phase, 65);
-          tc_fence_after();
-          if (sc == 0) NSVD_TL(i, 1);
-          const uint32_t b_hi = smem_u32(sA + stage * T_STAGE_BYTES), b_lo = b_hi + HCHUNK;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256 + s * HROWS);
-#ifdef NSVD_T_NOMMA
-#pragma unroll
-          for (int kk = 0; kk < 1; ++kk) {
-#else
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-#endif
-            const uint32_t ow = c * CHUNK + kk * 32, ob = kk * 32;
-            uint64_t ah = make_sdesc_sw128(w_hi + ow, 16, 1024), al = make_sdesc_sw128(w_lo + ow, 16, 1024);
-            uint64_t bh = make_sdesc_sw128(b_hi + ob, 16, 1024), bl = make_sdesc_sw128(b_lo + ob, 16, 1024);
-            umma_f16(d_tmem, al, bh, idesc, (c > 0 || kk > 0) ? 1u : 0u);
-            umma_f16(d_tmem, ah, bl, idesc, 1u);
-            umma_f16(d_tmem, ah, bh, idesc, 1u);
-          }
-          umma_commit(&empty[stage]);
-          if (++stage == T_STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        umma_commit(&tfull[buf]);
-        umma_commit(wfree);
-        NSVD_TL(i, 2);
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== 16 epilogue warps: lane quarter q (32 units) x point group cg (16 points) ==========
-    const int ewarp = warp - 4, q = ewarp & 3, cg = ewarp >> 2;
-    const int et = threadIdx.x - 128;
-    const int u = q * 32 + lane;
-    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
-    int cur_l = -1;
-    float b1 = 0.f, b2 = 0.f, w3 = 0.f;
-    float un1[4], un2[4], so1[4], so2 = 1.f;
-    for (int i = 0; i < n_items; ++i) {
-      const int g = i >> 2, layer = (i >> 1) & 1, half = i & 1, t = t_begin + g;
-      const int l = t / args.m_tiles, mt = t % args.m_tiles;
-      const bool last = layer != 0;
-      if (l != cur_l) {
-        b1 = __ldg(args.bias1 + l * kHidden + u);
-        b2 = __ldg(args.bias2 + l * kHidden + u);
-        w3 = __ldg(args.W3 + l * kHidden + u);
-        const float* pl = args.plan + (long)l * PL_STRIDE;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          const int ss = vm ? 0 : s;             // value-only pass: every slot carries a value stream
-          un1[s] = __ldg(pl + PL_U1 + ss) * (1.f + kTruncPerMma * 24.f);   // K = 128: chains of 24 MMAs
-          un2[s] = __ldg(pl + PL_U2 + ss) * (1.f + kTruncPerMma * 24.f);
-          so1[s] = __ldg(pl + PL_SA1 + ss);
-        }
-        so2 = __ldg(pl + PL_SA2);
-        cur_l = l;
-      }
-      const float bias = last ? b2 : b1;
-      mbar_wait(&tfull[half], (uint32_t)((i >> 1) & 1), 66);
-      tc_fence_after();
-      if (et == 0) NSVD_TL(i, 3);
-      const int prow = mt * 128 + half * 64 + cg * 16;            // first of this thread's 16 points in the micro-batch
-      const int xs = ((int)blockIdx.x * 2 + half) * 4;
-      float hsum[2] = {0.f, 0.f};
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        float z[4][8];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) tmem_ld8(tl + (uint32_t)(half * 256 + s * HROWS + cg * 16 + hh * 8), z[s]);
-        tmem_ld_wait();
-        if (hh == 1) {                       // last TMEM read of this item: hand the accumulator back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[half]);
-        }
-#ifndef NSVD_T_NOMATH
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (!vm) {
-            const float zb = fmaf(z[0][k], last ? un2[0] : un1[0], bias);
-            act_streams(zb, z[1][k] * (last ? un2[1] : un1[1]), z[2][k] * (last ? un2[2] : un1[2]),
-                        z[3][k] * (last ? un2[3] : un1[3]), z[0][k], z[1][k], z[2][k], z[3][k]);
-          } else {
-#pragma unroll
-            for (int s = 0; s < 4; ++s) z[s][k] = softplus_fast(fmaf(z[s][k], last ? un2[s] : un1[s], bias));
-          }
-        }
-#endif
-        // ---- stores: 2-byte elements, a warp instruction covers the 32 consecutive units of one point (64 bytes)
-#ifdef NSVD_T_NOSTORE
-        const bool do_store = z[0][0] == 12345.678f;
-#else
-        const bool do_store = true;
-#endif
-        if (!last && do_store) {
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const bool to_saved = (s == 0 && !vm);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              uint16_t h16, l16;
-              split1<PF_HH>(z[s][k] * so1[s], h16, l16);
-              const int pr = cg * 16 + hh * 8 + k;                 // point row inside the item
-              if (to_saved) {
-                const int pt = prow + hh * 8 + k;
-                if (pt < args.P) {
-                  const long o = ((long)l * args.Btot + args.p_off + pt) * kHidden + u;
-                  st_global_u16_hint(out.s1_hi + o, h16, pol_keep);
-                  st_global_u16_hint(out.s1_lo + o, l16, pol_keep);
-                }
-              } else {
-                const long o = ((long)(xs + s) * HROWS + pr) * kHidden + u;
-                st_global_u16_hint(out.scr_hi + o, h16, pol_keep);
-                st_global_u16_hint(out.scr_lo + o, l16, pol_keep);
-              }
-            }
-          }
-        } else if (last) {
-          if (!vm && do_store) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int pt = prow + hh * 8 + k;
-              if (pt < args.P) {
-                uint16_t h16, l16;
-                split1<PF_HH>(z[0][k] * so2, h16, l16);
-                const long o = ((long)l * args.Btot + args.p_off + pt) * kHidden + u;
-                st_global_u16_hint(out.s2_hi + o, h16, pol_once);
-                st_global_u16_hint(out.s2_lo + o, l16, pol_once);
-              }
-            }
-          }
-          // head partial sums: value index s * 8 + k, summed over the 32 units of this warp
-          float hv[32];
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) hv[s * 8 + k] = z[s][k] * w3;
-#ifdef NSVD_T_NOHEAD
-          hsum[hh] = hv[lane & 31];
-#else
-          hsum[hh] = lane_transpose_sum32(hv, lane);
-#endif
-        }
-      }
-      if (et == 0) NSVD_TL(i, 4);
-      if (!last) {
-        // the item's outputs are the operands of the layer-2 item of the same half: make the generic-proxy global
-        // writes visible to the async proxy, then tell the producer
-#ifndef NSVD_T_NOFENCE
-        fence_proxy_async_all();
-#endif
-        named_bar_sync(1, F_EPI_WARPS * 32);
-        if (et == 0) mbar_arrive(&adone[half]);
-      } else {
-        float* ub = ubuf + (half * 4 + cg) * 256;                  // [q][hh][32]
-        ub[(q * 2 + 0) * 32 + lane] = hsum[0];
-        ub[(q * 2 + 1) * 32 + lane] = hsum[1];
-        named_bar_sync(2 + cg, 128);                               // the four q-warps of this point group
-        if (q == 0 && lane < 16) {
-          const int hh = lane >> 3, k = lane & 7;
-          float us[4];
-#pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            float a = 0.f;
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) a += ub[(qq * 2 + hh) * 32 + s * 8 + k];
-            us[s] = a;
-          }
-          const int pt = prow + lane;
-          if (pt < args.P) {
-            const long pg = args.p_off + pt;
-            const float msc = args.pb.has_exp_mask ? args.mscales[l] : 1.f;
-            if (vm) {        // finite differences of the four shifted values around the central one (first pass)
-              const float b3v = __ldg(args.b3 + l);
-#pragma unroll
-              for (int s = 0; s < 4; ++s) us[s] += b3v;
-              args.TF[pg * args.L + l] = fd_operator(args.x[2 * pg], args.x[2 * pg + 1], args.pb,
-                                                     args.pb.has_exp_mask != 0, msc, args.U0[pg * args.L + l], us);
-            } else {
-              us[0] += __ldg(args.b3 + l);
-              PointGeom gm = point_geom(args.x[2 * pg], args.x[2 * pg + 1], args.pb);
-              float f, tf;
-              operator_epilogue(gm, args.pb, args.pb.has_exp_mask != 0, msc, us[0], us[1], us[2], us[3], f, tf);
-              args.F[pg * args.L + l] = f;
-              args.TF[pg * args.L + l] = tf;
-              args.U0[pg * args.L + l] = us[0];
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 struct HidBwdArgs {
   int L, P, m_tiles;
   long Btot, p_off;
@@ -3286,83 +2886,7 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
       if ((rc = launch_big2s<false, L0FwdEpi, kFmtHH>(mPh, mPl, mW0h, mW0l, s, (int)L, sub, sub_first, e0, st))) return rc;
     }
     // ---- hidden layers 1, 2 (+ head + operator)
-    static const int fused = env_int("NSVD_HIDDEN_FUSED", 1);   // 2 = transposed double-buffered experiment (slower, see profiles/README.md)
-    if (fused == 2) {
-      // transposed, double-buffered kernel (64-point items, W1 + W2 resident)
-      HidFwd12TMaps hm;
-      const uint64_t PH = (uint64_t)P * H * 2, BH = (uint64_t)B * H * 2;
-      const int T = (int)L * m_tiles, grid = T < kHidGrid ? T : kHidGrid;
-      const uint32_t hr = hid::HROWS;
-      if ((rc = make_tmap_bf16_3d(&hm.a0h, wk + t.str_hi[0], H, P, 4 * L, H * 2, PH, 64, hr))) return rc;
-      if ((rc = make_tmap_bf16_3d(&hm.a0l, wk + t.str_lo[0], H, P, 4 * L, H * 2, PH, 64, hr))) return rc;
-      if ((rc = make_tmap_bf16_3d(&hm.v0h, sv + t.av_hi[0], H, B, L, H * 2, BH, 64, hr))) return rc;
-      if ((rc = make_tmap_bf16_3d(&hm.v0l, sv + t.av_lo[0], H, B, L, H * 2, BH, 64, hr))) return rc;
-      if ((rc = make_tmap_bf16_3d(&hm.v1h, sv + t.av_hi[1], H, B, L, H * 2, BH, 64, hr))) return rc;
-      if ((rc = make_tmap_bf16_3d(&hm.v1l, sv + t.av_lo[1], H, B, L, H * 2, BH, 64, hr))) return rc;
-      const uint64_t nslot = (uint64_t)kHidGrid * 8;
-      if ((rc = make_tmap_bf16_3d(&hm.xh, wk + t.scr_hi, H, hr, nslot, H * 2, hid::HPLANE, 64, hr))) return rc;
-      if ((rc = make_tmap_bf16_3d(&hm.xl, wk + t.scr_lo, H, hr, nslot, H * 2, hid::HPLANE, 64, hr))) return rc;
-      hm.w1h = mWh[0];
-      hm.w1l = mWl[0];
-      hm.w2h = mWh[1];
-      hm.w2l = mWl[1];
-      HidFwd12TPtrs op{BF(wk + t.scr_hi), BF(wk + t.scr_lo), BF(sv + t.av_hi[1]), BF(sv + t.av_lo[1]),
-                       BF(sv + t.av_hi[2]), BF(sv + t.av_lo[2])};
-      HidFwd12Args a{};
-      a.L = (int)L;
-      a.P = P;
-      a.m_tiles = m_tiles;
-      a.Btot = B;
-      a.p_off = p0;
-      a.bias1 = pr.b[1];
-      a.bias2 = pr.b[2];
-      a.plan = plan;
-      a.W3 = pr.W[3];
-      a.b3 = pr.b[3];
-      a.x = x;
-      a.mscales = pr.mask_scales;
-      a.F = F;
-      a.TF = TF;
-      a.U0 = reinterpret_cast<float*>(sv + t.u0);
-      a.pb = pb;
-      NSVD_SMEM_OPTIN(hidden_fwd12t_kernel, hid::SMEM_FWDT);
-      {
-        ProfScope ps(KC_HID_FWD, st);
-        hidden_fwd12t_kernel<<<grid, hid::F_THREADS, hid::SMEM_FWDT, st>>>(hm, op, a);
-        NSVD_LAUNCH_CHECK();
-      }
-      if (pb.fd_eps > 0.f) {
-        // ---- finite-difference Laplacian (pde/diff_ops.py:25-52): second pass over this micro-batch (see below)
-        const float* xm = x + 2 * p0;
-        features_shift_f16_kernel<<<cdiv(4L * P * (M / 4), 256), 256, 0, st>>>(xm, pr.Bff, BF(wk + t.phis_hi),
-                                                                              BF(wk + t.phis_lo), P, (int)M, pb.fd_eps);
-        NSVD_LAUNCH_CHECK();
-        CUtensorMap mXh, mXl, mVh, mVl;
-        if ((rc = make_tmap_bf16_3d(&mXh, wk + t.phis_hi, K0, 4 * (uint64_t)P, 1, K0 * 2, 4 * (uint64_t)P * K0 * 2, 64, big::BM))) return rc;
-        if ((rc = make_tmap_bf16_3d(&mXl, wk + t.phis_lo, K0, 4 * (uint64_t)P, 1, K0 * 2, 4 * (uint64_t)P * K0 * 2, 64, big::BM))) return rc;
-        if ((rc = make_tmap_bf16_3d(&mVh, wk + t.w0v_hi, K0, L * H, 1, K0 * 2, L * H * K0 * 2, 64, big::BN / 2))) return rc;
-        if ((rc = make_tmap_bf16_3d(&mVl, wk + t.w0v_lo, K0, L * H, 1, K0 * 2, L * H * K0 * 2, 64, big::BN / 2))) return rc;
-        BigShape sv2{};
-        sv2.m_tiles = cdiv(4L * P, 2 * big::BM);
-        sv2.n_tiles = cdiv(L * H, big::BN);
-        sv2.batches = 1;
-        sv2.k_slices = 1;
-        sv2.k_chunks_total = cdiv(K0, big::BK);
-        sv2.k_chunks_per_slice = sv2.k_chunks_total;
-        sv2.m_group = 16;
-        L0ValEpi ev{pr.b[0], plan, BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), P, (int)L};
-        {
-          ProfScope ps(KC_L0_FWD, st);
-          static const int sub = env_int("NSVD_L0_SUBCHUNKS", 4), sub_first = env_int("NSVD_L0_SUBFIRST", 6);
-          if ((rc = launch_big2s<false, L0ValEpi, kFmtHH>(mXh, mXl, mVh, mVl, sv2, 1, sub, sub_first, ev, st))) return rc;
-        }
-        a.vmode = 1;
-        ProfScope ps(KC_HID_FWD, st);
-        hidden_fwd12t_kernel<<<grid, hid::F_THREADS, hid::SMEM_FWDT, st>>>(hm, op, a);
-        NSVD_LAUNCH_CHECK();
-      }
-      continue;
-    }
+    static const int fused = env_int("NSVD_HIDDEN_FUSED", 1);
     if (fused) {
       HidFwd12Maps hm;
       const uint64_t PH = (uint64_t)P * H * 2, BH = (uint64_t)B * H * 2;
