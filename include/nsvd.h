@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NSVD_ABI_VERSION 3
+#define NSVD_ABI_VERSION 4
 
 enum {
   NSVD_E_BADARG = 10001,   /* shape / enum / alignment violation */
@@ -81,7 +81,8 @@ typedef struct nsvd_problem {
   float box_lim;           /* half-width `lim` of the Dirichlet box                             */
   float fd_eps;            /* laplacian_eps (ABI 3): <= 0 exact Laplacian (forward-mode streams); > 0 the
                             * finite-difference Laplacian of the shipped scripts, pde/diff_ops.py:25-52      */
-  int32_t reserved_;       /* keeps the struct a multiple of 8 bytes                                      */
+  int32_t ndim;            /* spatial dimension D (ABI 4; 0 = 2): x is (n_points, D), Bff (D, n_fourier).  D = 3
+                            * (problems.py:62-71: hydrogen, H2+ ion) runs on NSVD_ENGINE_FP32_SIMT only         */
 } nsvd_problem_t;
 
 /* Parameters in the reference's own layout (ParallelMLP, mlp.py:181-199):

@@ -19,7 +19,7 @@ class Problem(C.Structure):
                 ("pot_coef", C.c_float), ("scale_kinetic", C.c_float), ("op_scale", C.c_float),
                 ("op_shift", C.c_float), ("sampling_sigma", C.c_float), ("hard_mul_const", C.c_float),
                 ("importance", C.c_int32), ("box_mask", C.c_int32), ("pot_coef2", C.c_float),
-                ("box_lim", C.c_float), ("fd_eps", C.c_float), ("reserved_", C.c_int32)]
+                ("box_lim", C.c_float), ("fd_eps", C.c_float), ("ndim", C.c_int32)]
 
 
 class Params(C.Structure):
@@ -95,7 +95,7 @@ def load():
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)        # AttributeError if a declared symbol is missing
                 fn.restype, fn.argtypes = res, args
-            if lib.nsvd_abi_version() != 3:
+            if lib.nsvd_abi_version() != 4:
                 raise RuntimeError("libnsvd.so ABI version mismatch")
             for which, cls in enumerate((Problem, Params, Grads)):
                 if lib.nsvd_struct_size(which) != C.sizeof(cls):

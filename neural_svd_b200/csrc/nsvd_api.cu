@@ -58,6 +58,10 @@ static int check_problem(const nsvd_problem_t* pb) {
   NSVD_CHECK_ARG(pb->box_mask >= NSVD_BOX_NONE && pb->box_mask <= NSVD_BOX_EXP, "unknown box mask mode %d", pb->box_mask);
   NSVD_CHECK_ARG(pb->box_mask == NSVD_BOX_NONE || pb->box_lim > 0.f, "box_lim must be > 0");
   NSVD_CHECK_ARG(pb->fd_eps == pb->fd_eps && pb->fd_eps < 1e30f, "fd_eps must be finite (got %f)", (double)pb->fd_eps);
+  NSVD_CHECK_ARG(pb->ndim == 0 || pb->ndim == 2 || pb->ndim == 3, "ndim must be 2 or 3 (got %d)", pb->ndim);
+  NSVD_CHECK_ARG(pb->ndim != 3 || pb->potential == NSVD_POT_HYDROGEN || pb->potential == NSVD_POT_HYDROGEN_MOL_ION ||
+                     pb->potential == NSVD_POT_HARMONIC,
+                 "ndim = 3 is defined for the hydrogen, H2+ ion and harmonic potentials (got potential %d)", pb->potential);
   return 0;
 }
 static int check_params(const nsvd_problem_t* pb, const nsvd_params_t* pr) {
@@ -131,8 +135,10 @@ int nsvd_scratch_bytes(const nsvd_problem_t* pb, int engine, size_t* saved_bytes
   if (rc) return rc;
   NSVD_CHECK_ARG(saved_bytes && work_bytes, "output pointers are NULL");
   if (engine == NSVD_ENGINE_FP32_SIMT) simt_scratch_bytes(*pb, saved_bytes, work_bytes);
-  else if (engine == NSVD_ENGINE_BF16X3_TC) tc_scratch_bytes(*pb, saved_bytes, work_bytes);
-  else NSVD_CHECK_ARG(false, "unknown engine %d", engine);
+  else if (engine == NSVD_ENGINE_BF16X3_TC) {
+    NSVD_CHECK_ARG(pb->ndim != 3, "ndim = 3 (five forward-mode streams) runs on NSVD_ENGINE_FP32_SIMT only");
+    tc_scratch_bytes(*pb, saved_bytes, work_bytes);
+  } else NSVD_CHECK_ARG(false, "unknown engine %d", engine);
   return 0;
 }
 

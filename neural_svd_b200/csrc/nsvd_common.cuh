@@ -248,6 +248,183 @@ __device__ __forceinline__ void fd_shift(int s, float eps, float& y0, float& y1)
   else y1 += d;
 }
 
+// ------------------------------------------------------------------------------------------
+// D-dimensional versions (D = 2 or 3; pb.ndim, 0 meaning 2) of the per-point operator math above, used by the fp32
+// CUDA-core engine: S = D + 2 forward-mode streams (value, d/dx_1 .. d/dx_D, Laplacian).  ndim = 3 is what
+// pde/problems.py:62-71 runs for hydrogen and the H2+ ion.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxDim = 3;
+__host__ __device__ __forceinline__ int problem_ndim(const nsvd_problem_t& pb) { return pb.ndim == 3 ? 3 : 2; }
+
+struct PointGeomN {
+  int D;
+  float x[kMaxDim], r, rho, V;
+  float gq[kMaxDim], lapq;          // grad / Laplacian of ln sqrt(w)   (exp-mask part added per copy)
+  float mb, gmb[kMaxDim], lapmb;    // Dirichlet box mask and its derivatives (1, 0, 0 without one)
+};
+
+__device__ __forceinline__ float sqrt_w_n(const float* y, int D, const nsvd_problem_t& pb) {
+  const float sg = pb.sampling_sigma;
+  float r2 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int d = 0; d < kMaxDim; ++d) {
+    const float yd = d < D ? y[d] : 0.f;
+    r2 = fmaf(yd, yd, r2);
+    a1 += fabsf(yd);
+  }
+  if (pb.importance == NSVD_IMP_GAUSSIAN) {
+    const float s2 = sg * sg;
+    return sqrtf(expf(-r2 / (2.f * s2) - 0.5f * D * logf(6.283185307179586f * s2)));
+  }
+  if (pb.importance == NSVD_IMP_LAPLACE) return sqrtf(expf(-a1 / sg - D * logf(2.f * sg)));
+  if (pb.importance == NSVD_IMP_UNIFORM) return sqrtf(D == 3 ? 1.f / (8.f * sg * sg * sg) : 1.f / (4.f * sg * sg));
+  return 1.f;
+}
+
+// y must have kMaxDim entries (zero beyond D)
+__device__ __forceinline__ float potential_n(const float* x, int D, float r, const nsvd_problem_t& pb) {
+  switch (pb.potential) {                                   // schrodinger/potentials.py
+    case NSVD_POT_HYDROGEN: return -(pb.pot_coef / r);                              // :5-8
+    case NSVD_POT_HARMONIC: return pb.pot_coef * (r * r);                           // :24-27
+    case NSVD_POT_HYDROGEN_MOL_ION: {                                               // :11-17, nuclei at (0, .., +-R)
+      const float last = D == 3 ? x[2] : x[1];
+      const float q = D == 3 ? fmaf(x[1], x[1], x[0] * x[0]) : x[0] * x[0];
+      const float ym = last - pb.pot_coef2, yp = last + pb.pot_coef2;
+      return -(pb.pot_coef / sqrtf(q + ym * ym)) - (pb.pot_coef / sqrtf(q + yp * yp));
+    }
+    case NSVD_POT_COSINE: return pb.pot_coef * cosf(x[0]) + pb.pot_coef2 * cosf(x[1]);   // :30-31 (2D only)
+    default: return 0.f;                                                            // infinite well, :20-21
+  }
+}
+
+__device__ __forceinline__ PointGeomN point_geom_n(const float* xs, const nsvd_problem_t& pb) {
+  PointGeomN g;
+  const int D = problem_ndim(pb);
+  g.D = D;
+  g.x[0] = xs[0];
+  g.x[1] = xs[1];
+  g.x[2] = D == 3 ? xs[2] : 0.f;
+  g.r = sqrtf(fmaf(g.x[2], g.x[2], fmaf(g.x[1], g.x[1], g.x[0] * g.x[0])));
+  const float sg = pb.sampling_sigma;
+  const float sw = sqrt_w_n(g.x, D, pb);
+  g.lapq = 0.f;
+  g.gq[0] = g.gq[1] = g.gq[2] = 0.f;
+  if (pb.importance == NSVD_IMP_GAUSSIAN) {
+    g.rho = sw / fmaxf(sw, 1e-5f);  // diff_ops.py:15-18
+    const float inv = -1.f / (2.f * sg * sg);
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d) g.gq[d] = g.x[d] * inv;     // x[2] = 0 in 2D
+    g.lapq = D * inv;
+  } else if (pb.importance == NSVD_IMP_LAPLACE) {
+    g.rho = sw / fmaxf(sw, 1e-5f);
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d) g.gq[d] = d < D ? -sgnf(g.x[d]) / (2.f * sg) : 0.f;
+  } else {
+    g.rho = sw / fmaxf(sw, pb.importance == NSVD_IMP_UNIFORM ? 1e-5f : 0.f);
+  }
+  g.V = potential_n(g.x, D, g.r, pb);
+  g.mb = 1.f;
+  g.lapmb = 0.f;
+  g.gmb[0] = g.gmb[1] = g.gmb[2] = 0.f;
+  if (pb.box_mask != NSVD_BOX_NONE) {
+    float m[kMaxDim] = {1.f, 1.f, 1.f}, a[kMaxDim] = {0.f, 0.f, 0.f}, c[kMaxDim] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d)
+      if (d < D) box_factor(g.x[d], pb.box_lim, pb.box_mask, m[d], a[d], c[d]);
+    g.mb = m[0] * m[1] * m[2];
+    g.gmb[0] = a[0] * (m[1] * m[2]);
+    g.gmb[1] = a[1] * (m[0] * m[2]);
+    g.gmb[2] = a[2] * (m[0] * m[1]);
+    g.lapmb = c[0] * (m[1] * m[2]) + c[1] * (m[0] * m[2]) + c[2] * (m[0] * m[1]);
+  }
+  return g;
+}
+
+__device__ __forceinline__ float head_factor_n(const PointGeomN& g, const nsvd_problem_t& pb, float mexp) {
+  return pb.hard_mul_const * mexp * g.rho * g.mb;
+}
+
+// (F, TF) of one (point, copy) from the raw network streams u[0] = value, u[1 .. D] = gradient, u[D + 1] = Laplacian.
+// All loops run over kMaxDim with a predicate, so every array index is a compile-time constant (registers, no local
+// memory): the version with run-time trip counts was mis-evaluated by the device compiler in the exp-mask branch
+// (caught by the golden tests; host build of the same source was right).
+__device__ __forceinline__ void operator_epilogue_n(const PointGeomN& g, const nsvd_problem_t& pb, bool has_mask,
+                                                    float mscale, const float* u, float& f, float& tf) {
+  const int D = g.D;
+  const float u0 = u[0], ulap = D == 3 ? u[4] : u[3];
+  const float ud[kMaxDim] = {u[1], u[2], D == 3 ? u[3] : 0.f};
+  float m = 1.f, irs = 0.f;
+  if (has_mask) {
+    m = expf(-g.r / mscale);          // boundary.py:48-49
+    irs = 1.f / (g.r * mscale);
+  }
+  const float lapq = g.lapq - (float)(D - 1) * irs;
+  float dot = 0.f, gq2 = 0.f, box = 0.f;
+#pragma unroll
+  for (int d = 0; d < kMaxDim; ++d) {
+    const float gqd = d < D ? g.gq[d] - g.x[d] * irs : 0.f;
+    const float udd = d < D ? ud[d] : 0.f;
+    dot = fmaf(gqd, udd, dot);
+    gq2 = fmaf(gqd, gqd, gq2);
+    box = fmaf(d < D ? g.gmb[d] : 0.f, udd + u0 * gqd, box);
+  }
+  const float ce = pb.hard_mul_const * m * g.rho;
+  float inner = ulap + 2.f * dot + u0 * (lapq + gq2);
+  inner = g.mb * inner + 2.f * box + u0 * g.lapmb;
+  const float lap = ce * inner;
+  f = ce * g.mb * u0;
+  const float negH = pb.scale_kinetic * lap - g.V * f;   // schrodinger/__init__.py:19-22
+  tf = pb.op_scale * negH + pb.op_shift * f;             // examples/__init__.py:9
+}
+
+// g(y) = sqrt(w(y)) * hard_mul_const * exp-mask_l(y) * box-mask(y) * u   (y has kMaxDim entries, zero beyond D)
+__device__ __forceinline__ float weighted_value_n(const float* y, int D, const nsvd_problem_t& pb, bool has_mask,
+                                                  float mscale, float u) {
+  float m = 1.f;
+  if (has_mask) m = expf(-sqrtf(fmaf(y[2], y[2], fmaf(y[1], y[1], y[0] * y[0]))) / mscale);
+  if (pb.box_mask != NSVD_BOX_NONE) {
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d) {
+      if (d < D) {
+        float md, a, c;
+        box_factor(y[d], pb.box_lim, pb.box_mask, md, a, c);
+        m *= md;
+      }
+    }
+  }
+  return sqrt_w_n(y, D, pb) * (pb.hard_mul_const * m * u);
+}
+// TF of one (point, copy) from the raw network values at x (uc) and at the 2 D shifted points x + eps e_d (us[2 d]),
+// x - eps e_d (us[2 d + 1]); the accumulation order is the reference's (diff_ops.py:40-48)
+__device__ __forceinline__ float fd_operator_n(const float* xs, const nsvd_problem_t& pb, bool has_mask, float mscale,
+                                               float uc, const float* us) {
+  const int D = problem_ndim(pb);
+  const float eps = pb.fd_eps;
+  const float x[kMaxDim] = {xs[0], xs[1], D == 3 ? xs[2] : 0.f};
+  const float gc = weighted_value_n(x, D, pb, has_mask, mscale, uc);
+  float lap = -2.f * D * gc;
+#pragma unroll
+  for (int d = 0; d < kMaxDim; ++d) {
+    if (d < D) {
+      const float yp[kMaxDim] = {d == 0 ? x[0] + eps : x[0], d == 1 ? x[1] + eps : x[1], d == 2 ? x[2] + eps : x[2]};
+      const float ym[kMaxDim] = {d == 0 ? x[0] - eps : x[0], d == 1 ? x[1] - eps : x[1], d == 2 ? x[2] - eps : x[2]};
+      lap += weighted_value_n(yp, D, pb, has_mask, mscale, us[2 * d]) +
+             weighted_value_n(ym, D, pb, has_mask, mscale, us[2 * d + 1]);
+    }
+  }
+  lap = lap / (float)((double)eps * (double)eps);
+  float fs = gc;
+  if (pb.importance != NSVD_IMP_NONE) {
+    const float sw = fmaxf(sqrt_w_n(x, D, pb), 1e-5f);          // diff_ops.py:15
+    lap = lap / sw;
+    fs = gc / sw;
+  }
+  const float r = sqrtf(fmaf(x[2], x[2], fmaf(x[1], x[1], x[0] * x[0])));
+  const float V = potential_n(x, D, r, pb);
+  const float negH = pb.scale_kinetic * lap - V * fs;            // schrodinger/__init__.py:19-22
+  return pb.op_scale * negH + pb.op_shift * fs;                  // examples/__init__.py:9
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -113,40 +113,45 @@ int colsum(const float* X, float* out, int M, int N, int batch, long x_bs, int a
 }
 
 // ------------------------------------------------------------------------------------------
-// Fourier features, all four streams (examples/utils.py:126-143 + derivatives)
-//   phis[s][p][k], k in [0,2M): [sin | cos] blocks
+// Fourier features, all S = D + 2 streams (examples/utils.py:126-143 + derivatives)
+//   phis[s][p][k], k in [0,2M): [sin | cos] blocks; s = 0 value, 1 .. D gradient, D + 1 Laplacian
 // ------------------------------------------------------------------------------------------
 __global__ void features_f32_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
                                     float* __restrict__ phis, float* __restrict__ phi_saved, int P,
-                                    int M) {
+                                    int M, int D) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)P * M) return;
   int p = (int)(i / M), j = (int)(i % M);
-  float b0 = Bff[j], b1 = Bff[M + j];
-  float ph = fmaf(x[2 * p + 1], b1, x[2 * p] * b0);
+  const float b[kMaxDim] = {Bff[j], Bff[M + j], D == 3 ? Bff[2L * M + j] : 0.f};
+  const float b2 = fmaf(b[2], b[2], fmaf(b[1], b[1], b[0] * b[0]));
+  float ph;
+  if (D == 2) ph = fmaf(x[2 * p + 1], b[1], x[2 * p] * b[0]);
+  else ph = fmaf(x[3L * p + 2], b[2], fmaf(x[3L * p + 1], b[1], x[3L * p] * b[0]));
   float s, c;
   sincosf(ph, &s, &c);
   const long K0 = 2L * M, SP = (long)P * K0;
   float* o = phis + (long)p * K0;
-  float nb2 = -(b0 * b0 + b1 * b1);
   o[j] = s;
   o[M + j] = c;
-  o[SP + j] = c * b0;
-  o[SP + M + j] = -s * b0;
-  o[2 * SP + j] = c * b1;
-  o[2 * SP + M + j] = -s * b1;
-  o[3 * SP + j] = nb2 * s;
-  o[3 * SP + M + j] = nb2 * c;
+#pragma unroll
+  for (int d = 0; d < kMaxDim; ++d) {
+    if (d < D) {
+      o[(1 + d) * SP + j] = c * b[d];
+      o[(1 + d) * SP + M + j] = -s * b[d];
+    }
+  }
+  o[(D + 1) * SP + j] = -b2 * s;
+  o[(D + 1) * SP + M + j] = -b2 * c;
   if (phi_saved) {
     phi_saved[(long)p * K0 + j] = s;
     phi_saved[(long)p * K0 + M + j] = c;
   }
 }
 
-// softplus on the 4-stream pre-activations Z[l][s][p][h] (in place) ; saves the value stream.
+// softplus on the S-stream pre-activations Z[l][s][p][h] (in place) ; saves the value stream.
 __global__ void softplus_streams_kernel(float* __restrict__ Z, const float* __restrict__ bias,
                                         float* __restrict__ a_saved, int L, int P, long Btot,
-                                        long p_off) {
+                                        long p_off, int D) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   long n = (long)L * P * kHidden;
   if (i >= n) return;
@@ -154,19 +159,22 @@ __global__ void softplus_streams_kernel(float* __restrict__ Z, const float* __re
   int p = (int)((i / kHidden) % P);
   int l = (int)(i / ((long)kHidden * P));
   long SP = (long)P * kHidden;
-  float* z = Z + (long)l * 4 * SP + (long)p * kHidden + h;
+  float* z = Z + (long)l * (D + 2) * SP + (long)p * kHidden + h;
   float z0 = z[0] + bias[l * kHidden + h];
-  float z1 = z[SP], z2 = z[2 * SP], z3 = z[3 * SP];
   float a, sg;
   softplus_sig(z0, a, sg);
   z[0] = a;
-  z[SP] = sg * z1;
-  z[2 * SP] = sg * z2;
-  z[3 * SP] = sg * z3 + sg * (1.f - sg) * (z1 * z1 + z2 * z2);
+  float q = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float zd = z[(1 + d) * SP];
+    q = fmaf(zd, zd, q);
+    z[(1 + d) * SP] = sg * zd;
+  }
+  z[(D + 1) * SP] = sg * z[(D + 1) * SP] + sg * (1.f - sg) * q;
   a_saved[((long)l * Btot + p_off + p) * kHidden + h] = a;
 }
 
-// last layer (128 -> 1) on 4 streams + operator epilogue.  One warp per (point, copy).
+// last layer (128 -> 1) on the S streams + operator epilogue.  One warp per (point, copy).
 __global__ void head_operator_kernel(const float* __restrict__ A2, const float* __restrict__ W3,
                                      const float* __restrict__ b3, const float* __restrict__ x,
                                      const float* __restrict__ mscales, nsvd_problem_t pb,
@@ -175,63 +183,75 @@ __global__ void head_operator_kernel(const float* __restrict__ A2, const float* 
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   int L = pb.n_copies;
   if (w >= P * L) return;
+  const int D = problem_ndim(pb), S = D + 2;
   int p = w / L, l = w % L;
   long SP = (long)P * kHidden;
-  const float* a = A2 + (long)l * 4 * SP + (long)p * kHidden;
-  float u[4] = {0, 0, 0, 0};
+  const float* a = A2 + (long)l * S * SP + (long)p * kHidden;
+  float u[kMaxDim + 2] = {0, 0, 0, 0, 0};       // every index below is a compile-time constant (registers)
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     int h = lane + 32 * q;
     float wv = W3[l * kHidden + h];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) u[s] = fmaf(a[s * SP + h], wv, u[s]);
+    for (int s = 0; s < kMaxDim + 2; ++s)
+      if (s < S) u[s] = fmaf(a[s * SP + h], wv, u[s]);
   }
 #pragma unroll
-  for (int s = 0; s < 4; ++s) u[s] = warp_sum(u[s]);
+  for (int s = 0; s < kMaxDim + 2; ++s) u[s] = warp_sum(u[s]);
   if (lane == 0) {
     u[0] += b3[l];
     long pg = p_off + p;
-    PointGeom g = point_geom(x[2 * pg], x[2 * pg + 1], pb);
+    PointGeomN g = point_geom_n(x + (long)D * pg, pb);
     float f, tf;
-    operator_epilogue(g, pb, pb.has_exp_mask != 0, pb.has_exp_mask ? mscales[l] : 1.f, u[0], u[1],
-                      u[2], u[3], f, tf);
+    operator_epilogue_n(g, pb, pb.has_exp_mask != 0, pb.has_exp_mask ? mscales[l] : 1.f, u, f, tf);
     F[pg * L + l] = f;
     TF[pg * L + l] = tf;
     U0[pg * L + l] = u[0];
   }
 }
 
-// ---- finite-difference mode (pb.fd_eps > 0): the four stream slots carry the four SHIFTED point sets
-// x + eps e_0, x - eps e_0, x + eps e_1, x - eps e_1 through the same contractions, value stream only.
+// ---- finite-difference mode (pb.fd_eps > 0): 2 D stream slots carry the 2 D SHIFTED point sets
+// x + eps e_0, x - eps e_0, x + eps e_1, ... through the same contractions, value stream only.
 __global__ void features_shift_f32_kernel(const float* __restrict__ x, const float* __restrict__ Bff,
-                                          float* __restrict__ phis, int P, int M, float eps) {
+                                          float* __restrict__ phis, int P, int M, float eps, int D) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)P * M) return;
   int p = (int)(i / M), j = (int)(i % M);
-  const float b0 = Bff[j], b1 = Bff[M + j];
+  const float b[kMaxDim] = {Bff[j], Bff[M + j], D == 3 ? Bff[2L * M + j] : 0.f};
+  const float y[kMaxDim] = {x[(long)D * p], x[(long)D * p + 1], D == 3 ? x[3L * p + 2] : 0.f};
   const long K0 = 2L * M, SP = (long)P * K0;
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    float y0 = x[2 * p], y1 = x[2 * p + 1];
-    fd_shift(s, eps, y0, y1);
+  for (int s = 0; s < 2 * kMaxDim; ++s) {
+    if (s >= 2 * D) break;
+    float ph;
+    if (D == 2) {
+      float y0 = y[0], y1 = y[1];
+      fd_shift(s, eps, y0, y1);
+      ph = fmaf(y1, b[1], y0 * b[0]);
+    } else {
+      const float dlt = (s & 1) ? -eps : eps;
+      const float y0 = (s >> 1) == 0 ? y[0] + dlt : y[0], y1 = (s >> 1) == 1 ? y[1] + dlt : y[1],
+                  y2 = (s >> 1) == 2 ? y[2] + dlt : y[2];
+      ph = fmaf(y2, b[2], fmaf(y1, b[1], y0 * b[0]));
+    }
     float sn, cs;
-    sincosf(fmaf(y1, b1, y0 * b0), &sn, &cs);
+    sincosf(ph, &sn, &cs);
     phis[s * SP + (long)p * K0 + j] = sn;
     phis[s * SP + (long)p * K0 + M + j] = cs;
   }
 }
-// plain softplus on all four slots of Z[l][s][p][h] (in place)
-__global__ void softplus_values_kernel(float* __restrict__ Z, const float* __restrict__ bias, int L, int P) {
+// plain softplus on all `slots` slots of Z[l][s][p][h] (in place)
+__global__ void softplus_values_kernel(float* __restrict__ Z, const float* __restrict__ bias, int L, int P, int slots) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  long n = (long)L * 4 * P * kHidden;
+  long n = (long)L * slots * P * kHidden;
   if (i >= n) return;
   int h = (int)(i % kHidden);
-  int l = (int)(i / ((long)kHidden * P * 4));
+  int l = (int)(i / ((long)kHidden * P * slots));
   float a, sg;
   softplus_sig(Z[i] + bias[l * kHidden + h], a, sg);
   Z[i] = a;
 }
-// last layer on the four shifted slots + finite-difference operator; the central value comes from U0 (exact pass)
+// last layer on the 2 D shifted slots + finite-difference operator; the central value comes from U0 (exact pass)
 __global__ void head_fd_kernel(const float* __restrict__ A2, const float* __restrict__ W3,
                                const float* __restrict__ b3, const float* __restrict__ x,
                                const float* __restrict__ mscales, nsvd_problem_t pb,
@@ -239,23 +259,25 @@ __global__ void head_fd_kernel(const float* __restrict__ A2, const float* __rest
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   int L = pb.n_copies;
   if (w >= P * L) return;
+  const int D = problem_ndim(pb), S = 2 * D;
   int p = w / L, l = w % L;
   long SP = (long)P * kHidden;
-  const float* a = A2 + (long)l * 4 * SP + (long)p * kHidden;
-  float u[4] = {0, 0, 0, 0};
+  const float* a = A2 + (long)l * S * SP + (long)p * kHidden;
+  float u[2 * kMaxDim] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     int h = lane + 32 * q;
     float wv = W3[l * kHidden + h];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) u[s] = fmaf(a[s * SP + h], wv, u[s]);
+    for (int s = 0; s < 2 * kMaxDim; ++s)
+      if (s < S) u[s] = fmaf(a[s * SP + h], wv, u[s]);
   }
 #pragma unroll
-  for (int s = 0; s < 4; ++s) u[s] = warp_sum(u[s]) + b3[l];
+  for (int s = 0; s < 2 * kMaxDim; ++s) u[s] = warp_sum(u[s]) + b3[l];
   if (lane == 0) {
     long pg = p_off + p;
-    TF[pg * L + l] = fd_operator(x[2 * pg], x[2 * pg + 1], pb, pb.has_exp_mask != 0,
-                                 pb.has_exp_mask ? mscales[l] : 1.f, U0[pg * L + l], u);
+    TF[pg * L + l] = fd_operator_n(x + (long)D * pg, pb, pb.has_exp_mask != 0,
+                                   pb.has_exp_mask ? mscales[l] : 1.f, U0[pg * L + l], u);
   }
 }
 
@@ -271,13 +293,13 @@ __global__ void head_bwd_kernel(const float* __restrict__ dF, const float* __res
   if (w >= P * L) return;
   int p = w / L, l = w % L;
   long pg = p_off + p;
-  PointGeom g = point_geom(x[2 * pg], x[2 * pg + 1], pb);
+  PointGeomN g = point_geom_n(x + (long)problem_ndim(pb) * pg, pb);
   float m = 1.f, sc = 1.f;
   if (pb.has_exp_mask) {
     sc = mscales[l];
     m = expf(-g.r / sc);
   }
-  float cm = head_factor(g, pb, m);
+  float cm = head_factor_n(g, pb, m);
   float df = dF[pg * L + l];
   float du = df * cm;
   if (lane == 0) {
@@ -309,15 +331,21 @@ __global__ void dact_kernel(float* __restrict__ dA, const float* __restrict__ a_
 }
 
 // ------------------------------------------------------------------------------------------
-// fp32 engine: forward and backward drivers
+// fp32 engine: forward and backward drivers.  `slots` = stream slots of the work buffers: S = D + 2 in the exact
+// pass, 2 D shifted point sets in the finite-difference pass (D = 3: 5 and 6).
 // ------------------------------------------------------------------------------------------
 static const int kSimtMicroBatch = 2048;
+static inline int simt_slots(const nsvd_problem_t& pb) {
+  const int D = problem_ndim(pb);
+  return (pb.fd_eps > 0.f && 2 * D > D + 2) ? 2 * D : D + 2;
+}
 
 void simt_scratch_bytes(const nsvd_problem_t& pb, size_t* saved, size_t* work) {
   long B = pb.n_points, L = pb.n_copies, K0 = 2L * pb.n_fourier;
   long P = B < kSimtMicroBatch ? B : kSimtMicroBatch;
+  const long NS = simt_slots(pb);
   *saved = sizeof(float) * (size_t)(B * K0 + 3 * L * B * kHidden + B * L) + 256;
-  size_t fwd = (size_t)(4 * P * K0 + 2 * 4 * L * P * kHidden);
+  size_t fwd = (size_t)(NS * P * K0 + 2 * NS * L * P * kHidden);
   size_t bwd = (size_t)(3 * L * P * kHidden + 2 * P * L);
   *work = sizeof(float) * (fwd > bwd ? fwd : bwd) + 256;
 }
@@ -339,70 +367,64 @@ static SimtSaved carve_saved(const nsvd_problem_t& pb, void* saved) {
   return s;
 }
 
+// the three dense layers on `slots` stacked (slots x P)-row operands; `streams` selects the activation
+static int simt_layers(const nsvd_params_t& pr, const SimtSaved& sv, float* phis, float* bufA, float* bufB, int slots,
+                       bool streams, int D, long L, int P, long B, long p0, long K0, float** out, cudaStream_t st) {
+  SGemm g{};
+  g.A = phis; g.a_rs = K0; g.a_cs = 1; g.a_bs = 0;
+  g.B = pr.W[0]; g.b_rs = 1; g.b_cs = K0; g.b_bs = (long)kHidden * K0;
+  g.C = bufA; g.c_rs = kHidden; g.c_bs = (long)slots * P * kHidden;
+  g.M = slots * P; g.N = kHidden; g.K = (int)K0; g.alpha = 1.f; g.accumulate = 0;
+  int rc = sgemm_strided(g, (int)L, st);
+  if (rc) return rc;
+  const long ne = L * P * kHidden, nall = ne * slots;
+  if (streams) softplus_streams_kernel<<<cdiv(ne, 256), 256, 0, st>>>(bufA, pr.b[0], sv.a[0], (int)L, P, B, p0, D);
+  else softplus_values_kernel<<<cdiv(nall, 256), 256, 0, st>>>(bufA, pr.b[0], (int)L, P, slots);
+  NSVD_LAUNCH_CHECK();
+  float* cur = bufA;
+  float* nxt = bufB;
+  for (int i = 1; i <= 2; ++i) {
+    SGemm h{};
+    h.A = cur; h.a_rs = kHidden; h.a_cs = 1; h.a_bs = (long)slots * P * kHidden;
+    h.B = pr.W[i]; h.b_rs = 1; h.b_cs = kHidden; h.b_bs = (long)kHidden * kHidden;
+    h.C = nxt; h.c_rs = kHidden; h.c_bs = (long)slots * P * kHidden;
+    h.M = slots * P; h.N = kHidden; h.K = kHidden; h.alpha = 1.f; h.accumulate = 0;
+    if ((rc = sgemm_strided(h, (int)L, st))) return rc;
+    if (streams) softplus_streams_kernel<<<cdiv(ne, 256), 256, 0, st>>>(nxt, pr.b[i], sv.a[i], (int)L, P, B, p0, D);
+    else softplus_values_kernel<<<cdiv(nall, 256), 256, 0, st>>>(nxt, pr.b[i], (int)L, P, slots);
+    NSVD_LAUNCH_CHECK();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  *out = cur;
+  return 0;
+}
+
 int simt_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x, float* F,
                  float* TF, void* saved, void* work, cudaStream_t st) {
   const long B = pb.n_points, L = pb.n_copies, M = pb.n_fourier, K0 = 2 * M;
+  const int D = problem_ndim(pb), S = D + 2, NS = simt_slots(pb);
   SimtSaved sv = carve_saved(pb, saved);
   for (long p0 = 0; p0 < B; p0 += kSimtMicroBatch) {
     int P = (int)((B - p0) < kSimtMicroBatch ? (B - p0) : kSimtMicroBatch);
     float* phis = (float*)work;
-    float* bufA = phis + 4L * P * K0;
-    float* bufB = bufA + 4L * L * P * kHidden;
+    float* bufA = phis + (long)NS * P * K0;
+    float* bufB = bufA + (long)NS * L * P * kHidden;
     long n = (long)P * M;
-    features_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(x + 2 * p0, pr.Bff, phis, sv.phi + p0 * K0, P,
-                                                      (int)M);
+    features_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(x + D * p0, pr.Bff, phis, sv.phi + p0 * K0, P, (int)M, D);
     NSVD_LAUNCH_CHECK();
-    // layer 0: Z[l] (4P x H) = phis (4P x K0) . W0[l]^T
-    SGemm g{};
-    g.A = phis; g.a_rs = K0; g.a_cs = 1; g.a_bs = 0;
-    g.B = pr.W[0]; g.b_rs = 1; g.b_cs = K0; g.b_bs = (long)kHidden * K0;
-    g.C = bufA; g.c_rs = kHidden; g.c_bs = 4L * P * kHidden;
-    g.M = 4 * P; g.N = kHidden; g.K = (int)K0; g.alpha = 1.f; g.accumulate = 0;
-    int rc = sgemm_strided(g, (int)L, st);
+    float* cur = nullptr;
+    int rc = simt_layers(pr, sv, phis, bufA, bufB, S, true, D, L, P, B, p0, K0, &cur, st);
     if (rc) return rc;
-    long ne = L * P * kHidden;
-    softplus_streams_kernel<<<cdiv(ne, 256), 256, 0, st>>>(bufA, pr.b[0], sv.a[0], (int)L, P, B, p0);
-    NSVD_LAUNCH_CHECK();
-    float* cur = bufA;
-    float* nxt = bufB;
-    for (int i = 1; i <= 2; ++i) {
-      SGemm h{};
-      h.A = cur; h.a_rs = kHidden; h.a_cs = 1; h.a_bs = 4L * P * kHidden;
-      h.B = pr.W[i]; h.b_rs = 1; h.b_cs = kHidden; h.b_bs = (long)kHidden * kHidden;
-      h.C = nxt; h.c_rs = kHidden; h.c_bs = 4L * P * kHidden;
-      h.M = 4 * P; h.N = kHidden; h.K = kHidden; h.alpha = 1.f; h.accumulate = 0;
-      rc = sgemm_strided(h, (int)L, st);
-      if (rc) return rc;
-      softplus_streams_kernel<<<cdiv(ne, 256), 256, 0, st>>>(nxt, pr.b[i], sv.a[i], (int)L, P, B, p0);
-      NSVD_LAUNCH_CHECK();
-      float* t = cur; cur = nxt; nxt = t;
-    }
     long nw = (long)P * L;
     head_operator_kernel<<<cdiv(nw * 32, 256), 256, 0, st>>>(cur, pr.W[3], pr.b[3], x, pr.mask_scales,
                                                              pb, F, TF, sv.u0, P, p0);
     NSVD_LAUNCH_CHECK();
     if (pb.fd_eps > 0.f) {
-      // finite-difference Laplacian: second pass, the four slots = the four shifted point sets, values only;
+      // finite-difference Laplacian: second pass, the 2 D slots = the shifted point sets, values only;
       // TF is overwritten, F / U0 / the saved activations of the central pass stay (the backward uses them)
-      features_shift_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(x + 2 * p0, pr.Bff, phis, P, (int)M, pb.fd_eps);
+      features_shift_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(x + D * p0, pr.Bff, phis, P, (int)M, pb.fd_eps, D);
       NSVD_LAUNCH_CHECK();
-      if ((rc = sgemm_strided(g, (int)L, st))) return rc;
-      long n4 = 4 * ne;
-      softplus_values_kernel<<<cdiv(n4, 256), 256, 0, st>>>(bufA, pr.b[0], (int)L, P);
-      NSVD_LAUNCH_CHECK();
-      cur = bufA;
-      nxt = bufB;
-      for (int i = 1; i <= 2; ++i) {
-        SGemm h{};
-        h.A = cur; h.a_rs = kHidden; h.a_cs = 1; h.a_bs = 4L * P * kHidden;
-        h.B = pr.W[i]; h.b_rs = 1; h.b_cs = kHidden; h.b_bs = (long)kHidden * kHidden;
-        h.C = nxt; h.c_rs = kHidden; h.c_bs = 4L * P * kHidden;
-        h.M = 4 * P; h.N = kHidden; h.K = kHidden; h.alpha = 1.f; h.accumulate = 0;
-        if ((rc = sgemm_strided(h, (int)L, st))) return rc;
-        softplus_values_kernel<<<cdiv(n4, 256), 256, 0, st>>>(nxt, pr.b[i], (int)L, P);
-        NSVD_LAUNCH_CHECK();
-        float* t = cur; cur = nxt; nxt = t;
-      }
+      if ((rc = simt_layers(pr, sv, phis, bufA, bufB, 2 * D, false, D, L, P, B, p0, K0, &cur, st))) return rc;
       head_fd_kernel<<<cdiv(nw * 32, 256), 256, 0, st>>>(cur, pr.W[3], pr.b[3], x, pr.mask_scales, pb, sv.u0, TF, P, p0);
       NSVD_LAUNCH_CHECK();
     }

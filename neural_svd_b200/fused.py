@@ -63,8 +63,8 @@ def describe_model(model):
     Bff = fm._B.detach()
     if not Bff.is_contiguous():          # the deterministic map is built as a transposed view (utils.py:108-111)
         Bff = Bff.contiguous()
-    if Bff.shape[0] != 2:
-        raise NotImplementedError("fused path is built for ndim=2, n_particles=1")
+    if Bff.shape[0] not in (2, 3):
+        raise NotImplementedError("fused path is built for one particle in ndim = 2 or 3")
     L, H, K0 = ws[0].shape
     Mff = Bff.shape[1]
     ok = (H == 128 and K0 == 2 * Mff and tuple(ws[1].shape) == (L, 128, 128) and tuple(ws[2].shape) == (L, 128, 128)
@@ -82,7 +82,8 @@ def describe_model(model):
             raise NotImplementedError("fused path is fp32 (reference default, --use_amp off)")
         if not p.is_contiguous():
             raise RuntimeError("parameters must be contiguous")
-    return dict(Bff=Bff, ws=ws, bs=bs, scales=scales, L=L, Mff=Mff, box_mode=box_mode, box_lim=box_lim,
+    return dict(Bff=Bff, ws=ws, bs=bs, scales=scales, L=L, Mff=Mff, ndim=int(Bff.shape[0]), box_mode=box_mode,
+                box_lim=box_lim,
                 hard_mul_const=float(getattr(m, "hard_mul_const", 1.0)))
 
 
@@ -107,7 +108,7 @@ def _problem(md, od, imp, B) -> _lib.Problem:
                         pot_coef=od["pot_coef"], scale_kinetic=od["scale_kinetic"], op_scale=od["op_scale"],
                         op_shift=od["op_shift"], sampling_sigma=imp["sigma"], hard_mul_const=md["hard_mul_const"],
                         importance=imp["importance"], box_mask=md["box_mode"], pot_coef2=od.get("pot_coef2", 0.0),
-                        box_lim=md["box_lim"], fd_eps=od.get("fd_eps", 0.0), reserved_=0)
+                        box_lim=md["box_lim"], fd_eps=od.get("fd_eps", 0.0), ndim=md["ndim"])
 
 
 def _params_struct(md) -> _lib.Params:
@@ -153,18 +154,35 @@ def _scratch_of(owner) -> _Scratch:
     return sc
 
 
-def _prep_x(x, dev):
+def _prep_x(x, dev, ndim=2):
     if x.dim() == 3:
         x = x.reshape(x.shape[0], -1)
-    if x.dim() != 2 or x.shape[1] != 2:
-        raise NotImplementedError(f"fused path expects x of shape (B, 2); got {tuple(x.shape)}")
+    if x.dim() != 2 or x.shape[1] != ndim:
+        raise NotImplementedError(f"fused path expects x of shape (B, {ndim}); got {tuple(x.shape)}")
     return x.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+_warned_3d = False
+
+
+def engine_for(md) -> int:
+    """Engine code of a step: the selected one, except that ndim = 3 (five forward-mode streams: 640 accumulator columns
+    per 128 units exceed the 512 TMEM columns the tcgen05 tiles are built around) always runs on the fp32 CUDA-core
+    engine of the same library - still hand-written sm_100a kernels on the device, never a CPU path."""
+    global _warned_3d
+    if md["ndim"] == 3:
+        if _ENGINE not in ("fp32", "fp32_simt") and not _warned_3d:
+            import warnings
+            warnings.warn("neural_svd_b200: ndim = 3 runs on the fp32 CUDA-core engine (the tensor-core engine is 2D)")
+            _warned_3d = True
+        return _lib.ENGINE_FP32_SIMT
+    return _lib.ENGINES[_ENGINE]
 
 
 def _forward_kernels(lib, owner, md, od, imp, x, engine):
     dev = md["Bff"].device
     _require_cuda(dev)
-    x = _prep_x(x, dev)
+    x = _prep_x(x, dev, md["ndim"])
     B, L = x.shape[0], md["L"]
     pb = _problem(md, od, imp, B)
     sc = _scratch_of(owner).ensure(lib, pb, engine, dev)
@@ -182,10 +200,9 @@ def apply_operator(model, operator, x, importance):
     """`operator(model, x, importance) -> (Tf, f)` on the fused forward kernel (no autograd graph)."""
     lib = _lib.load()
     md, od = describe_model(model), describe_operator(operator)
-    imp = describe_importance(importance)
+    imp = describe_importance(importance, md["ndim"])
     with torch.no_grad():
-        _, _, _, _, F, TF = _forward_kernels(lib, getattr(model, "model", model), md, od, imp, x,
-                                             _lib.ENGINES[_ENGINE])
+        _, _, _, _, F, TF = _forward_kernels(lib, getattr(model, "model", model), md, od, imp, x, engine_for(md))
     return TF, F
 
 
@@ -196,8 +213,7 @@ def model_values(model, x):
     od = dict(potential=_lib.POT_INFINITE_WELL, pot_coef=0.0, scale_kinetic=1.0, op_scale=1.0, op_shift=0.0)
     with torch.no_grad():
         _, _, _, _, F, _ = _forward_kernels(lib, getattr(model, "model", model), md, od,
-                                            dict(importance=_lib.IMP_NONE, sigma=1.0), x,
-                                            _lib.ENGINES[_ENGINE])
+                                            dict(importance=_lib.IMP_NONE, sigma=1.0), x, engine_for(md))
     return F
 
 
@@ -209,8 +225,8 @@ class _FusedOperatorStep(torch.autograd.Function):
     def forward(ctx, method, operator, importance, x, dp, *params):
         lib = _lib.load()
         md, od = describe_model(method), describe_operator(operator)
-        imp = describe_importance(importance)
-        engine = _lib.ENGINES[_ENGINE]
+        imp = describe_importance(importance, md["ndim"])
+        engine = engine_for(md)
         x, pb, pr, sc, F, TF = _forward_kernels(lib, method, md, od, imp, x, engine)
         dev = F.device
         B, L = F.shape

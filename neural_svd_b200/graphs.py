@@ -25,14 +25,15 @@ class GraphedOperatorStep:
         self.method = method
         md = self.md = fused.describe_model(method)
         od = describe_operator(operator)
-        imp = describe_importance(importance)
+        imp = describe_importance(importance, md["ndim"])
         if getattr(method, "data_parallel", None) is not None:
             raise NotImplementedError("GraphedOperatorStep is single-GPU; use compute_loss_operator with data_parallel")
         dev = self.dev = md["Bff"].device
         fused._require_cuda(dev)
         B, L = batch_size, md["L"]
         self.B, self.L = B, L
-        self.engine = _lib.ENGINES[fused.get_engine()]
+        self.engine = fused.engine_for(md)
+        self.ndim = md["ndim"]
         self.pb = fused._problem(md, od, imp, B)
         ns, nw = C.c_size_t(), C.c_size_t()
         _lib.check(lib.nsvd_scratch_bytes(C.byref(self.pb), self.engine, C.byref(ns), C.byref(nw)), "nsvd_scratch_bytes")
@@ -40,7 +41,7 @@ class GraphedOperatorStep:
         self.saved = torch.empty(ns.value, dtype=torch.uint8, device=dev)
         self.work = torch.empty(nw.value, dtype=torch.uint8, device=dev)
         self.partials = torch.empty(lib.nsvd_gram_partials_bytes(B, L), dtype=torch.uint8, device=dev)
-        self.x = torch.zeros((B, 2), **f32)
+        self.x = torch.zeros((B, md["ndim"]), **f32)
         self.F, self.TF, self.dF = (torch.empty((B, L), **f32) for _ in range(3))
         self.terms = torch.empty(2 * L * L + 1, **f32)
         self.coef = torch.empty(2 * L * L, **f32)
@@ -88,8 +89,8 @@ class GraphedOperatorStep:
     def __call__(self, x):
         if x.dim() == 3:
             x = x.reshape(x.shape[0], -1)
-        if tuple(x.shape) != (self.B, 2):
-            raise ValueError(f"GraphedOperatorStep was captured for x of shape ({self.B}, 2); got {tuple(x.shape)}")
+        if tuple(x.shape) != (self.B, self.ndim):
+            raise ValueError(f"GraphedOperatorStep was captured for x of shape ({self.B}, {self.ndim}); got {tuple(x.shape)}")
         self.x.copy_(x, non_blocking=True)
         self.graph.replay()
         for t, g in zip(self.tensors, self.views):

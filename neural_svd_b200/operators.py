@@ -148,7 +148,7 @@ def describe_operator(operator):
     elif name == "cosine_potential":
         cs = list(kw.get("cs", ()))
         if len(cs) != 2:
-            raise NotImplementedError("cosine_potential: the fused path is 2D (two coefficients)")
+            raise NotImplementedError("cosine_potential: the fused path covers the 2D case (two coefficients)")
         kind, coef, coef2 = 4, float(cs[0]), float(cs[1])
     else:
         raise NotImplementedError(f"unsupported potential {name!r}")
@@ -174,6 +174,8 @@ def describe_importance(importance, dim=2) -> dict:
         return dict(importance=3, sigma=1.0)
     if hasattr(importance, "sampling_scale"):
         mode = getattr(importance, "sampling_mode", "gaussian")
+        if getattr(importance, "dim", dim) != dim:
+            raise NotImplementedError(f"importance density is over {importance.dim} coordinates, the model over {dim}")
         return dict(importance=_IMP_CODES[mode], sigma=float(importance.sampling_scale))
     for cell in (getattr(importance, "__closure__", None) or ()):
         obj = cell.cell_contents
@@ -183,17 +185,17 @@ def describe_importance(importance, dim=2) -> dict:
             loc = obj.loc.detach().cpu().double()
             d = cov.shape[0]
             if d != dim or loc.abs().max() != 0 or not torch.allclose(cov, cov[0, 0] * torch.eye(d, dtype=cov.dtype)):
-                raise NotImplementedError("importance must be a zero-mean isotropic Gaussian in 2D")
+                raise NotImplementedError(f"importance must be a zero-mean isotropic Gaussian in {dim}D")
             return dict(importance=0, sigma=float(cov[0, 0].sqrt()))
         if type(obj).__name__ == "Laplace" and hasattr(obj, "loc") and hasattr(obj, "scale"):
             loc, sc = obj.loc.detach().cpu().double().reshape(-1), obj.scale.detach().cpu().double().reshape(-1)
             if loc.numel() != dim or loc.abs().max() != 0 or (sc != sc[0]).any():
-                raise NotImplementedError("importance must be a zero-mean Laplace density with one scale in 2D")
+                raise NotImplementedError(f"importance must be a zero-mean Laplace density with one scale in {dim}D")
             return dict(importance=1, sigma=float(sc[0]))
         mode = getattr(obj, "sampling_mode", None)          # the `args` namespace the closure reads
         if mode in ("laplacian", "uniform") and hasattr(obj, "sampling_scale"):
             if getattr(obj, "ndim", dim) != dim or getattr(obj, "n_particles", 1) != 1:
-                raise NotImplementedError("importance must be over one particle in 2D")
+                raise NotImplementedError(f"importance must be over one particle in {dim}D")
             return dict(importance=_IMP_CODES[mode], sigma=float(obj.sampling_scale))
     raise NotImplementedError("cannot recognise the importance density; pass neural_svd_b200.GaussianImportance / "
                               "LaplaceImportance / UniformImportance")
@@ -232,15 +234,26 @@ _COSINE_2D = [-0.591624518674115, 0.623365592493771, 0.662887867122419, 0.891545
               5.275223862927211, 8.047887977307184, 8.049390622352888, 8.050173877109360, 8.051676522155063]
 
 
+def hydrogen3d_eigvals(neigs, charge=1.0):
+    """E_n = -Z^2 / (4 n^2), n = 1, 2, ... with degeneracy n^2 (schrodinger/ground_truths.py:162-175).  As there, shells
+    are enumerated up to n = ceil(neigs^(1/3)), so the result can be SHORTER than neigs (14 values for neigs = 16)."""
+    max_n = int(np.ceil(neigs ** (1.0 / 3))) + 1
+    qn = np.array([n for n in range(1, max_n) for _ in range(n * n)])
+    return -(charge ** 2) / (4 * qn[:neigs] ** 2)
+
+
 def get_problem(args, device=None):
-    """pde/problems.py:23-130 for problem='sch', ndim=2, one particle."""
-    if args.problem != "sch" or args.ndim != 2:
-        raise NotImplementedError("fused path covers the 2D Schroedinger problems")
+    """pde/problems.py:23-130 for problem='sch', one particle: every 2D potential, and in 3D the two the reference itself
+    runs there (hydrogen, H2+ ion: its oscillator / well / cosine branches assert other dimensions)."""
+    if args.problem != "sch" or args.ndim not in (2, 3):
+        raise NotImplementedError("fused path covers the Schroedinger problems in ndim = 2 or 3")
+    if args.ndim == 3 and args.potential_type not in ("hydrogen", "hydrogen_mol_ion"):
+        raise NotImplementedError("ndim = 3: hydrogen and hydrogen_mol_ion (what pde/problems.py runs in 3D)")
     args.n_particles = 1
     gt = None
     if args.potential_type == "hydrogen":
         pot = partial(hydrogen_potential, charge=args.charge)
-        gt = -hydrogen2d_eigvals(args.neigs, args.charge)
+        gt = -(hydrogen2d_eigvals if args.ndim == 2 else hydrogen3d_eigvals)(args.neigs, args.charge)
     elif args.potential_type == "harmonic_oscillator":
         pot = partial(harmonic_oscillator_potential, k=1.0)
         gt = -oscillator2d_eigvals(args.neigs, 1.0)

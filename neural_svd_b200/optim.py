@@ -67,28 +67,38 @@ class FusedRMSpropEMA:
         self.t += 1
 
 
-def sample_gaussian(n_points: int, sigma: float, seed: int, offset: int = 0, device="cuda"):
-    """x (n_points, 2) = sigma * N(0, I), generated on the device (the CPU draw of main_pde.py:92-93 remains the
+def _pairs(n_points: int, ndim: int) -> int:
+    """the device samplers draw iid coordinate PAIRS: (n_points, ndim) coordinates take ceil(n ndim / 2) of them"""
+    if ndim not in (2, 3):
+        raise NotImplementedError("device samplers: ndim must be 2 or 3")
+    return (n_points * ndim + 1) // 2
+
+
+def sample_gaussian(n_points: int, sigma: float, seed: int, offset: int = 0, device="cuda", ndim: int = 2):
+    """x (n_points, ndim) = sigma * N(0, I), generated on the device (the CPU draw of main_pde.py:92-93 remains the
     RNG-parity mode)."""
     lib = _lib.load()
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("sample_gaussian has no CPU path")
-    x = torch.empty((n_points, 2), dtype=torch.float32, device=dev)
+    npair = _pairs(n_points, ndim)
+    x = torch.empty((npair, 2), dtype=torch.float32, device=dev)
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(lib.nsvd_sample_gaussian(_lib.ptr(x), n_points, sigma, seed, offset, st), "nsvd_sample_gaussian")
-    return x
+    _lib.check(lib.nsvd_sample_gaussian(_lib.ptr(x), npair, sigma, seed, offset, st), "nsvd_sample_gaussian")
+    return x if ndim == 2 else x.reshape(-1)[:n_points * ndim].reshape(n_points, ndim)
 
 
-def sample_points(n_points: int, sampling_mode: str, scale: float, seed: int, offset: int = 0, device="cuda"):
-    """x (n_points, 2) from the sampler of `sampling_mode` in {'gaussian', 'laplacian', 'uniform'} (main_pde.py:89-118),
+def sample_points(n_points: int, sampling_mode: str, scale: float, seed: int, offset: int = 0, device="cuda",
+                  ndim: int = 2):
+    """x (n_points, ndim) from the sampler of `sampling_mode` in {'gaussian', 'laplacian', 'uniform'} (main_pde.py:89-118),
     generated on the device; pairs with GaussianImportance / LaplaceImportance / UniformImportance."""
     lib = _lib.load()
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("sample_points has no CPU path")
     code = {"gaussian": _lib.IMP_GAUSSIAN, "laplacian": _lib.IMP_LAPLACE, "uniform": _lib.IMP_UNIFORM}[sampling_mode]
-    x = torch.empty((n_points, 2), dtype=torch.float32, device=dev)
+    npair = _pairs(n_points, ndim)
+    x = torch.empty((npair, 2), dtype=torch.float32, device=dev)
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(lib.nsvd_sample_points(_lib.ptr(x), n_points, code, scale, seed, offset, st), "nsvd_sample_points")
-    return x
+    _lib.check(lib.nsvd_sample_points(_lib.ptr(x), npair, code, scale, seed, offset, st), "nsvd_sample_points")
+    return x if ndim == 2 else x.reshape(-1)[:n_points * ndim].reshape(n_points, ndim)

@@ -72,6 +72,18 @@ CASES = {
     "osc_small_fd0p01": dict(cfg=O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64, sequential=True), B=64,
                              seed=15, eps=0.01),
     "hyd_b512_jnt_L16_fd0p01": dict(cfg=O.PathConfig.hydrogen(), B=512, seed=16, eps=0.01),
+    # ndim = 3 (problems.py:62-71: hydrogen and the H2+ ion are the potentials the reference runs in 3D -
+    # the oscillator / well / cosine branches assert other dimensions); five forward-mode streams, fp32 CUDA-core engine
+    "hyd3d_small": dict(cfg=O.PathConfig.hydrogen(ndim=3, neigs=4, fourier_mapping_size=64, sampling_scale=8.0), B=96,
+                        seed=17),
+    "molion3d_laplace_boxexp": dict(cfg=O.PathConfig(potential="hydrogen_mol_ion", ndim=3, neigs=4,
+                                                     fourier_mapping_size=64, fourier_scale=0.2, operator_scale=10.0,
+                                                     sampling_mode="laplacian", sampling_scale=3.0, lim=12.0,
+                                                     apply_boundary=True, boundary_mode="dir_box_exp",
+                                                     apply_exp_mask=True, exp_mask_init_scale=8.0,
+                                                     hydrogen_mol_ion_R=1.5), B=80, seed=19),
+    "hyd3d_small_fd0p05": dict(cfg=O.PathConfig.hydrogen(ndim=3, neigs=4, fourier_mapping_size=64, sampling_scale=8.0),
+                               B=96, seed=20, eps=0.05),
     "osc_no_importance": dict(cfg=O.PathConfig.oscillator(neigs=4, fourier_mapping_size=64, sampling_mode="none"),
                               B=64, seed=9),
 }

@@ -16,7 +16,9 @@ PDE_CASES = ["hyd_small_odd", "osc_small_seq", "hyd_small_sorted", "hyd_b128_seq
              "hyd_b64_jnt_L64",
              # infinite well / cosine / H2+ potentials, uniform / Laplace / no importance,
              # Dirichlet box masks (sqrt, exp; alone and under the exp mask), deterministic Fourier features
-             "well_uniform_boxsqrt", "cosine_uniform_detff", "molion_laplace_boxexp_mask", "osc_no_importance"]
+             "well_uniform_boxsqrt", "cosine_uniform_detff", "molion_laplace_boxexp_mask", "osc_no_importance",
+             # ndim = 3 (five streams; both engine settings resolve to the fp32 CUDA-core engine, see test_ndim3_*)
+             "hyd3d_small", "molion3d_laplace_boxexp"]
 
 
 def _step(name, engine):
@@ -47,7 +49,7 @@ def test_step_matches_reference_golden(name, engine):
     assert max(errs.values()) < TOL, errs
 
 
-PDE_FD = ["hyd_small_fd0p1", "osc_small_fd0p01", "hyd_b512_jnt_L16_fd0p01"]
+PDE_FD = ["hyd_small_fd0p1", "osc_small_fd0p01", "hyd_b512_jnt_L16_fd0p01", "hyd3d_small_fd0p05"]
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -82,6 +84,47 @@ def test_finite_difference_step_matches_reference(name, engine):
     method0, operator0, _, _ = build_problem(cfg, int(d["seed"]), "cuda")
     _, aux0 = method0.compute_loss_operator(operator0, x, importance=importance)
     assert rel(aux0["Tf"].cpu().numpy(), aux["Tf"].cpu().numpy()) > 1e-7
+
+
+def test_ndim3_runs_on_the_cuda_core_engine_across_micro_batches():
+    """ndim = 3 (problems.py:62-71): fresh seeded inputs against the oracle at a size that spans two micro-batches of the
+    fp32 engine with a ragged tail, exp mask + hard_mul_const, perturbed biases; the tensor-core setting resolves to the
+    same CUDA-core engine (and says so once), the graph-captured step and the 3D device sampler work."""
+    import warnings
+    from neural_svd_b200 import fused
+    cfg = O.PathConfig(potential="hydrogen_mol_ion", ndim=3, neigs=5, fourier_mapping_size=48, fourier_scale=0.3,
+                       operator_scale=10.0, sampling_scale=3.0, apply_exp_mask=True, exp_mask_init_scale=6.0,
+                       hard_mul_const=0.7, hydrogen_mol_ion_R=0.8, sequential=True)
+    N.set_engine("f16x3")
+    method, operator, importance, _ = build_problem(cfg, 31, "cuda")
+    g = torch.Generator().manual_seed(6)
+    x = cfg.sampling_scale * torch.randn(2048 + 173, 3, generator=g)
+    with torch.no_grad():
+        for b in method.model.base.bs:
+            b.add_(0.1 * torch.randn(b.shape, generator=g).to(b.device))
+    params = {n: p.detach().cpu().numpy().astype(np.float64) for n, p in method.named_parameters()}
+    r = O.train_step(x.numpy().astype(np.float64), params, cfg)
+    fused._warned_3d = False
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        loss, aux = method.compute_loss_operator(operator, x.cuda(), importance=importance)
+    assert any("fp32 CUDA-core engine" in str(m.message) for m in w)
+    assert fused.engine_for(fused.describe_model(method)) == 0
+    loss.backward()
+    assert abs(float(loss.detach()) - r["loss"]) <= TOL * abs(r["loss"])
+    assert rel(aux["f"].cpu().numpy(), r["f"]) < TOL and rel(aux["Tf"].cpu().numpy(), r["Tf"]) < TOL
+    grads = {n: p.grad.clone() for n, p in method.named_parameters() if p.grad is not None}
+    for n, gr in grads.items():
+        assert rel(gr.cpu().numpy(), r["grads"][n]) < TOL, n
+    step = N.GraphedOperatorStep(method, operator, importance, x.shape[0])
+    l2 = step(x.cuda())
+    assert abs(float(l2) - float(loss.detach())) < 1e-5 * abs(float(loss.detach()))
+    for n, p in method.named_parameters():
+        if n in grads:
+            assert rel(p.grad.cpu().numpy(), grads[n].cpu().numpy()) < 1e-5, n
+    xs = N.sample_points(4001, "gaussian", 2.0, seed=3, ndim=3)
+    assert xs.shape == (4001, 3) and abs(float(xs.std()) - 2.0) < 0.05 and abs(float(xs.mean())) < 0.05
+    assert torch.equal(xs, N.sample_gaussian(4001, 2.0, seed=3, ndim=3))
 
 
 @pytest.mark.parametrize("neigs", [6, 5])

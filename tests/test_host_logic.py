@@ -118,6 +118,29 @@ def test_unsupported_configurations_raise():
         N.get_wavefunctions(a)
     with pytest.raises(NotImplementedError):
         N.NestedLoRA(None, 4).compute_loss_operator(None, None, evd=False)
+    # ndim = 3 exists for the potentials the reference runs there (problems.py:62-71); its oscillator / well / cosine
+    # branches assert other dimensions, and so does the mirror; other dimensions and several particles raise
+    a = ref_args(O.PathConfig.oscillator(neigs=2, fourier_mapping_size=8, ndim=3))
+    with pytest.raises(NotImplementedError):
+        N.get_problem(a)
+    a = ref_args(O.PathConfig.hydrogen(neigs=2, fourier_mapping_size=8, ndim=4))
+    with pytest.raises(NotImplementedError):
+        N.get_problem(a)
+
+
+def test_ndim3_problem_is_recognised():
+    from neural_svd_b200 import fused
+    d, cfg = load_golden("hyd3d_small")
+    method, operator, importance, gt = build_problem(cfg, int(d["seed"]))
+    md = fused.describe_model(method)
+    assert md["ndim"] == 3 and tuple(md["Bff"].shape) == (3, cfg.fourier_mapping_size)
+    assert np.allclose(gt, d["gt"])                                  # Hydrogen3D.get_eigvals, scaled (problems.py:126-128)
+    assert len(operators.hydrogen3d_eigvals(16)) == 14               # the reference's enumeration stops at n = 3
+    assert operators.describe_importance(importance, 3) == dict(importance=0, sigma=cfg.sampling_scale)
+    with pytest.raises(NotImplementedError):
+        operators.describe_importance(N.GaussianImportance(1.0, 2), 3)
+    with pytest.raises(NotImplementedError, match=r"\(B, 3\)"):
+        fused._prep_x(torch.zeros(4, 2), torch.device("cpu"), 3)
 
 
 def test_no_cpu_fallback():

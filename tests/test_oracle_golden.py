@@ -8,10 +8,12 @@ from oracle import nsvd_oracle as O
 
 PDE_SMALL = ["hyd_small_odd", "osc_small_seq", "hyd_small_sorted",
              # other potentials, samplers, Dirichlet box masks, deterministic features
-             "well_uniform_boxsqrt", "cosine_uniform_detff", "molion_laplace_boxexp_mask", "osc_no_importance"]
+             "well_uniform_boxsqrt", "cosine_uniform_detff", "molion_laplace_boxexp_mask", "osc_no_importance",
+             # ndim = 3: hydrogen and the H2+ ion (the 3D potentials the reference runs, problems.py:62-71)
+             "hyd3d_small", "molion3d_laplace_boxexp"]
 PDE_FULL = ["hyd_b128_seq_L16", "osc_b512_jnt_L16", "hyd_b512_jnt_L16"]
 # finite-difference Laplacian (laplacian_eps > 0, the scripts' mode): fp64 parity only - FD in fp32 is noise-limited
-PDE_FD = ["hyd_small_fd0p1", "osc_small_fd0p01", "hyd_b512_jnt_L16_fd0p01"]
+PDE_FD = ["hyd_small_fd0p1", "osc_small_fd0p01", "hyd_b512_jnt_L16_fd0p01", "hyd3d_small_fd0p05"]
 
 
 def _run(name, dtype):
