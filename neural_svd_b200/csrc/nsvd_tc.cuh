@@ -70,12 +70,20 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 // the next kernel reads only after gigabytes of other traffic), so that it does not push the re-used lines out.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p;
+#ifdef NSVD_NO_L2_HINTS
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+#else
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+#endif
   return p;
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;
+#ifdef NSVD_NO_L2_HINTS
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+#else
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+#endif
   return p;
 }
 __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
