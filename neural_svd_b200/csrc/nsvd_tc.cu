@@ -1549,27 +1549,29 @@ struct L0FwdEpi {
   }
 };
 
-// layer-0 VALUE-ONLY epilogue (finite-difference pass): tile = (256 stacked rows of the 4 P shifted points, 2 copies x 128
-// units); a0 = softplus(W0 phi + b0) goes to slot s = row / P of the stream buffer [L][4][P][128]
+// layer-0 VALUE-ONLY epilogue (finite-difference mode): tile = (256 stacked rows, 2 copies x 128 units);
+// a0 = softplus(W0 phi + b0) of stacked row R = s * slot_rows + p goes to dst[l * copy_stride + s * slot_stride + p * 128].
+//   shifted pass : 4 P rows (the four shifted point sets) -> slot s of the stream buffer [L][4][P][128]
+//   central pass : P rows -> the saved value stream a0 [L][Btot][128] at row p_off + p (dst already offset)
 struct L0ValEpi {
   const float* bias;            // b0 (L,128)
   const float* plan;
-  __nv_bfloat16 *str_hi, *str_lo;
-  int P, L;
+  __nv_bfloat16 *dst_hi, *dst_lo;
+  long rows_total, slot_rows, slot_stride, copy_stride;
+  int L;
   __device__ static __forceinline__ uint32_t col0(int sub, int j) { return (uint32_t)(sub * 64 + j * 16); }
   __device__ __forceinline__ void operator()(float (&r)[64], const TileCoord& c, int q, int sub, int lane,
                                              uint8_t*) const {
     const long R = (long)c.mt * big::BM + q * 32 + lane;
     const int l = 2 * c.nt + (sub >> 1), u0 = (sub & 1) * 64;
-    if (R >= 4L * P || l >= L) return;
-    const int s = (int)(R / P);
-    const long p = R % P;
+    if (R >= rows_total || l >= L) return;
+    const long s = R / slot_rows, p = R % slot_rows;
     const float inv = __ldg(plan + (long)l * PL_STRIDE + PL_INV_W0), sa = __ldg(plan + (long)l * PL_STRIDE + PL_SA0);
 #pragma unroll
     for (int i = 0; i < 64; ++i) r[i] = softplus_fast(fmaf(r[i], inv, __ldg(bias + l * kHidden + u0 + i))) * sa;
-    const long o = (((long)l * 4 + s) * P + p) * kHidden + u0;
+    const long o = (long)l * copy_stride + s * slot_stride + p * kHidden + u0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) store_split16h(&r[j * 16], str_hi + o + j * 16, str_lo + o + j * 16);
+    for (int j = 0; j < 4; ++j) store_split16h(&r[j * 16], dst_hi + o + j * 16, dst_lo + o + j * 16);
   }
 };
 
@@ -1973,8 +1975,10 @@ struct HidFwd12Args {
   const float* mscales;              // (L) or null
   float *F, *TF, *U0;                // (Btot, L)
   nsvd_problem_t pb;
-  int vmode;                         // finite-difference pass: the 4 stream slots are 4 shifted point sets, values only;
-                                     // reads U0 (central pass), writes TF, stores nothing else
+  int vmode;                         // finite-difference mode, values only.  1: the 4 stream slots are the 4 shifted point
+                                     // sets; reads U0, writes TF, stores nothing else.  2: central pass, tile = 512 points,
+                                     // slot s = its s-th 128-point block; saves a1 / a2, writes F and U0 (no derivative
+                                     // streams are needed when TF comes from differences: a quarter of the exact pass)
 };
 
 #ifndef NSVD_HID_GROUP
@@ -2065,8 +2069,8 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           fence_proxy_async_all();
         }
         const int xs = ((int)blockIdx.x * G + slot) * 4;
-        const bool vm = args.vmode != 0;
-        {
+        const bool vm = args.vmode != 0, cen = args.vmode == 2;
+        if (!cen) {
           // L2 prefetch of the layer-1 operands (256 KB from DRAM) of the tile that starts one or two items later:
           // a layer-2 item announces the same slot of the next group, A(t0) of a two-tile group announces t1
           const int tn = layer ? t + G : ((G == 2 && slot == 0) ? t + 1 : -1);
@@ -2090,7 +2094,11 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           uint8_t* d = sA + stage * F_STAGE_BYTES;
           mbar_arrive_expect_tx(&full[stage], F_STAGE_BYTES);
           // operands read once (a0 from DRAM; a1 / the scratch for the last time) leave the L2 first
-          if (s == 0 && !vm) {   // value stream: from `saved` (whole-batch rows)
+          if (cen) {             // central value-only pass: slot s = the s-th 128-point block of this 512-point tile
+            const int row = (int)args.p_off + (mt * 4 + s) * 128;
+            tma_load_3d_hint(d, layer ? &tm.v1h : &tm.v0h, &full[stage], 64 * c, row, l, pol_once);
+            tma_load_3d_hint(d + CHUNK, layer ? &tm.v1l : &tm.v0l, &full[stage], 64 * c, row, l, pol_once);
+          } else if (s == 0 && !vm) {   // value stream: from `saved` (whole-batch rows)
             tma_load_3d_hint(d, layer ? &tm.v1h : &tm.v0h, &full[stage], 64 * c, (int)args.p_off + mt * 128, l, pol_once);
             tma_load_3d_hint(d + CHUNK, layer ? &tm.v1l : &tm.v0l, &full[stage], 64 * c, (int)args.p_off + mt * 128, l,
                              pol_once);
@@ -2168,7 +2176,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
     uint32_t tphase = 0;
     int cur_key = -1;
     float un[4] = {1.f, 1.f, 1.f, 1.f}, so[4] = {1.f, 1.f, 1.f, 1.f};
-    const bool vm = args.vmode != 0;
+    const bool vm = args.vmode != 0, cen = args.vmode == 2;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
     for (int i = 0; i < n_items; ++i) {
       const int g = i / (2 * G), layer = (i / G) & 1, slot = i % G, t = t_begin + G * g + slot;
@@ -2235,8 +2243,9 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
         // layer 2 stages the value stream only: two box pairs alternate between rounds, so a round never waits for its
         // predecessor's bulk store (one barrier per round); layer 1 needs all 8 boxes per round and first lets the
         // previous round's stores drain them.
-        const int sb = last ? 2 * (r & 1) : 0;
-        if (!last) {
+        const bool wide = !last || cen;      // all 8 staging boxes are written this round
+        const int sb = wide ? 0 : 2 * (r & 1);
+        if (wide) {
           if (et == 0) {
             if (r == 0 && slot == 1) {       // A(t0)'s stores were issued a whole MMA phase ago: they are complete
               tma_store_wait_all();
@@ -2250,7 +2259,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           if (et == 0) tma_store_wait_read();
           named_bar_sync(2, F_EPI_WARPS * 32);
         }
-        const int ns = last ? (vm ? 0 : 1) : 4;
+        const int ns = wide ? 4 : (vm ? 0 : 1);
         for (int s = 0; s < ns; ++s) {
           uint32_t h[4], lo[4];
 #pragma unroll
@@ -2264,7 +2273,15 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
         if (last && et == 0) tma_store_wait_read();
         named_bar_sync(3, F_EPI_WARPS * 32);
         if (et == 0) {
-          if (!last) {
+          if (cen) {       // the four 128-point blocks of the tile: a1 (read back by layer 2, then by the backward) / a2
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              const int row0 = (int)args.p_off + (mt * 4 + s) * 128;
+              tma_store_3d_hint(last ? &tm.s2h : &tm.s1h, sO + (2 * s) * F_BOX, r * 32, row0, l, last ? pol_once : pol_keep);
+              tma_store_3d_hint(last ? &tm.s2l : &tm.s1l, sO + (2 * s + 1) * F_BOX, r * 32, row0, l,
+                                last ? pol_once : pol_keep);
+            }
+          } else if (!last) {
 #pragma unroll
             for (int s = 1; s < 4; ++s) {
               tma_store_3d_hint(&tm.xsh, sO + (2 * s) * F_BOX, r * 32, 0, xs + s, pol_keep);
@@ -2290,19 +2307,37 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
         else mbar_arrive(&adone[1]);
       }
       if (last) {
+        if (cen) {         // this mode staged through boxes 6-7 too: the last round's stores must have read them
+          if (et == 0) tma_store_wait_read();
+          named_bar_sync(2, F_EPI_WARPS * 32);
+        }
         if (sub != 0) {
 #pragma unroll
           for (int s = 0; s < 4; ++s) ubuf[(row * 3 + sub - 1) * 4 + s] = u[s];
         }
         named_bar_sync(1, F_EPI_WARPS * 32);
-        if (sub == 0 && pt < args.P) {
+        if (sub == 0 && (pt < args.P || cen)) {
 #pragma unroll
           for (int j = 0; j < 3; ++j)
 #pragma unroll
             for (int s = 0; s < 4; ++s) u[s] += ubuf[(row * 3 + j) * 4 + s];
           const long pg = args.p_off + pt;
           const float msc = args.pb.has_exp_mask ? args.mscales[l] : 1.f;
-          if (vm) {        // finite differences of the four shifted values around the central one (first pass)
+          if (cen) {       // values only: F and U0 of the four blocks (TF comes from the shifted pass)
+            const float b3v = __ldg(args.b3 + l);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              const int pts = (mt * 4 + s) * 128 + row;
+              if (pts < args.P) {
+                const long pgs = args.p_off + pts;
+                const float u0 = u[s] + b3v;
+                PointGeom gm = point_geom(args.x[2 * pgs], args.x[2 * pgs + 1], args.pb);
+                const float mexp = args.pb.has_exp_mask ? expf(-gm.r / msc) : 1.f;
+                args.F[pgs * args.L + l] = head_factor(gm, args.pb, mexp) * u0;
+                args.U0[pgs * args.L + l] = u0;
+              }
+            }
+          } else if (vm) {        // finite differences of the four shifted values around the central one (first pass)
             const float b3v = __ldg(args.b3 + l);
 #pragma unroll
             for (int s = 0; s < 4; ++s) u[s] += b3v;
@@ -2839,7 +2874,7 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
   }
   pa.B = B; pa.L = (int)L; pa.M = (int)M;
   pa.n_feat = (unsigned)cdiv(B * (M / 4), 256);
-  pa.n_fold = (unsigned)cdiv(L * H * (M / 8), 256);
+  pa.n_fold = pb.fd_eps > 0.f ? 0u : (unsigned)cdiv(L * H * (M / 8), 256);   // FD mode never runs the 4-stream GEMM
   pa.n_split = (unsigned)(2 * L * 16);   // 32 x 32 tiles of the 128 x 128 hidden matrices
   unsigned n_w0v = 0;
   if (pb.fd_eps > 0.f) {
@@ -2876,7 +2911,8 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
     static const int mgroup = env_int("NSVD_L0_MGROUP", 16);
     s.m_group = mgroup;   // 4096 points x 8 KB of Phi per group
     L0FwdEpi e0{pr.b[0], plan, BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), BF(sv + t.av_hi[0]), BF(sv + t.av_lo[0]), P, B, p0};
-    {
+    const bool fd = pb.fd_eps > 0.f;
+    if (!fd) {   // (finite-difference mode needs no derivative streams: its central pass is value-only, below)
       ProfScope ps(KC_L0_FWD, st);
       // K0 in sub-chains of 4 chunks (K = 256, 48 chained MMAs per TMEM accumulation), the first two of a tile 6 chunks.
       // Chains of 8 chunks miss the fixed-seed trajectory tolerance (profiles/trajectory_probe.py: 1.6e-3 vs 4.7e-4).
@@ -2928,24 +2964,49 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
       a.U0 = reinterpret_cast<float*>(sv + t.u0);
       a.pb = pb;
       NSVD_SMEM_OPTIN(hidden_fwd12_kernel, hid::SMEM_FWD);
-      {
+      if (!fd) {
         ProfScope ps(KC_HID_FWD, st);
         hidden_fwd12_kernel<<<grid, hid::F_THREADS, hid::SMEM_FWD, st>>>(hm, a);
         NSVD_LAUNCH_CHECK();
-      }
-      if (pb.fd_eps > 0.f) {
-        // ---- finite-difference Laplacian (pde/diff_ops.py:25-52): second pass over this micro-batch.  The four
-        // stream slots carry the four shifted point sets, value stream only; F, U0 and the saved activations of the
-        // central pass stay (the backward needs exactly those), TF is overwritten.
+      } else {
+        // ---- finite-difference Laplacian (pde/diff_ops.py:25-52), value streams only.
+        // (1) central pass: F, U0 and the saved activations (what the backward needs) on the un-folded W0 - a quarter
+        //     of the exact pass, since no derivative stream is propagated;
+        // (2) shifted pass: the four stream slots carry the four shifted point sets, TF from their differences.
+        CUtensorMap mVh, mVl;
+        if ((rc = make_tmap_bf16_3d(&mVh, wk + t.w0v_hi, K0, L * H, 1, K0 * 2, L * H * K0 * 2, 64, big::BN / 2))) return rc;
+        if ((rc = make_tmap_bf16_3d(&mVl, wk + t.w0v_lo, K0, L * H, 1, K0 * 2, L * H * K0 * 2, 64, big::BN / 2))) return rc;
+        static const int sub = env_int("NSVD_L0_SUBCHUNKS", 4), sub_first = env_int("NSVD_L0_SUBFIRST", 6);
+        {
+          BigShape sc{};
+          sc.m_tiles = cdiv(P, 2 * big::BM);
+          sc.n_tiles = cdiv(L * H, big::BN);
+          sc.batches = 1;
+          sc.k_slices = 1;
+          sc.k_chunks_total = cdiv(K0, big::BK);
+          sc.k_chunks_per_slice = sc.k_chunks_total;
+          sc.m_group = 16;
+          L0ValEpi ec{pr.b[0], plan, BF(sv + t.av_hi[0]) + p0 * H, BF(sv + t.av_lo[0]) + p0 * H, (long)P, (long)P, 0L,
+                      (long)B * H, (int)L};
+          ProfScope ps(KC_L0_FWD, st);
+          if ((rc = launch_big2s<false, L0ValEpi, kFmtHH>(mPh, mPl, mVh, mVl, sc, 1, sub, sub_first, ec, st))) return rc;
+        }
+        {
+          HidFwd12Args ac = a;
+          ac.vmode = 2;
+          ac.m_tiles = cdiv(P, 512);
+          const int Tc = (int)L * ac.m_tiles;
+          ProfScope ps(KC_HID_FWD, st);
+          hidden_fwd12_kernel<<<Tc < kHidGrid ? Tc : kHidGrid, hid::F_THREADS, hid::SMEM_FWD, st>>>(hm, ac);
+          NSVD_LAUNCH_CHECK();
+        }
         const float* xm = x + 2 * p0;
         features_shift_f16_kernel<<<cdiv(4L * P * (M / 4), 256), 256, 0, st>>>(xm, pr.Bff, BF(wk + t.phis_hi),
                                                                               BF(wk + t.phis_lo), P, (int)M, pb.fd_eps);
         NSVD_LAUNCH_CHECK();
-        CUtensorMap mXh, mXl, mVh, mVl;
+        CUtensorMap mXh, mXl;
         if ((rc = make_tmap_bf16_3d(&mXh, wk + t.phis_hi, K0, 4 * (uint64_t)P, 1, K0 * 2, 4 * (uint64_t)P * K0 * 2, 64, big::BM))) return rc;
         if ((rc = make_tmap_bf16_3d(&mXl, wk + t.phis_lo, K0, 4 * (uint64_t)P, 1, K0 * 2, 4 * (uint64_t)P * K0 * 2, 64, big::BM))) return rc;
-        if ((rc = make_tmap_bf16_3d(&mVh, wk + t.w0v_hi, K0, L * H, 1, K0 * 2, L * H * K0 * 2, 64, big::BN / 2))) return rc;
-        if ((rc = make_tmap_bf16_3d(&mVl, wk + t.w0v_lo, K0, L * H, 1, K0 * 2, L * H * K0 * 2, 64, big::BN / 2))) return rc;
         BigShape sv2{};
         sv2.m_tiles = cdiv(4L * P, 2 * big::BM);
         sv2.n_tiles = cdiv(L * H, big::BN);
@@ -2954,10 +3015,9 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
         sv2.k_chunks_total = cdiv(K0, big::BK);
         sv2.k_chunks_per_slice = sv2.k_chunks_total;
         sv2.m_group = 16;
-        L0ValEpi ev{pr.b[0], plan, BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), P, (int)L};
+        L0ValEpi ev{pr.b[0], plan, BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), 4L * P, (long)P, (long)P * H, 4L * P * H, (int)L};
         {
           ProfScope ps(KC_L0_FWD, st);
-          static const int sub = env_int("NSVD_L0_SUBCHUNKS", 4), sub_first = env_int("NSVD_L0_SUBFIRST", 6);
           if ((rc = launch_big2s<false, L0ValEpi, kFmtHH>(mXh, mXl, mVh, mVl, sv2, 1, sub, sub_first, ev, st))) return rc;
         }
         a.vmode = 1;
