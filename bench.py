@@ -189,10 +189,10 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # problem builders (the product API only: no oracle, no test code) and per-config timing
 # ------------------------------------------------------------------------------------------
-def script_args(kind, neigs, laplacian_eps=0.0):
+def script_args(kind, neigs, laplacian_eps=0.0, ndim=2):
     """Hyper-parameters of scripts/exps/pde/{hydrogen,oscillator}.sh with BASELINE's L."""
     from types import SimpleNamespace
-    base = dict(problem="sch", ndim=2, neigs=neigs, charge=1.0, laplacian_eps=laplacian_eps, lim=50.0, use_fourier_feature=True,
+    base = dict(problem="sch", ndim=ndim, neigs=neigs, charge=1.0, laplacian_eps=laplacian_eps, lim=50.0, use_fourier_feature=True,
                 fourier_deterministic=False, fourier_append_raw=False, mlp_hidden_dims="128,128,128",
                 nonlinearity="softplus", parallel=True, apply_boundary=False, boundary_mode="dir_box_sqrt",
                 hard_mul_const=1.0)
@@ -206,9 +206,9 @@ def script_args(kind, neigs, laplacian_eps=0.0):
     return SimpleNamespace(**base)
 
 
-def make_problem(N, kind, neigs, sequential, dev, seed=0, laplacian_eps=0.0):
+def make_problem(N, kind, neigs, sequential, dev, seed=0, laplacian_eps=0.0, ndim=2):
     import torch
-    cfg = script_args(kind, neigs, laplacian_eps)
+    cfg = script_args(kind, neigs, laplacian_eps, ndim)
     torch.manual_seed(seed)
     operator, _gt = N.get_problem(cfg)
     model = N.get_wavefunctions(cfg)
@@ -525,6 +525,19 @@ def run_ours(args):
             ms32 = time_events(step32, 2, 1, lambda: torch.cuda.synchronize(dev))
             configs["fp32_engine_headline_workload"] = {"points": P, "ms_per_step": ms32, "points_per_s": P / (ms32 * 1e-3)}
             del m32, x32
+            # ndim = 3 hydrogen (pde/problems.py:62-68): five forward-mode streams on the CUDA-core engine
+            c3, m3, o3, i3 = make_problem(N, "hydrogen", args.neigs, False, dev, ndim=3)
+            x3 = (c3.sampling_scale * torch.randn((16384, 1, 3))).reshape(16384, 3).to(dev)
+
+            def step3d():
+                m3.zero_grad(set_to_none=True)
+                loss, _ = m3.compute_loss_operator(o3, x3, importance=i3)
+                loss.backward()
+
+            ms3 = time_events(step3d, 3, 1, lambda: torch.cuda.synchronize(dev))
+            configs["hydrogen_ndim3_fp32_engine"] = {"points": 16384, "neigs": args.neigs, "ms_per_step": ms3,
+                                                     "points_per_s": 16384 / (ms3 * 1e-3)}
+            del m3, x3
             N.set_engine(args.engine)
             torch.cuda.empty_cache()
         configs["config4_hydrogen_2p20_L64_strong"] = strong_scaling_config(N, dev, dp, world, rank)
