@@ -2481,6 +2481,7 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
         tma_load_3d(st + 2 * HPLANE + HCHUNK, &tmAh, &full[s], 64, pa, l);
         tma_load_3d(st + 3 * HPLANE, &tmAl, &full[s], 0, pa, l);
         tma_load_3d(st + 3 * HPLANE + HCHUNK, &tmAl, &full[s], 64, pa, l);
+        NSVD_TL(j, 0);
       }
     }
   } else if (warp == 1) {
@@ -2506,6 +2507,7 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
         ++hrun;
         mbar_wait(&full[s], (uint32_t)(u & 1), 43);   // implies stage s and TMEM buffer s were released
         tc_fence_after();
+        NSVD_TL(j, 1);
         const uint32_t z_hi = smem_u32(sS + s * B2_STAGE), z_lo = z_hi + HPLANE;
         const uint32_t a_hi = z_hi + 2 * HPLANE, a_lo = z_hi + 3 * HPLANE;
         const uint32_t acc = tmem_base + (uint32_t)s * HROWS;
@@ -2528,6 +2530,7 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
           umma_f16(tmem_w, ah, bh, idesc_w, 1u);
         }
         umma_commit(&mma_done[s]);
+        NSVD_TL(j, 2);
       }
     }
   } else if (warp == 3) {
@@ -2545,6 +2548,7 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
         tma_store_commit();
         tma_store_wait_read();
         mbar_arrive(&empty[s]);
+        NSVD_TL(j, 5);
       }
       __syncwarp();
     }
@@ -2578,6 +2582,7 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
       ++hrun;
       mbar_wait(&mma_done[s], (uint32_t)(u & 1), 45);
       tc_fence_after();
+      if (warp == 4 && lane == 0) NSVD_TL(j, 3);
       float v[16];
       tmem_ld16(tl + (uint32_t)(s * HROWS + cg * 16), v);
       uint8_t* st = sS + s * B2_STAGE;
@@ -2623,6 +2628,7 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
       }
       fence_proxy_async_smem();
       tc_fence_before();
+      if (warp == 4 && lane == 0) NSVD_TL(j, 4);
       named_bar_arrive(2 + s, NBAR);
     }
   }
