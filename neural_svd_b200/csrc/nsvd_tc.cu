@@ -1628,7 +1628,7 @@ constexpr int HROWS = 64;
 constexpr int HCHUNK = HROWS * 128;       // [64 rows][128 B]
 constexpr int HPLANE = 2 * HCHUNK;        // one 64 x 128 bf16 plane
 constexpr int B2_STAGE = 4 * HPLANE;      // dZ hi | dZ lo | a hi | a lo  = 64 KB
-constexpr int SMEM_BWD2 = 2 * PLANE + 2 * B2_STAGE + 1024 + 1024;
+constexpr int SMEM_BWD2 = 2 * PLANE + 2 * B2_STAGE + 2 * HPLANE + 1024 + 1024;   // W | 2 stages | output staging
 }  // namespace hid
 
 // Optional phase timeline of block 0 (development builds: nvcc -DNSVD_TIMELINE; see profiles/timeline_probe.py)
@@ -2406,10 +2406,11 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;                 // W_i^T hi | lo  (128 rows k, K = j)
   uint8_t* sS = smem + 2 * PLANE;     // 2 stages
-  uint64_t* bars = (uint64_t*)(sS + 2 * B2_STAGE);
+  uint8_t* sOut = sS + 2 * B2_STAGE;  // output staging: dZ_{i-1} half tile hi | lo (32 KB), drained by the store warp
+  uint64_t* bars = (uint64_t*)(sOut + 2 * HPLANE);
   uint64_t* full = bars;              // [2] stage landed
   uint64_t* mma_done = bars + 2;      // [2] dgrad + wgrad of the stage retired
-  uint64_t* empty = bars + 4;         // [2] stage drained (stores have read it), TMEM buffer free
+  uint64_t* empty = bars + 4;         // [2] the 16 epilogue warps are done with the stage and its TMEM buffers
   uint64_t* wfull = bars + 6;
   uint32_t* tmem_slot = (uint32_t*)(bars + 7);
 
@@ -2435,7 +2436,7 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&mma_done[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], F_EPI_WARPS);
     }
     mbar_init(wfull, 1);
     fence_barrier_init();
@@ -2540,17 +2541,16 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
       const int l = t / h_tiles, ht = t % h_tiles;
       named_bar_sync(2 + s, NBAR);
       if (lane == 0) {
-        const uint8_t* st = sS + s * B2_STAGE;
-        tma_store_3d(&tmOh, st, 0, ht * HROWS, l);
-        tma_store_3d(&tmOh, st + HCHUNK, 64, ht * HROWS, l);
-        tma_store_3d(&tmOl, st + HPLANE, 0, ht * HROWS, l);
-        tma_store_3d(&tmOl, st + HPLANE + HCHUNK, 64, ht * HROWS, l);
+        tma_store_3d(&tmOh, sOut, 0, ht * HROWS, l);
+        tma_store_3d(&tmOh, sOut + HCHUNK, 64, ht * HROWS, l);
+        tma_store_3d(&tmOl, sOut + HPLANE, 0, ht * HROWS, l);
+        tma_store_3d(&tmOl, sOut + HPLANE + HCHUNK, 64, ht * HROWS, l);
         tma_store_commit();
         tma_store_wait_read();
-        mbar_arrive(&empty[s]);
         NSVD_TL(j, 5);
       }
       __syncwarp();
+      if (t + 1 < t_end) named_bar_arrive(4, NBAR);   // the staging buffer may be written again
     }
     if (lane == 0) tma_store_wait_all();
   } else if (warp >= 4) {
@@ -2585,8 +2585,9 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
       if (warp == 4 && lane == 0) NSVD_TL(j, 3);
       float v[16];
       tmem_ld16(tl + (uint32_t)(s * HROWS + cg * 16), v);
-      uint8_t* st = sS + s * B2_STAGE;
+      const uint8_t* st = sS + s * B2_STAGE;
       tmem_ld_wait();
+      uint32_t packed[16];                // hi | lo << 16 of this thread's 16 outputs
       // rows beyond P carry dZ_i = 0 (TMA zero fill), hence D1 = 0 and the product is 0 without a mask
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -2599,8 +2600,7 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
         dbacc += val;
         uint16_t h16, l16;
         split1<PF_HH>(val * sdz, h16, l16);
-        *reinterpret_cast<uint16_t*>(st + off) = h16;
-        *reinterpret_cast<uint16_t*>(st + HPLANE + off) = l16;
+        packed[i] = (uint32_t)h16 | ((uint32_t)l16 << 16);
       }
       const bool last_of_run = (t + 1 == t_end) || ((t + 1) / h_tiles != l);
       if (last_of_run || (hrun % kWgradFlush) == 0) {       // the wgrad chain in buffer cidx & 1 is complete
@@ -2626,8 +2626,20 @@ hidden_bwd2_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_consta
         atomicAdd(args.db_prev + l * kHidden + k, dbacc);
         dbacc = 0.f;
       }
-      fence_proxy_async_smem();
+      // the stage (dZ_i, a_{i-1}) and both TMEM buffers of this half tile are no longer needed: hand them back now - the
+      // producer reloads the stage while the outputs are staged and stored from their own buffer
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (j > 0) named_bar_sync(4, NBAR);       // the store of the previous half tile has read the staging buffer
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int pt = cg * 16 + i;
+        const uint32_t off = koff + (uint32_t)(pt * 128 + ((piece ^ (pt & 7)) << 4));
+        *reinterpret_cast<uint16_t*>(sOut + off) = (uint16_t)(packed[i] & 0xffffu);
+        *reinterpret_cast<uint16_t*>(sOut + HPLANE + off) = (uint16_t)(packed[i] >> 16);
+      }
+      fence_proxy_async_smem();
       if (warp == 4 && lane == 0) NSVD_TL(j, 4);
       named_bar_arrive(2 + s, NBAR);
     }
