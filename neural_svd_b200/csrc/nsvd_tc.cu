@@ -97,6 +97,9 @@ struct BigShape {
                                             // while every (batch, n-tile) of B sweeps over them
   int k_group;                              // k-slices per group (0 = off): same idea for the weight-gradient GEMM,
                                             // whose long dimension is K (points)
+  int b_group;                              // batches per group (0 = off), K-major GEMMs with k_slices = 1: a group of
+                                            // batches (copies) keeps its B tiles (weights) L2-resident while the m-tiles
+                                            // stream past it ONCE per group - order: group, m-tile, (batch, n-tile) fastest
   int a_xbatch;                             // big2s, MN-major: batches of A are column blocks of ONE matrix, batch b starts
                                             // at column b * a_xbatch (0 = batches are the third TMA coordinate)
 };
@@ -105,6 +108,21 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const BigShape& s, int t) {
   TileCoord c;
+  if (s.b_group > 0) {
+    const int G = s.b_group;
+    const int per_group_full = G * s.n_tiles * s.m_tiles;
+    const int g = t / per_group_full;
+    t -= g * per_group_full;
+    const int b0 = g * G;
+    const int gb = (s.batches - b0) < G ? (s.batches - b0) : G;   // batches in this (possibly last, smaller) group
+    const int inner = gb * s.n_tiles;
+    c.mt = t / inner;
+    t -= c.mt * inner;
+    c.nt = t % s.n_tiles;
+    c.b = b0 + t / s.n_tiles;
+    c.ks = 0;
+    return c;
+  }
   if (s.k_group > 0) {   // k-slice groups outermost; inside a group: ks fastest, then mt, nt, batch
     const int G = s.k_group;
     const int per_group_full = G * s.m_tiles * s.n_tiles * s.batches;
@@ -570,6 +588,7 @@ big2s_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol_keep = l2_policy_evict_last();
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         TileCoord c = decode_tile(shape, t);
         const int kc0 = c.ks * shape.k_chunks_per_slice;
@@ -587,8 +606,13 @@ big2s_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             const int arow = (2 * c.mt + (int)rank) * BM, brow = c.nt * BN + (int)rank * (BN / 2);
             tma_load_3d_pair(sA, &tmAh, lead_full, kc * BK, arow, ab);
             tma_load_3d_pair(sA + A_BYTES, &tmAl, lead_full, kc * BK, arow, ab);
-            tma_load_3d_pair(sB, &tmBh, lead_full, kc * BK, brow, bb);
-            tma_load_3d_pair(sB + BH_BYTES, &tmBl, lead_full, kc * BK, brow, bb);
+            if (shape.b_group > 0) {   // the weight tiles of the copy group are re-read for every m-tile: keep them in the L2
+              tma_load_3d_pair_hint(sB, &tmBh, lead_full, kc * BK, brow, bb, pol_keep);
+              tma_load_3d_pair_hint(sB + BH_BYTES, &tmBl, lead_full, kc * BK, brow, bb, pol_keep);
+            } else {
+              tma_load_3d_pair(sB, &tmBh, lead_full, kc * BK, brow, bb);
+              tma_load_3d_pair(sB + BH_BYTES, &tmBl, lead_full, kc * BK, brow, bb);
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -2926,8 +2950,9 @@ int tc_forward(const nsvd_problem_t& pb, const nsvd_params_t& pr, const float* x
     s.k_chunks_per_slice = s.k_chunks_total;
     s.a_batched = 0;
     s.b_batched = 1;
-    static const int mgroup = env_int("NSVD_L0_MGROUP", 16);
+    static const int mgroup = env_int("NSVD_L0_MGROUP", 16), bgroup = env_int("NSVD_L0_BGROUP", 0);
     s.m_group = mgroup;   // 4096 points x 8 KB of Phi per group
+    s.b_group = bgroup;   // alternative order: copies per group, Phi streamed once per group (profiles/README.md)
     L0FwdEpi e0{pr.b[0], plan, BF(wk + t.str_hi[0]), BF(wk + t.str_lo[0]), BF(sv + t.av_hi[0]), BF(sv + t.av_lo[0]), P, B, p0};
     const bool fd = pb.fd_eps > 0.f;
     if (!fd) {   // (finite-difference mode needs no derivative streams: its central pass is value-only, below)
