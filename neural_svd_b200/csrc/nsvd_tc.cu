@@ -30,9 +30,39 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// A training loop encodes the same ~45 descriptors every step (same scratch buffers, same shapes): the encoded maps are
+// memoised per host thread in a small direct-mapped table keyed by every argument of the encoding (a descriptor is a
+// pure function of them), which takes the driver call out of the launch-bound small-batch steps.
+struct TmapKey {
+  const void* base;
+  uint64_t d0, d1, d2, s1, s2;
+  uint32_t box0, box1;
+  int swizzle, valid;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 && box0 == o.box0 &&
+           box1 == o.box1 && swizzle == o.swizzle && valid == o.valid;
+  }
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+};
+constexpr int kTmapSlots = 512;
+
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1,
                       int swizzle_bytes) {
+  static thread_local TmapSlot* table = nullptr;
+  if (!table) table = new TmapSlot[kTmapSlots]();   // (zero-initialised: valid = 0; lives as long as the thread)
+  const TmapKey key{base, d0, d1, d2, stride1_bytes, stride2_bytes, box0, box1, swizzle_bytes, 1};
+  uint64_t h = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
+  h ^= (d1 + 0x632BE59BD9B4E019ull * d2 + ((uint64_t)box1 << 20) + ((uint64_t)box0 << 8) + (uint64_t)swizzle_bytes) *
+       0xC2B2AE3D27D4EB4Full;
+  TmapSlot& slot = table[(h >> 40) % kTmapSlots];
+  if (slot.key == key) {
+    *out = slot.map;
+    return 0;
+  }
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -53,6 +83,8 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
               (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, box0, box1);
     return NSVD_E_BADARG;
   }
+  slot.key = key;
+  slot.map = *out;
   return 0;
 }
 

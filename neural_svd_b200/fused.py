@@ -46,13 +46,41 @@ def _require_cuda(dev: torch.device):
 # ------------------------------------------------------------------------------------------
 # model / problem description (duck-typed: the reference's own modules are accepted)
 # ------------------------------------------------------------------------------------------
+def _param_objects(plist):
+    """The Parameter objects of an nn.ParameterList without its per-item string indexing (a few us per item)."""
+    d = getattr(plist, "_parameters", None)
+    return tuple(d.values()) if d else tuple(plist)
+
+
 def describe_model(model):
-    """Pull the parameter tensors out of WaveFunctions(ParallelMLP(GaussianFourierFeatureTransform))."""
+    """Pull the parameter tensors out of WaveFunctions(ParallelMLP(GaussianFourierFeatureTransform)).
+
+    The structural checks run once per module: the description is cached on it and reused while the parameter OBJECTS
+    (held by the cache, so their identities cannot be recycled), their dtypes / devices and the scalar settings are
+    unchanged.  Data pointers are never cached - the kernels always receive the tensors' current storage."""
     m = getattr(model, "model", model)          # NestedLoRA(...) -> .model
     base = getattr(m, "base", None)
     if base is None or not hasattr(base, "ws") or not hasattr(base, "bs"):
         raise NotImplementedError("fused path needs WaveFunctions(base=ParallelMLP(...)) (--parallel 1)")
     fm = getattr(base, "feature_map", None)
+    mask = getattr(m, "boundary_mask", None)
+    scales = getattr(mask, "scales", None)
+    box = mask if scales is None else getattr(mask, "boundary_mask", None)
+    objs = (fm, getattr(fm, "_B", None)) + _param_objects(base.ws) + _param_objects(base.bs) + (scales, box)
+    settings = (getattr(fm, "append_raw", False), getattr(base, "weight_normalization", False), getattr(base, "bias", True),
+                getattr(m, "hard_mul_const", 1.0), getattr(box, "mode", None), getattr(box, "lim", None),
+                tuple((t.dtype, t.device) for t in objs[1:-1] if t is not None))
+    hit = m.__dict__.get("_nsvd_md")
+    if (hit is not None and hit[1] == settings and len(hit[0]) == len(objs)
+            and all(a is b for a, b in zip(hit[0], objs))):
+        if fm._B._version == hit[3]:     # (a non-contiguous _B is described through a copy: redo it when _B changes)
+            return hit[2]
+    md = _describe_model_uncached(m, base, fm, mask, scales, box)
+    m.__dict__["_nsvd_md"] = (objs, settings, md, fm._B._version)
+    return md
+
+
+def _describe_model_uncached(m, base, fm, mask, scales, box):
     if fm is None or not hasattr(fm, "_B") or getattr(fm, "append_raw", False):
         raise NotImplementedError("fused path needs the Fourier feature map without raw append")
     if getattr(base, "weight_normalization", False) or not getattr(base, "bias", True):
@@ -72,9 +100,6 @@ def describe_model(model):
           and tuple(bs[3].shape) == (L, 1, 1))
     if not ok:
         raise NotImplementedError("unexpected ParallelMLP parameter shapes for the fused path")
-    mask = getattr(m, "boundary_mask", None)
-    scales = getattr(mask, "scales", None)
-    box = mask if scales is None else getattr(mask, "boundary_mask", None)
     box_mode, box_lim = _describe_box(box)
     params = [Bff] + ws + bs + ([scales] if scales is not None else [])
     for p in params:
@@ -190,10 +215,11 @@ def _forward_kernels(lib, owner, md, od, imp, x, engine):
     F = torch.empty((B, L), dtype=torch.float32, device=dev)
     TF = torch.empty((B, L), dtype=torch.float32, device=dev)
     pr = _params_struct(md)
+    st = _stream(dev)
     _lib.check(lib.nsvd_fwd_streams(C.byref(pb), C.byref(pr), engine, _lib.ptr(x), _lib.ptr(F), _lib.ptr(TF),
                                     _lib.ptr(sc.saved), sc.saved.numel(), _lib.ptr(sc.work), sc.work.numel(),
-                                    _stream(dev)), "nsvd_fwd_streams")
-    return x, pb, pr, sc, F, TF
+                                    st), "nsvd_fwd_streams")
+    return x, pb, pr, sc, F, TF, st
 
 
 def apply_operator(model, operator, x, importance):
@@ -202,7 +228,7 @@ def apply_operator(model, operator, x, importance):
     md, od = describe_model(model), describe_operator(operator)
     imp = describe_importance(importance, md["ndim"])
     with torch.no_grad():
-        _, _, _, _, F, TF = _forward_kernels(lib, getattr(model, "model", model), md, od, imp, x, engine_for(md))
+        _, _, _, _, F, TF, _ = _forward_kernels(lib, getattr(model, "model", model), md, od, imp, x, engine_for(md))
     return TF, F
 
 
@@ -212,8 +238,8 @@ def model_values(model, x):
     md = describe_model(model)
     od = dict(potential=_lib.POT_INFINITE_WELL, pot_coef=0.0, scale_kinetic=1.0, op_scale=1.0, op_shift=0.0)
     with torch.no_grad():
-        _, _, _, _, F, _ = _forward_kernels(lib, getattr(model, "model", model), md, od,
-                                            dict(importance=_lib.IMP_NONE, sigma=1.0), x, engine_for(md))
+        _, _, _, _, F, _, _ = _forward_kernels(lib, getattr(model, "model", model), md, od,
+                                               dict(importance=_lib.IMP_NONE, sigma=1.0), x, engine_for(md))
     return F
 
 
@@ -227,14 +253,14 @@ class _FusedOperatorStep(torch.autograd.Function):
         md, od = describe_model(method), describe_operator(operator)
         imp = describe_importance(importance, md["ndim"])
         engine = engine_for(md)
-        x, pb, pr, sc, F, TF = _forward_kernels(lib, method, md, od, imp, x, engine)
+        x, pb, pr, sc, F, TF, st = _forward_kernels(lib, method, md, od, imp, x, engine)
         dev = F.device
         B, L = F.shape
         b1 = (B + 1) // 2                                     # torch.chunk(f, 2), nestedlora.py:263
         v, Mm = _nesting_masks(method, dev)
         terms = torch.empty(2 * L * L + 5, dtype=torch.float32, device=dev)   # + 4 count floats (data parallel)
         _lib.check(lib.nsvd_gram_reduce(_lib.ptr(F), _lib.ptr(TF), _lib.ptr(v), B, L, b1, _lib.ptr(terms),
-                                        _lib.ptr(sc.partials), _stream(dev)), "nsvd_gram_reduce")
+                                        _lib.ptr(sc.partials), st), "nsvd_gram_reduce")
         Bg, B1g, B2g = B, b1, B - b1
         if dp is not None:
             dp.allreduce_terms(terms, B, b1)                  # all-reduce #1; the global counts travel inside it
@@ -242,7 +268,7 @@ class _FusedOperatorStep(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=dev)
         coef = torch.empty(2 * L * L + 1, dtype=torch.float32, device=dev)
         _lib.check(lib.nsvd_loss_finalize(_lib.ptr(terms), _lib.ptr(Mm), L, Bg, B1g, B2g, _lib.ptr(loss),
-                                          _lib.ptr(coef), _stream(dev)), "nsvd_loss_finalize")
+                                          _lib.ptr(coef), st), "nsvd_loss_finalize")
         ctx.state = dict(md=md, pb=pb, sc=sc, version=sc.version, x=x, F=F, TF=TF, v=v, coef=coef, b1=b1,
                          Bg=Bg, engine=engine, dp=dp, nparams=len(params))
         ctx.mark_non_differentiable(F, TF)
@@ -260,9 +286,10 @@ class _FusedOperatorStep(torch.autograd.Function):
         dev = F.device
         B, L = F.shape
         gl = gloss.to(device=dev, dtype=torch.float32).contiguous()
+        st = _stream(dev)                # the backward engine's stream for this device
         dF = torch.empty_like(F)
         _lib.check(lib.nsvd_loss_dF(_lib.ptr(F), _lib.ptr(TF), _lib.ptr(s["v"]), _lib.ptr(s["coef"]), _lib.ptr(gl),
-                                    B, L, s["b1"], s["Bg"], _lib.ptr(dF), _stream(dev)), "nsvd_loss_dF")
+                                    B, L, s["b1"], s["Bg"], _lib.ptr(dF), st), "nsvd_loss_dF")
         tensors = md["ws"] + md["bs"] + ([md["scales"]] if md["scales"] is not None else [])
         sizes = [t.numel() for t in tensors]
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
@@ -275,7 +302,7 @@ class _FusedOperatorStep(torch.autograd.Function):
         pr = _params_struct(md)
         _lib.check(lib.nsvd_mlp_bwd(C.byref(pb), C.byref(pr), s["engine"], _lib.ptr(s["x"]), _lib.ptr(dF),
                                     _lib.ptr(sc.saved), sc.saved.numel(), C.byref(gr), _lib.ptr(sc.work),
-                                    sc.work.numel(), _stream(dev)), "nsvd_mlp_bwd")
+                                    sc.work.numel(), st), "nsvd_mlp_bwd")
         if s["dp"] is not None:
             s["dp"].allreduce_grads(flat)                      # all-reduce #2
         # params were passed as (Bff, ws0..3, bs0..3[, scales]); Bff gets no gradient (utils.py:116-118)
@@ -287,24 +314,35 @@ def _sort_permutation(method):
     si = getattr(method, "sort_indices", None)
     if si is None or not getattr(method, "training", True):
         return None
-    return si.to(torch.long)
+    return si
 
 
 def _nesting_masks(method, dev):
     """(vector_mask, matrix_mask) on the device.  With registered eigenvalues the reference permutes the model's OUTPUT
     columns, f'[:, j] = f[:, s_j] (nestedlora.py:197-198), before the loss; the loss of f' under (v, M) equals the loss of
     the unpermuted f under v'[s_j] = v[j], M'[s_j, s_k] = M[j, k], so the kernels run on the network's own column order
-    with permuted masks and dF comes out in that order too."""
-    v = method.vector_mask.to(device=dev, dtype=torch.float32)
-    Mm = method.matrix_mask.to(device=dev, dtype=torch.float32)
-    si = _sort_permutation(method)
+    with permuted masks and dF comes out in that order too.
+    The reference keeps the masks on the CPU and moves them every call (nestedlora.py:87-88: two pageable H2D copies,
+    ~60 us of host time per step); here the device copies are cached until the mask / sort_indices objects or their
+    contents (tensor version counters) change."""
+    vm, mm, si = method.vector_mask, method.matrix_mask, _sort_permutation(method)
+    ver = (vm._version, mm._version, -1 if si is None else si._version, dev)
+    hit = method.__dict__.get("_nsvd_masks")
+    if hit is not None and hit[0] is vm and hit[1] is mm and hit[2] is si and hit[3] == ver:
+        return hit[4], hit[5]
+    v = vm.to(device=dev, dtype=torch.float32)
+    Mm = mm.to(device=dev, dtype=torch.float32)
     if si is not None:
-        si = si.to(dev)
+        sd = si.to(device=dev, dtype=torch.long)
         v2, M2 = torch.empty_like(v), torch.empty_like(Mm)
-        v2[si] = v
-        M2[si[:, None], si[None, :]] = Mm
+        v2[sd] = v
+        M2[sd[:, None], sd[None, :]] = Mm
         v, Mm = v2, M2
-    return v.contiguous(), Mm.contiguous()
+    v, Mm = v.contiguous(), Mm.contiguous()
+    if v is vm or Mm is mm:              # already on the device in fp32: `.to` returned the caller's own tensors
+        v, Mm = v.clone(), Mm.clone()    # (the cache must not alias what the caller may modify between steps)
+    method.__dict__["_nsvd_masks"] = (vm, mm, si, ver, v, Mm)
+    return v, Mm
 
 
 def compute_loss_operator(method, operator, x, importance, dp=None):
@@ -316,6 +354,6 @@ def compute_loss_operator(method, operator, x, importance, dp=None):
     loss, F, TF = _FusedOperatorStep.apply(method, operator, importance, x, dp, *params)
     si = _sort_permutation(method)
     if si is not None:                       # the caller sees the permuted columns, as operator(self, x) returns them
-        si = si.to(F.device)
+        si = si.to(device=F.device, dtype=torch.long)
         F, TF = F[:, si], TF[:, si]
     return loss, dict(f=F, Tf=TF, eigvals=None)

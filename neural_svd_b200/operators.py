@@ -165,13 +165,30 @@ def describe_operator(operator):
 _IMP_CODES = {"gaussian": 0, "laplacian": 1, "uniform": 2}
 
 
+_IMP_SEEN = []   # [(closure, dim, description)], newest first: a training loop passes the SAME closure every step
+
+
 def describe_importance(importance, dim=2) -> dict:
     """{importance: NSVD_IMP_* code, sigma: scale} of the sampler's density.  Accepts the classes above, `None`
     (no re-weighting, diff_ops.py:10-11) and the reference's own `importance_train` closures: over a zero-mean
     isotropic MultivariateNormal (main_pde.py:94-100) or over `args` with sampling_mode laplacian / uniform
-    (main_pde.py:101-118)."""
+    (main_pde.py:101-118).  Inspecting a closure reads its distribution's tensors back to the host (a device
+    synchronisation), so the result is remembered per closure object; the classes above are read every call."""
     if importance is None:
         return dict(importance=3, sigma=1.0)
+    if not hasattr(importance, "sampling_scale"):
+        for obj, d, desc in _IMP_SEEN:
+            if obj is importance and d == dim:
+                return dict(desc)
+        desc = _describe_importance(importance, dim)
+        if desc.pop("_from_tensors", False):      # (a closure over a mutable `args` namespace is cheap and re-read)
+            _IMP_SEEN.insert(0, (importance, dim, dict(desc)))
+            del _IMP_SEEN[8:]
+        return desc
+    return _describe_importance(importance, dim)
+
+
+def _describe_importance(importance, dim) -> dict:
     if hasattr(importance, "sampling_scale"):
         mode = getattr(importance, "sampling_mode", "gaussian")
         if getattr(importance, "dim", dim) != dim:
@@ -186,12 +203,12 @@ def describe_importance(importance, dim=2) -> dict:
             d = cov.shape[0]
             if d != dim or loc.abs().max() != 0 or not torch.allclose(cov, cov[0, 0] * torch.eye(d, dtype=cov.dtype)):
                 raise NotImplementedError(f"importance must be a zero-mean isotropic Gaussian in {dim}D")
-            return dict(importance=0, sigma=float(cov[0, 0].sqrt()))
+            return dict(importance=0, sigma=float(cov[0, 0].sqrt()), _from_tensors=True)
         if type(obj).__name__ == "Laplace" and hasattr(obj, "loc") and hasattr(obj, "scale"):
             loc, sc = obj.loc.detach().cpu().double().reshape(-1), obj.scale.detach().cpu().double().reshape(-1)
             if loc.numel() != dim or loc.abs().max() != 0 or (sc != sc[0]).any():
                 raise NotImplementedError(f"importance must be a zero-mean Laplace density with one scale in {dim}D")
-            return dict(importance=1, sigma=float(sc[0]))
+            return dict(importance=1, sigma=float(sc[0]), _from_tensors=True)
         mode = getattr(obj, "sampling_mode", None)          # the `args` namespace the closure reads
         if mode in ("laplacian", "uniform") and hasattr(obj, "sampling_scale"):
             if getattr(obj, "ndim", dim) != dim or getattr(obj, "n_particles", 1) != 1:

@@ -199,3 +199,50 @@ def test_sketchy_encoder_shapes_and_cpu_guards():
     lap = Laplace(torch.zeros(2), 2.5 * torch.ones(2))
     closure = lambda x: lap.log_prob(x).sum(-1).exp().view(-1, 1)  # noqa: E731
     assert operators.describe_importance(closure) == dict(importance=1, sigma=2.5)
+
+
+def test_description_and_mask_caches_follow_their_sources():
+    """The per-step host work (structural checks of the module, the reference's CPU-resident masks moved to the device,
+    nestedlora.py:87-88) is cached; the caches must notice every change of what they describe."""
+    cfg = O.PathConfig.hydrogen()
+    method, operator, importance, _ = build_problem(cfg, 0)
+    md = fused.describe_model(method)
+    assert fused.describe_model(method) is md                      # same module, same parameter objects: a hit
+    assert md["ws"][0] is method.model.base.ws[0]                  # the caller's own Parameter objects, never copies
+    method.model.hard_mul_const = 3.0                              # a scalar setting changes
+    md2 = fused.describe_model(method)
+    assert md2 is not md and md2["hard_mul_const"] == 3.0
+    method.model.base.ws[1] = torch.nn.Parameter(torch.zeros_like(method.model.base.ws[1]))   # a parameter is replaced
+    md3 = fused.describe_model(method)
+    assert md3 is not md2 and md3["ws"][1] is method.model.base.ws[1]
+    method.model.base.double()                                     # dtype changes under the same Parameter objects
+    with pytest.raises(NotImplementedError):
+        fused.describe_model(method)
+
+    method, operator, importance, _ = build_problem(cfg, 0)
+    dev = torch.device("cpu")
+    v, M = fused._nesting_masks(method, dev)
+    assert fused._nesting_masks(method, dev)[0] is v
+    assert v is not method.vector_mask and torch.equal(v, method.vector_mask)     # never an alias of the caller's tensor
+    method.vector_mask.mul_(2.0)                                   # in-place edit: the version counter moves
+    v2, _ = fused._nesting_masks(method, dev)
+    assert v2 is not v and torch.equal(v2, method.vector_mask)
+    method.matrix_mask = method.matrix_mask.clone() + 1.0          # replaced object
+    _, M2 = fused._nesting_masks(method, dev)
+    assert torch.equal(M2, method.matrix_mask)
+    method.register_eigvals(torch.arange(cfg.neigs, dtype=torch.float32))         # sort_indices appear (nestedlora.py:202-208)
+    v3, M3 = fused._nesting_masks(method, dev)
+    si = method.sort_indices
+    assert torch.equal(v3[si], method.vector_mask) and torch.equal(M3[si][:, si], method.matrix_mask)
+    method.reset_eigvals()
+    assert torch.equal(fused._nesting_masks(method, dev)[0], method.vector_mask)
+
+    from torch.distributions import MultivariateNormal
+    mvn = MultivariateNormal(torch.zeros(2), 16.0 * torch.eye(2))
+
+    def importance_train(x):
+        return mvn.log_prob(x).exp().view(-1, 1)
+    d = operators.describe_importance(importance_train)
+    assert d == dict(importance=0, sigma=4.0) and operators.describe_importance(importance_train) == d
+    d["sigma"] = -1.0                                              # the caller's copy is not the cached one
+    assert operators.describe_importance(importance_train)["sigma"] == 4.0
