@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NSVD_ABI_VERSION 4
+#define NSVD_ABI_VERSION 5
 
 enum {
   NSVD_E_BADARG = 10001,   /* shape / enum / alignment violation */
@@ -186,20 +186,25 @@ int nsvd_mlp_bwd(const nsvd_problem_t* pb, const nsvd_params_t* pr, int engine, 
  *   bwd: grad_f, grad_g (B, L).  rs_joint (B) = diag(Fp Gp^T) is produced by fwd when non-NULL;
  *   nsvd_cdk_offdiag writes off_diagonal(Fp Gp^T) (B*B-B) on request (methods/utils.py:16-22).
  *   With NSVD_ENGINE_BF16X3_TC the Grams (MN-major operands, K = rows), the backward GEMMs and
- *   Fp Gp^T run on the tcgen05 GEMM block; the row dots stay exact fp32.                        */
+ *   Fp Gp^T run on the tcgen05 GEMM block; the row dots stay exact fp32.
+ *   ABI 5: nsvd_cdk_finalize runs on many blocks and takes `scratch`, NSVD_CDK_FINALIZE_SCRATCH bytes of
+ *   device memory (8-byte aligned, contents irrelevant; the LAST that many bytes of the cdk work buffer are
+ *   reserved for it, so no extra allocation is needed).  `planes_ready` != 0 tells bwd / offdiag that `work`
+ *   still holds what nsvd_cdk_fwd built from these same f, g (the operand planes are then not rebuilt).  */
+#define NSVD_CDK_FINALIZE_SCRATCH 1024
 size_t nsvd_cdk_work_bytes(int32_t n_rows, int32_t n_feat, int32_t first_const, int engine);
 int nsvd_cdk_fwd(const float* f, const float* g, const float* vector_mask, int32_t n_rows,
                  int32_t n_feat, int32_t first_const, int engine, float* terms, float* rs_joint,
                  void* work, size_t work_bytes, void* stream);
 int nsvd_cdk_finalize(const float* terms, const float* matrix_mask, int32_t Lp, int64_t Bg,
-                      float* losses, float* coef, void* stream);
+                      float* losses, float* coef, void* scratch, void* stream);
 int nsvd_cdk_bwd(const float* f, const float* g, const float* vector_mask, const float* coef,
                  const float* grad_scale, int32_t n_rows, int32_t n_feat, int32_t first_const,
                  int64_t Bg, int engine, float* grad_f, float* grad_g, void* work, size_t work_bytes,
-                 void* stream);
+                 int32_t planes_ready, void* stream);
 int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_feat,
                      int32_t first_const, int engine, float* rs_indep, void* work, size_t work_bytes,
-                     void* stream);
+                     int32_t planes_ready, void* stream);
 
 /* ---- "next" rows of the scope table ------------------------------------------
  * Fused optimizer step for up to 16 tensors in one launch: RMSprop with momentum 0 / weight decay 0

@@ -35,6 +35,7 @@ POT_HYDROGEN, POT_HARMONIC, POT_HYDROGEN_MOL_ION, POT_INFINITE_WELL, POT_COSINE 
 IMP_GAUSSIAN, IMP_LAPLACE, IMP_UNIFORM, IMP_NONE = 0, 1, 2, 3
 BOX_NONE, BOX_SQRT, BOX_EXP = 0, 1, 2
 ENGINE_FP32_SIMT, ENGINE_F16X3_TC = 0, 1
+CDK_FINALIZE_SCRATCH = 1024      # NSVD_CDK_FINALIZE_SCRATCH (include/nsvd.h)
 # "f16x3": tcgen05 tensor cores, every fp32 operand as two fp16 planes (three bf16 products in the CDK loss);
 # "bf16x3" is the round-1 name of the same engine slot and stays accepted.
 ENGINES = {"fp32": ENGINE_FP32_SIMT, "fp32_simt": ENGINE_FP32_SIMT, "f16x3": ENGINE_F16X3_TC, "tc": ENGINE_F16X3_TC,
@@ -64,9 +65,9 @@ SIGNATURES = {
     "nsvd_mlp_bwd": (C.c_int, [_PB, _PR, C.c_int, _vp, _vp, _vp, _sz, _GR, _vp, _sz, _vp]),
     "nsvd_cdk_work_bytes": (_sz, [_i32, _i32, _i32, C.c_int]),
     "nsvd_cdk_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, C.c_int, _vp, _vp, _vp, _sz, _vp]),
-    "nsvd_cdk_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
-    "nsvd_cdk_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, C.c_int, _vp, _vp, _vp, _sz, _vp]),
-    "nsvd_cdk_offdiag": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_int, _vp, _vp, _sz, _vp]),
+    "nsvd_cdk_finalize": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "nsvd_cdk_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, C.c_int, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "nsvd_cdk_offdiag": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_int, _vp, _vp, _sz, _i32, _vp]),
     "nsvd_rmsprop_ema_step": (C.c_int, [_i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                                         C.POINTER(_i64), C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
     "nsvd_sample_gaussian": (C.c_int, [_vp, _i64, C.c_float, C.c_uint64, C.c_uint64, _vp]),
@@ -95,7 +96,7 @@ def load():
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)        # AttributeError if a declared symbol is missing
                 fn.restype, fn.argtypes = res, args
-            if lib.nsvd_abi_version() != 4:
+            if lib.nsvd_abi_version() != 5:
                 raise RuntimeError("libnsvd.so ABI version mismatch")
             for which, cls in enumerate((Problem, Params, Grads)):
                 if lib.nsvd_struct_size(which) != C.sizeof(cls):

@@ -223,8 +223,10 @@ int nsvd_loss_dF(const float* F, const float* TF, const float* vector_mask, cons
 }
 
 size_t nsvd_cdk_work_bytes(int32_t n_rows, int32_t n_feat, int32_t first_const, int engine) {
-  return engine == NSVD_ENGINE_BF16X3_TC ? tc_cdk_work_bytes(n_rows, n_feat, first_const)
-                                         : cdk_work_bytes(n_rows, n_feat, first_const);
+  // + the tail reserved for nsvd_cdk_finalize (and slack to align it)
+  return (engine == NSVD_ENGINE_BF16X3_TC ? tc_cdk_work_bytes(n_rows, n_feat, first_const)
+                                          : cdk_work_bytes(n_rows, n_feat, first_const)) +
+         NSVD_CDK_FINALIZE_SCRATCH + 16;
 }
 static int cdk_check(int engine, const void* work, size_t work_bytes, int n_rows, int n_feat, int fc) {
   NSVD_CHECK_ARG(engine == NSVD_ENGINE_FP32_SIMT || engine == NSVD_ENGINE_BF16X3_TC, "unknown engine %d", engine);
@@ -248,32 +250,33 @@ int nsvd_cdk_fwd(const float* f, const float* g, const float* vector_mask, int32
   return cdk_fwd(f, g, vector_mask, n_rows, n_feat, first_const, terms, rs_joint, work, (cudaStream_t)stream);
 }
 int nsvd_cdk_finalize(const float* terms, const float* matrix_mask, int32_t Lp, int64_t Bg, float* losses,
-                      float* coef, void* stream) {
+                      float* coef, void* scratch, void* stream) {
   DeviceGuard dg_(terms);
   NSVD_CHECK_ARG(terms && matrix_mask && losses && coef && Lp >= 1 && Bg >= 1, "bad args");
-  return cdk_finalize(terms, matrix_mask, Lp, Bg, losses, coef, (cudaStream_t)stream);
+  NSVD_CHECK_ARG(scratch && ((uintptr_t)scratch & 7) == 0, "scratch must be 8-byte aligned device memory");
+  return cdk_finalize(terms, matrix_mask, Lp, Bg, losses, coef, (double*)scratch, (cudaStream_t)stream);
 }
 int nsvd_cdk_bwd(const float* f, const float* g, const float* vector_mask, const float* coef,
                  const float* grad_scale, int32_t n_rows, int32_t n_feat, int32_t first_const, int64_t Bg, int engine,
-                 float* grad_f, float* grad_g, void* work, size_t work_bytes, void* stream) {
+                 float* grad_f, float* grad_g, void* work, size_t work_bytes, int32_t planes_ready, void* stream) {
   DeviceGuard dg_(f);
   NSVD_CHECK_ARG(f && g && vector_mask && coef && grad_f && grad_g, "NULL buffer");
   int rc = cdk_check(engine, work, work_bytes, n_rows, n_feat, first_const);
   if (rc) return rc;
   if (engine == NSVD_ENGINE_BF16X3_TC)
     return tc_cdk_bwd(f, g, vector_mask, coef, grad_scale, n_rows, n_feat, first_const, Bg, grad_f, grad_g, work,
-                      (cudaStream_t)stream);
+                      planes_ready, (cudaStream_t)stream);
   return cdk_bwd(f, g, vector_mask, coef, grad_scale, n_rows, n_feat, first_const, Bg, grad_f, grad_g,
                  (cudaStream_t)stream);
 }
 int nsvd_cdk_offdiag(const float* f, const float* g, int32_t n_rows, int32_t n_feat, int32_t first_const, int engine,
-                     float* rs_indep, void* work, size_t work_bytes, void* stream) {
+                     float* rs_indep, void* work, size_t work_bytes, int32_t planes_ready, void* stream) {
   DeviceGuard dg_(f);
   NSVD_CHECK_ARG(f && g && rs_indep, "NULL buffer");
   int rc = cdk_check(engine, work, work_bytes, n_rows, n_feat, first_const);
   if (rc) return rc;
   if (engine == NSVD_ENGINE_BF16X3_TC)
-    return tc_cdk_offdiag(f, g, n_rows, n_feat, first_const, rs_indep, work, (cudaStream_t)stream);
+    return tc_cdk_offdiag(f, g, n_rows, n_feat, first_const, rs_indep, work, planes_ready, (cudaStream_t)stream);
   return cdk_offdiag(f, g, n_rows, n_feat, first_const, rs_indep, (cudaStream_t)stream);
 }
 

@@ -104,8 +104,31 @@ __global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ o
   }
 }
 
+// sum of ONE vector (the CDK operator term: n_rows row dots), one block, fixed order: the general kernel above would
+// leave 8 threads adding 512 values each with dependent loads (56 us at 4096 rows)
+__global__ void __launch_bounds__(1024) vecsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M,
+                                                      int accumulate) {
+  __shared__ float sw[32];
+  float s = 0.f;
+  for (int m = threadIdx.x; m < M; m += 1024) s += X[m];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += sw[i];
+    *out = accumulate ? *out + t : t;
+  }
+}
+
 int colsum(const float* X, float* out, int M, int N, int batch, long x_bs, int accumulate,
            cudaStream_t st) {
+  if (N == 1 && batch == 1) {
+    vecsum_kernel<<<1, 1024, 0, st>>>(X, out, M, accumulate);
+    NSVD_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid(cdiv(N, 32), batch);
   colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(X, out, M, N, x_bs, accumulate);
   NSVD_LAUNCH_CHECK();
@@ -585,16 +608,19 @@ gram_stage1_kernel(const float* __restrict__ F, const float* __restrict__ TF,
 }
 
 // L == 16 specialisation (the benchmark shape): ONE launch for the whole K2.
-//   warp-cooperative register tiling: lane = (ib, jb) owns the 4 x 2 block G[4 ib + a][2 jb + c]; per row
-//   one 16-byte and one 8-byte load of the (L1-resident) 64-byte row and 8 FFMA; the operator sum is
-//   taken on a coalesced (row pair x 16) load.  Blocks [0, nb1) cover the first half of the rows, the
-//   rest the second half.  Each block writes a 257-float partial; the last block to finish (ticket
-//   counter) adds the partials in block order, so the result is deterministic.
+//   warp-cooperative register tiling: lane = (ib, jb) owns the 4 x 2 block G[4 ib + a][2 jb + c].  A warp loads row
+//   pairs with one coalesced 128-byte load per array (8 pairs per iteration, the next iteration's loads in flight while
+//   the current one is consumed), parks the F pairs in its private 1 KB of shared memory and reads its Gram operands
+//   back as ONE 16-byte and ONE 8-byte broadcast load per row (4 + 8 distinct addresses inside 64 contiguous bytes:
+//   a single wavefront each) - the first version fetched them with 6 shuffles per row and was bound by the shuffle
+//   rate (profiles/README.md).  The operator sum is taken on the coalesced registers.  Blocks [0, nb1) cover the first
+//   half of the rows, the rest the second half.  Each block writes a 257-float partial; the last block to finish
+//   (ticket counter) adds the partials in block order, so the result is deterministic.
 __global__ void __launch_bounds__(1024)
 gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, const float* __restrict__ vmask,
                     long B, long b1, int rows_per_block, int nb1, float* __restrict__ partials,
                     unsigned int* __restrict__ counter, float* __restrict__ terms) {
-  __shared__ float sacc[32][257];
+  __shared__ __align__(16) float sacc[32][257];
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int i0 = (lane >> 3) * 4, j0 = (lane & 7) * 2;
@@ -605,12 +631,8 @@ gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, c
   float acc[4][2] = {};
   float ops = 0.f;
   const float vm = vmask[lane & 15];
-  // each of the 32 warps owns row pairs (r, r+1), r = r0 + 2 warp (mod 64); 4 pairs are loaded before use
-  // (memory-level parallelism: 4 x 256 B per warp in flight, 32 KB per SM)
-  // One coalesced 128-byte load per row pair and array; the Gram operands are taken from it by shuffles.
-  // 8 row pairs per iteration and the next iteration's loads are issued before the current one is consumed
-  // (software pipeline): ~4 KB per warp = 128 KB per SM in flight, enough to cover HBM latency.
-  constexpr int U = 8;
+  constexpr int U = 8;   // row pairs per iteration: 2 x 8 x 128 B per warp and array, ~128 KB per SM in flight
+  float* stage = &sacc[0][0] + warp * (U * 32);   // this warp's 8 row pairs (16-byte aligned; sacc proper is used at the end)
   float fo[U], to[U], fn[U], tn[U];
   auto load8 = [&](long r, float* f8, float* t8) {
 #pragma unroll
@@ -627,32 +649,34 @@ gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, c
     load8(r + 64 * U, fn, tn);   // rows beyond r1 load as zeros
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      stage[u * 32 + lane] = fo[u];
       ops = fmaf(vm * fo[u], to[u], ops);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int src = 16 * k;
-        const float ax = __shfl_sync(0xffffffffu, fo[u], src + i0);
-        const float ay = __shfl_sync(0xffffffffu, fo[u], src + i0 + 1);
-        const float az = __shfl_sync(0xffffffffu, fo[u], src + i0 + 2);
-        const float aw = __shfl_sync(0xffffffffu, fo[u], src + i0 + 3);
-        const float cx = __shfl_sync(0xffffffffu, fo[u], src + j0);
-        const float cy = __shfl_sync(0xffffffffu, fo[u], src + j0 + 1);
-        acc[0][0] = fmaf(ax, cx, acc[0][0]);
-        acc[0][1] = fmaf(ax, cy, acc[0][1]);
-        acc[1][0] = fmaf(ay, cx, acc[1][0]);
-        acc[1][1] = fmaf(ay, cy, acc[1][1]);
-        acc[2][0] = fmaf(az, cx, acc[2][0]);
-        acc[2][1] = fmaf(az, cy, acc[2][1]);
-        acc[3][0] = fmaf(aw, cx, acc[3][0]);
-        acc[3][1] = fmaf(aw, cy, acc[3][1]);
+        const float4 a = *reinterpret_cast<const float4*>(stage + u * 32 + 16 * k + i0);
+        const float2 c = *reinterpret_cast<const float2*>(stage + u * 32 + 16 * k + j0);
+        acc[0][0] = fmaf(a.x, c.x, acc[0][0]);
+        acc[0][1] = fmaf(a.x, c.y, acc[0][1]);
+        acc[1][0] = fmaf(a.y, c.x, acc[1][0]);
+        acc[1][1] = fmaf(a.y, c.y, acc[1][1]);
+        acc[2][0] = fmaf(a.z, c.x, acc[2][0]);
+        acc[2][1] = fmaf(a.z, c.y, acc[2][1]);
+        acc[3][0] = fmaf(a.w, c.x, acc[3][0]);
+        acc[3][1] = fmaf(a.w, c.y, acc[3][1]);
       }
     }
+    __syncwarp();                // the next iteration overwrites the staged pairs
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       fo[u] = fn[u];
       to[u] = tn[u];
     }
   }
+  __syncthreads();               // every warp is done with its staging area before sacc is reused for the block sum
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -675,15 +699,18 @@ gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, c
   if (!s_last) return;
   __threadfence();
   const int nb = gridDim.x;
-  // warp w sums partial rows w, w+32, ... of each half; lane handles columns lane + 32 c; 4 rows in flight
-  for (int halfsel = 0; halfsel < 2; ++halfsel) {
+  // both halves at once: warps 0-15 add the partials of the first half, warps 16-31 those of the second, warp w taking
+  // rows w, w + 16, ... of its half in block order with 5 rows (40 loads per lane) in flight; lane handles columns
+  // lane + 32 c.  The 16 warp sums of a half are then added in warp order - a fixed order, so the result is deterministic.
+  {
+    const int halfsel = warp >> 4, w16 = warp & 15;
     const int pb = halfsel ? nb1 : 0, pe = halfsel ? nb : nb1;
     float a8[8] = {}, a_ops = 0.f;
-    for (int bb = pb + warp; bb < pe; bb += 128) {
-      float v[4][8], vo[4];
+    for (int bb = pb + w16; bb < pe; bb += 16 * 5) {
+      float v[5][8], vo[5];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int b2 = bb + 32 * u;
+      for (int u = 0; u < 5; ++u) {
+        const int b2 = bb + 16 * u;
         const bool ok = b2 < pe;
         const float* prow = partials + (long)(ok ? b2 : pb) * 257;
 #pragma unroll
@@ -691,7 +718,7 @@ gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, c
         vo[u] = (ok && lane == 0) ? __ldcg(prow + 256) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 5; ++u) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) a8[c] += v[u][c];
         a_ops += vo[u];
@@ -702,18 +729,18 @@ gram16_fused_kernel(const float* __restrict__ F, const float* __restrict__ TF, c
     for (int c = 0; c < 8; ++c) sacc[warp][lane + 32 * c] = a8[c];
     if (lane == 0) sacc[warp][256] = a_ops;
     __syncthreads();
-    if (tid < 256) {
+    if (tid < 512) {
+      const int hs = tid >> 8, col = tid & 255;
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 32; ++w) t += sacc[w][tid];
-      terms[halfsel * 256 + tid] = t;
+      for (int w = 0; w < 16; ++w) t += sacc[hs * 16 + w][col];
+      terms[hs * 256 + col] = t;
     }
-    if (tid == 256) {
+    if (tid == 512) {
       float o = 0.f;
 #pragma unroll
       for (int w = 0; w < 32; ++w) o += sacc[w][256];
-      if (halfsel == 0) terms[512] = o;
-      else terms[512] += o;
+      terms[512] = o;
     }
   }
   if (tid == 0) *counter = 0u;
@@ -1299,13 +1326,20 @@ int cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int fc
   return colsum(opdot, terms + 2L * Lp * Lp, B, 1, 1, 0, 0, st);
 }
 
-__global__ void cdk_finalize_kernel(const float* __restrict__ terms, const float* __restrict__ Mm,
-                                    int Lp, double Bg, float* __restrict__ losses,
-                                    float* __restrict__ coef) {
+// loss_metric = sum M (.) Lambda_f (.) Lambda_g and the two masked coefficient matrices of the backward, in fp64.
+// Lp = 513 means 263 k entries and 3.2 MB of reads: on ONE block (the first version) that is a memory-latency-bound
+// 364 us, 40 % of the whole CDK step.  Now <= 64 blocks each reduce a contiguous slice to one fp64 partial (fixed
+// in-block order) and a second one-warp launch adds the partials in block order - deterministic, ~5 us.
+constexpr int kCdkFinBlocks = 64;
+__global__ void __launch_bounds__(1024)
+cdk_finalize_kernel(const float* __restrict__ terms, const float* __restrict__ Mm, int Lp, double Bg,
+                    float* __restrict__ coef, double* __restrict__ partial) {
   __shared__ double sred[32];
-  int LL = Lp * Lp;
+  const int LL = Lp * Lp;
+  const int per = (LL + gridDim.x - 1) / gridDim.x;
+  const int e0 = blockIdx.x * per, e1 = min(LL, e0 + per);
   double s = 0.0;
-  for (int e = threadIdx.x; e < LL; e += blockDim.x) {
+  for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
     double lf = (double)terms[e] / Bg, lg = (double)terms[LL + e] / Bg;
     double m = Mm[e];
     s += m * lf * lg;
@@ -1318,6 +1352,19 @@ __global__ void cdk_finalize_kernel(const float* __restrict__ terms, const float
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sred[i];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void cdk_finalize_sum_kernel(const float* __restrict__ terms, const double* __restrict__ partial, int nb,
+                                        int Lp, double Bg, float* __restrict__ losses) {
+  double p = (int)threadIdx.x < nb ? partial[threadIdx.x] : 0.0;   // nb <= 64: all partials in flight at once
+  __shared__ double sp[kCdkFinBlocks];
+  sp[threadIdx.x] = p;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nb; ++i) t += sp[i];
+    const int LL = Lp * Lp;
     double lop = -2.0 * (double)terms[2 * LL] / Bg;
     losses[0] = (float)(lop + t);
     losses[1] = (float)lop;
@@ -1325,9 +1372,15 @@ __global__ void cdk_finalize_kernel(const float* __restrict__ terms, const float
   }
 }
 
-int cdk_finalize(const float* terms, const float* Mm, int Lp, long Bg, float* losses, float* coef,
+int cdk_finalize(const float* terms, const float* Mm, int Lp, long Bg, float* losses, float* coef, double* scratch,
                  cudaStream_t st) {
-  cdk_finalize_kernel<<<1, 1024, 0, st>>>(terms, Mm, Lp, (double)Bg, losses, coef);
+  const long LL = (long)Lp * Lp;
+  int nb = (int)((LL + 4095) / 4096);            // >= 4 entries per thread before another block pays off
+  if (nb > kCdkFinBlocks) nb = kCdkFinBlocks;
+  static_assert(kCdkFinBlocks * sizeof(double) <= NSVD_CDK_FINALIZE_SCRATCH, "finalize scratch");
+  cdk_finalize_kernel<<<nb, 1024, 0, st>>>(terms, Mm, Lp, (double)Bg, coef, scratch);
+  NSVD_LAUNCH_CHECK();
+  cdk_finalize_sum_kernel<<<1, kCdkFinBlocks, 0, st>>>(terms, scratch, nb, Lp, (double)Bg, losses);
   NSVD_LAUNCH_CHECK();
   return 0;
 }

@@ -39,7 +39,7 @@ int cdk_pad_rowdots(const float* f, const float* g, const float* v, int B, int L
                     float* opdot, float* rs_joint, cudaStream_t st);
 int cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int fc, float* terms,
             float* rs_joint, void* work, cudaStream_t st);
-int cdk_finalize(const float* terms, const float* Mm, int Lp, long Bg, float* losses, float* coef,
+int cdk_finalize(const float* terms, const float* Mm, int Lp, long Bg, float* losses, float* coef, double* scratch,
                  cudaStream_t st);
 int cdk_bwd(const float* f, const float* g, const float* v, const float* coef, const float* gscale, int B,
             int L, int fc, long Bg, float* grad_f, float* grad_g, cudaStream_t st);
@@ -68,8 +68,9 @@ size_t tc_cdk_work_bytes(int B, int L, int fc);
 int tc_cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int fc, float* terms, float* rs_joint,
                void* work, cudaStream_t st);
 int tc_cdk_bwd(const float* f, const float* g, const float* v, const float* coef, const float* gscale, int B, int L,
-               int fc, long Bg, float* grad_f, float* grad_g, void* work, cudaStream_t st);
-int tc_cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* out, void* work, cudaStream_t st);
+               int fc, long Bg, float* grad_f, float* grad_g, void* work, int planes_ready, cudaStream_t st);
+int tc_cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* out, void* work, int planes_ready,
+                   cudaStream_t st);
 size_t tc_linear_work_bytes(int rows, int in_f, int out_f);
 int tc_linear_fwd(const float* x, const float* W, const float* bias, float* y, int rows, int in_f, int out_f, int act,
                   float slope, void* work, size_t work_bytes, cudaStream_t st);

@@ -2038,7 +2038,7 @@ struct HidFwd12Args {
 };
 
 #ifndef NSVD_HID_GROUP
-#define NSVD_HID_GROUP 1
+#define NSVD_HID_GROUP 2
 #endif
 constexpr int kHidGroup = NSVD_HID_GROUP;   // tiles per group (1 or 2): the scratch holds kHidGroup tile slots per CTA
 
@@ -2170,6 +2170,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
             phase ^= 1;
           }
         }
+        NSVD_TL(i, 6);   // all loads of the item issued
         ++done;
       }
     }
@@ -2192,12 +2193,16 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           wphase ^= 1;
           cur_key = key;
         }
+        NSVD_TL(i, 7);   // weights of the item present
         mbar_wait(tempty, tphase ^ 1, 64);
         tc_fence_after();
+        NSVD_TL(i, 0);   // accumulators handed back
         for (int sc = 0; sc < 8; ++sc) {
           const int s = sc >> 1, c = sc & 1;
           mbar_wait(&full[stage], phase, 65);
           tc_fence_after();
+          if (sc == 0) NSVD_TL(i, 1);   // first operand stage present
+          if (sc == 7) NSVD_TL(i, 2);   // last operand stage present
           const uint32_t a_hi = smem_u32(sA + stage * F_STAGE_BYTES), a_lo = a_hi + CHUNK;
           const uint32_t d_tmem = tmem_base + s * 128;
 #pragma unroll
@@ -2262,6 +2267,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
       mbar_wait(tfull, tphase, 66);
       tphase ^= 1;
       tc_fence_after();
+      if (et == 0) NSVD_TL(i, 3);       // MMAs of the item retired
       float u[4] = {0.f, 0.f, 0.f, 0.f};
       const int xs = ((int)blockIdx.x * G + slot) * 4;
 #pragma unroll 1
@@ -2275,6 +2281,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty);
+          if (et == 0) NSVD_TL(i, 4);   // last TMEM read of the item
         }
         if (!vm) {
 #pragma unroll
@@ -2357,6 +2364,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
           tma_store_commit();
         }
       }
+      if (et == 0) NSVD_TL(i, 5);           // epilogue of the item done (stores issued)
       if (closes_a && et == 0) {             // every store of this group's layer-1 items has completed
         tma_store_wait_all();
         if (slot == 0) mbar_arrive(&adone[0]);
@@ -3308,6 +3316,48 @@ __global__ void cdk_planes_kernel(const float* __restrict__ in, __nv_bfloat16* _
   hi[i] = a;
   lo[i] = d;
 }
+// Forward preparation in ONE launch (it was five: two padded fp32 copies, the row dots over them, two plane splits):
+// a warp per row reads f[b], g[b] once, writes the hi/lo planes of both padded rows and takes the exact fp32 row dots
+//   opdot[b] = sum_c v_c Fp[b][c] Gp[b][c],   rs_joint[b] = diag(Fp Gp^T)[b]
+// in the lane-strided order of cdk_rowdots_kernel (same values to the last bit).
+__global__ void __launch_bounds__(256)
+cdk_prep_kernel(const float* __restrict__ f, const float* __restrict__ g, const float* __restrict__ v,
+                __nv_bfloat16* __restrict__ fh, __nv_bfloat16* __restrict__ fl, __nv_bfloat16* __restrict__ gh,
+                __nv_bfloat16* __restrict__ gl, float* __restrict__ opdot, float* __restrict__ rs_joint, long B, int L,
+                int fc, int Lpad) {
+  const long b = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int Lp = L + fc;
+  float a = 0.f, d = 0.f;
+  for (int c = lane; c < Lpad; c += 32) {
+    float fv = 0.f, gv = 0.f;
+    if (c < Lp) {
+      const bool one = fc && c == 0;
+      fv = one ? 1.f : f[b * L + c - fc];
+      gv = one ? 1.f : g[b * L + c - fc];
+      const float p = fv * gv;
+      d += p;
+      a = fmaf(v[c], p, a);
+    }
+    __nv_bfloat16 h, l;
+    tc::split_bf16(fv, h, l);
+    fh[b * Lpad + c] = h;
+    fl[b * Lpad + c] = l;
+    tc::split_bf16(gv, h, l);
+    gh[b * Lpad + c] = h;
+    gl[b * Lpad + c] = l;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+  }
+  if (lane == 0) {
+    opdot[b] = a;
+    if (rs_joint) rs_joint[b] = d;
+  }
+}
 // transposed coefficient planes: out[which][c][i] = coef[which][i][c]  (K-major B operand of the backward GEMM)
 __global__ void cdk_coefT_planes_kernel(const float* __restrict__ coef, __nv_bfloat16* __restrict__ hi,
                                         __nv_bfloat16* __restrict__ lo, int Lp, int Lpad) {
@@ -3324,6 +3374,28 @@ __global__ void cdk_coefT_planes_kernel(const float* __restrict__ coef, __nv_bfl
   lo[i] = d;
 }
 
+// In-register transpose of a 32 x 32 fp32 block held one ROW per lane (a[k] = element (lane, k), what a 32x32b TMEM load
+// delivers) into one COLUMN per lane (a[k] = element (k, lane)): five butterfly stages of 16 shuffles with static
+// register indices.  The CDK epilogues below write row-major matrices whose row starts are not 16-byte aligned (the
+// dropped constant column / the removed diagonal shift every row by one element), so vector stores per row are not
+// available; with a column per lane every store and every load of a warp is one contiguous 128-byte segment.  The
+// first versions stored one row per lane (32 sectors per instruction): 65 us per backward GEMM, 147 us for Fp Gp^T.
+__device__ __forceinline__ void warp_transpose32(float (&a)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if ((i & s) == 0) {
+        const float send = up ? a[i] : a[i + s];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+        if (up) a[i] = recv;
+        else a[i + s] = recv;
+      }
+    }
+  }
+}
+
 // grad[b][c - fc] = gs * ( acc[b][c] - c2 v[c] other[b][c - fc] )
 struct CdkBwdEpi {
   float* grad;
@@ -3334,21 +3406,24 @@ struct CdkBwdEpi {
   float c2;
   __device__ __forceinline__ void operator()(uint32_t tmem_acc, const TileCoord& c, int ewarp, int lane) const {
     const int q = ewarp & 3, half = ewarp >> 2;
-    const int b = c.mt * big::BM + q * 32 + lane;
+    const int b0 = c.mt * big::BM + q * 32;          // first of this warp's 32 rows
     const float gs = gscale ? gscale[0] : 1.f;
 #pragma unroll 1
-    for (int ch = 0; ch < 8; ++ch) {
-      const int col0 = half * 128 + ch * 16;
-      float a[16];
+    for (int ch = 0; ch < 4; ++ch) {
+      const int col0 = half * 128 + ch * 32;
+      float a[32];
       tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, a);
+      tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + col0 + 16, a + 16);
       tc::tmem_ld_wait();
-      if (b < B) {
+      warp_transpose32(a, lane);                     // a[k] = acc[b0 + k][col0 + lane]
+      const int cc = c.nt * big::BN + col0 + lane;
+      if (cc >= fc && cc < L + fc) {
+        const float cv = c2 * v[cc];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          int cc = c.nt * big::BN + col0 + i;
-          if (cc >= fc && cc < L + fc) {
-            long o = (long)b * L + cc - fc;
-            grad[o] = gs * (a[i] - c2 * v[cc] * other[o]);
+        for (int k = 0; k < 32; ++k) {
+          if (b0 + k < B) {
+            const long o = (long)(b0 + k) * L + cc - fc;
+            grad[o] = gs * (a[k] - cv * other[o]);
           }
         }
       }
@@ -3362,18 +3437,21 @@ struct CdkOffdiagEpi {
   int B;
   __device__ __forceinline__ void operator()(uint32_t tmem_acc, const TileCoord& c, int ewarp, int lane) const {
     const int q = ewarp & 3, half = ewarp >> 2;
-    const int i = c.mt * big::BM + q * 32 + lane;
+    const int i0 = c.mt * big::BM + q * 32;
 #pragma unroll 1
-    for (int ch = 0; ch < 8; ++ch) {
-      const int col0 = half * 128 + ch * 16;
-      float a[16];
+    for (int ch = 0; ch < 4; ++ch) {
+      const int col0 = half * 128 + ch * 32;
+      float a[32];
       tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, a);
+      tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + col0 + 16, a + 16);
       tc::tmem_ld_wait();
-      if (i < B) {
+      warp_transpose32(a, lane);                     // a[k] = acc[i0 + k][col0 + lane]
+      const int j = c.nt * big::BN + col0 + lane;
+      if (j < B) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          int j = c.nt * big::BN + col0 + k;
-          if (j < B && j != i) out[(long)i * (B - 1) + j - (j > i ? 1 : 0)] = a[k];
+        for (int k = 0; k < 32; ++k) {
+          const int i = i0 + k;
+          if (i < B && j != i) __stcs(out + (long)i * (B - 1) + j - (j > i ? 1 : 0), a[k]);   // 67 MB, written once
         }
       }
     }
@@ -3381,7 +3459,7 @@ struct CdkOffdiagEpi {
 };
 
 struct CdkLayout {
-  size_t fp32_f, fp32_g, opdot, f_hi, f_lo, g_hi, g_lo, c_hi, c_lo, total;
+  size_t opdot, f_hi, f_lo, g_hi, g_lo, c_hi, c_lo, total;
 };
 static CdkLayout cdk_layout(long B, int L, int fc) {
   CdkLayout t{};
@@ -3392,8 +3470,6 @@ static CdkLayout cdk_layout(long B, int L, int fc) {
     o += align_up(bytes, 1024);
     return r;
   };
-  t.fp32_f = take(B * Lp * 4);
-  t.fp32_g = take(B * Lp * 4);
   t.opdot = take(B * 4);
   t.f_hi = take(B * Lpad * 2);
   t.f_lo = take(B * Lpad * 2);
@@ -3423,13 +3499,12 @@ int tc_cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int
   CdkLayout t = cdk_layout(B, L, fc);
   uint8_t* wk = align1k(work);
   int rc;
-  // exact fp32 row dots (operator term, diag(Fp Gp^T)) on the padded fp32 copies
-  float* fp = reinterpret_cast<float*>(wk + t.fp32_f);
-  float* gp = reinterpret_cast<float*>(wk + t.fp32_g);
+  // operand planes of the padded rows + exact fp32 row dots (operator term, diag(Fp Gp^T)), one launch
   float* opdot = reinterpret_cast<float*>(wk + t.opdot);
-  if ((rc = cdk_pad_rowdots(f, g, v, B, L, fc, fp, gp, opdot, rs_joint, st))) return rc;
+  cdk_prep_kernel<<<cdiv((long)B * 32, 256), 256, 0, st>>>(f, g, v, BF(wk + t.f_hi), BF(wk + t.f_lo), BF(wk + t.g_hi),
+                                                           BF(wk + t.g_lo), opdot, rs_joint, B, L, fc, Lpad);
+  NSVD_LAUNCH_CHECK();
   // Grams: X^T X with both operands MN-major straight from the [B][Lpad] planes, K = rows in slices
-  if ((rc = cdk_make_planes(f, g, B, L, fc, wk, t, st))) return rc;
   NSVD_CUDA(cudaMemsetAsync(terms, 0, sizeof(float) * 2L * Lp * Lp, st));
   if ((rc = colsum(opdot, terms + 2L * Lp * Lp, B, 1, 1, 0, 0, st))) return rc;
   for (int which = 0; which < 2; ++which) {
@@ -3452,12 +3527,12 @@ int tc_cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int
 }
 
 int tc_cdk_bwd(const float* f, const float* g, const float* v, const float* coef, const float* gscale, int B, int L,
-               int fc, long Bg, float* grad_f, float* grad_g, void* work, cudaStream_t st) {
+               int fc, long Bg, float* grad_f, float* grad_g, void* work, int planes_ready, cudaStream_t st) {
   const int Lp = L + fc, Lpad = (int)cdk_lpad(Lp);
   CdkLayout t = cdk_layout(B, L, fc);
   uint8_t* wk = align1k(work);
   int rc;
-  if ((rc = cdk_make_planes(f, g, B, L, fc, wk, t, st))) return rc;
+  if (!planes_ready && (rc = cdk_make_planes(f, g, B, L, fc, wk, t, st))) return rc;
   long nc = 2L * Lp * Lpad;
   cdk_coefT_planes_kernel<<<cdiv(nc, 256), 256, 0, st>>>(coef, BF(wk + t.c_hi), BF(wk + t.c_lo), Lp, Lpad);
   NSVD_LAUNCH_CHECK();
@@ -3492,12 +3567,13 @@ int tc_cdk_bwd(const float* f, const float* g, const float* v, const float* coef
   return 0;
 }
 
-int tc_cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* out, void* work, cudaStream_t st) {
+int tc_cdk_offdiag(const float* f, const float* g, int B, int L, int fc, float* out, void* work, int planes_ready,
+                   cudaStream_t st) {
   const int Lp = L + fc, Lpad = (int)cdk_lpad(Lp);
   CdkLayout t = cdk_layout(B, L, fc);
   uint8_t* wk = align1k(work);
   int rc;
-  if ((rc = cdk_make_planes(f, g, B, L, fc, wk, t, st))) return rc;
+  if (!planes_ready && (rc = cdk_make_planes(f, g, B, L, fc, wk, t, st))) return rc;
   const bool pair = tc_use_pair();
   const uint32_t bbox = pair ? big::BN / 2 : big::BN;
   CUtensorMap mah, mal, mbh, mbl;

@@ -272,12 +272,15 @@ class _FusedOperatorStep(torch.autograd.Function):
         ctx.state = dict(md=md, pb=pb, sc=sc, version=sc.version, x=x, F=F, TF=TF, v=v, coef=coef, b1=b1,
                          Bg=Bg, engine=engine, dp=dp, nparams=len(params))
         ctx.mark_non_differentiable(F, TF)
+        ctx.set_materialize_grads(False)     # no zero-filled (B, L) gradients for the two auxiliary outputs
         return loss, F, TF
 
     @staticmethod
     def backward(ctx, gloss, gF, gTF):
         lib = _lib.load()
         s = ctx.state
+        if gloss is None:                    # only f / Tf were used downstream: they carry no gradient (utils of the aux dict)
+            return (None,) * (5 + s["nparams"])
         md, pb, sc = s["md"], s["pb"], s["sc"]
         if sc.version != s["version"]:
             raise RuntimeError("the scratch buffers of this NestedLoRA object were overwritten by a later forward "

@@ -187,17 +187,20 @@ class NestedLoRALossFunctionForCDK(torch.autograd.Function):
             Bg = dp.global_counts(B, B, dev)[0]
         losses = torch.empty(3, dtype=torch.float32, device=dev)
         coef = torch.empty(2 * Lp * Lp, dtype=torch.float32, device=dev)
-        _lib.check(lib.nsvd_cdk_finalize(_lib.ptr(terms), _lib.ptr(Mm), Lp, Bg, _lib.ptr(losses), _lib.ptr(coef), st),
-                   "nsvd_cdk_finalize")
-        if diagnostics:
+        # the last NSVD_CDK_FINALIZE_SCRATCH bytes of the work buffer are reserved for the finalize partials (nsvd.h)
+        fin = C.c_void_p((work.data_ptr() + nwork - _lib.CDK_FINALIZE_SCRATCH) & ~15)
+        _lib.check(lib.nsvd_cdk_finalize(_lib.ptr(terms), _lib.ptr(Mm), Lp, Bg, _lib.ptr(losses), _lib.ptr(coef), fin,
+                                         st), "nsvd_cdk_finalize")
+        if diagnostics:       # (planes_ready = 1: `work` still holds the operand planes nsvd_cdk_fwd built from fd, gd)
             rs_indep = torch.empty(B * B - B, dtype=torch.float32, device=dev)
             _lib.check(lib.nsvd_cdk_offdiag(_lib.ptr(fd), _lib.ptr(gd), B, L, fc, engine, _lib.ptr(rs_indep),
-                                            _lib.ptr(work), nwork, st), "nsvd_cdk_offdiag")
+                                            _lib.ptr(work), nwork, 1, st), "nsvd_cdk_offdiag")
         else:
             rs_indep = torch.empty(0, dtype=torch.float32, device=dev)
         ctx.save_for_backward(fd, gd, v, coef)
         ctx.fc, ctx.Bg, ctx.engine, ctx.work = fc, Bg, engine, work
         ctx.mark_non_differentiable(rs_joint, rs_indep)
+        ctx.set_materialize_grads(False)   # no zero-filled gradients for the unused outputs (rs_indep alone is B^2 - B floats)
         return losses[0], losses[1], losses[2], rs_joint, rs_indep
 
     @staticmethod
@@ -206,11 +209,14 @@ class NestedLoRALossFunctionForCDK(torch.autograd.Function):
         fd, gd, v, coef = ctx.saved_tensors
         dev = fd.device
         B, L = fd.shape
+        # like the reference's backward (nestedlora.py:320-332) only the gradient of the first output (loss) is used
+        if grad_output is None:
+            return None, None, None, None, None, None, None, None
         gl = _dev_f32(grad_output, dev)
         gf, gg = torch.empty_like(fd), torch.empty_like(gd)
         _lib.check(lib.nsvd_cdk_bwd(_lib.ptr(fd), _lib.ptr(gd), _lib.ptr(v), _lib.ptr(coef), _lib.ptr(gl), B, L,
                                     ctx.fc, ctx.Bg, ctx.engine, _lib.ptr(gf), _lib.ptr(gg), _lib.ptr(ctx.work),
-                                    ctx.work.numel(), _stream(dev)), "nsvd_cdk_bwd")
+                                    ctx.work.numel(), 1, _stream(dev)), "nsvd_cdk_bwd")
         return gf, gg, None, None, None, None, None, None
 
 
@@ -230,6 +236,9 @@ class NestedLoRAForCDK(nn.Module):
         return self.model(*args)
 
     def compute_loss(self, f, g, batch_weights=None) -> torch.Tensor:
-        return NestedLoRALossFunctionForCDK.apply(f, g, self.vector_mask, self.matrix_mask,
-                                                  self.set_first_mode_const, batch_weights, self.data_parallel,
-                                                  self.diagnostics)
+        # the reference moves its CPU-resident masks to the device on every call (nestedlora.py:283-284: 1 MB of
+        # pageable H2D copy for L = 512); here the device copies are cached until the mask tensors change
+        v, Mm = (fused._nesting_masks(self, f.device) if f.device.type == "cuda"
+                 else (self.vector_mask, self.matrix_mask))
+        return NestedLoRALossFunctionForCDK.apply(f, g, v, Mm, self.set_first_mode_const, batch_weights,
+                                                  self.data_parallel, self.diagnostics)

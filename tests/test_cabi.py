@@ -21,7 +21,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), n
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.nsvd_abi_version() == 4
+    assert lib.nsvd_abi_version() == 5
     import ctypes as C
     assert [lib.nsvd_struct_size(i) for i in range(3)] == [C.sizeof(_lib.Problem), C.sizeof(_lib.Params), C.sizeof(_lib.Grads)]
 
