@@ -550,14 +550,15 @@ def run_ours(args):
         roof = None
         if l0_n:
             ach = flops_l0 / (l0_ms * 1e-3) / 1e12
-            # DRAM traffic of this kernel from the committed ncu capture (profiles/r2_ncu_full.csv: 6.687 GB read +
-            # 2.558 GB written by one launch over 65536 points), scaled to the points one launch covers here
+            # DRAM traffic of this kernel from the committed ncu capture of the final build (profiles/r2g_ncu_full.csv:
+            # 2.905 GB read + 2.378 GB written by one launch over 65536 points; earlier captures of the same kernel read
+            # 4.8 - 6.7 GB: how much of a 32 MB Phi group survives in the L2 varies), scaled to the points of a launch here
             pts_per_launch = P * args.steps / l0_n
-            traffic = (6.687070e9 + 2.558065e9) / 65536 * pts_per_launch
+            traffic = (2.904602e9 + 2.377896e9) / 65536 * pts_per_launch
             roof = {"kernel": "big2s_gemm_kernel<K-major, L0FwdEpi> (layer-0 4-stream forward GEMM, tcgen05 cta_group::2, fp16 hi/lo planes x 3 products)",
                     "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                     "frac": ach / pk["tf_sust"], "traffic": traffic,
-                    "traffic_note": "bytes per launch = ncu dram read+write per point (141.1 KB, profiles/r2_ncu_full.csv) x "
+                    "traffic_note": "bytes per launch = ncu dram read+write per point (80.6 KB, profiles/r2g_ncu_full.csv) x "
                                     "points per launch; algorithmic bytes are 8 KB (Phi) + 32 KB (3 derivative streams + the saved value "
                                     "stream out) per point + 67 MB of folded weights per 4096-point group: the Phi group is re-read "
                                     "(L2 thrash next to the output streams); the kernel is tensor-bound (pipe 96 % active, DRAM 24 %)",

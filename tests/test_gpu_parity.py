@@ -235,6 +235,62 @@ def test_cdk_full_size_config5(engine):
     assert rel(rsi.cpu().numpy()[d["rsi_idx"]], d["rsi_val"]) < TOL
 
 
+def test_cdk_cabi_planes_ready_and_finalize_scratch():
+    """ABI 5 contracts of the CDK entry points, called directly (include/nsvd.h): bwd / offdiag with planes_ready = 0
+    rebuild the operand planes from f, g (a scribbled work buffer must not matter) and give what planes_ready = 1 gives on
+    the untouched buffer of the forward; finalize only needs its scratch to be writable (contents irrelevant) and is
+    deterministic; all against the golden vectors of the reference (nestedlora.py:270-332)."""
+    import ctypes as C
+    from neural_svd_b200 import _lib
+    d, _ = load_golden("cdk_small_seq")
+    lib = _lib.load()
+    eng = _lib.ENGINES["f16x3"]
+    f, g = torch.from_numpy(d["f"]).cuda(), torch.from_numpy(d["g"]).cuda()
+    B, L = f.shape
+    fc = int(bool(d["const"]))
+    Lp = L + fc
+    m = N.NestedLoRAForCDK(None, L, step=1, sequential=bool(d["sequential"]), set_first_mode_const=bool(fc))
+    v, Mm = m.vector_mask.cuda(), m.matrix_mask.cuda().contiguous()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nwork = lib.nsvd_cdk_work_bytes(B, L, fc, eng)
+    work = torch.empty(nwork, dtype=torch.uint8, device="cuda")
+    terms = torch.empty(2 * Lp * Lp + 1, device="cuda")
+    rsj = torch.empty(B, device="cuda")
+    _lib.check(lib.nsvd_cdk_fwd(_lib.ptr(f), _lib.ptr(g), _lib.ptr(v), B, L, fc, eng, _lib.ptr(terms), _lib.ptr(rsj),
+                                _lib.ptr(work), nwork, st), "fwd")
+    outs = []
+    for fill in (0x00, 0xFF):                        # the scratch contents do not matter
+        scratch = torch.full((_lib.CDK_FINALIZE_SCRATCH,), fill, dtype=torch.uint8, device="cuda")
+        losses, coef = torch.empty(3, device="cuda"), torch.empty(2 * Lp * Lp, device="cuda")
+        _lib.check(lib.nsvd_cdk_finalize(_lib.ptr(terms), _lib.ptr(Mm), Lp, B, _lib.ptr(losses), _lib.ptr(coef),
+                                         _lib.ptr(scratch), st), "finalize")
+        outs.append((losses.clone(), coef.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    losses, coef = outs[0]
+    assert abs(float(losses[0]) - float(d["loss64"])) < TOL * abs(float(d["loss64"]))
+    one = torch.ones((), device="cuda")
+
+    def bwd_and_offdiag(ready):
+        gf, gg = torch.empty_like(f), torch.empty_like(g)
+        rsi = torch.empty(B * B - B, device="cuda")
+        _lib.check(lib.nsvd_cdk_offdiag(_lib.ptr(f), _lib.ptr(g), B, L, fc, eng, _lib.ptr(rsi), _lib.ptr(work), nwork,
+                                        ready, st), "offdiag")
+        _lib.check(lib.nsvd_cdk_bwd(_lib.ptr(f), _lib.ptr(g), _lib.ptr(v), _lib.ptr(coef), _lib.ptr(one), B, L, fc, B, eng,
+                                    _lib.ptr(gf), _lib.ptr(gg), _lib.ptr(work), nwork, ready, st), "bwd")
+        return gf, gg, rsi
+    a = bwd_and_offdiag(1)                           # the planes of the forward
+    work.fill_(0x7F)                                 # scribble: planes_ready = 0 must rebuild them
+    b = bwd_and_offdiag(0)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert rel(a[0].cpu().numpy(), d["gf64"]) < TOL and rel(a[1].cpu().numpy(), d["gg64"]) < TOL
+    assert rel(a[2].cpu().numpy(), d["rsi64"]) < TOL
+    with pytest.raises(RuntimeError):                # a misaligned scratch pointer is refused, not dereferenced
+        bad = C.c_void_p(scratch.data_ptr() + 4)
+        _lib.check(lib.nsvd_cdk_finalize(_lib.ptr(terms), _lib.ptr(Mm), Lp, B, _lib.ptr(losses), _lib.ptr(coef), bad, st),
+                   "finalize")
+
+
 def test_large_batch_properties():
     # BASELINE-size inputs where the oracle is too slow: size-independent properties instead.
     # (1) permuting points inside each half leaves loss and gradients unchanged;
