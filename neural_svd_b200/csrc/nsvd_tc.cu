@@ -1014,6 +1014,19 @@ __device__ __forceinline__ void act_streams(float z0, float z1, float z2, float 
   a2 = sg * z2;
   a3 = fmaf(sg, z3, sg * (1.f - sg) * fmaf(z1, z1, z2 * z2));
 }
+// the value-stream half of act_streams: a = softplus(z), sg = sigmoid(z) (same arithmetic, so both epilogue orders agree)
+__device__ __forceinline__ void softplus_sigmoid(float z0, float& a0, float& sg) {
+  float e = __expf(-fabsf(z0));
+  float u = 1.f + e;
+#ifdef NSVD_RCP_RN
+  float inv = __frcp_rn(u);
+#else
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(u));
+#endif
+  sg = z0 >= 0.f ? inv : e * inv;
+  a0 = fmaxf(z0, 0.f) + __logf(u);
+}
 // sigmoid(z) from a = softplus(z) at epilogue rate: 1 - exp(-a)  (absolute error ~6e-8)
 __device__ __forceinline__ float sig_fast(float a) { return 1.f - __expf(-a); }
 
@@ -2058,10 +2071,10 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
   uint64_t* empty = bars + 3;               // [3]
   uint64_t* wfull = bars + 6;
   uint64_t* wfree = bars + 7;
-  uint64_t* tfull = bars + 8;
-  uint64_t* tempty = bars + 9;
-  uint64_t* adone = bars + 10;              // [2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+  uint64_t* tempty = bars + 8;
+  uint64_t* adone = bars + 9;               // [2]
+  uint64_t* sfull = bars + 11;              // [4] accumulator of stream s complete
+  uint32_t* tmem_slot = (uint32_t*)(bars + 15);
   float* bias_s = (float*)(bars + 16);      // [128]
   float* w3_s = bias_s + 128;               // [128]
   float* ubuf = (float*)(sO + 6 * F_BOX);   // [128][3][4] head partial sums (layer 2: boxes 2..7 are unused)
@@ -2086,7 +2099,7 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
     }
     mbar_init(wfull, 1);
     mbar_init(wfree, 1);
-    mbar_init(tfull, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&sfull[i], 1);
     mbar_init(tempty, F_EPI_WARPS);
     mbar_init(&adone[0], 1);
     mbar_init(&adone[1], 1);
@@ -2216,24 +2229,32 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
             umma_f16(d_tmem, ah, bh, idesc, 1u);
           }
           umma_commit(&empty[stage]);
+          if (c == 1) umma_commit(&sfull[s]);   // the accumulator of stream s is complete: its epilogue round may start
           if (++stage == F_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(tfull);
         umma_commit(wfree);
         tphase ^= 1;
       }
     }
   } else if (warp >= 4) {
-    // ===================== 16 epilogue warps (as hidden_fwd_kernel) =====================
+    // ===================== 16 epilogue warps, STREAM-major =====================
+    // The MMAs of an item are issued stream by stream, so the accumulator of stream s is complete a quarter / half /
+    // three quarters of the way through the MMA phase (sfull[s]).  Round s of the epilogue handles stream s for the whole
+    // tile as soon as it is there: rounds 0-2 run UNDER the MMAs of the later streams instead of after them (the
+    // unit-major epilogue this replaces needed all four accumulators before its first round: MMA phase and epilogue ran
+    // back to back, profiles/README.md timeline).  What the later streams need from the earlier ones stays in TMEM:
+    // round 0 writes sigma = sigmoid(z0) over z0 (tcgen05.st), rounds 1-3 read it back, round 3 also re-reads z1, z2.
+    // Thread = (point row, 32 consecutive units): the same thread owns the same TMEM cells in every round.
     const int ewarp = warp - 4, q = ewarp & 3, sub = ewarp >> 2;
     const int et = threadIdx.x - 128;        // 0..511 among the epilogue threads
     const int row = q * 32 + lane;           // point row inside the tile == TMEM lane
-    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 32);   // + 128 s + 8 k
     const uint32_t sw = (uint32_t)((row >> 1) & 3);
-    const uint32_t piece0 = (uint32_t)row * 64 + (((uint32_t)sub ^ sw) << 4);
+    uint8_t* const my_hi = sO + (2 * sub) * F_BOX + row * 64;   // this thread's 64-byte row in the box of its unit quarter
+    uint8_t* const my_lo = my_hi + F_BOX;
     uint32_t tphase = 0;
     int cur_key = -1;
     float un[4] = {1.f, 1.f, 1.f, 1.f}, so[4] = {1.f, 1.f, 1.f, 1.f};
@@ -2264,53 +2285,18 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
         cur_key = key;
         named_bar_sync(1, F_EPI_WARPS * 32);
       }
-      mbar_wait(tfull, tphase, 66);
-      tphase ^= 1;
-      tc_fence_after();
-      if (et == 0) NSVD_TL(i, 3);       // MMAs of the item retired
       float u[4] = {0.f, 0.f, 0.f, 0.f};
       const int xs = ((int)blockIdx.x * G + slot) * 4;
-#pragma unroll 1
-      for (int r = 0; r < 4; ++r) {          // h-quarters of 32 hidden units; this warp takes 8 of them
-        const int h0 = r * 32 + sub * 8;
-        float z[4][8];
+      const bool wide = !last || cen;          // every stream of this item is staged and stored
 #pragma unroll
-        for (int s = 0; s < 4; ++s) tmem_ld8(tl + s * 128 + h0, z[s]);
-        tmem_ld_wait();
-        if (r == 3) {                        // last TMEM read of this item: hand the accumulator back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty);
-          if (et == 0) NSVD_TL(i, 4);   // last TMEM read of the item
-        }
-        if (!vm) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float zb = fmaf(z[0][k], un[0], bias_s[h0 + k]);
-            act_streams(zb, z[1][k] * un[1], z[2][k] * un[2], z[3][k] * un[3], z[0][k], z[1][k], z[2][k], z[3][k]);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-#pragma unroll
-            for (int s = 0; s < 4; ++s) z[s][k] = softplus_fast(fmaf(z[s][k], un[s], bias_s[h0 + k]));
-        }
-        if (last) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float w = w3_s[h0 + k];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) u[s] = fmaf(z[s][k], w, u[s]);
-          }
-        }
-        // layer 2 stages the value stream only: two box pairs alternate between rounds, so a round never waits for its
-        // predecessor's bulk store (one barrier per round); layer 1 needs all 8 boxes per round and first lets the
-        // previous round's stores drain them.
-        const bool wide = !last || cen;      // all 8 staging boxes are written this round
-        const int sb = wide ? 0 : 2 * (r & 1);
-        if (wide) {
+      for (int s = 0; s < 4; ++s) {
+        mbar_wait(&sfull[s], tphase, 66);
+        tc_fence_after();
+        if (s == 0 && et == 0) NSVD_TL(i, 3);  // first accumulator of the item complete
+        const bool stores = wide || (s == 0 && !vm);
+        if (stores) {      // the staging boxes must have been read by the bulk stores that used them last
           if (et == 0) {
-            if (r == 0 && slot == 1) {       // A(t0)'s stores were issued a whole MMA phase ago: they are complete
+            if (!last && s == 0 && slot == 1) {   // A(t0)'s stores were issued a whole item ago: they are complete
               tma_store_wait_all();
               mbar_arrive(&adone[0]);
             } else {
@@ -2318,52 +2304,105 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
             }
           }
           named_bar_sync(2, F_EPI_WARPS * 32);
-        } else if (r == 0) {                 // the previous item may have been a layer-1 one that used all 8 boxes
-          if (et == 0) tma_store_wait_read();
-          named_bar_sync(2, F_EPI_WARPS * 32);
         }
-        const int ns = wide ? 4 : (vm ? 0 : 1);
-        for (int s = 0; s < ns; ++s) {
-          uint32_t h[4], lo[4];
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {          // 8 of this thread's 32 units
+          const int h0 = sub * 32 + 8 * k;
+          float a[8];
+          if (vm) {                            // value-only pass: the four slots are independent value streams
+            tmem_ld8(tl + s * 128 + 8 * k, a);
+            tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) split2<PF_HH>(z[s][2 * k] * so[s], z[s][2 * k + 1] * so[s], h[k], lo[k]);
-          uint8_t* bh = sO + (sb + 2 * s) * F_BOX;
-          uint8_t* bl = bh + F_BOX;
-          *reinterpret_cast<uint4*>(bh + piece0) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(bl + piece0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        fence_proxy_async_smem();
-        if (last && et == 0) tma_store_wait_read();
-        named_bar_sync(3, F_EPI_WARPS * 32);
-        if (et == 0) {
-          if (cen) {       // the four 128-point blocks of the tile: a1 (read back by layer 2, then by the backward) / a2
+            for (int j = 0; j < 8; ++j) a[j] = softplus_fast(fmaf(a[j], un[s], bias_s[h0 + j]));
+          } else if (s == 0) {
+            float sg[8];
+            tmem_ld8(tl + 8 * k, a);
+            tmem_ld_wait();
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              const int row0 = (int)args.p_off + (mt * 4 + s) * 128;
-              tma_store_3d_hint(last ? &tm.s2h : &tm.s1h, sO + (2 * s) * F_BOX, r * 32, row0, l, last ? pol_once : pol_keep);
-              tma_store_3d_hint(last ? &tm.s2l : &tm.s1l, sO + (2 * s + 1) * F_BOX, r * 32, row0, l,
-                                last ? pol_once : pol_keep);
-            }
-          } else if (!last) {
+            for (int j = 0; j < 8; ++j) softplus_sigmoid(fmaf(a[j], un[0], bias_s[h0 + j]), a[j], sg[j]);
+            tmem_st8(tl + 8 * k, sg);          // sigma replaces z0 for rounds 1-3
+          } else if (s < 3) {
+            float sg[8];
+            tmem_ld8(tl + s * 128 + 8 * k, a);
+            tmem_ld8(tl + 8 * k, sg);
+            tmem_ld_wait();
 #pragma unroll
-            for (int s = 1; s < 4; ++s) {
-              tma_store_3d_hint(&tm.xsh, sO + (2 * s) * F_BOX, r * 32, 0, xs + s, pol_keep);
-              tma_store_3d_hint(&tm.xsl, sO + (2 * s + 1) * F_BOX, r * 32, 0, xs + s, pol_keep);
+            for (int j = 0; j < 8; ++j) a[j] = sg[j] * (a[j] * un[s]);
+          } else {
+            float sg[8], z1[8], z2[8];
+            tmem_ld8(tl + 3 * 128 + 8 * k, a);
+            tmem_ld8(tl + 8 * k, sg);
+            tmem_ld8(tl + 128 + 8 * k, z1);
+            tmem_ld8(tl + 256 + 8 * k, z2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float d1 = z1[j] * un[1], d2 = z2[j] * un[2];
+              a[j] = fmaf(sg[j], a[j] * un[3], sg[j] * (1.f - sg[j]) * fmaf(d1, d1, d2 * d2));
             }
-            if (vm) {      // slot 0 is a shifted point set too: scratch, not `saved`
-              tma_store_3d_hint(&tm.xsh, sO, r * 32, 0, xs, pol_keep);
-              tma_store_3d_hint(&tm.xsl, sO + F_BOX, r * 32, 0, xs, pol_keep);
-            } else {       // a1 value stream: read back by layer 2 of this tile, then by the backward
-              tma_store_3d_hint(&tm.s1h, sO, r * 32, (int)args.p_off + mt * 128, l, pol_keep);
-              tma_store_3d_hint(&tm.s1l, sO + F_BOX, r * 32, (int)args.p_off + mt * 128, l, pol_keep);
-            }
-          } else if (!vm) {
-            tma_store_3d_hint(&tm.s2h, sO + sb * F_BOX, r * 32, (int)args.p_off + mt * 128, l, pol_once);
-            tma_store_3d_hint(&tm.s2l, sO + (sb + 1) * F_BOX, r * 32, (int)args.p_off + mt * 128, l, pol_once);
           }
-          tma_store_commit();
+          if (last) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[s] = fmaf(a[j], w3_s[h0 + j], u[s]);
+          }
+          if (stores) {
+            uint32_t h[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split2<PF_HH>(a[2 * j] * so[s], a[2 * j + 1] * so[s], h[j], lo[j]);
+            const uint32_t piece = ((uint32_t)k ^ sw) << 4;
+            *reinterpret_cast<uint4*>(my_hi + piece) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(my_lo + piece) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        if (s == 0 && !vm) tmem_st_wait();     // sigma is in TMEM before this thread reads it back
+        if (s == 3) {                          // last TMEM access of this item: hand the accumulators back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty);
+          if (et == 0) NSVD_TL(i, 4);
+        }
+        if (stores) {
+          fence_proxy_async_smem();
+          named_bar_sync(3, F_EPI_WARPS * 32);
+          if (et == 0) {   // boxes 2 j (hi), 2 j + 1 (lo): units 32 j .. 32 j + 31 of stream s
+            const CUtensorMap *mh, *ml;
+            int y, z;
+            uint64_t pol;
+            if (cen) {           // slot s = the s-th 128-point block of the tile: a1 (re-read by layer 2 and the backward) / a2
+              mh = last ? &tm.s2h : &tm.s1h;
+              ml = last ? &tm.s2l : &tm.s1l;
+              y = (int)args.p_off + (mt * 4 + s) * 128;
+              z = l;
+              pol = last ? pol_once : pol_keep;
+            } else if (last) {   // a2 value stream for the backward
+              mh = &tm.s2h;
+              ml = &tm.s2l;
+              y = (int)args.p_off + mt * 128;
+              z = l;
+              pol = pol_once;
+            } else if (s == 0 && !vm) {   // a1 value stream: read back by layer 2 of this tile, then by the backward
+              mh = &tm.s1h;
+              ml = &tm.s1l;
+              y = (int)args.p_off + mt * 128;
+              z = l;
+              pol = pol_keep;
+            } else {             // derivative streams of a1 (shifted value streams in finite-difference mode): scratch
+              mh = &tm.xsh;
+              ml = &tm.xsl;
+              y = 0;
+              z = xs + s;
+              pol = pol_keep;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              tma_store_3d_hint(mh, sO + (2 * j) * F_BOX, 32 * j, y, z, pol);
+              tma_store_3d_hint(ml, sO + (2 * j + 1) * F_BOX, 32 * j, y, z, pol);
+            }
+            tma_store_commit();
+          }
         }
       }
+      tphase ^= 1;
       if (et == 0) NSVD_TL(i, 5);           // epilogue of the item done (stores issued)
       if (closes_a && et == 0) {             // every store of this group's layer-1 items has completed
         tma_store_wait_all();
@@ -2371,10 +2410,9 @@ hidden_fwd12_kernel(const __grid_constant__ HidFwd12Maps tm, const HidFwd12Args 
         else mbar_arrive(&adone[1]);
       }
       if (last) {
-        if (cen) {         // this mode staged through boxes 6-7 too: the last round's stores must have read them
-          if (et == 0) tma_store_wait_read();
-          named_bar_sync(2, F_EPI_WARPS * 32);
-        }
+        // the head partial sums go through staging boxes 6-7: the stores of this item must have read them
+        if (et == 0) tma_store_wait_read();
+        named_bar_sync(2, F_EPI_WARPS * 32);
         if (sub != 0) {
 #pragma unroll
           for (int s = 0; s < 4; ++s) ubuf[(row * 3 + sub - 1) * 4 + s] = u[s];
