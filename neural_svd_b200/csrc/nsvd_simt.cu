@@ -865,16 +865,174 @@ gram_mma_kernel(const float* __restrict__ F, const float* __restrict__ TF, const
   if (tid == 0) out[L * L] = (s_ops[0] + s_ops[1]) + (s_ops[2] + s_ops[3]);   // slot read by stage 2 (cross = 0)
 }
 
-// stage 2: out[e] (+)= sum over blocks [b0, b1) of partials[b][src_off + e]
-__global__ void gram_stage2_kernel(const float* __restrict__ partials, int partial_stride, int b0,
-                                   int b1, int src_off, int n, float* __restrict__ out,
-                                   int accumulate) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
-  float s = 0.f;
-  for (int b = b0; b < b1; ++b) s += partials[(long)b * partial_stride + src_off + e];
-  out[e] = accumulate ? out[e] + s : s;
+// Second version of the tensor-core K2 for 16 < L <= 64, L a multiple of 4 (the config-4 shape L = 64): the kernel above
+// loads a 32-row chunk, synchronises, multiplies, synchronises - nothing is in flight while it multiplies - and every
+// fragment element is split into its two TF32 parts again by every warp that uses it: 1.4 TB/s.  Here a block reads a
+// chunk with 16-byte loads into REGISTERS one chunk ahead (the loads of chunk c + 1 are in flight while chunk c is
+// multiplied) and splits every value ONCE on its way into two shared-memory planes (tf32 hi / lo).  The m16n8k8 shape
+// needs 12 fragment words per 3 products, so the multiply is bound by shared-memory loads unless fragments are reused in
+// registers: a warp owns WM x WN Gram tiles (2 x 4 at LP = 64: 32 fragment loads per 24 MMAs; one tile per warp, the
+// first attempt, needs 36 per 12 and ran at 1.9 TB/s).  Chunk sums leave the tensor-core accumulator after 32 rows and
+// are added in fp32 registers, as before.  Blocks of 4 warps, several per SM.
+template <int LP>
+__global__ void __launch_bounds__(128)
+gram_mma2_kernel(const float* __restrict__ F, const float* __restrict__ TF, const float* __restrict__ vmask, int L,
+                 long row_begin, long row_end, int rows_per_block, float* __restrict__ partials, int partial_stride,
+                 int block_off) {
+  constexpr int TM = LP / 16, TN = LP / 8;      // Gram tiles: 16 rows x 8 columns each
+  constexpr int WM = TM / 2, WN = TN / 2;       // tiles per warp; the 4 warps form a 2 x 2 grid
+  constexpr int SS = LP + 8, CH = 32;           // row stride of the planes: fragment loads are bank-conflict free
+  constexpr int NV = (CH * LP / 4 + 127) / 128; // float4 per thread and chunk
+  __shared__ __align__(16) uint32_t Sh[CH][SS];
+  __shared__ __align__(16) uint32_t Sl[CH][SS];
+  __shared__ float s_ops[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp >> 1) * WM, n0 = (warp & 1) * WN;
+  const long r0 = row_begin + (long)blockIdx.x * rows_per_block;
+  const long r1 = r0 + rows_per_block < row_end ? r0 + rows_per_block : row_end;
+  float tot[WM][WN][4];
+#pragma unroll
+  for (int i = 0; i < WM; ++i)
+#pragma unroll
+    for (int j = 0; j < WN; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tot[i][j][k] = 0.f;
+  float ops = 0.f;
+  for (int i = tid; i < CH * SS; i += 128) {    // columns >= L stay zero
+    (&Sh[0][0])[i] = 0u;
+    (&Sl[0][0])[i] = 0u;
+  }
+  // a chunk is CH * L contiguous floats = 8 L float4: thread owns float4 tid + 128 u of it
+  const int q4 = 8 * L;
+  float4 fr[NV], tr[NV];
+  auto load_chunk = [&](long c0) {
+    const long nel4 = ((r1 - c0) < CH ? (r1 - c0) : CH) * (long)(L >> 2);
+    const float4* f4 = reinterpret_cast<const float4*>(F + c0 * L);
+    const float4* t4 = reinterpret_cast<const float4*>(TF + c0 * L);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int e = tid + 128 * u;
+      const bool ok = e < q4 && e < nel4;
+      fr[u] = ok ? __ldcs(f4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      tr[u] = ok ? __ldcs(t4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (r0 < r1) load_chunk(r0);
+  __syncthreads();
+  for (long c0 = r0; c0 < r1; c0 += CH) {
+    // registers -> operator sum + the two tf32 planes
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int e = tid + 128 * u;
+      if (e < q4) {
+        const int row = (4 * e) / L, col = (4 * e) % L;
+        const float4 v4 = *reinterpret_cast<const float4*>(vmask + col);
+        ops = fmaf(v4.x * fr[u].x, tr[u].x, ops);
+        ops = fmaf(v4.y * fr[u].y, tr[u].y, ops);
+        ops = fmaf(v4.z * fr[u].z, tr[u].z, ops);
+        ops = fmaf(v4.w * fr[u].w, tr[u].w, ops);
+        uint4 h, l;
+        h.x = to_tf32(fr[u].x); l.x = to_tf32(fr[u].x - __uint_as_float(h.x));
+        h.y = to_tf32(fr[u].y); l.y = to_tf32(fr[u].y - __uint_as_float(h.y));
+        h.z = to_tf32(fr[u].z); l.z = to_tf32(fr[u].z - __uint_as_float(h.z));
+        h.w = to_tf32(fr[u].w); l.w = to_tf32(fr[u].w - __uint_as_float(h.w));
+        *reinterpret_cast<uint4*>(&Sh[row][col]) = h;
+        *reinterpret_cast<uint4*>(&Sl[row][col]) = l;
+      }
+    }
+    __syncthreads();
+    if (c0 + CH < r1) load_chunk(c0 + CH);      // in flight while this chunk is multiplied
+    float acc[WM][WN][4];
+#pragma unroll
+    for (int i = 0; i < WM; ++i)
+#pragma unroll
+      for (int j = 0; j < WN; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < CH / 8; ++ks) {
+      const int k0 = ks * 8 + t;
+      // B (K = data row, N = Gram column): b0 (k = t, n = g), b1 (k = t + 4, n = g)
+      uint32_t bh[WN][2], bl[WN][2];
+#pragma unroll
+      for (int j = 0; j < WN; ++j) {
+        const int c = 8 * (n0 + j) + g;
+        bh[j][0] = Sh[k0][c]; bh[j][1] = Sh[k0 + 4][c];
+        bl[j][0] = Sl[k0][c]; bl[j][1] = Sl[k0 + 4][c];
+      }
+#pragma unroll
+      for (int i = 0; i < WM; ++i) {
+        // A = F^T (M = Gram row, K = data row): a0 (g, t), a1 (g + 8, t), a2 (g, t + 4), a3 (g + 8, t + 4)
+        const int c = 16 * (m0 + i) + g;
+        const uint32_t ah[4] = {Sh[k0][c], Sh[k0][c + 8], Sh[k0 + 4][c], Sh[k0 + 4][c + 8]};
+        const uint32_t al[4] = {Sl[k0][c], Sl[k0][c + 8], Sl[k0 + 4][c], Sl[k0 + 4][c + 8]};
+#pragma unroll
+        for (int j = 0; j < WN; ++j) {
+          mma_tf32_16x8x8(acc[i][j], al, bh[j]);
+          mma_tf32_16x8x8(acc[i][j], ah, bl[j]);
+          mma_tf32_16x8x8(acc[i][j], ah, bh[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < WM; ++i)
+#pragma unroll
+      for (int j = 0; j < WN; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tot[i][j][k] += acc[i][j][k];
+    __syncthreads();                            // the planes are rewritten by the next chunk
+  }
+  // C fragment: c0 (g, 2t), c1 (g, 2t + 1), c2 (g + 8, 2t), c3 (g + 8, 2t + 1) inside tile (mt, nt)
+  float* out = partials + (long)(block_off + blockIdx.x) * partial_stride;
+#pragma unroll
+  for (int i = 0; i < WM; ++i)
+#pragma unroll
+    for (int j = 0; j < WN; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i_ = 16 * (m0 + i) + g + (k >> 1) * 8, j_ = 8 * (n0 + j) + 2 * t + (k & 1);
+        if (i_ < L && j_ < L) out[i_ * L + j_] = tot[i][j][k];
+      }
+  ops = warp_sum(ops);
+  if (lane == 0) s_ops[warp] = ops;
+  __syncthreads();
+  if (tid == 0) out[L * L] = (s_ops[0] + s_ops[1]) + (s_ops[2] + s_ops[3]);   // slot read by stage 2 (cross = 0)
 }
+
+// stage 2: out[e] (+)= sum over blocks [b0, b1) of partials[b][src_off + e], in a fixed order (deterministic).
+// A block of 8 warps owns 32 consecutive elements; warp w adds the partials b0 + w, b0 + w + 8, ... with four loads in
+// flight, the 8 warp sums are then added in warp order.  (The first version gave one thread the whole loop over up to
+// 592 partials - a chain of dependent-latency loads, ~70 us per launch at L = 64: half of the measured K2 time.)
+__global__ void __launch_bounds__(256)
+gram_stage2_kernel(const float* __restrict__ partials, int partial_stride, int b0, int b1, int src_off, int n,
+                   float* __restrict__ out, int accumulate) {
+  __shared__ float sw[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (e < n) {
+    const float* p = partials + src_off + e;
+    int b = b0 + warp;
+    for (; b + 24 < b1; b += 32) {
+      const float v0 = __ldcg(p + (long)b * partial_stride), v1 = __ldcg(p + (long)(b + 8) * partial_stride),
+                  v2 = __ldcg(p + (long)(b + 16) * partial_stride), v3 = __ldcg(p + (long)(b + 24) * partial_stride);
+      s += v0;
+      s += v1;
+      s += v2;
+      s += v3;
+    }
+    for (; b < b1; b += 8) s += __ldcg(p + (long)b * partial_stride);
+  }
+  sw[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && e < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sw[w][lane];
+    out[e] = accumulate ? out[e] + t : t;
+  }
+}
+static inline int stage2_blocks(int n) { return (n + 31) / 32; }
 
 static int gram_blocks_for(long rows) {
   // aim for >= 2 waves of 148 SMs x 2 CTAs when there is enough work; >= 256 rows per block
@@ -919,10 +1077,16 @@ static int gram_dispatch(const float* F, const float* TF, const float* vmask, co
       return 0;
     }
     int nb = gram_blocks_for(rows);
+    const bool v2 = (L & 3) == 0 && ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(TF) |
+                                      reinterpret_cast<uintptr_t>(vmask)) & 15) == 0;
+    if (v2 && nb > 444) nb = 444;               // 128-thread blocks of 154 registers: three per SM, one wave
     int rpb = (int)((rows + nb - 1) / nb);
     rpb = (rpb + 31) / 32 * 32;                 // whole 32-row chunks per block
     nb = (int)((rows + rpb - 1) / rpb);
-    if (L <= 32) gram_mma_kernel<32><<<nb, 128, 0, st>>>(F, TF, vmask, L, rb, re, rpb, partials, stride, block_off);
+    if (v2) {
+      if (L <= 32) gram_mma2_kernel<32><<<nb, 128, 0, st>>>(F, TF, vmask, L, rb, re, rpb, partials, stride, block_off);
+      else gram_mma2_kernel<64><<<nb, 128, 0, st>>>(F, TF, vmask, L, rb, re, rpb, partials, stride, block_off);
+    } else if (L <= 32) gram_mma_kernel<32><<<nb, 128, 0, st>>>(F, TF, vmask, L, rb, re, rpb, partials, stride, block_off);
     else gram_mma_kernel<64><<<nb, 128, 0, st>>>(F, TF, vmask, L, rb, re, rpb, partials, stride, block_off);
     NSVD_LAUNCH_CHECK();
     *nblocks = nb;
@@ -959,11 +1123,11 @@ int gram_reduce(const float* F, const float* TF, const float* vmask, int B, int 
   if ((rc = gram_dispatch(F, TF, vmask, nullptr, nullptr, L, 0, b1, 0, partials, stride, 0, &n1, st))) return rc;
   if ((rc = gram_dispatch(F, TF, vmask, nullptr, nullptr, L, b1, B, 0, partials, stride, n1, &n2, st))) return rc;
   int LL = L * L;
-  gram_stage2_kernel<<<cdiv(LL, 128), 128, 0, st>>>(partials, stride, 0, n1, 0, LL, terms, 0);
+  gram_stage2_kernel<<<stage2_blocks(LL), 256, 0, st>>>(partials, stride, 0, n1, 0, LL, terms, 0);
   NSVD_LAUNCH_CHECK();
-  gram_stage2_kernel<<<cdiv(LL, 128), 128, 0, st>>>(partials, stride, n1, n1 + n2, 0, LL, terms + LL, 0);
+  gram_stage2_kernel<<<stage2_blocks(LL), 256, 0, st>>>(partials, stride, n1, n1 + n2, 0, LL, terms + LL, 0);
   NSVD_LAUNCH_CHECK();
-  gram_stage2_kernel<<<1, 32, 0, st>>>(partials, stride, 0, n1 + n2, LL, 1, terms + 2 * LL, 0);
+  gram_stage2_kernel<<<1, 256, 0, st>>>(partials, stride, 0, n1 + n2, LL, 1, terms + 2 * LL, 0);
   NSVD_LAUNCH_CHECK();
   return 0;
 }
@@ -974,9 +1138,9 @@ int cross_gram(const float* F, const float* TF, const float* roww, const float* 
   int stride = 2 * L * L + 1, n1 = 0, rc;
   if ((rc = gram_dispatch(F, TF, nullptr, roww, xrow, L, 0, B, 1, partials, stride, 0, &n1, st))) return rc;
   int LL = L * L;
-  gram_stage2_kernel<<<cdiv(LL, 128), 128, 0, st>>>(partials, stride, 0, n1, 0, LL, cov, 1);
+  gram_stage2_kernel<<<stage2_blocks(LL), 256, 0, st>>>(partials, stride, 0, n1, 0, LL, cov, 1);
   NSVD_LAUNCH_CHECK();
-  gram_stage2_kernel<<<cdiv(LL, 128), 128, 0, st>>>(partials, stride, 0, n1, LL, LL, quad, 1);
+  gram_stage2_kernel<<<stage2_blocks(LL), 256, 0, st>>>(partials, stride, 0, n1, LL, LL, quad, 1);
   NSVD_LAUNCH_CHECK();
   return 0;
 }
