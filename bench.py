@@ -347,6 +347,42 @@ def strong_scaling_config(N, dev, dp, world, rank, total_points=1 << 20, neigs=6
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def hbm_kernel_probe(N, dev, hbm_peak_gbps, B=1 << 20):
+    """K2 (nsvd_gram_reduce, 8 B L algorithmic bytes) and K3 (nsvd_loss_dF, 12 B L) alone at 2^20 points - large enough to
+    be HBM-bound instead of launch-latency sized as at the headline batch - against the measured copy peak.
+    Direct C-ABI calls back to back on the current stream, CUDA events, inputs (134 / 537 MB) larger than the L2."""
+    import ctypes as C
+    import torch
+    from neural_svd_b200 import _lib
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    out = {"points": B, "peak_GBps": hbm_peak_gbps}
+    for L in (16, 64):
+        F, TF = torch.randn(B, L, device=dev), torch.randn(B, L, device=dev)
+        v = torch.ones(L, device=dev)
+        terms = torch.empty(2 * L * L + 5, device=dev)
+        coef = torch.randn(2 * L * L + 1, device=dev)
+        dF = torch.empty_like(F)
+        part = torch.empty(lib.nsvd_gram_partials_bytes(B, L), dtype=torch.uint8, device=dev)
+
+        def k2():
+            _lib.check(lib.nsvd_gram_reduce(_lib.ptr(F), _lib.ptr(TF), _lib.ptr(v), B, L, B // 2, _lib.ptr(terms),
+                                            _lib.ptr(part), st), "nsvd_gram_reduce")
+
+        def k3():
+            _lib.check(lib.nsvd_loss_dF(_lib.ptr(F), _lib.ptr(TF), _lib.ptr(v), _lib.ptr(coef), None, B, L, B // 2, B,
+                                        _lib.ptr(dF), st), "nsvd_loss_dF")
+
+        for name, fn, nbytes in (("gram_reduce", k2, 8.0 * B * L), ("loss_dF", k3, 12.0 * B * L)):
+            ms = time_events(fn, 20, 3, lambda: torch.cuda.synchronize(dev))
+            gbps = nbytes / (ms * 1e-3) / 1e9
+            out[f"{name}_L{L}"] = {"us": ms * 1e3, "algorithmic_mbytes": nbytes / 1e6, "achieved_GBps": gbps,
+                                   "hbm_frac": gbps / hbm_peak_gbps}
+        del F, TF, dF, part
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -575,6 +611,10 @@ def run_ours(args):
         if df_n:
             kernels["loss_dF"]["achieved_GBps"] = 12.0 * P * L * args.steps / (df_ms * 1e-3) / 1e9
             kernels["loss_dF"]["hbm_frac"] = kernels["loss_dF"]["achieved_GBps"] / pk["hbm"]
+        if world == 1 and not args.no_configs:
+            # the HBM-bound kernels alone at a size where the HBM, not the launch latency, bounds them (the two entries
+            # above are timed inside the step at the headline batch: 17 - 25 MB, latency sized)
+            kernels["hbm_probe_2p20_points"] = hbm_kernel_probe(N, dev, pk["hbm"])
         flop_pt = L * (2 * 4 * (K0 * 128 + 2 * 128 * 128 + 128) + 2 * (K0 * 128 + 4 * 128 * 128 + 2 * 128))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -1365,6 +1365,149 @@ loss_dF16_kernel(const float* __restrict__ F, const float* __restrict__ TF, cons
   }
 }
 
+// K3 for 16 < L <= 64, L a multiple of 4, on warp-level tensor cores (mma.sync m16n8k8, 3xTF32 - the arithmetic of K2):
+//   dF[b][m] = gs * ( sum_l F[b][l] C_h[l][m] - c4 v_m TF[b][m] ),   h = (b >= b1)
+// is a (rows x L) . (L x L) product per half.  A block walks a contiguous row range; per half it splits the coefficient
+// block ONCE into tf32 hi / lo planes in shared memory, then per 64-row chunk: F is read with 16-byte loads into
+// registers one chunk ahead, split once into planes, a warp multiplies 2 x WN tiles (fragments reused in registers),
+// the epilogue reads TF and writes dF as 8-byte pairs straight from the accumulator layout.  (The CUDA-core kernel above
+// is bound by shared-memory loads - 5 per 16 FMAs - with nothing in flight while it multiplies: 1.9 TB/s at L = 64.)
+template <int LP>
+__global__ void __launch_bounds__(128)
+loss_dF_mma_kernel(const float* __restrict__ F, const float* __restrict__ TF, const float* __restrict__ vmask,
+                   const float* __restrict__ coef, const float* __restrict__ gscale, int B, int L, int b1, float c4,
+                   int rows_per_block, float* __restrict__ dF) {
+  constexpr int TN = LP / 8, WN = TN / 2, WM = 2, CH = 64, KS = LP / 8;
+  constexpr int SF = LP + 4;                    // F planes [row][k]: A fragments (8 rows x 4 k) hit 32 distinct banks
+  constexpr int SC = LP + 8;                    // C planes [k][m]:  B fragments (4 k x 8 m) hit 32 distinct banks
+  constexpr int NV = CH * LP / 4 / 128;         // float4 per thread and chunk
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  uint32_t* Ch = smem_u;                        // [LP][SC]
+  uint32_t* Cl = Ch + LP * SC;
+  uint32_t* Fh = Cl + LP * SC;                  // [CH][SF]
+  uint32_t* Fl = Fh + CH * SF;
+  if (c4 <= 0.f) c4 = coef[2 * L * L];          // 4 / B_global left by loss_finalize (device-side counts)
+  const float gs = gscale ? gscale[0] : 1.f;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp >> 1) * WM, n0 = (warp & 1) * WN;
+  const long R0 = (long)blockIdx.x * rows_per_block;
+  const long R1 = R0 + rows_per_block < B ? R0 + rows_per_block : B;
+  for (int i = tid; i < CH * SF; i += 128) {    // columns >= L of the F planes stay zero
+    Fh[i] = 0u;
+    Fl[i] = 0u;
+  }
+  const int q4 = CH * (L >> 2);                 // float4 per full chunk
+  float4 fr[NV];
+  for (int h = 0; h < 2; ++h) {
+    const long r0 = h == 0 ? R0 : (R0 > b1 ? R0 : (long)b1);
+    const long r1 = h == 0 ? (R1 < b1 ? R1 : (long)b1) : R1;
+    if (r0 >= r1) continue;
+    __syncthreads();                            // the previous half's multiplies are done with the C planes
+    for (int e = tid; e < LP * LP; e += 128) {  // coefficient block of this half, zero beyond L
+      const int l = e / LP, m = e % LP;
+      const float c = (l < L && m < L) ? coef[(long)h * L * L + l * L + m] : 0.f;
+      const uint32_t hi = to_tf32(c);
+      Ch[l * SC + m] = hi;
+      Cl[l * SC + m] = to_tf32(c - __uint_as_float(hi));
+    }
+    auto load_chunk = [&](long c0) {
+      const long nel4 = ((r1 - c0) < CH ? (r1 - c0) : CH) * (long)(L >> 2);
+      const float4* f4 = reinterpret_cast<const float4*>(F + c0 * L);
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int e = tid + 128 * u;
+        fr[u] = (e < q4 && e < nel4) ? __ldcs(f4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_chunk(r0);
+    for (long c0 = r0; c0 < r1; c0 += CH) {
+      __syncthreads();                          // the previous chunk's multiplies are done with the F planes
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int e = tid + 128 * u;
+        if (e < q4) {
+          const int row = (4 * e) / L, col = (4 * e) % L;
+          uint4 hi, lo;
+          hi.x = to_tf32(fr[u].x); lo.x = to_tf32(fr[u].x - __uint_as_float(hi.x));
+          hi.y = to_tf32(fr[u].y); lo.y = to_tf32(fr[u].y - __uint_as_float(hi.y));
+          hi.z = to_tf32(fr[u].z); lo.z = to_tf32(fr[u].z - __uint_as_float(hi.z));
+          hi.w = to_tf32(fr[u].w); lo.w = to_tf32(fr[u].w - __uint_as_float(hi.w));
+          *reinterpret_cast<uint4*>(Fh + row * SF + col) = hi;
+          *reinterpret_cast<uint4*>(Fl + row * SF + col) = lo;
+        }
+      }
+      __syncthreads();
+      if (c0 + CH < r1) load_chunk(c0 + CH);    // in flight while this chunk is multiplied
+      // the TF values of this thread's outputs, also in flight under the multiply
+      float2 tfv[WM][WN][2];
+#pragma unroll
+      for (int i = 0; i < WM; ++i)
+#pragma unroll
+        for (int j = 0; j < WN; ++j)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int col = 8 * (n0 + j) + 2 * t;
+            const long row = c0 + 16 * (m0 + i) + g + 8 * hh;
+            tfv[i][j][hh] = (col < L && row < r1) ? __ldcs(reinterpret_cast<const float2*>(TF + row * L + col))
+                                                  : make_float2(0.f, 0.f);
+          }
+      float acc[WM][WN][4];
+#pragma unroll
+      for (int i = 0; i < WM; ++i)
+#pragma unroll
+        for (int j = 0; j < WN; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int k0 = ks * 8 + t;
+        // B = C_h (K = l, N = m): b0 (k = t, n = g), b1 (k = t + 4, n = g)
+        uint32_t bh[WN][2], bl[WN][2];
+#pragma unroll
+        for (int j = 0; j < WN; ++j) {
+          const int c = 8 * (n0 + j) + g;
+          bh[j][0] = Ch[k0 * SC + c]; bh[j][1] = Ch[(k0 + 4) * SC + c];
+          bl[j][0] = Cl[k0 * SC + c]; bl[j][1] = Cl[(k0 + 4) * SC + c];
+        }
+#pragma unroll
+        for (int i = 0; i < WM; ++i) {
+          // A = F chunk (M = row, K = l): a0 (g, t), a1 (g + 8, t), a2 (g, t + 4), a3 (g + 8, t + 4)
+          const int r = 16 * (m0 + i) + g;
+          const uint32_t ah[4] = {Fh[r * SF + k0], Fh[(r + 8) * SF + k0], Fh[r * SF + k0 + 4], Fh[(r + 8) * SF + k0 + 4]};
+          const uint32_t al[4] = {Fl[r * SF + k0], Fl[(r + 8) * SF + k0], Fl[r * SF + k0 + 4], Fl[(r + 8) * SF + k0 + 4]};
+#pragma unroll
+          for (int j = 0; j < WN; ++j) {
+            mma_tf32_16x8x8(acc[i][j], al, bh[j]);
+            mma_tf32_16x8x8(acc[i][j], ah, bl[j]);
+            mma_tf32_16x8x8(acc[i][j], ah, bh[j]);
+          }
+        }
+      }
+      // C fragment: c0 (g, 2t), c1 (g, 2t + 1), c2 (g + 8, 2t), c3 (g + 8, 2t + 1) inside tile (m0 + i, n0 + j)
+#pragma unroll
+      for (int i = 0; i < WM; ++i)
+#pragma unroll
+        for (int j = 0; j < WN; ++j) {
+          const int col = 8 * (n0 + j) + 2 * t;
+          if (col < L) {
+            const float2 vv = *reinterpret_cast<const float2*>(vmask + col);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const long row = c0 + 16 * (m0 + i) + g + 8 * hh;
+              if (row < r1) {
+                const float2 tf = tfv[i][j][hh];
+                float2 o;
+                o.x = gs * (acc[i][j][2 * hh] - c4 * vv.x * tf.x);
+                o.y = gs * (acc[i][j][2 * hh + 1] - c4 * vv.y * tf.y);
+                __stcs(reinterpret_cast<float2*>(dF + row * L + col), o);
+              }
+            }
+          }
+        }
+    }
+  }
+}
+
 int loss_dF(const float* F, const float* TF, const float* vmask, const float* coef,
             const float* gscale, int B, int L, int b1, long Bg, float* dF, cudaStream_t st) {
   float c4 = Bg > 0 ? (float)(4.0 / (double)Bg) : 0.f;   // Bg <= 0: the kernels read 4 / B_global from coef[2 L^2]
@@ -1383,6 +1526,26 @@ int loss_dF(const float* F, const float* TF, const float* vmask, const float* co
   if (L > 64) {
     set_error("loss_dF: n_copies %d > 64", L);
     return NSVD_E_BADARG;
+  }
+  if (L > 16 && (L & 3) == 0 && coef && TF &&
+      ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(TF) | reinterpret_cast<uintptr_t>(dF) |
+        reinterpret_cast<uintptr_t>(vmask)) & 15) == 0) {   // tensor-core kernel
+    const int LPP = L <= 32 ? 32 : 64;
+    const size_t smem_m = sizeof(uint32_t) * (size_t)(2 * LPP * (LPP + 8) + 2 * 64 * (LPP + 4));
+    int nbm = cdiv(B, 256);                    // >= 4 chunks per block, at most three blocks per SM
+    if (nbm > 444) nbm = 444;
+    int rpbm = cdiv(B, nbm);
+    rpbm = (rpbm + 63) / 64 * 64;
+    nbm = cdiv(B, rpbm);
+    if (LPP == 32) {
+      NSVD_SMEM_OPTIN(loss_dF_mma_kernel<32>, 100 * 1024);
+      loss_dF_mma_kernel<32><<<nbm, 128, smem_m, st>>>(F, TF, vmask, coef, gscale, B, L, b1, c4, rpbm, dF);
+    } else {
+      NSVD_SMEM_OPTIN(loss_dF_mma_kernel<64>, 100 * 1024);
+      loss_dF_mma_kernel<64><<<nbm, 128, smem_m, st>>>(F, TF, vmask, coef, gscale, B, L, b1, c4, rpbm, dF);
+    }
+    NSVD_LAUNCH_CHECK();
+    return 0;
   }
   if (L > 16) {   // register-tiled kernel
     const int LTT = L <= 32 ? 32 : 64, rows = (256 / (LTT / 4)) * 4;
