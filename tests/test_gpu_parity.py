@@ -499,13 +499,14 @@ def test_config4_shape_L64_engines_agree():
         assert rel(res["f16x3"][3][n], res["fp32"][3][n]) < TOL, n
 
 
-def test_config4_full_size_L64_gradient_parity():
+@pytest.mark.parametrize("neigs,B", [(64, 65536), (16, 131072)])
+def test_full_size_gradient_parity(neigs, B):
     # BASELINE configs[3] at a full micro-batch: hydrogen, L=64, B=65536 (one tensor-core micro-batch: 1024 half tiles
-    # per copy in the hidden-layer weight gradient, 64 k-slices in the layer-0 one).  Tensor-core engine against the
-    # CUDA-core fp32 engine (pinned to the reference at B <= 512 above) on loss, f, Tf and EVERY gradient tensor, and
-    # against the numpy oracle on a sample of rows of f / Tf.
-    cfg = O.PathConfig.hydrogen(neigs=64)
-    B = 65536
+    # per copy in the hidden-layer weight gradient, 64 k-slices in the layer-0 one), and the bench workload itself:
+    # L=16, B=131072 (two micro-batches).  Tensor-core engine against the CUDA-core fp32 engine (pinned to the
+    # reference at B <= 512 above) on loss, f, Tf and EVERY gradient tensor, and against the numpy oracle on a sample of
+    # rows of f / Tf.
+    cfg = O.PathConfig.hydrogen(neigs=neigs)
     g = torch.Generator().manual_seed(65)
     x = (cfg.sampling_scale * torch.randn(B, 2, generator=g)).cuda()
     res = {}
@@ -524,7 +525,7 @@ def test_config4_full_size_L64_gradient_parity():
     assert abs(tc[0] - ref[0]) < TOL * abs(ref[0])
     assert rel(tc[1], ref[1]) < TOL and rel(tc[2], ref[2]) < TOL
     errs = {n: rel(tc[3][n], ref[3][n]) for n in ref[3]}
-    print("L=64 B=65536 grads tc-vs-fp32:", " ".join(f"{n.split('.')[-2]}{n.split('.')[-1]}={v:.1e}" for n, v in errs.items()))
+    print(f"L={neigs} B={B} grads tc-vs-fp32:", " ".join(f"{n.split('.')[-2]}{n.split('.')[-1]}={v:.1e}" for n, v in errs.items()))
     assert max(errs.values()) < TOL, errs
     rows = np.random.RandomState(0).choice(B, 1024, replace=False)
     xs = x[torch.from_numpy(rows).cuda()].cpu().numpy().astype(np.float64)
