@@ -1365,6 +1365,73 @@ loss_dF16_kernel(const float* __restrict__ F, const float* __restrict__ TF, cons
   }
 }
 
+// K3 at L = 16, second version (fused-step shape: TF and coef both present): the kernel further down stages 256 rows
+// through shared memory between two block-wide synchronisations - while a block computes, nothing of its next rows is in
+// flight (3.9 TB/s).  Here, as in the L = 16 Gram kernel, a warp owns row pairs: one coalesced 128-byte load per array
+// and pair, 8 pairs per iteration with the next iteration's loads already issued; lane = (row of the pair, column m)
+// keeps column m of BOTH coefficient halves in registers, parks its F value in the warp's 128-byte shared-memory slot
+// and reads the 16 values of its row back as four 16-byte broadcast loads; 16 FMAs, one coalesced 128-byte store.
+__global__ void __launch_bounds__(512)
+loss_dF16_pipe_kernel(const float* __restrict__ F, const float* __restrict__ TF, const float* __restrict__ vmask,
+                      const float* __restrict__ coef, const float* __restrict__ gscale, long B, long b1, float c4,
+                      int rows_per_block, float* __restrict__ dF) {
+  constexpr int U = 8, W = 16;                  // row pairs per iteration and warp; warps per block
+  __shared__ __align__(16) float stage[W][U * 32];
+  if (c4 <= 0.f) c4 = coef[512];                // 4 / B_global left by loss_finalize (device-side counts)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, m = lane & 15, rr = lane >> 4;
+  const float gs = gscale ? gscale[0] : 1.f;
+  float c0[16], c1[16];                         // column m of the two coefficient halves
+#pragma unroll
+  for (int l = 0; l < 16; ++l) {
+    c0[l] = coef[l * 16 + m];
+    c1[l] = coef[256 + l * 16 + m];
+  }
+  const float cv = c4 * vmask[m];
+  const long r0 = (long)blockIdx.x * rows_per_block;
+  const long r1 = r0 + rows_per_block < B ? r0 + rows_per_block : B;
+  float fo[U], to[U], fn[U], tn[U];
+  auto load8 = [&](long r, float* f8, float* t8) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long row = r + 2 * W * u + rr;
+      const bool ok = row < r1;
+      f8[u] = ok ? __ldcs(F + row * 16 + m) : 0.f;
+      t8[u] = ok ? __ldcs(TF + row * 16 + m) : 0.f;
+    }
+  };
+  float* st = &stage[warp][0];
+  long r = r0 + 2 * warp;
+  load8(r, fo, to);
+  for (; r < r1; r += 2 * W * U) {
+    load8(r + 2 * W * U, fn, tn);               // rows beyond r1 load as zeros
+#pragma unroll
+    for (int u = 0; u < U; ++u) st[u * 32 + lane] = fo[u];
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long row = r + 2 * W * u + rr;
+      const float4* f4 = reinterpret_cast<const float4*>(st + u * 32 + 16 * rr);
+      const float4 a = f4[0], b = f4[1], c = f4[2], d = f4[3];
+      const float fv[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+      float o = 0.f;
+      if (row < b1) {
+#pragma unroll
+        for (int l = 0; l < 16; ++l) o = fmaf(fv[l], c0[l], o);
+      } else {
+#pragma unroll
+        for (int l = 0; l < 16; ++l) o = fmaf(fv[l], c1[l], o);
+      }
+      if (row < r1) __stcs(dF + row * 16 + m, gs * (o - cv * to[u]));
+    }
+    __syncwarp();                               // the next iteration overwrites the staged pairs
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      fo[u] = fn[u];
+      to[u] = tn[u];
+    }
+  }
+}
+
 // K3 for 16 < L <= 64, L a multiple of 4, on warp-level tensor cores (mma.sync m16n8k8, 3xTF32 - the arithmetic of K2):
 //   dF[b][m] = gs * ( sum_l F[b][l] C_h[l][m] - c4 v_m TF[b][m] ),   h = (b >= b1)
 // is a (rows x L) . (L x L) product per half.  A block walks a contiguous row range; per half it splits the coefficient
@@ -1514,6 +1581,16 @@ int loss_dF(const float* F, const float* TF, const float* vmask, const float* co
   if (Bg <= 0 && (!coef || !TF)) {
     set_error("loss_dF: device-side counts (Bg <= 0) need both TF and coef");
     return NSVD_E_BADARG;
+  }
+  if (L == 16 && coef && TF && B >= 4096) {     // software-pipelined warp-per-row-pair kernel
+    int nbp = cdiv(B, 2048);                    // >= 8 iterations of 256 rows per block ...
+    if (nbp > 148) nbp = 148;                   // ... one 512-thread block (97 registers per thread) per SM
+    int rpb = cdiv(B, nbp);
+    rpb = (rpb + 255) / 256 * 256;
+    nbp = cdiv(B, rpb);
+    loss_dF16_pipe_kernel<<<nbp, 512, 0, st>>>(F, TF, vmask, coef, gscale, B, b1, c4, rpb, dF);
+    NSVD_LAUNCH_CHECK();
+    return 0;
   }
   if (L == 16) {
     int nb16 = cdiv(B, 256);
