@@ -291,6 +291,45 @@ def test_cdk_cabi_planes_ready_and_finalize_scratch():
                    "finalize")
 
 
+@pytest.mark.parametrize("B,L,b1", [(5000, 16, 2500), (4096 + 77, 16, 2001), (3000, 64, 1500), (1001, 40, 333), (777, 24, 400),
+                                     (513, 33, 257), (70000, 64, 35000), (300000, 16, 150001)])
+def test_k2_k3_kernels_against_fp64(B, L, b1):
+    """K2 (nsvd_gram_reduce) and K3 (nsvd_loss_dF) through the C-ABI on every kernel variant behind them - the L = 16
+    one-launch Gram and the pipelined / block-staged dF kernels, the mma.sync kernels for 16 < L <= 64 (L a multiple of 4,
+    padded tiles, ragged chunks, halves of odd size) and the CUDA-core fallbacks - against an fp64 evaluation of
+    nestedlora.py:57-64, 98-111.  Both arithmetic engines share these kernels, so engine-vs-engine tests cannot see them."""
+    import ctypes as C
+    from neural_svd_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B + L)
+    F = torch.randn(B, L, generator=g).cuda()
+    TF = (3.0 * torch.randn(B, L, generator=g)).cuda()
+    v = torch.rand(L, generator=g).cuda() + 0.1
+    coef = torch.randn(2 * L * L + 1, generator=g).cuda()
+    gs = torch.tensor(0.7).cuda()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    terms = torch.empty(2 * L * L + 5).cuda()
+    part = torch.empty(lib.nsvd_gram_partials_bytes(B, L), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.nsvd_gram_reduce(_lib.ptr(F), _lib.ptr(TF), _lib.ptr(v), B, L, b1, _lib.ptr(terms), _lib.ptr(part), st),
+               "nsvd_gram_reduce")
+    dF = torch.empty_like(F)
+    _lib.check(lib.nsvd_loss_dF(_lib.ptr(F), _lib.ptr(TF), _lib.ptr(v), _lib.ptr(coef), _lib.ptr(gs), B, L, b1, B,
+                                _lib.ptr(dF), st), "nsvd_loss_dF")
+    Fd, Td, vd, cd = F.double(), TF.double(), v.double(), coef.double()
+    G1, G2 = Fd[:b1].T @ Fd[:b1], Fd[b1:].T @ Fd[b1:]
+    ops = (vd * Fd * Td).sum()
+    t = terms.double()
+    LL = L * L
+    assert rel(t[:LL].cpu().numpy(), G1.reshape(-1).cpu().numpy()) < 2e-6
+    assert rel(t[LL:2 * LL].cpu().numpy(), G2.reshape(-1).cpu().numpy()) < 2e-6
+    assert abs(float(t[2 * LL]) - float(ops)) < 2e-6 * float((vd * Fd * Td).abs().sum())
+    ref = -(4.0 / B) * vd * Td
+    ref[:b1] += Fd[:b1] @ cd[:LL].reshape(L, L)
+    ref[b1:] += Fd[b1:] @ cd[LL:2 * LL].reshape(L, L)
+    ref *= 0.7
+    assert rel(dF.double().cpu().numpy(), ref.cpu().numpy()) < 2e-6
+
+
 def test_large_batch_properties():
     # BASELINE-size inputs where the oracle is too slow: size-independent properties instead.
     # (1) permuting points inside each half leaves loss and gradients unchanged;
