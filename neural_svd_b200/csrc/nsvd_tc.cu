@@ -2012,14 +2012,18 @@ hidden_fwd_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 
 // ------------------------------------------------------------------------------------------
 // S2-fwd fused: hidden layers 1 AND 2 (+ head + operator) in one persistent kernel.  The three derivative streams of
-// a1 never reach DRAM: a CTA writes them (TMA bulk stores) into a private scratch of two tile slots (2 x 192 KB per CTA,
-// 57 MB for the grid - resident in the 126 MB L2, rewritten every group before it could be evicted) and reads them
-// straight back as the A operand of layer 2.  Only the value streams (needed by the backward) and F / TF leave the chip:
-// 48 KB per point and 16 copies instead of 107 KB with one kernel per layer.  (Keeping a1 in shared memory is not
-// possible: 4 streams x 128 units x 4 B = 2 KB per point next to 128 KB of W1 + W2 planes.)
+// a1 go through a private scratch of kHidGroup tile slots per CTA (TMA bulk stores, evict_last; 192 KB per slot) and
+// come straight back as the A operand of layer 2; only the value streams (needed by the backward) and F / TF are meant
+// to leave the chip: 48 KB per point and 16 copies algorithmic instead of 107 KB with one kernel per layer.  Measured
+// (profiles/README.md): single-tile groups keep the 28 MB of scratch L2-resident (60 KB per point of DRAM traffic) but
+// stall 4.7 us per tile on the store -> load round trip; two-tile groups (57 MB of scratch, 108 KB per point) put a whole
+// item between a tile's stores and their re-load, keep the weights of a layer for two items and are 9-10 % faster: the
+// default.  (Keeping a1 in shared memory is not possible: 4 streams x 128 units x 4 B = 2 KB per point next to the
+// weight planes.)
 //   work items of a CTA, in groups of kHidGroup tiles of its range:  A(t0) [A(t1)] B(t0) [B(t1)]   (A = layer 1, B = layer 2)
 //   smem : W planes of the layer in use (64 KB, reloaded when (layer, copy) changes) | ring 3 x 32 KB | 64 KB staging
-//   TMEM : 4 x 128 columns (one block per stream), one item at a time
+//   TMEM : 4 x 128 columns (one block per stream), one item at a time; the MMAs of an item are issued stream by stream
+//          and commit sfull[s] per stream, so the stream-major epilogue starts on stream 0 a quarter into the MMA phase
 //   adone[slot] : the bulk stores of A(slot) have completed (cp.async.bulk.wait_group 0 by the issuing thread) - the
 //                 producer waits for it before loading B(slot)'s operands.
 // ------------------------------------------------------------------------------------------
