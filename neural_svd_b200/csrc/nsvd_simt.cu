@@ -1685,20 +1685,6 @@ __global__ void cdk_rowdots_kernel(const float* __restrict__ fp, const float* __
   }
 }
 
-// padded fp32 copies + exact row dots (shared by both engines)
-int cdk_pad_rowdots(const float* f, const float* g, const float* v, int B, int L, int fc, float* fp, float* gp,
-                    float* opdot, float* rs_joint, cudaStream_t st) {
-  int Lp = L + fc;
-  long n = (long)B * Lp;
-  cdk_pad_kernel<<<cdiv(n, 256), 256, 0, st>>>(f, fp, B, L, fc);
-  NSVD_LAUNCH_CHECK();
-  cdk_pad_kernel<<<cdiv(n, 256), 256, 0, st>>>(g, gp, B, L, fc);
-  NSVD_LAUNCH_CHECK();
-  cdk_rowdots_kernel<<<cdiv((long)B * 32, 256), 256, 0, st>>>(fp, gp, v, B, Lp, opdot, rs_joint);
-  NSVD_LAUNCH_CHECK();
-  return 0;
-}
-
 size_t cdk_work_bytes(int B, int L, int fc) {
   long Lp = L + fc;
   return sizeof(float) * (size_t)(2L * B * Lp + B + 64) + 256;

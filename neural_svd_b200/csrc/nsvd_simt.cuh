@@ -35,8 +35,6 @@ int loss_dF(const float* F, const float* TF, const float* vmask, const float* co
             int B, int L, int b1, long Bg, float* dF, cudaStream_t st);
 
 size_t cdk_work_bytes(int B, int L, int fc);
-int cdk_pad_rowdots(const float* f, const float* g, const float* v, int B, int L, int fc, float* fp, float* gp,
-                    float* opdot, float* rs_joint, cudaStream_t st);
 int cdk_fwd(const float* f, const float* g, const float* v, int B, int L, int fc, float* terms,
             float* rs_joint, void* work, cudaStream_t st);
 int cdk_finalize(const float* terms, const float* Mm, int Lp, long Bg, float* losses, float* coef, double* scratch,
